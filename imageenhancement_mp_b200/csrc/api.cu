@@ -1,0 +1,70 @@
+// Library-wide pieces of the C ABI: version, error string, device info, tensor-map encoding.
+#include <cstring>
+#include <mutex>
+
+#include "ie_common.cuh"
+
+namespace ie {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                      uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  IE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p is not 16-byte aligned", base);
+  IE_REQUIRE((pitch_elems * 2) % 16 == 0, "tensor map: row pitch must be a multiple of 16 bytes");
+  IE_REQUIRE(box_cols * 2 == 128 && box_rows >= 1 && box_rows <= 256, "tensor map: bad box %u x %u", box_cols, box_rows);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (cols %llu rows %llu pitch %llu box %ux%u)",
+             (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems, box_cols, box_rows);
+  return IE_OK;
+}
+
+}  // namespace ie
+
+extern "C" int ie_version(void) { return IE_VERSION; }
+extern "C" const char* ie_last_error(void) { return ie::g_err; }
+extern "C" int ie_sm_count(void) { return ie::sm_count(); }

@@ -1,0 +1,43 @@
+// Shared host-side helpers for the C-ABI library: error reporting, launch checks, device info.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/imgenh_b200.h"
+
+namespace ie {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
+// rank-2 bf16 tensor [rows][cols] with `pitch_elems` elements between rows; box = box_cols x box_rows;
+// 128-byte swizzle (box_cols must be 64).  Returns 0 or <0 with the error set.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
+                      uint32_t box_cols, uint32_t box_rows);
+
+}  // namespace ie
+
+#define IE_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      ie::set_error(__VA_ARGS__);    \
+      return IE_ERR_INVALID;         \
+    }                                \
+  } while (0)
+
+#define IE_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ie::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return IE_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define IE_LAUNCH_CHECK() IE_CUDA(cudaGetLastError())
+
+static inline int ie_ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }

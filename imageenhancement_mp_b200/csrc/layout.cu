@@ -1,0 +1,333 @@
+// Bandwidth kernels around the convolutions: weight / input packing, max-pool, bilinear up-sampling
+// into concat slices, per-image channel means, broadcast, raster -> NHWC, basis softmax.
+// All bf16 raster traffic moves as 16-byte vectors (8 channels); grids cover the tensor exactly.
+#include <cuda_bf16.h>
+
+#include "ie_common.cuh"
+#include "ie_ptx.cuh"
+
+namespace ie {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------- weights
+__global__ void pack_weights_kernel(const float* __restrict__ hwio, int taps, int cin, int cout, int ktot_pad,
+                                    __nv_bfloat16* __restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)cout * ktot_pad;
+  if (idx >= total) return;
+  const int o = (int)(idx / ktot_pad);
+  const int k = (int)(idx - (long long)o * ktot_pad);
+  float v = 0.f;
+  if (k < taps * cin) v = hwio[(long long)k * cout + o];   // HWIO flat index = ((i*kw+j)*cin + c)*cout + o
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------- input im2col
+// One thread per (raster row, 16-byte chunk): 8 consecutive k of the 64-wide im2col row.
+__global__ void im2col3x3_kernel(const float* __restrict__ x, int n, int h, int w, int c, uint4* __restrict__ out,
+                                 long long rows) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= rows * 8) return;
+  const long long r = t >> 3;
+  const int chunk = (int)(t & 7);
+  const int wp = w + 2, plane = (h + 2) * wp;
+  const int img = (int)(r / plane);
+  const int pr = (int)(r - (long long)img * plane);
+  const int y = pr / wp - 1, xx = pr % wp - 1;
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = 0.f;
+  if (y >= 0 && y < h && xx >= 0 && xx < w) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = chunk * 8 + e;
+      if (k < 9 * c) {
+        const int tap = k / c, ch = k - tap * c;
+        const int sy = y + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        if (sy >= 0 && sy < h && sx >= 0 && sx < w) f[e] = x[(((long long)img * h + sy) * w + sx) * c + ch];
+      }
+    }
+  }
+  out[t] = pack8(f);
+}
+
+// ------------------------------------------------------------------------------- max-pool 2x2
+__global__ void maxpool2_kernel(const uint4* __restrict__ x, int n, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
+                                uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+  const int ho = h >> 1, wo = w >> 1;
+  const long long total = (long long)n * (ho + 2) * (wo + 2) * cvec;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int cv = (int)(t % cvec);
+  const long long ro = t / cvec;
+  const int wpo = wo + 2, plo = (ho + 2) * wpo;
+  const int img = (int)(ro / plo);
+  const int pr = (int)(ro - (long long)img * plo);
+  const int oy = pr / wpo, ox = pr % wpo;
+  uint4 res = make_uint4(0, 0, 0, 0);
+  if (oy >= 1 && oy <= ho && ox >= 1 && ox <= wo) {
+    const int wpi = w + 2;
+    const long long rin = ((long long)img * (h + 2) + (2 * oy - 1)) * wpi + (2 * ox - 1);
+    const uint4* p = x + rin * x_pitch_v + x_coff_v + cv;
+    float a[8], b[8], c[8], d[8], m[8];
+    unpack8(p[0], a);
+    unpack8(p[x_pitch_v], b);
+    unpack8(p[(long long)wpi * x_pitch_v], c);
+    unpack8(p[(long long)(wpi + 1) * x_pitch_v], d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
+    res = pack8(m);
+  }
+  y[ro * y_pitch_v + y_coff_v + cv] = res;
+}
+
+// ------------------------------------------------------------------------------- bilinear upsample
+// Half-pixel centres: src = (dst + 0.5)/s - 0.5; lower = max(floor(src),0), upper = min(ceil(src), size-1).
+__global__ void upsample_kernel(const uint4* __restrict__ x, int n, int h, int w, int cvec, int x_pitch_v,
+                                int x_coff_v, int s, uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+  const int ho = h * s, wo = w * s;
+  const long long total = (long long)n * (ho + 2) * (wo + 2) * cvec;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int cv = (int)(t % cvec);
+  const long long ro = t / cvec;
+  const int wpo = wo + 2, plo = (ho + 2) * wpo;
+  const int img = (int)(ro / plo);
+  const int pr = (int)(ro - (long long)img * plo);
+  const int oy = pr / wpo - 1, ox = pr % wpo - 1;
+  uint4 res = make_uint4(0, 0, 0, 0);
+  if (oy >= 0 && oy < ho && ox >= 0 && ox < wo) {
+    const float inv = 1.f / (float)s;
+    const float sy = ((float)oy + 0.5f) * inv - 0.5f;
+    const float sx = ((float)ox + 0.5f) * inv - 0.5f;
+    const float fy = floorf(sy), fx = floorf(sx);
+    const int y0 = max((int)fy, 0), y1 = min((int)ceilf(sy), h - 1);
+    const int x0 = max((int)fx, 0), x1 = min((int)ceilf(sx), w - 1);
+    const float ly = sy - fy, lx = sx - fx;
+    const int wpi = w + 2;
+    const long long base = (long long)img * (h + 2) * wpi;
+    const uint4* p = x + x_coff_v + cv;
+    float a[8], b[8], c[8], d[8], o[8];
+    unpack8(p[(base + (long long)(y0 + 1) * wpi + (x0 + 1)) * x_pitch_v], a);
+    unpack8(p[(base + (long long)(y0 + 1) * wpi + (x1 + 1)) * x_pitch_v], b);
+    unpack8(p[(base + (long long)(y1 + 1) * wpi + (x0 + 1)) * x_pitch_v], c);
+    unpack8(p[(base + (long long)(y1 + 1) * wpi + (x1 + 1)) * x_pitch_v], d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float top = a[e] + (b[e] - a[e]) * lx;
+      const float bot = c[e] + (d[e] - c[e]) * lx;
+      o[e] = top + (bot - top) * ly;
+    }
+    res = pack8(o);
+  }
+  y[ro * y_pitch_v + y_coff_v + cv] = res;
+}
+
+// ------------------------------------------------------------------------------- channel means
+// block = 256 threads = 32 pixel lanes x 8 vector lanes (64 channels); grid = (c/64, n, splits).
+__global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, int x_pitch_v, int x_coff_v,
+                                    float* __restrict__ mean, int c, float scale) {
+  const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int cb = blockIdx.x, img = blockIdx.y;
+  const int wp = w + 2;
+  const long long base = (long long)img * (h + 2) * wp;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const int npix = h * w;
+  for (int pix = blockIdx.z * 32 + pl; pix < npix; pix += gridDim.z * 32) {
+    const int yy = pix / w, xx = pix - yy * w;
+    float f[8];
+    unpack8(x[(base + (long long)(yy + 1) * wp + (xx + 1)) * x_pitch_v + x_coff_v + cb * 8 + vl], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+  __shared__ float red[32][65];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][vl * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    atomicAdd(&mean[(long long)img * c + cb * 64 + threadIdx.x], s * scale);
+  }
+}
+
+__global__ void broadcast_kernel(const float* __restrict__ vec, int n, int kh, int kw, int cvec, int c,
+                                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+  const long long total = (long long)n * (kh + 2) * (kw + 2) * cvec;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int cv = (int)(t % cvec);
+  const long long ro = t / cvec;
+  const int wp = kw + 2, pl = (kh + 2) * wp;
+  const int img = (int)(ro / pl);
+  const int pr = (int)(ro - (long long)img * pl);
+  const int oy = pr / wp, ox = pr % wp;
+  uint4 res = make_uint4(0, 0, 0, 0);
+  if (oy >= 1 && oy <= kh && ox >= 1 && ox <= kw) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = vec[(long long)img * c + cv * 8 + e];
+    res = pack8(f);
+  }
+  y[ro * y_pitch_v + y_coff_v + cv] = res;
+}
+
+__global__ void raster_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int x_pitch,
+                                      int x_coff, float* __restrict__ y) {
+  const long long total = (long long)n * h * w * c;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int ch = (int)(t % c);
+  const long long pix = t / c;
+  const int xx = (int)(pix % w);
+  const int yy = (int)((pix / w) % h);
+  const int img = (int)(pix / ((long long)w * h));
+  const long long r = ((long long)img * (h + 2) + yy + 1) * (w + 2) + xx + 1;
+  y[t] = __bfloat162float(x[r * x_pitch + x_coff + ch]);
+}
+
+// ------------------------------------------------------------------------------- basis softmax
+// One block per (image, basis b): softmax over `taps` values strided by b.
+__global__ void softmax_taps_kernel(const float* __restrict__ in, int taps, int b, float* __restrict__ out) {
+  const int img = blockIdx.x / b, bi = blockIdx.x % b;
+  const float* src = in + (long long)img * taps * b + bi;
+  float* dst = out + (long long)img * taps * b + bi;
+  __shared__ float red[32];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < taps; i += blockDim.x) mx = fmaxf(mx, src[(long long)i * b]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < taps; i += blockDim.x) sum += expf(src[(long long)i * b] - mx);
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < taps; i += blockDim.x) dst[(long long)i * b] = expf(src[(long long)i * b] - mx) * inv;
+}
+
+}  // namespace ie
+
+using namespace ie;
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, int ktot_pad,
+                                    void* packed_bf16, void* stream) {
+  IE_REQUIRE(hwio && packed_bf16, "pack_conv_weights: null pointer");
+  IE_REQUIRE(kh > 0 && kw > 0 && cin > 0 && cout > 0 && ktot_pad >= kh * kw * cin, "pack_conv_weights: bad sizes");
+  const long long total = (long long)cout * ktot_pad;
+  pack_weights_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(hwio, kh * kw, cin, cout, ktot_pad,
+                                                                     static_cast<__nv_bfloat16*>(packed_bf16));
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* raster_bf16, void* stream) {
+  IE_REQUIRE(x && raster_bf16, "pack_input: null pointer");
+  IE_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && 9 * c <= 64, "pack_input: need 9*c <= 64 (c=%d)", c);
+  const long long rows = (long long)n * (h + 2) * (w + 2);
+  im2col3x3_kernel<<<ie_ceil_div(rows * 8, 256), 256, 0, S(stream)>>>(x, n, h, w, c, static_cast<uint4*>(raster_bf16),
+                                                                     rows);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+static int check_slice(const char* who, int c, int pitch, int coff) {
+  IE_REQUIRE(c > 0 && c % 8 == 0 && pitch % 8 == 0 && coff % 8 == 0 && coff + c <= pitch,
+             "%s: bad channel slice (c %d, pitch %d, coff %d)", who, c, pitch, coff);
+  return IE_OK;
+}
+
+extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y,
+                                     int y_pitch, int y_coff, void* stream) {
+  IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "maxpool2: bad arguments (h %d, w %d)", h, w);
+  if (int rc = check_slice("maxpool2(x)", c, x_pitch, x_coff)) return rc;
+  if (int rc = check_slice("maxpool2(y)", c, y_pitch, y_coff)) return rc;
+  const long long total = (long long)n * (h / 2 + 2) * (w / 2 + 2) * (c / 8);
+  maxpool2_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(static_cast<const uint4*>(x), n, h, w, c / 8,
+                                                                 x_pitch / 8, x_coff / 8, static_cast<uint4*>(y),
+                                                                 y_pitch / 8, y_coff / 8);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff,
+                                              int scale, void* y, int y_pitch, int y_coff, void* stream) {
+  IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && scale >= 1, "upsample: bad arguments");
+  if (int rc = check_slice("upsample(x)", c, x_pitch, x_coff)) return rc;
+  if (int rc = check_slice("upsample(y)", c, y_pitch, y_coff)) return rc;
+  const long long total = (long long)n * (h * scale + 2) * (w * scale + 2) * (c / 8);
+  upsample_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(static_cast<const uint4*>(x), n, h, w, c / 8,
+                                                                 x_pitch / 8, x_coff / 8, scale,
+                                                                 static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff,
+                                         float* mean, void* stream) {
+  IE_REQUIRE(x && mean && n > 0 && h > 0 && w > 0, "channel_mean: bad arguments");
+  IE_REQUIRE(c % 64 == 0, "channel_mean: c must be a multiple of 64 (got %d)", c);
+  if (int rc = check_slice("channel_mean(x)", c, x_pitch, x_coff)) return rc;
+  IE_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
+  const int npix = h * w;
+  int splits = (2 * sm_count() + (c / 64) * n - 1) / ((c / 64) * n);
+  const int max_splits = (npix + 31) / 32;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  IE_REQUIRE(n <= 65535, "channel_mean: n too large");
+  dim3 grid(c / 64, n, splits);
+  channel_mean_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, x_pitch / 8, x_coff / 8, mean,
+                                                  c, 1.f / (float)npix);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int c, void* y, int y_pitch, int y_coff,
+                                    void* stream) {
+  IE_REQUIRE(vec && y && n > 0 && kh > 0 && kw > 0, "broadcast: bad arguments");
+  if (int rc = check_slice("broadcast(y)", c, y_pitch, y_coff)) return rc;
+  const long long total = (long long)n * (kh + 2) * (kw + 2) * (c / 8);
+  broadcast_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(vec, n, kh, kw, c / 8, c, static_cast<uint4*>(y),
+                                                                  y_pitch / 8, y_coff / 8);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* y,
+                                     void* stream) {
+  IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && x_coff + c <= x_pitch, "raster_to_nhwc: bad arguments");
+  const long long total = (long long)n * h * w * c;
+  raster_to_nhwc_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), n, h, w,
+                                                                       c, x_pitch, x_coff, y);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float* bas, void* stream) {
+  IE_REQUIRE(originbasis && bas && n > 0 && taps > 0 && b > 0, "softmax_taps: bad arguments");
+  softmax_taps_kernel<<<n * b, 256, 0, S(stream)>>>(originbasis, taps, b, bas);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}

@@ -1,0 +1,412 @@
+// Per-pixel quality metrics of /root/reference/data_utils.py:24-164 as eval.py:139-182 uses them:
+// white-level inversion, sRGB curve, 8-px crop, squared-error sums (PSNR) and the forward-difference
+// gradient L1 term of basic_img_loss - in ONE pass over the tensors instead of the reference's
+// 3T+4 separate invert_preproc calls.  Plus an SSIM extension (tf.image.ssim semantics).
+// fp32 arithmetic per pixel, fp64 for everything that is accumulated across pixels.
+#include "ie_common.cuh"
+
+namespace ie {
+
+// sRGBforward, data_utils.py:24-36.
+__device__ __forceinline__ float srgb_forward(float x) {
+  const float b = .0031308f, a = .055f, k0 = 12.92f;
+  const float gamma = 1.f / 2.4f;
+  const float k1 = (1.f + a) * gamma;
+  // x^gamma via exp2(gamma*log2(x)): x >= b > 0 so log2 is finite
+  const float g = (1.f + a) * exp2f(gamma * log2f(fmaxf(x, b))) - a;
+  float r = (x < b) ? k0 * x : g;
+  if (x > 1.f) r = k1 * x - k1 + 1.f;
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum NQ per-thread floats over a 256-thread block and add them (fp64) to dst[0..NQ).
+template <int NQ>
+__device__ __forceinline__ void block_accumulate(const float (&v)[NQ], double* dst, int nq) {
+  __shared__ float red[8][NQ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float s = warp_sum(v[q]);
+    if (lane == 0) red[warp][q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < nq) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
+    atomicAdd(&dst[threadIdx.x], s);
+  }
+}
+
+// ------------------------------------------------------------------------------- mean over H,W
+__global__ void mean_hw_kernel(const float* __restrict__ x, long long npix, int pitch, int coff, float scale,
+                               float* __restrict__ out) {
+  const int img = blockIdx.y;
+  const float* p = x + (long long)img * npix * pitch + coff;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x)
+    acc += p[i * pitch];
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(&out[img], (float)(s * scale));
+  }
+}
+
+// ------------------------------------------------------------------------------- invert_preproc
+__global__ void invert_preproc_kernel(const float* __restrict__ img, int pitch, int coff, int nch,
+                                      const float* __restrict__ wl, int h, int w, int crop, float* __restrict__ out,
+                                      long long total) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int wc = w - 2 * crop, hc = h - 2 * crop;
+  const int x = (int)(t % wc);
+  const int y = (int)((t / wc) % hc);
+  const int n = (int)(t / ((long long)wc * hc));
+  const float* p = img + (((long long)n * h + y + crop) * w + x + crop) * pitch + coff;
+  float v = p[0];
+  if (nch > 1) {                      // tf.reduce_mean(burst, axis=-1) of psnr_average_f (data_utils.py:162)
+    for (int c = 1; c < nch; ++c) v += p[c];
+    v /= (float)nch;
+  }
+  out[t] = srgb_forward(v / wl[n]);
+}
+
+// ------------------------------------------------------------------------------- fused eval metrics
+// Tile of 32 x 8 cropped pixels (+1 halo row/column for the forward differences).  For every pixel of
+// the haloed tile the error images d_k = sRGB(e_k/wl) - sRGB(gt/wl) go to shared memory, then each
+// interior thread accumulates d_k^2 and |d_k(y+1,x)-d_k(y,x)|/2 + |d_k(y,x+1)-d_k(y,x)|/2.
+constexpr int kMT_W = 32, kMT_H = 8, kMaxT = 8;
+
+__global__ void __launch_bounds__(256)
+eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ burst, int burst_pitch,
+                    const float* __restrict__ truth, const float* __restrict__ wl, int h, int w, int T, int crop,
+                    int tiles_x, int tiles_y, double* __restrict__ sums) {
+  __shared__ float s_d[kMaxT + 1][kMT_H + 1][kMT_W + 1];
+  int bid = blockIdx.x;
+  const int txi = bid % tiles_x; bid /= tiles_x;
+  const int tyi = bid % tiles_y;
+  const int n = bid / tiles_y;
+  const int hc = h - 2 * crop, wc = w - 2 * crop;
+  const int x0 = txi * kMT_W, y0 = tyi * kMT_H;
+  const float wln = wl[n];
+  const int nq = (T + 3) + (T + 1);
+
+  float acc[2 * kMaxT + 4];
+#pragma unroll
+  for (int q = 0; q < 2 * kMaxT + 4; ++q) acc[q] = 0.f;
+
+  for (int i = threadIdx.x; i < (kMT_H + 1) * (kMT_W + 1); i += 256) {
+    const int ly = i / (kMT_W + 1), lx = i - ly * (kMT_W + 1);
+    const int y = y0 + ly, x = x0 + lx;
+    const bool inside = (y < hc) && (x < wc);
+    const bool owner = inside && ly < kMT_H && lx < kMT_W;   // halo pixels are owned by the neighbouring tile
+    if (inside) {
+      const long long pix = ((long long)n * h + y + crop) * w + x + crop;
+      const float g = srgb_forward(truth[pix * 2] / wln);
+      const float* rp = recon + pix * (T + 1);
+      const float* bp = burst + pix * burst_pitch;
+      float bsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxT + 1; ++k) {
+        if (k <= T) {
+          const float d = srgb_forward(rp[k] / wln) - g;
+          s_d[k][ly][lx] = d;
+          if (owner) acc[k] += d * d;
+        }
+      }
+      float b0 = 0.f;
+#pragma unroll
+      for (int t = 0; t < kMaxT; ++t) {
+        if (t < T) {
+          const float v = bp[t];
+          if (t == 0) b0 = v;
+          bsum += v;
+        }
+      }
+      if (owner) {
+        const float d0 = srgb_forward(b0 / wln) - g;              // psnr_burst0, data_utils.py:152-154
+        const float da = srgb_forward((bsum / (float)T) / wln) - g;  // psnr_average_f, :162-164
+        acc[T + 1] += d0 * d0;
+        acc[T + 2] += da * da;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+    const int y = y0 + ly, x = x0 + lx;
+    if (y < hc - 1 && x < wc - 1) {
+#pragma unroll
+      for (int k = 0; k < kMaxT + 1; ++k) {
+        if (k <= T) {
+          const float c = s_d[k][ly][lx];
+          acc[T + 3 + k] += .5f * fabsf(s_d[k][ly + 1][lx] - c) + .5f * fabsf(s_d[k][ly][lx + 1] - c);
+        }
+      }
+    }
+  }
+  block_accumulate<2 * kMaxT + 4>(acc, sums + (long long)n * nq, nq);
+}
+
+// ------------------------------------------------------------------------------- pair reductions
+__global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long count,
+                                  double* __restrict__ sums) {
+  const int n = blockIdx.y;
+  const float* pa = a + (long long)n * count;
+  const float* pb = b + (long long)n * count;
+  float acc[1] = {0.f};
+  const bool vec = ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb)) & 15) == 0;
+  const long long nvec = vec ? count / 4 : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4* va = reinterpret_cast<const float4*>(pa);
+  const float4* vb = reinterpret_cast<const float4*>(pb);
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // 4 independent 16-byte loads per operand in flight
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    float4 x[4], y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { x[u] = __ldcs(va + i + u * stride); y[u] = __ldcs(vb + i + u * stride); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float d0 = x[u].x - y[u].x, d1 = x[u].y - y[u].y, d2 = x[u].z - y[u].z, d3 = x[u].w - y[u].w;
+      acc[0] += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const float4 x = __ldcs(va + i), y = __ldcs(vb + i);
+    const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    acc[0] += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (long long j = nvec * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count; j += stride) {
+    const float d = pa[j] - pb[j];
+    acc[0] += d * d;
+  }
+  block_accumulate<1>(acc, sums + n, 1);
+}
+
+__global__ void img_loss_sums_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
+                                     long long total, double* __restrict__ sums) {
+  float acc[2] = {0.f, 0.f};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % w);
+    const int y = (int)((t / w) % h);
+    const float d = a[t] - b[t];
+    acc[0] += d * d;
+    if (y < h - 1 && x < w - 1) {
+      const float dy = a[t + w] - b[t + w], dx = a[t + 1] - b[t + 1];
+      acc[1] += .5f * fabsf(dy - d) + .5f * fabsf(dx - d);
+    }
+  }
+  block_accumulate<2>(acc, sums, 2);
+}
+
+// ------------------------------------------------------------------------------- SSIM (extension)
+// Output tile 64 x 32 (VALID): input 74 x 42.  Horizontal 11-tap pass with 8 outputs per thread
+// (sliding window in registers) over the five moments a, b, a^2, b^2, ab, then the vertical pass.
+constexpr int kSW = 64, kSH = 32, kSR = 5, kSTaps = 11;
+constexpr int kSInW = kSW + 2 * kSR, kSInH = kSH + 2 * kSR;      // 74 x 42
+constexpr int kSInPitch = 76;
+
+__global__ void __launch_bounds__(256)
+ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, int tiles_x, int tiles_y,
+            double* __restrict__ sums) {
+  extern __shared__ float sm[];
+  float* s_a = sm;                                 // [42][76]
+  float* s_b = s_a + kSInH * kSInPitch;            // [42][76]
+  float* s_m = s_b + kSInH * kSInPitch;            // [5][42][64]
+  int bid = blockIdx.x;
+  const int txi = bid % tiles_x; bid /= tiles_x;
+  const int tyi = bid % tiles_y;
+  const int n = bid / tiles_y;
+  const int ho = h - 2 * kSR, wo = w - 2 * kSR;
+  const int x0 = txi * kSW, y0 = tyi * kSH;
+  const float* pa = a + (long long)n * h * w;
+  const float* pb = b + (long long)n * h * w;
+  for (int i = threadIdx.x; i < kSInH * kSInPitch; i += 256) {
+    const int ly = i / kSInPitch, lx = i - ly * kSInPitch;
+    const int y = y0 + ly, x = x0 + lx;
+    float va = 0.f, vb = 0.f;
+    if (lx < kSInW && y < h && x < w) { va = pa[(long long)y * w + x]; vb = pb[(long long)y * w + x]; }
+    s_a[i] = va;
+    s_b[i] = vb;
+  }
+  __syncthreads();
+  // normalised 11-tap Gaussian, sigma 1.5 (tf.image.ssim's _fspecial_gauss)
+  float g[kSTaps];
+  {
+    float gs = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSTaps; ++k) {
+      const float c = (float)(k - kSR);
+      g[k] = expf(-0.5f * c * c / (1.5f * 1.5f));
+      gs += g[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kSTaps; ++k) g[k] /= gs;
+  }
+  // horizontal: work item = (row, group of 8 columns)
+  for (int item = threadIdx.x; item < kSInH * (kSW / 8); item += 256) {
+    const int ly = item / (kSW / 8), gx = (item - ly * (kSW / 8)) * 8;
+    float ra[8 + 2 * kSR + 2], rb[8 + 2 * kSR + 2];
+    const float4* qa = reinterpret_cast<const float4*>(s_a + ly * kSInPitch + gx);
+    const float4* qb = reinterpret_cast<const float4*>(s_b + ly * kSInPitch + gx);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const float4 u = qa[v], z = qb[v];
+      ra[4 * v] = u.x; ra[4 * v + 1] = u.y; ra[4 * v + 2] = u.z; ra[4 * v + 3] = u.w;
+      rb[4 * v] = z.x; rb[4 * v + 1] = z.y; rb[4 * v + 2] = z.z; rb[4 * v + 3] = z.w;
+    }
+    float m[5][8];
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) m[q][p] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8 + 2 * kSR; ++k) {
+      const float va = ra[k], vb = rb[k];
+      const float aa = va * va, bb = vb * vb, ab = va * vb;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int tap = k - p;
+        if (tap >= 0 && tap < kSTaps) {
+          m[0][p] = fmaf(g[tap], va, m[0][p]);
+          m[1][p] = fmaf(g[tap], vb, m[1][p]);
+          m[2][p] = fmaf(g[tap], aa, m[2][p]);
+          m[3][p] = fmaf(g[tap], bb, m[3][p]);
+          m[4][p] = fmaf(g[tap], ab, m[4][p]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float4* dst = reinterpret_cast<float4*>(s_m + (q * kSInH + ly) * kSW + gx);
+      dst[0] = make_float4(m[q][0], m[q][1], m[q][2], m[q][3]);
+      dst[1] = make_float4(m[q][4], m[q][5], m[q][6], m[q][7]);
+    }
+  }
+  __syncthreads();
+  // vertical: thread = (column, group of 8 rows)
+  float acc[1] = {0.f};
+  {
+    const int lx = threadIdx.x & 63, gy = (threadIdx.x >> 6) * 8;
+    float m[5][8];
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int p = 0; p < 8; ++p) m[q][p] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8 + 2 * kSR; ++k) {
+      float v[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) v[q] = s_m[(q * kSInH + gy + k) * kSW + lx];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int tap = k - p;
+        if (tap >= 0 && tap < kSTaps) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) m[q][p] = fmaf(g[tap], v[q], m[q][p]);
+        }
+      }
+    }
+    const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int y = y0 + gy + p, x = x0 + lx;
+      if (y < ho && x < wo) {
+        const float mu_a = m[0][p], mu_b = m[1][p];
+        const float num0 = 2.f * mu_a * mu_b, den0 = mu_a * mu_a + mu_b * mu_b;
+        const float lum = (num0 + c1) / (den0 + c1);
+        const float cs = (2.f * m[4][p] - num0 + c2) / (m[2][p] + m[3][p] - den0 + c2);
+        acc[0] += lum * cs;
+      }
+    }
+  }
+  block_accumulate<1>(acc, sums + n, 1);
+}
+
+}  // namespace ie
+
+using namespace ie;
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" int ie_mean_hw_f32(const float* x, int n, int h, int w, int pitch, int coff, float* out, void* stream) {
+  IE_REQUIRE(x && out && n > 0 && n <= 65535 && h > 0 && w > 0 && coff >= 0 && coff < pitch, "mean_hw: bad arguments");
+  IE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n, S(stream)));
+  const long long npix = (long long)h * w;
+  int gx = (int)((npix + 256 * 8 - 1) / (256 * 8));
+  const int cap = (4 * sm_count() + n - 1) / n;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  mean_hw_kernel<<<dim3(gx, n), 256, 0, S(stream)>>>(x, npix, pitch, coff, 1.f / (float)npix, out);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_invert_preproc_f32(const float* img, int pitch, int coff, int nch, const float* wl, int n, int h,
+                                     int w, int crop, float* out, void* stream) {
+  IE_REQUIRE(img && wl && out && n > 0 && crop >= 0 && h > 2 * crop && w > 2 * crop && coff >= 0 && nch >= 1 &&
+                 coff + nch <= pitch,
+             "invert_preproc: bad arguments");
+  const long long total = (long long)n * (h - 2 * crop) * (w - 2 * crop);
+  invert_preproc_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(img, pitch, coff, nch, wl, h, w, crop, out, total);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                                   const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream) {
+  IE_REQUIRE(recon && burst && truth && wl && sums, "eval_metrics: null pointer");
+  IE_REQUIRE(n > 0 && T >= 1 && T <= kMaxT && burst_pitch >= T, "eval_metrics: bad T=%d (max %d)", T, kMaxT);
+  IE_REQUIRE(crop >= 0 && h > 2 * crop + 1 && w > 2 * crop + 1, "eval_metrics: image %dx%d too small for crop %d", h, w, crop);
+  const int tiles_x = (w - 2 * crop + kMT_W - 1) / kMT_W, tiles_y = (h - 2 * crop + kMT_H - 1) / kMT_H;
+  const long long blocks = (long long)n * tiles_x * tiles_y;
+  IE_REQUIRE(blocks < (1ll << 31), "eval_metrics: too many tiles");
+  eval_metrics_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(recon, burst, burst_pitch, truth, wl, h, w, T, crop,
+                                                              tiles_x, tiles_y, sums);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_sqdiff_sum_f32(const float* a, const float* b, int n, long long count, double* sums, void* stream) {
+  IE_REQUIRE(a && b && sums && n > 0 && n <= 65535 && count > 0, "sqdiff_sum: bad arguments");
+  long long gx = (count / 4 + 256 * 4 - 1) / (256 * 4);
+  const long long cap = (8ll * sm_count() + n - 1) / n;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  sqdiff_sum_kernel<<<dim3((unsigned)gx, n), 256, 0, S(stream)>>>(a, b, count, sums);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_img_loss_sums_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream) {
+  IE_REQUIRE(a && b && sums && n > 0 && h > 1 && w > 1, "img_loss_sums: bad arguments");
+  const long long total = (long long)n * h * w;
+  long long gx = (total + 255) / 256;
+  if (gx > 8ll * sm_count()) gx = 8ll * sm_count();
+  img_loss_sums_kernel<<<(unsigned)gx, 256, 0, S(stream)>>>(a, b, h, w, total, sums);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream) {
+  IE_REQUIRE(a && b && sums && n > 0 && h >= kSTaps && w >= kSTaps, "ssim: images must be at least 11x11");
+  const int tiles_x = (w - 2 * kSR + kSW - 1) / kSW, tiles_y = (h - 2 * kSR + kSH - 1) / kSH;
+  const long long blocks = (long long)n * tiles_x * tiles_y;
+  IE_REQUIRE(blocks < (1ll << 31), "ssim: too many tiles");
+  const size_t smem = sizeof(float) * (2 * kSInH * kSInPitch + 5 * kSInH * kSW);
+  IE_CUDA(cudaFuncSetAttribute(ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ssim_kernel<<<(unsigned)blocks, 256, smem, S(stream)>>>(a, b, h, w, tiles_x, tiles_y, sums);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}

@@ -1,0 +1,253 @@
+"""Drop-in for the metric / loss half of the reference's ``data_utils.py`` on B200.
+
+Same names, argument order and meaning as /root/reference/data_utils.py:24-164, but on
+``torch`` CUDA tensors and computed by the kernels in csrc/metrics.cu.  Two layers:
+
+* the reference's own fine-grained functions (``invert_preproc``, ``psnr_deblur`` ...), one or two
+  kernel launches each, for code written against the reference API;
+* ``eval_metrics`` - everything eval.py:144-182 computes for a batch from ONE fused pass.
+
+``preprocess_image`` is the arithmetic of ``DataLoader.preprocess_image`` (:198-265) with the
+random draws passed in (file I/O, decoding and tf.data plumbing are out of scope).
+"""
+from __future__ import annotations
+
+import math
+
+import psutil
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+LBUFF = 8      # border crop of invert_preproc, data_utils.py:43
+LAYER_TYPES = {"empty": 0, "singlestd": 1, "dualparams": 2}
+
+
+def getMemCpu():
+    """data_utils.py:17-23."""
+    data = psutil.virtual_memory()
+    return int(round(data.percent)), psutil.cpu_percent(interval=1)
+
+
+# ------------------------------------------------------------------ helpers
+def _nhw_view(img):
+    """Describe an [N,H,W] fp32 CUDA tensor as (base tensor, pitch, coff) without copying when it
+    is a channel slice ``y[..., k]`` of a contiguous NHWC tensor."""
+    _lib.require_cuda(img)
+    if img.dtype != torch.float32:
+        img = img.float()
+    n, h, w = img.shape
+    sn, sh, sw = img.stride()
+    if sw >= 1 and sh == w * sw and sn == h * sh:
+        return img, sw, 0              # data_ptr() already includes the channel offset; pitch = stride
+    img = img.contiguous()
+    return img, 1, 0
+
+
+def _wl_vec(white_level, n):
+    wl = white_level.reshape(-1).float().contiguous()
+    assert wl.numel() == n, "white_level must have one entry per image"
+    return wl
+
+
+def white_level_of(x_batch_truth):
+    """eval.py:144-145: per-image mean of truth[...,1] -> [N,1,1,1]."""
+    _lib.require_cuda(x_batch_truth)
+    t = x_batch_truth.contiguous().float()
+    n, h, w, c = t.shape
+    out = torch.empty(n, dtype=torch.float32, device=t.device)
+    call("ie_mean_hw_f32", ptr(t), n, h, w, c, 1, ptr(out), stream())
+    return out.view(n, 1, 1, 1)
+
+
+# ------------------------------------------------------------------ reference API
+def sRGBforward(x):
+    """data_utils.py:24-36 (elementwise)."""
+    _lib.require_cuda(x)
+    xf = x.contiguous().float()
+    one = torch.ones(1, dtype=torch.float32, device=x.device)
+    out = torch.empty_like(xf)
+    call("ie_invert_preproc_f32", ptr(xf), 1, 0, 1, ptr(one), 1, 1, xf.numel(), 0, ptr(out), stream())
+    return out
+
+
+def invert_preproc(imgs, white_level, _nch=1):
+    """data_utils.py:42-45: sRGBforward(imgs / white_level)[:, 8:-8, 8:-8]."""
+    base, pitch, coff = _nhw_view(imgs)
+    n, h, w = imgs.shape
+    wl = _wl_vec(white_level, n)
+    out = torch.empty(n, h - 2 * LBUFF, w - 2 * LBUFF, dtype=torch.float32, device=imgs.device)
+    call("ie_invert_preproc_f32", ptr(base), pitch, coff, _nch, ptr(wl), n, h, w, LBUFF, ptr(out), stream())
+    return out
+
+
+def _loss_sums(a, b):
+    _lib.require_cuda(a, b)
+    a, b = a.contiguous().float(), b.contiguous().float()
+    n, h, w = a.shape
+    sums = torch.zeros(2, dtype=torch.float64, device=a.device)
+    call("ie_img_loss_sums_f32", ptr(a), ptr(b), n, h, w, ptr(sums), stream())
+    return sums, n, h, w
+
+
+def gradient_loss(guess, truth):
+    """data_utils.py:40-41."""
+    sums, n, h, w = _loss_sums(guess, truth)
+    return (sums[1] / (n * (h - 1) * (w - 1) * 2)).float()
+
+
+def basic_img_loss(img, truth):
+    """data_utils.py:46-51: mean squared error + mean |grad img - grad truth|."""
+    sums, n, h, w = _loss_sums(img, truth)
+    return (sums[0] / (n * h * w) + sums[1] / (n * (h - 1) * (w - 1) * 2)).float()
+
+
+def deblur_loss(invert_deblur, invert_gt):
+    """data_utils.py:81-96."""
+    return basic_img_loss(invert_deblur, invert_gt)
+
+
+def deblur_layer_loss(y_pred, invert_gt, white_noise):
+    """data_utils.py:52-73."""
+    burst_size = y_pred.shape[-1] - 1
+    loss = basic_img_loss(invert_preproc(y_pred[..., 1], white_noise), invert_gt)
+    for i in range(burst_size - 1):
+        loss = loss + basic_img_loss(invert_preproc(y_pred[..., i + 2], white_noise), invert_gt)
+    return loss
+
+
+def invert_deblur_layer(y_pred, white_noise):
+    """data_utils.py:74-80: inverted frames concatenated along the last (width) axis."""
+    burst_size = y_pred.shape[-1] - 1
+    return torch.cat([invert_preproc(y_pred[..., i + 1], white_noise) for i in range(burst_size)], dim=-1)
+
+
+def psnr_tf_batch(estimate, truth):
+    """data_utils.py:118-119."""
+    _lib.require_cuda(estimate, truth)
+    a, b = estimate.contiguous().float(), truth.contiguous().float()
+    n = a.shape[0]
+    count = a.numel() // n
+    sums = torch.zeros(n, dtype=torch.float64, device=a.device)
+    call("ie_sqdiff_sum_f32", ptr(a), ptr(b), n, count, ptr(sums), stream())
+    return (-10.0 * torch.log10(sums / count)).mean().float()
+
+
+def psnr_deblur(invert_deblur, invert_gt):
+    """data_utils.py:121-130."""
+    return psnr_tf_batch(invert_deblur, invert_gt)
+
+
+def psnr_each_layer(invert_gt, white_noise, y_pred):
+    """data_utils.py:131-144."""
+    burst_size = y_pred.shape[-1] - 1
+    psnr = {}
+    for i in range(burst_size):
+        psnr['da{}_noshow'.format(i)] = psnr_tf_batch(invert_preproc(y_pred[..., i + 1], white_noise), invert_gt)
+    return psnr
+
+
+def psnr_burst0(invert_gt, white_noise, x_batch_burst):
+    """data_utils.py:145-154."""
+    return psnr_tf_batch(invert_preproc(x_batch_burst[..., 0], white_noise), invert_gt)
+
+
+def psnr_average_f(invert_gt, white_noise, x_batch_burst):
+    """data_utils.py:155-164: the burst mean is taken inside the invert kernel."""
+    T = x_batch_burst.shape[-1]
+    return psnr_tf_batch(invert_preproc(x_batch_burst[..., 0], white_noise, _nch=T), invert_gt)
+
+
+def ssim(a, b):
+    """EXTENSION (not in the reference): per-image SSIM of [N,H,W] pairs, tf.image.ssim semantics."""
+    _lib.require_cuda(a, b)
+    a, b = a.contiguous().float(), b.contiguous().float()
+    n, h, w = a.shape
+    sums = torch.zeros(n, dtype=torch.float64, device=a.device)
+    call("ie_ssim_f32", ptr(a), ptr(b), n, h, w, ptr(sums), stream())
+    return (sums / ((h - 10) * (w - 10))).float()
+
+
+# ------------------------------------------------------------------ fused path
+def eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=None):
+    """ONE pass over (recon, burst, truth): per-image fp64 sums [N, (T+3)+(T+1)] (see imgenh_b200.h)."""
+    _lib.require_cuda(reconstructed, x_batch_burst, x_batch_truth)
+    T = burst_length
+    rec = reconstructed.contiguous().float()
+    xb = x_batch_burst.contiguous().float()
+    tr = x_batch_truth.contiguous().float()
+    n, h, w, _ = rec.shape
+    assert rec.shape[-1] == T + 1 and tr.shape == (n, h, w, 2) and xb.shape[:3] == (n, h, w)
+    wl = (white_level_of(tr) if white_noise is None else white_noise).reshape(-1).float().contiguous()
+    sums = torch.zeros(n, 2 * T + 4, dtype=torch.float64, device=rec.device)
+    call("ie_eval_metrics_f32", ptr(rec), ptr(xb), xb.shape[-1], ptr(tr), ptr(wl), n, h, w, T, LBUFF, ptr(sums),
+         stream())
+    return sums
+
+
+def reduce_metric_sums(sums, h, w, T):
+    """Per-image sums -> additive totals (fp64, on device, no sync):
+
+    [ sum_n psnr_deblur, sum_n psnr_frame_0..T-1, sum_n psnr_burst0, sum_n psnr_average,
+      sum_n loss_deblur_n, sum_n loss_perlayer_n, n ]
+    where loss_n = mse_n + gradl1_n; batch losses of the reference (global means over equal-size
+    images) are these sums divided by n.
+    """
+    hc, wc = h - 2 * LBUFF, w - 2 * LBUFF
+    npx, ngr = hc * wc, (hc - 1) * (wc - 1) * 2
+    psnr = -10.0 * torch.log10(sums[:, :T + 3] / npx)                 # data_utils.py:118-119
+    loss = sums[:, :T + 1] / npx + sums[:, T + 3:] / ngr              # data_utils.py:46-51
+    n = torch.full((1,), float(sums.shape[0]), dtype=torch.float64, device=sums.device)
+    return torch.cat([psnr.sum(0), loss[:, :1].sum(0), loss[:, 1:].sum().reshape(1), n])
+
+
+def totals_to_report(tot, T):
+    """Host-side view of the additive totals (a list / 1-D tensor on CPU)."""
+    tot = [float(v) for v in tot]
+    n = tot[-1]
+    return {
+        "psnr": tot[0] / n,
+        "psnr_perlayer": [tot[1 + t] / n for t in range(T)],
+        "psnr_noise0": tot[T + 1] / n,
+        "psnr_average": tot[T + 2] / n,
+        "loss1": tot[T + 3] / n,
+        "perlayer_loss": tot[T + 4] / n,
+        "count": n,
+    }
+
+
+def eval_metrics(reconstructed, x_batch_burst, x_batch_truth, burst_length):
+    """Everything eval.py:144-182 computes for one batch, as a dict of python floats (one D2H copy)."""
+    n, h, w, _ = reconstructed.shape
+    sums = eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length)
+    tot = reduce_metric_sums(sums, h, w, burst_length).cpu()
+    return totals_to_report(tot, burst_length)
+
+
+# ------------------------------------------------------------------ preprocessing
+def preprocess_image(src_u8, org, params, white_level, sig_read, sig_shot, n_read=None, n_shot=None):
+    """Batched arithmetic of DataLoader.preprocess_image (data_utils.py:198-265).
+
+    src_u8 [N,Hs,Ws,C] uint8 CUDA; org [N,T,2] int32 crop origins (y,x) per frame in source pixels
+    (see oracle.preprocess.frame_origins for how the reference's nested crops map to them);
+    white_level / sig_read / sig_shot [N] fp32; n_read / n_shot [N,h,w,T] standard normals or None.
+    Returns (x [N,h,w,T+add], truth [N,h,w,2]) like the reference's (noisy++sig, truth++white_level).
+    """
+    _lib.require_cuda(src_u8, org, white_level, sig_read, sig_shot)
+    assert src_u8.dtype == torch.uint8 and org.dtype == torch.int32
+    n, hs, ws, c = src_u8.shape
+    T = params["BURST_LENGTH"]
+    h, w, up = params["height"], params["width"], params["upscale"]
+    lt = LAYER_TYPES[params["layer_type"]]
+    add = {0: 0, 1: 1, 2: 2}[lt]
+    dev = src_u8.device
+    x = torch.empty(n, h, w, T + add, dtype=torch.float32, device=dev)
+    truth = torch.empty(n, h, w, 2, dtype=torch.float32, device=dev)
+    f = lambda t: t.contiguous().float()
+    nr = f(n_read) if n_read is not None else None
+    ns = f(n_shot) if n_shot is not None else None
+    call("ie_preprocess_u8", ptr(src_u8.contiguous()), n, hs, ws, c, ptr(org.contiguous()), up,
+         float(params["degamma"]), ptr(f(white_level)), ptr(f(sig_read)), ptr(f(sig_shot)), ptr(nr), ptr(ns), lt,
+         h, w, T, ptr(x), ptr(truth), stream())
+    return x, truth

@@ -1,0 +1,213 @@
+"""Forward-pass engine for the reference's two networks on one B200.
+
+Table-driven restatement of the call graphs of ``Simplemodel.call``
+(/root/reference/model_library.py:372-452) and ``Basis_kpn.call`` (:231-295) as a
+sequence of C-ABI kernel launches on the current CUDA stream:
+
+    im2col pack -> [tcgen05 conv]* with max-pool / bilinear-upsample / channel-mean glue
+    -> coef conv with fused softmax -> basis branch (tiny rasters) -> basis softmax
+    -> fused per-pixel filter (kpn_apply).
+
+Concatenations are channel slices of shared rasters: the skip half is written by the
+encoder conv's epilogue, the up-sampled half by the upsample kernel.  No activation is
+copied, nothing is synchronised, and activation buffers are cached per input shape, so a
+forward is capturable in a CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX, ImgEnhError
+from .weights import ADD_LENGTHS, basis_kpn_layers, simplemodel_layers
+
+# (down blocks, bottleneck convs, coef up blocks (name, cout, skip), head convs,
+#  basis up blocks (name, cout, skip, k, scale), tail convs) - model_library.py:323-368 / 196-227
+ARCH = {
+    "simple": dict(
+        downs=[("down1", 64), ("down2", 128), ("down5", 1024)],
+        bottleneck=["layer1_1"],
+        coef_ups=[("Coef_up1", 512, "down5"), ("Coef_up4", 64, "down2"), ("Coef_up5", 64, "down1")],
+        head=["layer2_1"],
+        basis_ups=[("Basis_up1", 512, "down5", 2, 2), ("Basis_up4", 128, "down2", 16, 8)],
+        tail=["layer3_1", "layer3_3"],
+        layers=simplemodel_layers,
+    ),
+    "basis_kpn": dict(
+        downs=[("down1", 64), ("down2", 128), ("down3", 256), ("down4", 512), ("down5", 1024)],
+        bottleneck=["layer1_1", "layer1_2"],
+        coef_ups=[("Coef_up1", 512, "down5"), ("Coef_up2", 256, "down4"), ("Coef_up3", 128, "down3"),
+                  ("Coef_up4", 64, "down2"), ("Coef_up5", 64, "down1")],
+        head=["layer2_1", "layer2_2"],
+        basis_ups=[("Basis_up1", 512, "down5", 2, 2), ("Basis_up2", 256, "down4", 4, 2),
+                   ("Basis_up3", 256, "down3", 8, 2), ("Basis_up4", 128, "down2", 16, 2)],
+        tail=["layer3_1", "layer3_2", "layer3_3"],
+        layers=basis_kpn_layers,
+    ),
+}
+
+
+class Engine:
+    def __init__(self, arch, params, weights, device="cuda"):
+        if not torch.cuda.is_available():
+            raise ImgEnhError("a CUDA device is required (the hot path has no CPU fallback)")
+        self.arch = ARCH[arch]
+        self.params = params
+        self.T = params["BURST_LENGTH"]
+        self.K = params["Kernel_size"]
+        self.B = params["Basis_num"]
+        self.cin = self.T + ADD_LENGTHS[params["layer_type"]]
+        if 9 * self.cin > 64:
+            raise ImgEnhError(f"input channels {self.cin}: the im2col first layer needs 9*C <= 64")
+        if self.K != 15:
+            raise ImgEnhError("Kernel_size must be 15: the basis branch emits 15x15 kernels (model_library.py:364)")
+        self.device = torch.device(device)
+        self.stride = 2 ** len(self.arch["downs"])          # 8 for Simplemodel, 32 for Basis_kpn
+        self.wp, self.bias = {}, {}
+        self.load_weights(weights)
+        self._plans = {}
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, weights):
+        """weights: {name: (kernel HWIO, bias)} (CPU or CUDA).  Packs to bf16 [cout_pad, K] on the device."""
+        f32_heads = {"coef": IE_EPI_F32_SOFTMAX, "layer3_3": IE_EPI_F32_NHWC}
+        for name, k, cin, cout, _ in self.arch["layers"](self.params):
+            w, b = weights[name]
+            assert tuple(w.shape) == (k, k, cin, cout), (name, tuple(w.shape), (k, k, cin, cout))
+            w = w.to(self.device, torch.float32)
+            epi = f32_heads.get(name, IE_EPI_BF16_RASTER)
+            ktot_pad = 64 if name == "layer0" else None     # first layer runs as a 1x1 GEMM over im2col rows
+            self.wp[name] = ops.pack_conv_weights(w, epi, ktot_pad)
+            self.bias[name] = b.to(self.device, torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ buffers
+    def _plan(self, n, h, w):
+        key = (n, h, w)
+        if key in self._plans:
+            return self._plans[key]
+        A = self.arch
+        dev = self.device
+        R = lambda hh, ww, c: ops.new_raster(n, hh, ww, c, dev)
+        p = {}
+        chans = dict(A["downs"])
+        # encoder rasters per level l (resolution h >> l)
+        p["in0"] = R(h, w, 64)
+        p["x0"] = R(h, w, 64)
+        up_in = {}                                   # channels entering each coef up block
+        prev = 1024
+        for name, cout, skip in A["coef_ups"]:
+            up_in[skip] = prev
+            prev = cout
+        for l, (dname, c) in enumerate(A["downs"]):
+            hh, ww = h >> l, w >> l
+            p[dname + ".c1"] = R(hh, ww, c)
+            p["cat." + dname] = R(hh, ww, up_in[dname] + c)   # [0:up_in]=upsampled, [up_in:]=skip
+            p[dname + ".pool"] = R(hh >> 1, ww >> 1, c)
+        L = len(A["downs"])
+        for i, bname in enumerate(A["bottleneck"]):
+            p[bname] = R(h >> L, w >> L, 1024)
+        for name, cout, skip in A["coef_ups"]:
+            l = [d for d, _ in A["downs"]].index(skip)
+            for j in (1, 2, 3):
+                p[f"{name}.c{j}"] = R(h >> l, w >> l, cout)
+        for hname in A["head"]:
+            p[hname] = R(h, w, 64)
+        # basis branch
+        prev = 1024
+        for name, cout, skip, k, s in A["basis_ups"]:
+            p["bcat." + name] = R(k, k, prev + chans[skip])
+            for j in (1, 2, 3):
+                p[f"{name}.c{j}"] = R(k, k, cout)
+            prev = cout
+        p["seed"] = R(1, 1, 1024)
+        for tname in A["tail"][:-1]:
+            p[tname] = R(16, 16, 128)
+        self._plans[key] = p
+        return p
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, taps=None, conv_fn="ie_conv2d_nhwc_bf16"):
+        """x: fp32 NHWC [n,h,w,T+add] on CUDA, h and w multiples of the network stride.
+
+        Returns (output [n,h,w,T+1], Bas [n,K,K,T,B], originbasis [n,K,K,T*B]), all fp32.
+        ``taps``: optional dict filled with fp32 copies of intermediates (parity tests).
+        ``conv_fn``: tests may route every convolution through the naive validation kernel.
+        """
+        if not x.is_cuda:
+            raise ImgEnhError("input must be a CUDA tensor (no CPU fallback)")
+        n, h, w, c = x.shape
+        if c != self.cin:
+            raise ImgEnhError(f"expected {self.cin} input channels, got {c}")
+        if h % self.stride or w % self.stride:
+            raise ImgEnhError(f"H and W must be multiples of {self.stride} (got {h}x{w}); pad at the boundary")
+        x = x.contiguous().float()
+        A, W, Bv = self.arch, self.wp, self.bias
+        p = self._plan(n, h, w)
+        chans = dict(A["downs"])
+        dnames = [d for d, _ in A["downs"]]
+
+        def conv(name, src, dst, k=3, valid=None):
+            ops.conv2d(src, W[name], Bv[name], dst, k=k, relu=True, valid=valid, fn=conv_fn)
+            if taps is not None:
+                hv, wv = (dst.r.h, dst.r.w) if valid is None else valid
+                taps[name] = ops.raster_to_nhwc(dst)[:, :hv, :wv]
+
+        # ---- encoder (model_library.py:376-386 / 235-244)
+        ops.pack_input_im2col3x3(x, p["in0"])
+        conv("layer0", p["in0"].slice(), p["x0"].slice(), k=1)
+        cur = p["x0"].slice()
+        up_in = {}
+        prev = 1024
+        for name, cout, skip in A["coef_ups"]:
+            up_in[skip] = prev
+            prev = cout
+        for dname, cch in A["downs"]:
+            conv(dname + ".conv2d1", cur, p[dname + ".c1"].slice())
+            skip = p["cat." + dname].slice(up_in[dname], cch)
+            conv(dname + ".conv2d2", p[dname + ".c1"].slice(), skip)
+            ops.maxpool2(skip, p[dname + ".pool"].slice())
+            cur = p[dname + ".pool"].slice()
+        for bname in A["bottleneck"]:
+            conv(bname, cur, p[bname].slice())
+            cur = p[bname].slice()
+        bott = cur
+        # ---- coefficient decoder (model_library.py:391-406 / 246-255)
+        for name, cout, skip in A["coef_ups"]:
+            cat = p["cat." + skip]
+            ops.upsample_bilinear(cur, cat.slice(0, up_in[skip]), 2)
+            conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
+            conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())
+            conv(name + ".conv2d3", p[name + ".c2"].slice(), p[name + ".c3"].slice())
+            cur = p[name + ".c3"].slice()
+        for hname in A["head"]:
+            conv(hname, cur, p[hname].slice())
+            cur = p[hname].slice()
+        coef, logits = ops.conv2d_f32(cur, W["coef"], Bv["coef"], self.B, softmax=True,
+                                      want_logits=taps is not None, fn=conv_fn)
+        # ---- basis branch (model_library.py:409-438 / 258-281)
+        gavg = ops.channel_mean(bott)                                    # :409-410
+        ops.broadcast_hw(gavg, p["seed"].slice())
+        cur = p["seed"].slice()
+        for name, cout, skip, k, s in A["basis_ups"]:
+            cat = p["bcat." + name]
+            cin_up = cur.c
+            ops.upsample_bilinear(cur, cat.slice(0, cin_up), s)          # Upblock.upsampling :94
+            skip_mean = ops.channel_mean(p["cat." + skip].slice(up_in[skip], chans[skip]))   # Poolskip :110
+            ops.broadcast_hw(skip_mean, cat.slice(cin_up, chans[skip]))  # tile :112, concat :96
+            conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
+            conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())
+            conv(name + ".conv2d3", p[name + ".c2"].slice(), p[name + ".c3"].slice())
+            cur = p[name + ".c3"].slice()
+        tail = A["tail"]
+        conv(tail[0], cur, p[tail[0]].slice(), k=2, valid=(15, 15))      # 2x2 'valid' :364/424
+        cur = p[tail[0]].slice()
+        for tname in tail[1:-1]:
+            conv(tname, cur, p[tname].slice(), valid=(15, 15))
+            cur = p[tname].slice()
+        originbasis = ops.conv2d_f32(cur, W[tail[-1]], Bv[tail[-1]], self.T * self.B, valid=(15, 15), fn=conv_fn)
+        bas = ops.softmax_taps(originbasis, self.T, self.B)              # :436-438
+        # ---- per-pixel filter (model_library.py:439-451)
+        out = ops.kpn_apply(x, self.T, coef, bas)
+        if taps is not None:
+            taps["Coef"], taps["coef_logits"] = coef, logits
+        return out, bas, originbasis

@@ -1,0 +1,94 @@
+"""Drop-in for the model-builder entry points of the reference's ``model_library.py``.
+
+``Simplemodel(params)`` / ``Basis_kpn(params)`` keep the reference constructors
+(/root/reference/model_library.py:307-322, 180-195: a ``params`` dict with
+``BURST_LENGTH, Kernel_size, Basis_num, regu, ps, layer_type``), the attributes
+``burst_length, K, B`` and the call convention ``model(x)`` with ``x`` float32 NHWC
+``[N,H,W,T+add]`` returning ``(output, Bas, originbasis)`` (:452) or ``(output, Bas)`` (:295).
+Tensors are ``torch`` CUDA tensors; the forward runs the sm_100a kernels of csrc/ through
+the C ABI - there is no CPU fallback.
+
+Differences, all at the boundary: weights are random-initialised like Keras (glorot-uniform,
+zero bias) from a seeded CPU generator, or loaded from a flat ``.npz`` (weights.py) instead
+of a TF checkpoint; H and W that are not multiples of the network stride (8 / 32) are
+zero-padded at the bottom/right and the output cropped - the reference raises at its first
+``concatenate`` for such inputs (:96).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import weights as _weights
+from .engine import Engine
+from ._lib import ImgEnhError
+
+
+class _KpnModel:
+    _arch = None
+    _layers = None
+
+    def __init__(self, params, name=None, weights=None, seed=1234, init="glorot", device="cuda", **kwargs):
+        self.name = name
+        self.burst_length = params["BURST_LENGTH"]          # :312 / :185
+        self.K = params["Kernel_size"]                       # :313
+        self.B = params["Basis_num"]                         # :316
+        self.regu = params.get("regu", 0.0)
+        self.ps = params.get("ps", False)
+        self.params = dict(params)
+        if weights is None:
+            weights = _weights.init_weights(type(self)._layers(params), seed=seed, scheme=init)
+        elif isinstance(weights, str):
+            weights = _weights.load_npz(weights)
+        self._engine = Engine(type(self)._arch, self.params, weights, device=device)
+
+    # Keras-like conveniences
+    def load_weights(self, weights):
+        if isinstance(weights, str):
+            weights = _weights.load_npz(weights)
+        self._engine.load_weights(weights)
+
+    @property
+    def stride(self):
+        return self._engine.stride
+
+    def _forward(self, inputs, taps=None, conv_fn="ie_conv2d_nhwc_bf16"):
+        if not isinstance(inputs, torch.Tensor) or not inputs.is_cuda:
+            raise ImgEnhError("inputs must be a CUDA torch.Tensor [N,H,W,T+add] (no CPU fallback)")
+        n, h, w, c = inputs.shape
+        s = self._engine.stride
+        hp, wp = -(-h // s) * s, -(-w // s) * s
+        x = inputs
+        if (hp, wp) != (h, w):
+            x = torch.nn.functional.pad(inputs, (0, 0, 0, wp - w, 0, hp - h))
+        out, bas, ob = self._engine.forward(x, taps=taps, conv_fn=conv_fn)
+        if (hp, wp) != (h, w):
+            out = out[:, :h, :w, :].contiguous()
+        return out, bas, ob
+
+    def call(self, inputs):
+        return self.__call__(inputs)
+
+
+class Simplemodel(_KpnModel):
+    """model_library.py:306-452."""
+    _arch = "simple"
+    _layers = staticmethod(_weights.simplemodel_layers)
+
+    def __init__(self, params, name='simple_kpn', **kwargs):
+        super().__init__(params, name=name, **kwargs)
+
+    def __call__(self, inputs, **kw):
+        return self._forward(inputs, **kw)          # (output, Bas, originbasis)  :452
+
+
+class Basis_kpn(_KpnModel):
+    """model_library.py:179-295."""
+    _arch = "basis_kpn"
+    _layers = staticmethod(_weights.basis_kpn_layers)
+
+    def __init__(self, params, name='basis_kpn', **kwargs):
+        super().__init__(params, name=name, **kwargs)
+
+    def __call__(self, inputs, **kw):
+        out, bas, _ = self._forward(inputs, **kw)
+        return out, bas                              # :295

@@ -1,0 +1,170 @@
+"""Python-level wrappers of the C ABI, operating on torch CUDA tensors.
+
+A ``Raster`` is the library's activation container: bf16 ``[n*(h+2)*(w+2), pitch]`` with a
+one-pixel zero border per image (see include/imgenh_b200.h).  ``Slice`` is a channel window
+of a raster - how the reference's ``layers.concatenate([up, skip])``
+(/root/reference/model_library.py:96) is expressed without a copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX, call, ptr, stream
+
+
+@dataclass
+class Raster:
+    data: torch.Tensor      # bf16 [rows, pitch]
+    n: int
+    h: int
+    w: int
+
+    @property
+    def pitch(self):
+        return self.data.shape[1]
+
+    @property
+    def rows(self):
+        return self.n * (self.h + 2) * (self.w + 2)
+
+    def slice(self, coff=0, c=None):
+        return Slice(self, coff, self.pitch - coff if c is None else c)
+
+
+@dataclass
+class Slice:
+    r: Raster
+    coff: int
+    c: int
+
+
+def new_raster(n, h, w, c, device):
+    # torch.empty: every row (borders included) is written by the producing kernel
+    return Raster(torch.empty(n * (h + 2) * (w + 2), c, dtype=torch.bfloat16, device=device), n, h, w)
+
+
+def conv_n_tile(cout, epilogue):
+    """Mirror of choose_n_tile() in csrc/conv_tcgen05.cu: rows the packed weights must be padded to."""
+    if epilogue != IE_EPI_BF16_RASTER:
+        return ((cout + 15) // 16) * 16
+    return 256 if cout >= 256 else (128 if cout > 64 else 64)
+
+
+def pack_conv_weights(kernel_hwio, epilogue=IE_EPI_BF16_RASTER, ktot_pad=None):
+    """HWIO fp32 (CUDA) -> bf16 [cout_pad, ktot_pad], K index (i*kw+j)*cin + c."""
+    _lib.require_cuda(kernel_hwio)
+    kh, kw, cin, cout = kernel_hwio.shape
+    ktot = kh * kw * cin
+    ktot_pad = ktot if ktot_pad is None else ktot_pad
+    nt = conv_n_tile(cout, epilogue)
+    cout_pad = -(-cout // nt) * nt
+    out = torch.zeros(cout_pad, ktot_pad, dtype=torch.bfloat16, device=kernel_hwio.device)
+    src = kernel_hwio.contiguous().float()
+    call("ie_pack_conv_weights", ptr(src), kh, kw, cin, cout, ktot_pad, ptr(out), stream())
+    return out
+
+
+def pack_input_im2col3x3(x, out=None):
+    """fp32 NHWC [n,h,w,c] -> Raster(n,h,w) with 64 channels holding the 3x3xc neighbourhoods."""
+    _lib.require_cuda(x)
+    n, h, w, c = x.shape
+    x = x.contiguous()
+    if out is None:
+        out = new_raster(n, h, w, 64, x.device)
+    assert out.pitch == 64 and (out.n, out.h, out.w) == (n, h, w)
+    call("ie_pack_input_im2col3x3", ptr(x), n, h, w, c, ptr(out.data), stream())
+    return out
+
+
+def _desc(src: Slice, kh, kw, cout, relu, epilogue, dst: Slice | None, valid=None):
+    r = src.r
+    hv, wv = (r.h, r.w) if valid is None else valid
+    d = ConvDesc()
+    d.n_img, d.h, d.w, d.hv, d.wv = r.n, r.h, r.w, hv, wv
+    d.kh, d.kw = kh, kw
+    d.cin, d.x_pitch, d.x_coff = src.c, r.pitch, src.coff
+    d.cout = cout
+    d.y_pitch, d.y_coff = (dst.r.pitch, dst.coff) if dst is not None else (0, 0)
+    d.relu, d.epilogue = int(relu), epilogue
+    return d
+
+
+def conv2d(src: Slice, w_packed, bias, dst: Slice, k=3, relu=True, valid=None, fn="ie_conv2d_nhwc_bf16"):
+    """Conv2D(k, relu) from a raster slice into a raster slice (bf16 epilogue)."""
+    assert dst.r.rows == src.r.rows, "conv output must share the input raster geometry"
+    d = _desc(src, k, k, dst.c, relu, IE_EPI_BF16_RASTER, dst, valid)
+    call(fn, C.byref(d), ptr(src.r.data), ptr(w_packed), ptr(bias), ptr(dst.r.data), None, None, stream())
+
+
+def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, softmax=False, want_logits=False,
+               fn="ie_conv2d_nhwc_bf16"):
+    """Conv2D(k, relu) with an fp32 NHWC output [n,hv,wv,cout] (optionally softmax over channels)."""
+    r = src.r
+    hv, wv = (r.h, r.w) if valid is None else valid
+    epi = IE_EPI_F32_SOFTMAX if softmax else IE_EPI_F32_NHWC
+    d = _desc(src, k, k, cout, relu, epi, None, valid)
+    y = torch.empty(r.n, hv, wv, cout, dtype=torch.float32, device=r.data.device)
+    aux = torch.empty_like(y) if (softmax and want_logits) else None
+    call(fn, C.byref(d), ptr(r.data), ptr(w_packed), ptr(bias), None, ptr(y), ptr(aux), stream())
+    return (y, aux) if softmax else y
+
+
+def maxpool2(src: Slice, dst: Slice):
+    r = src.r
+    assert (dst.r.n, dst.r.h, dst.r.w) == (r.n, r.h // 2, r.w // 2) and dst.c == src.c
+    call("ie_maxpool2_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff,
+         ptr(dst.r.data), dst.r.pitch, dst.coff, stream())
+
+
+def upsample_bilinear(src: Slice, dst: Slice, scale):
+    r = src.r
+    assert (dst.r.n, dst.r.h, dst.r.w) == (r.n, r.h * scale, r.w * scale) and dst.c == src.c
+    call("ie_upsample_bilinear_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, scale,
+         ptr(dst.r.data), dst.r.pitch, dst.coff, stream())
+
+
+def channel_mean(src: Slice, out=None):
+    r = src.r
+    if out is None:
+        out = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device)
+    call("ie_channel_mean_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(out), stream())
+    return out
+
+
+def broadcast_hw(vec, dst: Slice):
+    assert vec.shape == (dst.r.n, dst.c) and vec.dtype == torch.float32
+    call("ie_broadcast_hw_bf16", ptr(vec), dst.r.n, dst.r.h, dst.r.w, dst.c, ptr(dst.r.data), dst.r.pitch,
+         dst.coff, stream())
+
+
+def raster_to_nhwc(src: Slice):
+    r = src.r
+    y = torch.empty(r.n, r.h, r.w, src.c, dtype=torch.float32, device=r.data.device)
+    call("ie_raster_to_nhwc_f32", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(y), stream())
+    return y
+
+
+def softmax_taps(originbasis, T, B):
+    """[n,K,K,T*B] fp32 -> Bas [n,K,K,T,B]: softmax over the K*K*T taps per basis (model_library.py:436)."""
+    n, K = originbasis.shape[0], originbasis.shape[1]
+    ob = originbasis.contiguous()
+    out = torch.empty_like(ob)
+    call("ie_softmax_taps_f32", ptr(ob), n, K * K * T, B, ptr(out), stream())
+    return out.view(n, K, K, T, B)
+
+
+def kpn_apply(x, T, coef, bas, out=None):
+    """Per-pixel filter (model_library.py:439-451).  x: fp32 NHWC whose first T channels are the burst."""
+    _lib.require_cuda(x, coef, bas)
+    n, h, w, pitch = x.shape
+    K, B = bas.shape[1], bas.shape[-1]
+    assert x.is_contiguous() and coef.is_contiguous() and bas.is_contiguous()
+    assert coef.shape == (n, h, w, B) and bas.shape == (n, K, K, T, B)
+    if out is None:
+        out = torch.empty(n, h, w, T + 1, dtype=torch.float32, device=x.device)
+    call("ie_kpn_apply_f32", ptr(x), pitch, ptr(coef), ptr(bas), ptr(out), n, h, w, T, K, B, stream())
+    return out

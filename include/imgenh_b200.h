@@ -1,0 +1,168 @@
+/* imgenh_b200 - C ABI of the B200-native hot path of hanxuel/ImageEnhancement_MP.
+ *
+ * The reference (/root/reference) is pure Python on TensorFlow/Keras and has no FFI layer of
+ * its own; its hot path is `Simplemodel.call` / `Basis_kpn.call` (model_library.py:372-452,
+ * 231-295) plus the metric functions of data_utils.py:24-164 that eval.py:139-195 drives.
+ * Each entry point below names the reference op(s) it replaces.  The Python shim
+ * (imageenhancement_mp_b200/) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless it says "host".
+ *   - the caller owns and allocates every buffer; the library keeps no state between calls
+ *     (besides a per-thread error string and the cached SM count).
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *   - return 0 on success, <0 on error; ie_last_error() gives the message for this thread.
+ *
+ * Activation layout ("raster"): bf16, NHWC, each image stored with a one-pixel zero border:
+ *   rows = n_img * (h+2) * (w+2), row r = (n*(h+2) + y)*(w+2) + x, `pitch` channels per row.
+ *   A k x k 'same' convolution tap is then a constant row shift of this 2-D [rows][pitch]
+ *   matrix, so TMA fetches every tap with a plain 2-D box and the zero border supplies the
+ *   padding.  Channel slices (coff, c) of a wider raster are how concatenation is expressed.
+ */
+#ifndef IMGENH_B200_H
+#define IMGENH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IE_VERSION 100
+
+#define IE_OK 0
+#define IE_ERR_INVALID (-1)
+#define IE_ERR_CUDA (-2)
+
+/* epilogue kinds for ie_conv2d_nhwc_bf16 */
+#define IE_EPI_BF16_RASTER 0 /* bias(+ReLU) -> bf16 raster slice (border rows zeroed)                    */
+#define IE_EPI_F32_NHWC 1    /* bias(+ReLU) -> fp32 [n][hv][wv][cout] (interior only), cout <= 64          */
+#define IE_EPI_F32_SOFTMAX 2 /* as 1, then softmax over cout; y_aux (nullable) receives the logits        */
+
+typedef struct ie_conv_desc {
+  int32_t n_img, h, w; /* interior size of the INPUT raster (rows = n_img*(h+2)*(w+2))                   */
+  int32_t hv, wv;      /* valid OUTPUT extent inside the same raster geometry: (h,w) for 'same',
+                          (h-1,w-1) for the 2x2 'valid' conv; everything outside is written as zero      */
+  int32_t kh, kw;      /* 3x3 ('same', centred), 2x2 ('valid', taps at +0/+1) or 1x1                     */
+  int32_t cin;         /* input channels consumed, multiple of 64                                        */
+  int32_t x_pitch;     /* channels per row of x                                                          */
+  int32_t x_coff;      /* first channel of x to read, multiple of 64                                     */
+  int32_t cout;        /* output channels                                                                */
+  int32_t y_pitch;     /* channels per row of y (IE_EPI_BF16_RASTER)                                     */
+  int32_t y_coff;      /* first channel of y to write, multiple of 64                                    */
+  int32_t relu;        /* 1: max(0, .) after the bias                                                    */
+  int32_t epilogue;    /* IE_EPI_*                                                                       */
+} ie_conv_desc;
+
+int ie_version(void);
+const char* ie_last_error(void);
+int ie_sm_count(void);
+
+/* ---- convolutions: layers.Conv2D(c, 3, 'same', relu) / Conv2D(128, 2, 'valid', relu)
+ *      (model_library.py:72-73, 89-91, 323-368) as tcgen05 implicit GEMM ----------------------------- */
+
+/* HWIO fp32 [kh][kw][cin][cout] -> bf16 [cout][ktot_pad], k = (i*kw+j)*cin + c, zero padded.       */
+int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, int ktot_pad, void* packed_bf16,
+                         void* stream);
+
+/* fp32 NHWC [n][h][w][c] (9*c <= 64) -> bf16 raster [n*(h+2)*(w+2)][64] holding each pixel's zero-padded
+ * 3x3xc neighbourhood, k = (i*3+j)*c + ch: turns the first conv (model_library.py:323/376) into a
+ * 1x1 GEMM with K = 64.                                                                               */
+int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* raster_bf16, void* stream);
+
+/* y = epilogue(conv(x, w) + bias).  w_packed from ie_pack_conv_weights with ktot_pad = kh*kw*cin.
+ * y_bf16 is used by IE_EPI_BF16_RASTER; y_f32 (and optional y_aux) by the fp32 epilogues.            */
+int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_bf16,
+                        float* y_f32, float* y_aux, void* stream);
+
+/* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at
+ * sizes the CPU oracle cannot reach).  Never called by the product path.                             */
+int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                          void* y_bf16, float* y_f32, float* y_aux, void* stream);
+
+/* ---- layout glue of the U-Net (bandwidth kernels) ------------------------------------------------- */
+
+/* MaxPooling2D(2,2) (model_library.py:74): raster (h,w) slice -> raster (h/2,w/2) slice, border zeroed. */
+int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y, int y_pitch,
+                          int y_coff, void* stream);
+
+/* UpSampling2D(scale, 'bilinear') half-pixel centres (model_library.py:92) written straight into a
+ * channel slice of the consumer's concat raster (model_library.py:96); border zeroed.               */
+int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, int scale,
+                                   void* y, int y_pitch, int y_coff, void* stream);
+
+/* Per-image channel means over the interior (reduce_mean x2 :409-410, GlobalAveragePooling2D :110):
+ * mean[n][c] fp32.                                                                                   */
+int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* mean,
+                              void* stream);
+
+/* tf.tile of a [n][c] vector to a k_h x k_w raster slice (Poolskip :111-112), border zeroed.          */
+int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int c, void* y, int y_pitch, int y_coff,
+                         void* stream);
+
+/* bf16 raster slice -> fp32 NHWC [n][h][w][c] (interior).  Debug / parity taps.                       */
+int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* y,
+                          void* stream);
+
+/* ---- basis softmax + per-pixel filter -------------------------------------------------------------- */
+
+/* softmax over the taps axis of [n][taps][b] (model_library.py:436-437).                              */
+int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float* bas, void* stream);
+
+/* Filter synthesis + Convolve + Convolve_perlayer (model_library.py:439-451, 114-168), fused:
+ *   out[n,y,x,1+t] = T * sum_b coef[n,y,x,b] * sum_{i,j} bas[n,i,j,t,b] * pad0(burst)[n,y+i-K/2,x+j-K/2,t]
+ *   out[n,y,x,0]   = mean_t out[n,y,x,1+t]
+ * burst: fp32 NHWC with `burst_pitch` channels per pixel (first T used); coef [n][h][w][B];
+ * bas [n][K][K][T][B]; out [n][h][w][T+1].  The per-pixel kernels are never materialised.            */
+int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, const float* bas, float* out, int n,
+                     int h, int w, int T, int K, int B, void* stream);
+
+/* ---- metrics (data_utils.py:24-164 as eval.py:139-182 calls them) --------------------------------- */
+
+/* mean over H,W of channel `coff` of an fp32 NHWC tensor: white level of eval.py:144-145. out [n].    */
+int ie_mean_hw_f32(const float* x, int n, int h, int w, int pitch, int coff, float* out, void* stream);
+
+/* invert_preproc (data_utils.py:42-45): sRGBforward(img / wl[n]) cropped by `crop` px per side.
+ * img: mean of channels [coff, coff+nch) of fp32 NHWC with `pitch` channels (nch = 1: one channel;
+ * nch = T: the burst average of psnr_average_f :162); out [n][h-2crop][w-2crop].                      */
+int ie_invert_preproc_f32(const float* img, int pitch, int coff, int nch, const float* wl, int n, int h, int w,
+                          int crop, float* out, void* stream);
+
+/* One pass over recon [n][h][w][T+1], burst (pitch channels, first T), truth [n][h][w][2] producing,
+ * per image, fp64 sums over the cropped sRGB'd images:
+ *   sums[n][k]        k in [0,T+3): sum (e_k - gt)^2, e = {deblur, frame_0..T-1, burst0, burst mean}
+ *   sums[n][T+3+k]    k in [0,T+1): sum |grad e_k - grad gt| (both components), e = {deblur, frames}
+ * from which psnr_deblur / psnr_each_layer / psnr_burst0 / psnr_average_f (data_utils.py:121-164)
+ * and deblur_loss / deblur_layer_loss (:52-96) follow.  `sums` must be zeroed by the caller.          */
+int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                        const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream);
+
+/* psnr_tf_batch's inner reduction (data_utils.py:118-119): sums[n] += sum (a-b)^2 over `count` px.    */
+int ie_sqdiff_sum_f32(const float* a, const float* b, int n, long long count, double* sums, void* stream);
+
+/* basic_img_loss pieces (data_utils.py:37-51) on [n][h][w] pairs: sums[0] += sum (a-b)^2,
+ * sums[1] += sum |grad a - grad b|.                                                                    */
+int ie_img_loss_sums_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream);
+
+/* SSIM, tf.image.ssim semantics (11x11 Gaussian sigma 1.5, VALID, K1=.01, K2=.03, max_val 1).
+ * EXTENSION: not in the reference.  sums[n] += sum of the SSIM map of image n ((h-10)*(w-10) values). */
+int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream);
+
+/* ---- preprocessing (data_utils.py:198-265 arithmetic with explicit random draws) ------------------ */
+
+/* src u8 [n][hs][ws][c]; per (image, frame) crop origin org[n][T][2] (y,x) in source pixels (may be
+ * negative / outside: zero padded like make_first_truth :436-438); each output pixel is the `up` x `up`
+ * box mean (AREA resize :459) of (src/255)^degamma averaged over c (:220), times wl[n] (:230);
+ * noisy = truth + sqrt(truth)*sig_shot[n]*n_shot + sig_read[n]*n_read (:462-466; noise nullable);
+ * x [n][h][w][T+add] = noisy ++ noise-level channel(s) (:256-264; layer_type 0 empty, 1 singlestd,
+ * 2 dualparams); truth [n][h][w][2] = clean frame 0 ++ white level (:265).                            */
+int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c, const int32_t* org, int up, float degamma,
+                     const float* wl, const float* sig_read, const float* sig_shot, const float* n_read,
+                     const float* n_shot, int layer_type, int h, int w, int T, float* x, float* truth,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMGENH_B200_H */

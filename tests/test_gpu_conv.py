@@ -1,0 +1,167 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (csrc/conv_tcgen05.cu) through the C ABI.
+
+Reference = torch fp32 conv on the CPU over the SAME bf16-rounded inputs and weights (the
+kernel accumulates in fp32; only the bf16 output rounding differs), plus the naive CUDA-core
+validation kernel at sizes where the CPU is slow.  Tolerance: bf16 output rounding
+(2^-8 relative) + fp32 accumulation-order noise.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def to_raster(x):
+    """fp32 NHWC (cuda) -> ops.Raster with a zero border."""
+    from imageenhancement_mp_b200 import ops
+    n, h, w, c = x.shape
+    data = F.pad(x, (0, 0, 1, 1, 1, 1)).reshape(-1, c).to(torch.bfloat16).contiguous()
+    return ops.Raster(data, n, h, w)
+
+
+def ref_conv(x, w, b, k, relu=True):
+    """x NHWC fp32 (already bf16-representable), w HWIO; 3x3 same / 2x2 valid / 1x1."""
+    pad = 1 if k == 3 else 0
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=pad)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def make_case(n, h, w, cin, cout, k, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(n, h, w, cin, generator=g))
+    wt = bf16_round(torch.randn(k, k, cin, cout, generator=g) * scale / (k * k * cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    return x, wt, b
+
+
+def assert_close_bf16(got, ref, what=""):
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-3 * ref.abs().max().clamp(min=1e-3)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} elements off, max err {float(err.max()):.4g} " \
+                          f"(ref max {float(ref.abs().max()):.4g})"
+
+
+CASES = [
+    # n, h, w, cin, cout, k
+    (2, 16, 16, 64, 64, 3),        # one K block per tap, N tile 64
+    (1, 8, 8, 128, 128, 3),        # two K blocks per tap, N tile 128
+    (1, 8, 8, 256, 512, 3),        # N tile 256, two N tiles
+    (2, 2, 2, 2048, 512, 3),       # basis-branch shape: 32 raster rows (< one 128-row TMA box), K = 18432
+    (1, 16, 16, 128, 128, 2),      # the 2x2 'valid' conv (model_library.py:364)
+    (2, 24, 40, 64, 64, 1),        # 1x1 (first layer over im2col rows), non-square
+    (3, 26, 26, 1024, 1024, 3),    # the dominant quarter-resolution layer shape
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", CASES)
+def test_conv_bf16_vs_cpu(cuda, n, h, w, cin, cout, k):
+    from imageenhancement_mp_b200 import ops
+    x, wt, b = make_case(n, h, w, cin, cout, k)
+    ref = bf16_round(ref_conv(x, wt, b, k))
+    src = to_raster(x.to(cuda))
+    dst = ops.new_raster(n, h, w, cout, cuda)
+    dst.data.fill_(float("nan"))
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    valid = (h - 1, w - 1) if k == 2 else None
+    ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice(), k=k, valid=valid)
+    torch.cuda.synchronize()
+    got = ops.raster_to_nhwc(dst.slice()).cpu()
+    if k == 2:
+        got = got[:, :h - 1, :w - 1]
+    assert_close_bf16(got, ref, f"conv {k}x{k} {cin}->{cout}")
+    # the zero border (and everything outside the valid extent) must be exactly zero
+    full = dst.data.float().view(n, h + 2, w + 2, cout)
+    hv, wv = (h - 1, w - 1) if k == 2 else (h, w)
+    mask = torch.ones(h + 2, w + 2, dtype=torch.bool, device=cuda)
+    mask[1:hv + 1, 1:wv + 1] = False
+    assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
+
+
+def test_conv_slices_and_concat(cuda):
+    """Input read from a channel window, output written into a channel window (concat by slices)."""
+    from imageenhancement_mp_b200 import ops
+    n, h, w = 2, 12, 20
+    x, wt, b = make_case(n, h, w, 128, 64, 3, seed=3)
+    g = torch.Generator().manual_seed(9)
+    junk_in = bf16_round(torch.randn(n, h, w, 64, generator=g))
+    wide = torch.cat([junk_in, x], dim=-1)                       # x lives at channels [64,192)
+    src = to_raster(wide.to(cuda))
+    dst = ops.new_raster(n, h, w, 256, cuda)
+    dst.data.fill_(7.0)
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    ops.conv2d(src.slice(64, 128), wp, b.to(cuda), dst.slice(128, 64))
+    torch.cuda.synchronize()
+    got = ops.raster_to_nhwc(dst.slice(128, 64)).cpu()
+    assert_close_bf16(got, bf16_round(ref_conv(x, wt, b, 3)), "sliced conv")
+    other = torch.cat([dst.data[:, :128], dst.data[:, 192:]], dim=1)
+    assert torch.all(other == 7.0), "conv wrote outside its output slice"
+
+
+def test_conv_many_tiles_vs_naive(cuda):
+    """More tiles than SMs: exercises the persistent loop, both TMEM buffers and all phase bits."""
+    from imageenhancement_mp_b200 import ops
+    n, h, w = 6, 104, 104
+    x, wt, b = make_case(n, h, w, 64, 64, 3, seed=5)
+    src = to_raster(x.to(cuda))
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    bias = b.to(cuda)
+    d1 = ops.new_raster(n, h, w, 64, cuda)
+    d2 = ops.new_raster(n, h, w, 64, cuda)
+    ops.conv2d(src.slice(), wp, bias, d1.slice())
+    ops.conv2d(src.slice(), wp, bias, d2.slice(), fn="ie_debug_conv2d_naive")
+    torch.cuda.synchronize()
+    a, r = d1.data.float(), d2.data.float()
+    assert_close_bf16(a.cpu(), r.cpu(), "tcgen05 vs naive, 64->64 @104x104")
+
+
+def test_conv_deep_k_vs_naive(cuda):
+    from imageenhancement_mp_b200 import ops
+    n, h, w = 8, 26, 26
+    x, wt, b = make_case(n, h, w, 2048, 512, 3, seed=6)
+    src = to_raster(x.to(cuda))
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    bias = b.to(cuda)
+    d1 = ops.new_raster(n, h, w, 512, cuda)
+    d2 = ops.new_raster(n, h, w, 512, cuda)
+    ops.conv2d(src.slice(), wp, bias, d1.slice())
+    ops.conv2d(src.slice(), wp, bias, d2.slice(), fn="ie_debug_conv2d_naive")
+    torch.cuda.synchronize()
+    assert_close_bf16(d1.data.float().cpu(), d2.data.float().cpu(), "tcgen05 vs naive, 2048->512 @26x26")
+
+
+@pytest.mark.parametrize("cout,softmax", [(10, True), (40, False), (16, True), (64, False)])
+def test_conv_f32_heads(cuda, cout, softmax):
+    """The two small fp32 epilogues: coef conv + softmax (model_library.py:405-406) and layer3_3."""
+    from imageenhancement_mp_b200 import ops
+    from imageenhancement_mp_b200._lib import IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX
+    n, h, w, cin = 2, 16, 16, 64 if softmax else 128
+    x, wt, b = make_case(n, h, w, cin, cout, 3, seed=11, scale=3.0)
+    ref = ref_conv(x, wt, b, 3)
+    src = to_raster(x.to(cuda))
+    wp = ops.pack_conv_weights(wt.to(cuda), IE_EPI_F32_SOFTMAX if softmax else IE_EPI_F32_NHWC)
+    if softmax:
+        y, logits = ops.conv2d_f32(src.slice(), wp, b.to(cuda), cout, softmax=True, want_logits=True)
+        torch.cuda.synchronize()
+        assert torch.allclose(logits.cpu(), ref, atol=2e-4, rtol=1e-4)
+        assert torch.allclose(y.cpu(), torch.softmax(ref, -1), atol=1e-5, rtol=1e-4)
+    else:
+        y = ops.conv2d_f32(src.slice(), wp, b.to(cuda), cout, valid=(15, 15))
+        torch.cuda.synchronize()
+        assert torch.allclose(y.cpu(), ref[:, :15, :15], atol=2e-4, rtol=1e-4)
+
+
+def test_conv_rejects_bad_descriptors(cuda):
+    from imageenhancement_mp_b200 import ops, ImgEnhError
+    src = ops.new_raster(1, 8, 8, 96, cuda)          # 96 is not a multiple of 64
+    dst = ops.new_raster(1, 8, 8, 64, cuda)
+    wp = torch.zeros(64, 9 * 96, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(ImgEnhError):
+        ops.conv2d(src.slice(), wp, None, dst.slice())

@@ -1,0 +1,250 @@
+"""GPU parity of the non-GEMM kernels against the CPU oracle (through the C ABI / ops wrappers)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import model as omodel
+from imageenhancement_mp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def to_raster(x):
+    from imageenhancement_mp_b200 import ops
+    n, h, w, c = x.shape
+    data = F.pad(x, (0, 0, 1, 1, 1, 1)).reshape(-1, c).to(torch.bfloat16).contiguous()
+    return ops.Raster(data, n, h, w)
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def border_is_zero(r):
+    full = r.data.float().view(r.n, r.h + 2, r.w + 2, -1)
+    return bool((full[:, 0] == 0).all() and (full[:, -1] == 0).all() and (full[:, :, 0] == 0).all()
+                and (full[:, :, -1] == 0).all())
+
+
+# ------------------------------------------------------------------ layout glue
+def test_im2col_first_layer(cuda):
+    """im2col pack + 1x1 GEMM == Conv2D(64, 3, 'same') on the raw input (model_library.py:323, 376)."""
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = bf16_round(torch.rand(2, 16, 24, 5, generator=g))
+    w = bf16_round(torch.randn(3, 3, 5, 64, generator=g) * 0.2)
+    b = torch.randn(64, generator=g) * 0.1
+    ref = omodel.conv2d_relu(x, (w, b), "same")
+    src = ops.pack_input_im2col3x3(x.to(cuda))
+    wp = ops.pack_conv_weights(w.to(cuda), ktot_pad=64)
+    dst = ops.new_raster(2, 16, 24, 64, cuda)
+    ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice(), k=1)
+    got = ops.raster_to_nhwc(dst.slice()).cpu()
+    assert torch.allclose(got, bf16_round(ref), atol=2e-2, rtol=2 ** -7)
+    assert border_is_zero(dst)
+
+
+def test_maxpool(cuda):
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = bf16_round(torch.randn(3, 12, 20, 192, generator=g))
+    src = to_raster(x.to(cuda))
+    dst = ops.new_raster(3, 6, 10, 128, cuda)
+    dst.data.fill_(5.0)
+    ops.maxpool2(src.slice(64, 64), dst.slice(64, 64))
+    got = ops.raster_to_nhwc(dst.slice(64, 64)).cpu()
+    assert torch.equal(got, omodel.maxpool2(x[..., 64:128]))
+    assert torch.all(dst.data[:, :64] == 5.0)
+    dst.data[:, :64] = 0
+    assert border_is_zero(dst)
+
+
+@pytest.mark.parametrize("scale,h,w", [(2, 5, 7), (8, 2, 2), (2, 1, 1)])
+def test_upsample_bilinear(cuda, scale, h, w):
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = bf16_round(torch.randn(2, h, w, 64, generator=g))
+    src = to_raster(x.to(cuda))
+    dst = ops.new_raster(2, h * scale, w * scale, 128, cuda)
+    dst.data.zero_()
+    ops.upsample_bilinear(src.slice(), dst.slice(0, 64), scale)
+    got = ops.raster_to_nhwc(dst.slice(0, 64)).cpu()
+    ref = omodel.upsample_bilinear(x, scale)
+    assert torch.allclose(got, ref, atol=2e-2, rtol=2 ** -7)
+    assert border_is_zero(dst)
+
+
+def test_channel_mean_and_broadcast(cuda):
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = bf16_round(torch.randn(3, 13, 26, 256, generator=g) + 0.5)
+    src = to_raster(x.to(cuda))
+    m = ops.channel_mean(src.slice(128, 128))
+    ref = x[..., 128:].mean(dim=(1, 2))
+    assert torch.allclose(m.cpu(), ref, atol=1e-5, rtol=1e-5)
+    dst = ops.new_raster(3, 16, 16, 192, cuda)
+    dst.data.zero_()
+    ops.broadcast_hw(m, dst.slice(64, 128))
+    got = ops.raster_to_nhwc(dst.slice(64, 128)).cpu()
+    assert torch.equal(got, bf16_round(ref)[:, None, None, :].expand(3, 16, 16, 128))
+    assert border_is_zero(dst)
+
+
+def test_softmax_taps(cuda):
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    ob = torch.relu(torch.randn(3, 15, 15, 40, generator=g) * 2)
+    got = ops.softmax_taps(ob.to(cuda), 4, 10).cpu()
+    ref = omodel.basis_softmax(ob, 15, 4, 10)
+    assert torch.allclose(got, ref, atol=1e-7, rtol=1e-5)
+    assert torch.allclose(got.sum(dim=(1, 2, 3)), torch.ones(3, 10), atol=1e-5)
+
+
+# ------------------------------------------------------------------ per-pixel filter
+def _kpn_inputs(n, h, w, T, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, h, w, T + 1, generator=g)
+    coef = torch.softmax(torch.randn(n, h, w, B, generator=g) * 2, -1)
+    bas = omodel.basis_softmax(torch.randn(n, 15, 15, T * B, generator=g) * 3, 15, T, B)
+    return x, coef, bas
+
+
+@pytest.mark.parametrize("n,h,w,T,B", [(2, 16, 24, 4, 10), (1, 40, 72, 2, 10), (1, 24, 24, 4, 7), (1, 19, 70, 3, 20)])
+def test_kpn_apply_vs_literal(cuda, n, h, w, T, B):
+    """Fused filter == the reference's tile/multiply/reduce_sum + Convolve (+perlayer), fp64 oracle."""
+    from imageenhancement_mp_b200 import ops
+    x, coef, bas = _kpn_inputs(n, h, w, T, B, 7)
+    ref = oracle.kpn_apply_literal(x[..., :T].double(), coef.double(), bas.double())
+    got = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda)).cpu()
+    assert torch.allclose(got.double(), ref, atol=2e-6, rtol=1e-5)
+
+
+def test_kpn_apply_large_vs_algebraic(cuda):
+    from imageenhancement_mp_b200 import ops
+    x, coef, bas = _kpn_inputs(2, 104, 104, 4, 10, 8)
+    ref = oracle.kpn_apply_algebraic(x[..., :4].double(), coef.double(), bas.double())
+    got = ops.kpn_apply(x.to(cuda), 4, coef.to(cuda), bas.to(cuda)).cpu()
+    assert torch.allclose(got.double(), ref, atol=2e-6, rtol=1e-5)
+    # partition of unity (two softmaxes): a constant burst stays constant >= 7 px from the border
+    ones = torch.ones_like(x).to(cuda)
+    got1 = ops.kpn_apply(ones, 4, coef.to(cuda), bas.to(cuda)).cpu()
+    assert torch.allclose(got1[:, 7:-7, 7:-7, 0], torch.ones(2, 90, 90), atol=1e-5)
+
+
+# ------------------------------------------------------------------ metrics
+def _metric_inputs(n, h, w, T, seed):
+    x, truth = synth.make_batch(n, h, w, {"BURST_LENGTH": T}, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    recon = (truth[..., :1] + 0.03 * torch.randn(n, h, w, T + 1, generator=g)).contiguous()
+    recon[0, 3, 3, 0] = 1.7 * truth[0, 3, 3, 1]          # exercise the x > 1 branch of the sRGB curve
+    return recon, x, truth
+
+
+def test_reference_api_metrics(cuda):
+    """Function-by-function parity of the data_utils API (fp64 oracle, <=1e-5 relative)."""
+    from imageenhancement_mp_b200 import data_utils as du
+    T = 4
+    recon, x, truth = _metric_inputs(3, 40, 56, T, 21)
+    rc, xc, tc = recon.to(cuda), x.to(cuda), truth.to(cuda)
+    wn_ref = truth[..., 1:2].double().mean(dim=1, keepdim=True).mean(dim=2, keepdim=True)
+    wn = du.white_level_of(tc)
+    assert torch.allclose(wn.cpu().double(), wn_ref, rtol=1e-6)
+    vals = torch.tensor([0., .001, .0031308, .5, 1., 2.], device=cuda)
+    assert torch.allclose(du.sRGBforward(vals).cpu().double(), oracle.sRGBforward(vals.cpu().double()), atol=1e-6)
+    igt_ref = oracle.invert_preproc(truth[..., 0].double(), wn_ref)
+    igt = du.invert_preproc(tc[..., 0], wn)
+    assert igt.shape == (3, 24, 40)
+    assert torch.allclose(igt.cpu().double(), igt_ref, atol=2e-6, rtol=1e-5)
+    ide_ref = oracle.invert_preproc(recon[..., 0].double(), wn_ref)
+    ide = du.invert_preproc(rc[..., 0], wn)
+    rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-12)
+    assert rel(du.deblur_loss(ide, igt), oracle.deblur_loss(ide_ref, igt_ref)) < 1e-5
+    assert rel(du.gradient_loss(ide, igt), oracle.gradient_loss(ide_ref, igt_ref)) < 1e-5
+    assert rel(du.deblur_layer_loss(rc, igt, wn), oracle.deblur_layer_loss(recon.double(), igt_ref, wn_ref)) < 1e-5
+    assert rel(du.psnr_deblur(ide, igt), oracle.psnr_deblur(ide_ref, igt_ref)) < 1e-5
+    per, per_ref = du.psnr_each_layer(igt, wn, rc), oracle.psnr_each_layer(igt_ref, wn_ref, recon.double())
+    for k in per_ref:
+        assert rel(per[k], per_ref[k]) < 1e-5
+    burst, burst_ref = xc[..., :T], x[..., :T].double()
+    assert rel(du.psnr_burst0(igt, wn, burst), oracle.psnr_burst0(igt_ref, wn_ref, burst_ref)) < 1e-5
+    assert rel(du.psnr_average_f(igt, wn, burst), oracle.psnr_average_f(igt_ref, wn_ref, burst_ref)) < 1e-5
+    lay = du.invert_deblur_layer(rc, wn)
+    assert lay.shape == (3, 24, 40 * T)
+    assert torch.allclose(lay.cpu().double(), oracle.invert_deblur_layer(recon.double(), wn_ref), atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,h,w,T", [(3, 40, 56, 4), (2, 104, 104, 4), (1, 33, 49, 2), (2, 100, 100, 8)])
+def test_fused_eval_metrics(cuda, n, h, w, T):
+    """One fused pass == the reference's per-batch numbers (eval.py:144-182), fp64 oracle."""
+    from imageenhancement_mp_b200 import data_utils as du
+    recon, x, truth = _metric_inputs(n, h, w, T, 31)
+    ref = oracle.eval_step(recon.double(), x.double(), truth.double(), T)
+    got = du.eval_metrics(recon.to(cuda), x.to(cuda), truth.to(cuda), T)
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-12)
+    assert rel(got["loss1"], ref["loss1"]) < 1e-5
+    assert rel(got["perlayer_loss"], ref["perlayer_loss"]) < 1e-5
+    assert rel(got["psnr"], ref["psnr"]) < 1e-5
+    for t in range(T):
+        assert rel(got["psnr_perlayer"][t], ref["psnr_perlayer"][t]) < 1e-5
+    assert rel(got["psnr_noise0"], ref["psnr_noise0"]) < 1e-5
+    assert rel(got["psnr_average"], ref["psnr_average"]) < 1e-5
+
+
+def test_psnr_known_answer(cuda):
+    from imageenhancement_mp_b200 import data_utils as du
+    a = torch.rand(4, 50, 60, device=cuda)
+    assert abs(float(du.psnr_tf_batch(a + 0.1, a)) - 20.0) < 1e-4      # constant error 0.1 -> 20 dB
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 11, 11), (2, 64, 80), (1, 100, 137), (1, 210, 330)])
+def test_ssim(cuda, n, h, w):
+    """SSIM extension vs the fp64 tf.image.ssim restatement."""
+    from imageenhancement_mp_b200 import data_utils as du
+    g = torch.Generator().manual_seed(41)
+    a = torch.rand(n, h, w, generator=g)
+    b = (a + 0.1 * torch.randn(n, h, w, generator=g)).clamp(0, 1)
+    got = du.ssim(a.to(cuda), b.to(cuda)).cpu().double()
+    assert torch.allclose(got, oracle.ssim(a, b), atol=2e-5, rtol=1e-4)
+    assert torch.allclose(du.ssim(a.to(cuda), a.to(cuda)).cpu(), torch.ones(n), atol=1e-5)
+
+
+# ------------------------------------------------------------------ preprocessing
+@pytest.mark.parametrize("layer_type,color", [("singlestd", False), ("dualparams", True), ("empty", False)])
+def test_preprocess(cuda, layer_type, color):
+    from oracle import preprocess as opre
+    from imageenhancement_mp_b200 import data_utils as du
+    params = dict(synth.DEFAULT_PARAMS, height=24, width=32, BURST_LENGTH=3, layer_type=layer_type)
+    C = 3 if color else 1
+    g = torch.Generator().manual_seed(51)
+    N, T, up, jit, sj = 2, 3, 4, 16, 2
+    hs, ws = 24 * up + 2 * jit * up + 7, 32 * up + 2 * jit * up + 5
+    xs, ts, orgs, wl, sr, ss, nr, ns = [], [], [], [], [], [], [], []
+    src = torch.randint(0, 256, (N, hs, ws, C), generator=g, dtype=torch.uint8)
+    for n in range(N):
+        draws = {
+            "crop0": (int(torch.randint(0, 8, (1,), generator=g)), int(torch.randint(0, 6, (1,), generator=g))),
+            "use_big": [bool(torch.rand(1, generator=g) < 0.5) for _ in range(T - 1)],
+            "white_level": float(10 ** (torch.rand(1, generator=g) - 1)),
+            "sig_read": float(10 ** (torch.rand(1, generator=g) * 1.5 - 3)),
+            "sig_shot": float(10 ** (torch.rand(1, generator=g) - 2)),
+            "n_read": torch.randn(24, 32, T, generator=g),
+            "n_shot": torch.randn(24, 32, T, generator=g),
+        }
+        draws["frame_off"] = []
+        for k in range(T - 1):
+            lim = 2 * jit * up if draws["use_big"][k] else 2 * sj * up
+            draws["frame_off"].append((int(torch.randint(0, lim + 1, (1,), generator=g)),
+                                       int(torch.randint(0, lim + 1, (1,), generator=g))))
+        x, t = opre.preprocess_image(src[n], params, draws, dtype=torch.float64)
+        xs.append(x); ts.append(t)
+        orgs.append(opre.frame_origins(params, draws))
+        wl.append(draws["white_level"]); sr.append(draws["sig_read"]); ss.append(draws["sig_shot"])
+        nr.append(draws["n_read"]); ns.append(draws["n_shot"])
+    f = lambda v: torch.tensor(v, dtype=torch.float32, device=cuda)
+    gx, gt = du.preprocess_image(src.to(cuda), torch.tensor(orgs, dtype=torch.int32, device=cuda), params,
+                                 f(wl), f(sr), f(ss), torch.stack(nr).to(cuda), torch.stack(ns).to(cuda))
+    assert torch.allclose(gx.cpu().double(), torch.stack(xs), atol=2e-6, rtol=2e-5)
+    assert torch.allclose(gt.cpu().double(), torch.stack(ts), atol=2e-6, rtol=2e-5)

@@ -1,0 +1,133 @@
+"""End-to-end GPU parity of the model forward + eval metrics against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  output max-abs <= 1e-2 on [0,1] pixels, PSNR within 0.05 dB;
+  because default (glorot, zero-bias) init collapses the output to a 15x15 box mean, the
+  trunk is additionally checked under a "stress" init on intermediates:
+  relative-L2 <= 2e-2 on the pre-softmax logits, Coef, originbasis and Bas.
+"""
+import pytest
+import torch
+
+import oracle
+from imageenhancement_mp_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-2
+PSNR_TOL = 0.05
+REL_L2_TOL = 2e-2
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-12))
+
+
+def run_pair(cuda, arch, params, n, h, w, scheme, seed=1234, conv_fn="ie_conv2d_nhwc_bf16"):
+    from imageenhancement_mp_b200 import model_library as ml
+    layers = weights.simplemodel_layers(params) if arch == "simple" else weights.basis_kpn_layers(params)
+    W = weights.init_weights(layers, seed=seed, scheme=scheme)
+    x, truth = synth.make_batch(n, h, w, params, seed=seed)
+    cls = ml.Simplemodel if arch == "simple" else ml.Basis_kpn
+    model = cls(params, weights=W)
+    taps_g = {}
+    res_g = model(x.to(cuda), taps=taps_g, conv_fn=conv_fn)
+    torch.cuda.synchronize()
+    s = model.stride
+    xp, _ = synth.pad_to_multiple(x, s)
+    taps_o = {}
+    fwd = oracle.simplemodel_forward if arch == "simple" else oracle.basis_kpn_forward
+    res_o = fwd(W, params, xp, taps=taps_o)
+    out_o = res_o[0][:, :h, :w]
+    return res_g, taps_g, (out_o,) + tuple(res_o[1:]), taps_o, x, truth
+
+
+@pytest.mark.parametrize("scheme", ["glorot", "stress"])
+@pytest.mark.parametrize("n,h,w", [(2, 32, 32), (2, 100, 100)])
+def test_simplemodel_parity(cuda, scheme, n, h, w):
+    from imageenhancement_mp_b200 import data_utils as du
+    params = dict(synth.DEFAULT_PARAMS)
+    res_g, taps_g, res_o, taps_o, x, truth = run_pair(cuda, "simple", params, n, h, w, scheme)
+    out_g, bas_g, ob_g = [t.cpu() for t in res_g]
+    out_o, bas_o, ob_o = res_o
+    assert out_g.shape == (n, h, w, 5) and bas_g.shape == (n, 15, 15, 4, 10) and ob_g.shape == (n, 15, 15, 40)
+    assert float((out_g - out_o).abs().max()) <= OUT_TOL
+    # intermediates (the only meaningful trunk check under default init is relative)
+    hp = -(-h // 8) * 8
+    worst = {}
+    for name in ["layer0", "down1.conv2d2", "down2.conv2d2", "down5.conv2d2", "layer1_1", "Coef_up1.conv2d3",
+                 "Coef_up4.conv2d3", "Coef_up5.conv2d3", "layer2_1", "Basis_up1.conv2d3", "Basis_up4.conv2d3",
+                 "layer3_1"]:
+        worst[name] = rel_l2(taps_g[name].cpu(), taps_o[name])
+    assert max(worst.values()) <= REL_L2_TOL, worst
+    assert rel_l2(taps_g["coef_logits"].cpu(), taps_o["coef_logits"]) <= REL_L2_TOL
+    assert rel_l2(taps_g["Coef"].cpu(), taps_o["Coef"]) <= REL_L2_TOL
+    assert rel_l2(ob_g, ob_o) <= REL_L2_TOL
+    assert rel_l2(bas_g, bas_o) <= REL_L2_TOL
+    # report numbers: PSNR within 0.05 dB of the oracle's eval step on the oracle's own output
+    ref = oracle.eval_step(out_o, x, truth, 4)
+    got = du.eval_metrics(res_g[0], x.to(cuda), truth.to(cuda), 4)
+    assert abs(got["psnr"] - ref["psnr"]) <= PSNR_TOL
+    for t in range(4):
+        assert abs(got["psnr_perlayer"][t] - ref["psnr_perlayer"][t]) <= PSNR_TOL
+    assert abs(got["psnr_noise0"] - ref["psnr_noise0"]) <= 1e-3
+    assert abs(got["psnr_average"] - ref["psnr_average"]) <= 1e-3
+    assert abs(got["loss1"] - ref["loss1"]) <= 1e-3 * max(1.0, abs(ref["loss1"]))
+
+
+def test_simplemodel_three_channel_reading(cuda):
+    """The literal 'x3' reading of BASELINE.json: T=2 + singlestd -> 3 input channels (run_training_val.py:28)."""
+    params = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=2)
+    res_g, taps_g, res_o, taps_o, x, truth = run_pair(cuda, "simple", params, 2, 40, 48, "stress")
+    assert res_g[0].shape == (2, 40, 48, 3)
+    assert float((res_g[0].cpu() - res_o[0]).abs().max()) <= OUT_TOL
+    assert rel_l2(res_g[1].cpu(), res_o[1]) <= REL_L2_TOL
+
+
+def test_basis_kpn_parity(cuda):
+    """Second entry point: the five-level Basis_kpn with the remote/ defaults (T=8, dualparams)."""
+    params = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=8, layer_type="dualparams")
+    res_g, taps_g, res_o, taps_o, x, truth = run_pair(cuda, "basis_kpn", params, 1, 64, 64, "stress")
+    out_g, bas_g = res_g
+    assert out_g.shape == (1, 64, 64, 9) and bas_g.shape == (1, 15, 15, 8, 10)
+    assert float((out_g.cpu() - res_o[0]).abs().max()) <= OUT_TOL
+    assert rel_l2(taps_g["coef_logits"].cpu(), taps_o["coef_logits"]) <= REL_L2_TOL
+    assert rel_l2(bas_g.cpu(), res_o[1]) <= REL_L2_TOL
+
+
+def test_zero_weights_known_answer(cuda):
+    """All-zero weights: Coef = 1/B, Bas = 1/(K*K*T) => each frame output is the zero-padded 15x15 box mean."""
+    from imageenhancement_mp_b200 import model_library as ml
+    import torch.nn.functional as F
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="zeros")
+    x, _ = synth.make_batch(2, 32, 40, params)
+    out, bas, ob = ml.Simplemodel(params, weights=W)(x.to(cuda))
+    b = x[..., :4].permute(0, 3, 1, 2)
+    box = F.avg_pool2d(F.pad(b, (7, 7, 7, 7)), 15, 1).permute(0, 2, 3, 1)
+    assert torch.allclose(out.cpu()[..., 1:], box, atol=1e-5)
+    assert torch.allclose(out.cpu()[..., 0], box.mean(-1), atol=1e-5)
+    assert torch.allclose(bas.cpu(), torch.full_like(bas.cpu(), 1 / 900.0), rtol=1e-5)
+    assert float(ob.abs().max()) == 0.0
+
+
+def test_tcgen05_forward_equals_naive_forward(cuda):
+    """Whole network with every conv routed through the naive validation kernel vs the tcgen05 path."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    x, _ = synth.make_batch(2, 48, 64, params)
+    m = ml.Simplemodel(params, weights=W)
+    a = m(x.to(cuda))
+    b = m(x.to(cuda), conv_fn="ie_debug_conv2d_naive")
+    assert float((a[0] - b[0]).abs().max()) <= 2e-3
+    assert rel_l2(a[2], b[2]) <= 1e-2
+
+
+def test_no_cpu_fallback(cuda):
+    from imageenhancement_mp_b200 import model_library as ml, ImgEnhError
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="zeros")
+    m = ml.Simplemodel(params, weights=W)
+    with pytest.raises(ImgEnhError):
+        m(torch.zeros(1, 32, 32, 5))
