@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Headline benchmark: megapixels/s enhanced (Simplemodel forward + PSNR/SSIM-style eval metrics).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: model forward
+(model_library.Simplemodel) + the fused eval metrics of eval.py:144-182 + the all-reduce of the
+metric totals.  Workload at N=1 is BASELINE.json configs[1]: batch 256 of 100x100 patches
+(T=4, singlestd -> 5 channels; computed at 104x104 because the network needs multiples of 8,
+pixels counted at 100x100).  Weak scaling: every rank gets its own batch of 256.
+
+`value`  : inputs already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same step through the public API from pinned HOST buffers (H2D of inputs + D2H of the
+           metric totals inside the timed region).
+`roofline`: the convolution kernel (conv_igemm_kernel, every launch of the step): algorithmic conv
+           FLOPs / summed CUDA-event kernel time, against the measured
+           sustained bf16 peak.
+`cpu_baseline` / `--impl reference`: the torch-CPU oracle port of the reference (TensorFlow is not
+           installable here, so the reference itself cannot run) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from imageenhancement_mp_b200 import synth, weights  # noqa: E402
+
+METRIC = "megapixels/sec enhanced (fwd+PSNR/SSIM)"
+UNIT = "MP/s"
+
+CONFIGS = {
+    # name: (batch per GPU, H, W, description)
+    "cfg1": (32, 100, 100, "configs[0]: 32x100x100x5 patches (reference CPU case)"),
+    "cfg2": (256, 100, 100, "configs[1]: batch 256 of 100x100 patches, bf16 trunk"),
+    "cfg3": (8, 720, 1280, "configs[2]: 1280x720 images, micro-batch 8 per step per GPU"),
+}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_sustained": p.get("bf16_tflops_sustained", 1393.7), "bf16_burst": p.get("bf16_tflops", 1667.0),
+                "hbm": p.get("hbm_gbs", 6553.0), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rate(n, h, w, params, W, repeats=1):
+    """Forward + eval metrics of the oracle port on all host cores; returns (MP/s, seconds, cores)."""
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, truth = synth.make_batch(n, h, w, params)
+    xp, _ = synth.pad_to_multiple(x, 8)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = oracle.simplemodel_forward(W, params, xp)[0][:, :h, :w]
+            oracle.eval_step(out, x, truth, params["BURST_LENGTH"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n * h * w / 1e6 / best, best, cores
+
+
+def run_reference(args, cfg_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nb, h, w, desc = CONFIGS[cfg_name]
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params))
+    sample_n = 16                                      # bounded sample of the workload per step
+    for _ in range(args.warmup):
+        cpu_oracle_rate(2, h, w, params, W)
+    times = []
+    for _ in range(args.steps):
+        _, dt, cores = cpu_oracle_rate(sample_n, h, w, params, W)
+        times.append(dt)
+    total = sum(times)
+    value = args.steps * sample_n * h * w / 1e6 / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "note": "torch-CPU oracle port of the reference (TensorFlow not installable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_n} images of {h}x{w} per step (forward + eval metrics), {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def run_ours(args, cfg_name):
+    from imageenhancement_mp_b200 import _lib, data_utils as du, dist as idist, model_library as ml, ops
+    import torch.distributed as dist
+
+    rank, world, local = idist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the hot path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    nb, h, w, desc = CONFIGS[cfg_name]
+    params = dict(synth.DEFAULT_PARAMS)
+    T = params["BURST_LENGTH"]
+    layers = weights.simplemodel_layers(params)
+    W = weights.init_weights(layers)                       # Keras default init, seed 1234
+    model = ml.Simplemodel(params, weights=W, device=dev)
+
+    # synthetic batches: NROT distinct host batches so successive steps never re-read a resident input
+    NROT = 4
+    host = []
+    for i in range(NROT):
+        x, truth = synth.make_batch(nb, h, w, params, seed=1234 + 17 * rank + i)
+        host.append((x.pin_memory(), truth.pin_memory()))
+    devb = [(x.to(dev), t.to(dev)) for x, t in host]
+    h2d_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 4
+
+    def step(xb, tb):
+        out = model(xb)[0]
+        sums = du.eval_metric_sums(out, xb, tb, T)
+        tot = du.reduce_metric_sums(sums, h, w, T)
+        idist.all_reduce_totals(tot)                       # the one collective of the step
+        return tot
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident-input timing
+    for i in range(args.warmup):
+        step(*devb[i % NROT])
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.LAUNCHES.clear()
+    ops.CONV_EVENTS = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        tot = step(*devb[i % NROT])
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(_lib.LAUNCHES.values())
+    conv_ms = sum(a.elapsed_time(b) for a, b in ops.CONV_EVENTS)
+    n_conv = len(ops.CONV_EVENTS)
+    ops.CONV_EVENTS = None
+    report = du.totals_to_report(tot.cpu(), T)
+
+    # ---- end-to-end timing from pinned host buffers through the public API
+    for i in range(max(1, args.warmup // 2)):
+        step(host[i % NROT][0].to(dev, non_blocking=True), host[i % NROT][1].to(dev, non_blocking=True)).cpu()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        xb = host[i % NROT][0].to(dev, non_blocking=True)
+        tb = host[i % NROT][1].to(dev, non_blocking=True)
+        res = step(xb, tb).cpu()                           # D2H read of the step's metric totals
+    e1.record()
+    sync_all()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms, e2e_ms, conv_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, conv_ms = [float(v) for v in t.cpu()]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    mp_per_step = world * nb * h * w / 1e6
+    value = mp_per_step * args.steps / (ms / 1e3)
+    e2e = mp_per_step * args.steps / (e2e_ms / 1e3)
+    peaks = read_peaks()
+    hp, wp = -(-h // 8) * 8, -(-w // 8) * 8
+    per_px, per_img = weights.conv_flops(layers, params, hp, wp)
+    conv_flops_step = nb * (per_px * hp * wp + per_img)     # per rank, at the computed (padded) size
+    achieved = conv_flops_step * args.steps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": nb, "global_batch": nb * world, "image": [h, w],
+                   "computed_at": [hp, wp], "channels": T + 1, "net": "Simplemodel T=4 K=15 B=10 singlestd, glorot init",
+                   "parallelism": f"image-sharded x{world}",
+                   "l2": f"{NROT} input batches rotated ({NROT * h2d_bytes >> 20} MiB) and >300 MB of activations per layer: inputs larger than L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(res.numel() * 8),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "conv_igemm_kernel (all %d launches per step)" % (n_conv // max(args.steps, 1)),
+                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + " sustained bf16", "frac_of_burst": achieved / peaks["bf16_burst"],
+                     "conv_ms_per_step": conv_ms / args.steps, "conv_tflop_per_step": conv_flops_step / 1e12},
+        "quality": {"psnr": report["psnr"], "psnr_noise0": report["psnr_noise0"], "psnr_average": report["psnr_average"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sample_n = 16
+        v, dt, cores = cpu_oracle_rate(sample_n, h, w, params, W)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{sample_n} images of {h}x{w}, forward + eval metrics, one pass ({dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args, args.config)
+    else:
+        run_ours(args, args.config)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,7 @@ and the current CUDA stream as ``void*``.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 
@@ -55,6 +56,7 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = collections.Counter()      # C-ABI calls made (each enqueues exactly one kernel of ours)
 
 
 def load():
@@ -90,6 +92,7 @@ def stream():
 
 def call(name, *args):
     lib = load()
+    LAUNCHES[name] += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.ie_last_error().decode("utf-8", "replace")

@@ -33,13 +33,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int taps, in
 }
 
 // ------------------------------------------------------------------------------- input im2col
-// One thread per (raster row, 16-byte chunk): 8 consecutive k of the 64-wide im2col row.
+// One thread per (raster row, 16-byte chunk): 8 consecutive k of the kvec*8-wide im2col row.
 __global__ void im2col3x3_kernel(const float* __restrict__ x, int n, int h, int w, int c, uint4* __restrict__ out,
-                                 long long rows) {
+                                 long long rows, int kvec) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= rows * 8) return;
-  const long long r = t >> 3;
-  const int chunk = (int)(t & 7);
+  if (t >= rows * kvec) return;
+  const long long r = t / kvec;
+  const int chunk = (int)(t - r * kvec);
   const int wp = w + 2, plane = (h + 2) * wp;
   const int img = (int)(r / plane);
   const int pr = (int)(r - (long long)img * plane);
@@ -244,10 +244,11 @@ extern "C" int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, 
 
 extern "C" int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* raster_bf16, void* stream) {
   IE_REQUIRE(x && raster_bf16, "pack_input: null pointer");
-  IE_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && 9 * c <= 64, "pack_input: need 9*c <= 64 (c=%d)", c);
+  IE_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && 9 * c <= 1024, "pack_input: need 9*c <= 1024 (c=%d)", c);
   const long long rows = (long long)n * (h + 2) * (w + 2);
-  im2col3x3_kernel<<<ie_ceil_div(rows * 8, 256), 256, 0, S(stream)>>>(x, n, h, w, c, static_cast<uint4*>(raster_bf16),
-                                                                     rows);
+  const int kvec = ((9 * c + 63) / 64) * 8;      // row width in 16-byte chunks: 9*c rounded up to 64 channels
+  im2col3x3_kernel<<<ie_ceil_div(rows * kvec, 256), 256, 0, S(stream)>>>(x, n, h, w, c,
+                                                                        static_cast<uint4*>(raster_bf16), rows, kvec);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

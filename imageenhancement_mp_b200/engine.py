@@ -57,8 +57,7 @@ class Engine:
         self.K = params["Kernel_size"]
         self.B = params["Basis_num"]
         self.cin = self.T + ADD_LENGTHS[params["layer_type"]]
-        if 9 * self.cin > 64:
-            raise ImgEnhError(f"input channels {self.cin}: the im2col first layer needs 9*C <= 64")
+        self.k0 = ops.im2col_width(self.cin)                 # K of the first layer as a 1x1 GEMM over im2col rows
         if self.K != 15:
             raise ImgEnhError("Kernel_size must be 15: the basis branch emits 15x15 kernels (model_library.py:364)")
         self.device = torch.device(device)
@@ -76,7 +75,7 @@ class Engine:
             assert tuple(w.shape) == (k, k, cin, cout), (name, tuple(w.shape), (k, k, cin, cout))
             w = w.to(self.device, torch.float32)
             epi = f32_heads.get(name, IE_EPI_BF16_RASTER)
-            ktot_pad = 64 if name == "layer0" else None     # first layer runs as a 1x1 GEMM over im2col rows
+            ktot_pad = self.k0 if name == "layer0" else None
             self.wp[name] = ops.pack_conv_weights(w, epi, ktot_pad)
             self.bias[name] = b.to(self.device, torch.float32).contiguous()
 
@@ -91,7 +90,7 @@ class Engine:
         p = {}
         chans = dict(A["downs"])
         # encoder rasters per level l (resolution h >> l)
-        p["in0"] = R(h, w, 64)
+        p["in0"] = R(h, w, self.k0)
         p["x0"] = R(h, w, 64)
         up_in = {}                                   # channels entering each coef up block
         prev = 1024

@@ -16,6 +16,21 @@ from . import _lib
 from ._lib import ConvDesc, IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX, call, ptr, stream
 
 
+# bench.py sets this to a list to collect (start, end) CUDA events around every convolution launch
+CONV_EVENTS = None
+
+
+def _timed_conv(fn, *args):
+    if CONV_EVENTS is None:
+        call(fn, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(fn, *args)
+    e1.record()
+    CONV_EVENTS.append((e0, e1))
+
+
 @dataclass
 class Raster:
     data: torch.Tensor      # bf16 [rows, pitch]
@@ -68,14 +83,19 @@ def pack_conv_weights(kernel_hwio, epilogue=IE_EPI_BF16_RASTER, ktot_pad=None):
     return out
 
 
+def im2col_width(c):
+    """Channels of the im2col raster of a c-channel input: 9*c rounded up to a multiple of 64."""
+    return -(-9 * c // 64) * 64
+
+
 def pack_input_im2col3x3(x, out=None):
-    """fp32 NHWC [n,h,w,c] -> Raster(n,h,w) with 64 channels holding the 3x3xc neighbourhoods."""
+    """fp32 NHWC [n,h,w,c] -> Raster(n,h,w) with im2col_width(c) channels holding the 3x3xc neighbourhoods."""
     _lib.require_cuda(x)
     n, h, w, c = x.shape
     x = x.contiguous()
     if out is None:
-        out = new_raster(n, h, w, 64, x.device)
-    assert out.pitch == 64 and (out.n, out.h, out.w) == (n, h, w)
+        out = new_raster(n, h, w, im2col_width(c), x.device)
+    assert out.pitch == im2col_width(c) and (out.n, out.h, out.w) == (n, h, w)
     call("ie_pack_input_im2col3x3", ptr(x), n, h, w, c, ptr(out.data), stream())
     return out
 
@@ -97,7 +117,7 @@ def conv2d(src: Slice, w_packed, bias, dst: Slice, k=3, relu=True, valid=None, f
     """Conv2D(k, relu) from a raster slice into a raster slice (bf16 epilogue)."""
     assert dst.r.rows == src.r.rows, "conv output must share the input raster geometry"
     d = _desc(src, k, k, dst.c, relu, IE_EPI_BF16_RASTER, dst, valid)
-    call(fn, C.byref(d), ptr(src.r.data), ptr(w_packed), ptr(bias), ptr(dst.r.data), None, None, stream())
+    _timed_conv(fn, C.byref(d), ptr(src.r.data), ptr(w_packed), ptr(bias), ptr(dst.r.data), None, None, stream())
 
 
 def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, softmax=False, want_logits=False,
@@ -109,7 +129,7 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
     d = _desc(src, k, k, cout, relu, epi, None, valid)
     y = torch.empty(r.n, hv, wv, cout, dtype=torch.float32, device=r.data.device)
     aux = torch.empty_like(y) if (softmax and want_logits) else None
-    call(fn, C.byref(d), ptr(r.data), ptr(w_packed), ptr(bias), None, ptr(y), ptr(aux), stream())
+    _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed), ptr(bias), None, ptr(y), ptr(aux), stream())
     return (y, aux) if softmax else y
 
 

@@ -66,9 +66,9 @@ int ie_sm_count(void);
 int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, int ktot_pad, void* packed_bf16,
                          void* stream);
 
-/* fp32 NHWC [n][h][w][c] (9*c <= 64) -> bf16 raster [n*(h+2)*(w+2)][64] holding each pixel's zero-padded
- * 3x3xc neighbourhood, k = (i*3+j)*c + ch: turns the first conv (model_library.py:323/376) into a
- * 1x1 GEMM with K = 64.                                                                               */
+/* fp32 NHWC [n][h][w][c] -> bf16 raster [n*(h+2)*(w+2)][kpad], kpad = 9*c rounded up to a multiple of 64,
+ * holding each pixel's zero-padded 3x3xc neighbourhood, k = (i*3+j)*c + ch (rest zero): turns the first
+ * conv (model_library.py:323/376, 196/235) into a 1x1 GEMM with K = kpad.                              */
 int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* raster_bf16, void* stream);
 
 /* y = epilogue(conv(x, w) + bias).  w_packed from ie_pack_conv_weights with ktot_pad = kh*kw*cin.
