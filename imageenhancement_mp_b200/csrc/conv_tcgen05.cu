@@ -1,21 +1,30 @@
-// Implicit-GEMM convolution for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma -> TMEM ->
-// fused epilogue.  Replaces layers.Conv2D(c,3,'same',relu) / Conv2D(128,2,'valid',relu) of
+// Implicit-GEMM convolution for sm_100a: TMA -> 128B-swizzled smem -> tcgen05.mma -> TMEM -> fused
+// epilogue.  Replaces layers.Conv2D(c,3,'same',relu) / Conv2D(128,2,'valid',relu) of
 // /root/reference/model_library.py:72-73,89-91,323-368.
 //
 // GEMM view.  Activations are bf16 "rasters" [R][pitch] (see include/imgenh_b200.h): one row per
 // padded pixel, zero border.  For output row r and tap (i,j) the input row is r + shift(i,j), so
 //     D[r][co] = sum_tap sum_c X[r + shift(tap)][c] * Wt[co][tap*cin + c]
-// A tile  = 128 consecutive raster rows x 64 channels  (one 2-D TMA box, OOB rows zero-filled)
-// B tile  = n_tile output channels x 64 K-elements of the packed weights [cout][ntaps*cin]
-// Both K-major, SWIZZLE_128B, so one smem descriptor + 32-byte advance per UMMA_K=16 step.
-// D lives in TMEM (128 lanes x n_tile fp32 columns), double-buffered (2 x 256 columns) so the
-// epilogue of tile i overlaps the main loop of tile i+1.
-//
-// Warp roles (192 threads, persistent CTA, one per SM):
+// Both operands are K-major with SWIZZLE_128B (rows of 64 bf16 = 128 B), so one shared-memory
+// descriptor + a 32-byte advance per UMMA_K=16 step addresses every MMA.  D lives in TMEM
+// (128 lanes x n_tile fp32 columns), double-buffered (2 x 256 columns) so the epilogue of tile i
+// overlaps the main loop of tile i+1.  Persistent CTAs, one per SM, 192 threads:
 //   warp 0      TMA producer (one elected lane)
-//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (warp-uniform loop, one elected lane issues)
 //   warps 2..5  epilogue: tcgen05.ld -> bias/ReLU/border mask -> bf16 -> swizzled smem -> TMA store
 //               (or fp32 global stores / per-pixel softmax for the two small heads)
+//
+// Two main-loop flavours share the epilogue:
+//   conv_stream_kernel    wide layers (n_tile 128/256): every (tap, 64-channel block) is one pipeline
+//                         stage = A box [128 rows x 64 ch] + B box [n_tile x 64]; MMA-bound (>90 %
+//                         tensor-pipe active in ncu).
+//   conv_resident_kernel  narrow layers (n_tile <= 64, 9*cin*n_tile*2 B of weights fit in smem): the
+//                         whole weight matrix is loaded once per CTA and stays resident; a stage is one
+//                         A box of 128+2 rows per (filter row, channel block), and the three horizontal
+//                         taps read it at +0/+1/+2 rows through the descriptor start address.  That cuts
+//                         L2->smem traffic per tile 4.4x and issues 12 MMAs per barrier round trip - the
+//                         narrow layers are bound by single-thread issue overhead and operand traffic,
+//                         not by the tensor pipe.
 #include "ie_common.cuh"
 #include "ie_ptx.cuh"
 
@@ -31,17 +40,15 @@ constexpr int kStgBytesPerWarp = 32 * 128;       // 32 rows x 64 bf16
 constexpr int kMaxCout = 1024;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator buffer
+constexpr int kTailBytes = 4 * kStgBytesPerWarp + kMaxCout * 4 + (2 * kMaxStages + 6) * 8 + 16;
+constexpr size_t kMaxSmem = 227 * 1024;
 
-struct ConvKernelParams {
+// Output-side description shared by both kernels.
+struct EpiParams {
   int R;             // raster rows
   int plane;         // (h+2)*(w+2)
   int wp;            // w+2
   int hv, wv;        // valid output extent
-  int ntaps;
-  int tap_shift[9];
-  int kblocks_per_tap;   // cin / 64
-  int x_coff;
-  int cin;
   int cout;
   int n_tile;
   int n_tiles;
@@ -49,92 +56,249 @@ struct ConvKernelParams {
   int y_coff;
   int relu;
   int epilogue;
-  int stages;
-  int b_stage_bytes;     // n_tile*128 rounded up to 1024
   const float* bias;
   float* y_f32;
   float* y_aux;
 };
 
-struct SmemLayout {
-  // dynamic smem, 1024-aligned base:
-  //   [stages x (A 16 KiB | B b_stage_bytes)] [4 x 4 KiB staging] [bias 4 KiB] [barriers]
-  uint8_t* base;
-  int stages, b_bytes;
-  __device__ uint8_t* a(int s) const { return base + s * (kABytes + b_bytes); }
-  __device__ uint8_t* b(int s) const { return a(s) + kABytes; }
-  __device__ uint8_t* stg(int warp) const { return base + stages * (kABytes + b_bytes) + warp * kStgBytesPerWarp; }
-  __device__ float* bias() const { return reinterpret_cast<float*>(stg(4)); }
-  __device__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias()) + kMaxCout * 4); }
+// Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
+struct SmemTail {
+  uint8_t* p;
+  __device__ uint8_t* stg(int warp) const { return p + warp * kStgBytesPerWarp; }
+  __device__ float* bias() const { return reinterpret_cast<float*>(p + 4 * kStgBytesPerWarp); }
+  __device__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(p + 4 * kStgBytesPerWarp + kMaxCout * 4); }
+  __device__ uint64_t* empty() const { return full() + kMaxStages; }
+  __device__ uint64_t* tfull() const { return empty() + kMaxStages; }     // [2]
+  __device__ uint64_t* tempty() const { return tfull() + 2; }              // [2]
+  __device__ uint64_t* bres() const { return tempty() + 2; }               // [1] resident weights landed
+  __device__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(bres() + 1); }
 };
 
-static size_t conv_smem_bytes(int stages, int b_bytes) {
-  return 1024 /*align slack*/ + static_cast<size_t>(stages) * (kABytes + b_bytes) + 4 * kStgBytesPerWarp +
-         kMaxCout * 4 + (2 * kMaxStages + 4) * 8 + 16;
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const __grid_constant__ CUtensorMap tm_y, const ConvKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  SmemLayout sm;
-  sm.base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  sm.stages = p.stages;
-  sm.b_bytes = p.b_stage_bytes;
-  uint64_t* full_bar = sm.bars();
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
-  const int kblocks = p.ntaps * p.kblocks_per_tap;
-
-  // ---- one-time setup
-  for (int i = threadIdx.x; i < kMaxCout; i += kThreads) sm.bias()[i] = (i < p.cout && p.bias) ? p.bias[i] : 0.f;
+// One-time CTA setup common to both kernels; returns the TMEM base address.
+__device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams& e, int stages, int warp, int lane) {
+  for (int i = threadIdx.x; i < kMaxCout; i += kThreads) t.bias()[i] = (i < e.cout && e.bias) ? e.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
-    tma_prefetch_desc(&tm_y);
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&t.full()[s], 1);
+      mbar_init(&t.empty()[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);   // one arrive per epilogue warp
+      mbar_init(&t.tfull()[b], 1);
+      mbar_init(&t.tempty()[b], 4);   // one arrive per epilogue warp
     }
+    mbar_init(t.bres(), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_alloc(t.tmem_slot(), kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  return *t.tmem_slot();
+}
+
+// Epilogue warps (4 warps, one TMEM lane quadrant each): walk the CTA's tiles and drain the accumulator
+// buffers as the MMA warp completes them.
+__device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensorMap* tm_y, const SmemTail& t,
+                                              uint32_t tmem_base, int warp, int lane) {
+  const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+  const int row_in_tile = q * 32 + lane;
+  uint8_t* stg = t.stg(warp - 2);
+  const float* sbias = t.bias();
+  uint64_t* tfull_bar = t.tfull();
+  uint64_t* tempty_bar = t.tempty();
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int m_tile = tile / p.n_tiles;
+    const int n_idx = tile - m_tile * p.n_tiles;
+    const int r0 = m_tile * kBlockM;
+    const int n0 = n_idx * p.n_tile;
+    const int buf = it & 1;
+    const uint32_t use = static_cast<uint32_t>(it >> 1);
+    const int r = r0 + row_in_tile;
+    // position inside the image raster -> is this an interior (kept) output?
+    const int img = r / p.plane;
+    const int pr = r - img * p.plane;
+    const int y = pr / p.wp;
+    const int x = pr - y * p.wp;
+    const bool valid = (r < p.R) && (y >= 1) && (y <= p.hv) && (x >= 1) && (x <= p.wv);
+
+    mbar_wait(&tfull_bar[buf], use & 1u);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+
+    if (p.epilogue == IE_EPI_BF16_RASTER) {
+      const int chunks = p.n_tile >> 6;
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(t_base + c * 64, v0);
+        tmem_ld_x32(t_base + c * 64 + 32, v1);
+        tmem_ld_wait();
+        if (c == chunks - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        uint32_t pk[32];
+        const float* bs = sbias + n0 + c * 64;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(v0[2 * j]) + bs[2 * j];
+          float b = __uint_as_float(v0[2 * j + 1]) + bs[2 * j + 1];
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          pk[j] = valid ? pack_bf16x2(a, b) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(v1[2 * j]) + bs[32 + 2 * j];
+          float b = __uint_as_float(v1[2 * j + 1]) + bs[32 + 2 * j + 1];
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          pk[16 + j] = valid ? pack_bf16x2(a, b) : 0u;
+        }
+        // staging buffer must have been read by the previous TMA store
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B)
+        uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = val;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_y, stg, p.y_coff + n0 + c * 64, r0 + q * 32);
+          tma_store_commit();
+        }
+      }
+    } else {
+      // small fp32 heads (single N tile, cout <= 256): each thread owns one pixel's channels and walks
+      // them 16 TMEM columns at a time; the softmax re-reads TMEM instead of holding them in registers.
+      const int nch = (p.cout + 15) >> 4;
+      const bool sm_mode = (p.epilogue == IE_EPI_F32_SOFTMAX);
+      const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + (x - 1);
+      float* dst = p.y_f32 + pix * p.cout;
+      float* aux = p.y_aux ? p.y_aux + pix * p.cout : nullptr;
+      float mx = -INFINITY, inv = 1.f;
+      uint32_t v[16];
+      if (sm_mode) {
+        for (int c = 0; c < nch; ++c) {
+          tmem_ld_x16(t_base + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c * 16 + j < p.cout) {
+              float a = __uint_as_float(v[j]) + sbias[c * 16 + j];
+              if (p.relu) a = fmaxf(a, 0.f);
+              mx = fmaxf(mx, a);
+            }
+          }
+        }
+        float sum = 0.f;
+        for (int c = 0; c < nch; ++c) {
+          tmem_ld_x16(t_base + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c * 16 + j < p.cout) {
+              float a = __uint_as_float(v[j]) + sbias[c * 16 + j];
+              if (p.relu) a = fmaxf(a, 0.f);
+              sum += __expf(a - mx);
+            }
+          }
+        }
+        inv = 1.f / sum;
+      }
+      for (int c = 0; c < nch; ++c) {
+        tmem_ld_x16(t_base + c * 16, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = c * 16 + j;
+            if (ch < p.cout) {
+              float a = __uint_as_float(v[j]) + sbias[ch];
+              if (p.relu) a = fmaxf(a, 0.f);
+              if (sm_mode) {
+                if (aux) aux[ch] = a;
+                dst[ch] = __expf(a - mx) * inv;
+              } else {
+                dst[ch] = a;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  if (lane == 0) tma_store_wait<0>();   // all bulk stores complete before smem goes away
+}
+
+// =================================================================================================
+// Streaming kernel: stage = (tap, 64-channel block) -> A box [128 x 64] + B box [n_tile x 64]
+// =================================================================================================
+struct StreamParams {
+  EpiParams e;
+  int ntaps;
+  int tap_shift[9];
+  int kblocks_per_tap;   // cin / 64
+  int x_coff;
+  int cin;
+  int stages;
+  int b_stage_bytes;     // n_tile*128 rounded up to 1024
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const __grid_constant__ CUtensorMap tm_y, const StreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  const int stage_bytes = kABytes + p.b_stage_bytes;
+  SmemTail t{base + p.stages * stage_bytes};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.e.m_tiles * p.e.n_tiles;
+  const int kblocks = p.ntaps * p.kblocks_per_tap;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+  }
+  const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane);
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.n_tile) * 128u;
+      const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.e.n_tile) * 128u;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_idx = tile - m_tile * p.n_tiles;
+        const int m_tile = tile / p.e.n_tiles;
+        const int n_idx = tile - m_tile * p.e.n_tiles;
         const int r0 = m_tile * kBlockM;
-        const int n0 = n_idx * p.n_tile;
+        const int n0 = n_idx * p.e.n_tile;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int row = r0 + p.tap_shift[tap];
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_2d(sm.a(stage), &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row);
-            tma_load_2d(sm.b(stage), &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
+            uint8_t* a_dst = base + stage * stage_bytes;
+            tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row);
+            tma_load_2d(a_dst + kABytes, &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -142,171 +306,182 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, p.n_tile);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = static_cast<uint32_t>(it >> 1);
-        mbar_wait(&tempty_bar[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+    // Warp-uniform loop (descriptors stay in uniform registers); one elected lane issues.
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, p.e.n_tile);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(base));
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(base + kABytes));
+    const uint32_t stage_stride = static_cast<uint32_t>(stage_bytes) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      for (int kbi = 0; kbi < kblocks; ++kbi) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
-        for (int kbi = 0; kbi < kblocks; ++kbi) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(sm.a(stage)));
-          const uint64_t db = umma_desc_sw128(smem_u32(sm.b(stage)));
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                         (kbi | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + stage * stage_stride;
+          const uint32_t b_lo = b_lo0 + stage * stage_stride;
+          // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
+          umma_bf16_ss_lo(d_tmem, a_lo, b_lo, idesc, kbi != 0 ? 1u : 0u);
+          umma_bf16_ss_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+          umma_commit(&empty_bar[stage]);                            // frees the smem slot when these retire
+          if (kbi == kblocks - 1) umma_commit(&t.tfull()[buf]);      // accumulator complete
         }
-        umma_commit(&tfull_bar[buf]);       // accumulator complete
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
-    // ================================ epilogue ====================================
-    const int q = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int row_in_tile = q * 32 + lane;
-    uint8_t* stg = sm.stg(warp - 2);
-    const float* sbias = sm.bias();
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_idx = tile - m_tile * p.n_tiles;
-      const int r0 = m_tile * kBlockM;
-      const int n0 = n_idx * p.n_tile;
-      const int buf = it & 1;
-      const uint32_t use = static_cast<uint32_t>(it >> 1);
-      const int r = r0 + row_in_tile;
-      // position inside the image raster -> is this an interior (kept) output?
-      const int img = r / p.plane;
-      const int pr = r - img * p.plane;
-      const int y = pr / p.wp;
-      const int x = pr - y * p.wp;
-      const bool valid = (r < p.R) && (y >= 1) && (y <= p.hv) && (x >= 1) && (x <= p.wv);
+    epilogue_loop(p.e, &tm_y, t, tmem_base, warp, lane);
+  }
 
-      mbar_wait(&tfull_bar[buf], use & 1u);
-      tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
 
-      if (p.epilogue == IE_EPI_BF16_RASTER) {
-        const int chunks = p.n_tile >> 6;
-        for (int c = 0; c < chunks; ++c) {
-          uint32_t v0[32], v1[32];
-          tmem_ld_x32(t_base + c * 64, v0);
-          tmem_ld_x32(t_base + c * 64 + 32, v1);
-          tmem_ld_wait();
-          if (c == chunks - 1) {
-            // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-          }
-          uint32_t pk[32];
-          const float* bs = sbias + n0 + c * 64;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v0[2 * j]) + bs[2 * j];
-            float b = __uint_as_float(v0[2 * j + 1]) + bs[2 * j + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            pk[j] = valid ? pack_bf16x2(a, b) : 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v1[2 * j]) + bs[32 + 2 * j];
-            float b = __uint_as_float(v1[2 * j + 1]) + bs[32 + 2 * j + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            pk[16 + j] = valid ? pack_bf16x2(a, b) : 0u;
-          }
-          // staging buffer must have been read by the previous TMA store
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-          // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B)
-          uint8_t* rowp = stg + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = val;
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tm_y, stg, p.y_coff + n0 + c * 64, r0 + q * 32);
-            tma_store_commit();
-          }
-        }
-      } else {
-        // small fp32 heads: n_tile <= 64, single N tile; each thread owns one pixel's channels
-        float acc[64];
-        {
-          uint32_t v[16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c * 16 < p.n_tile) {
-              tmem_ld_x16(t_base + c * 16, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[c * 16 + j] = __uint_as_float(v[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[c * 16 + j] = 0.f;
+// =================================================================================================
+// Resident-weights kernel: all taps' weights stay in smem; stage = one A box of 128+ndx-1 rows per
+// (filter row, channel block); the ndx horizontal taps address it at +dx rows.
+// =================================================================================================
+struct ResidentParams {
+  EpiParams e;
+  int ndy, ndx;
+  int dy_shift[3];       // raster-row shift of each filter row's box start (includes the leftmost dx)
+  int kb;                // cin / 64
+  int x_coff;
+  int cin;
+  int stages;
+  int box_rows;          // 128 + ndx - 1
+  int a_box_bytes;       // box_rows*128 rounded up to 1024
+  int a_slot_bytes;      // G boxes
+  int b_tile_bytes;      // n_tile*128
+  int use_base_offset;   // descriptor base-offset field = (start >> 7) & 7 for row-shifted starts
+};
+
+// NDX = horizontal taps; G = filter rows fused into one pipeline stage (G = 3 needs kb == 1: the whole
+// 3x3x64 tile is then ONE stage of 36 MMAs per barrier round trip).
+template <int NDX, int G>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_resident_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     const __grid_constant__ CUtensorMap tm_y, const ResidentParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  const int ntaps = p.ndy * p.ndx;
+  const int b_bytes = ntaps * p.kb * p.b_tile_bytes;      // resident weights, [tap][kb][n_tile x 64]
+  uint8_t* a_base_ptr = base + b_bytes;
+  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.e.m_tiles;                      // single N tile
+  const int stages_per_tile = p.ndy * p.kb / G;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+  }
+  const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane);
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      // weights: once per CTA
+      mbar_arrive_expect_tx(t.bres(), static_cast<uint32_t>(b_bytes));
+      for (int tap = 0; tap < ntaps; ++tap)
+        for (int kb = 0; kb < p.kb; ++kb)
+          tma_load_2d(base + (tap * p.kb + kb) * p.b_tile_bytes, &tm_b, t.bres(), tap * p.cin + kb * kBlockK, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.box_rows) * 128u * G;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int r0 = tile * kBlockM;
+        if constexpr (G == 1) {
+          for (int dy = 0; dy < p.ndy; ++dy) {
+            const int row = r0 + p.dy_shift[dy];
+            for (int kb = 0; kb < p.kb; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_2d(a_base_ptr + stage * p.a_slot_bytes, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-        if (valid) {
-          const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + (x - 1);
-          float* dst = p.y_f32 + pix * p.cout;
-          float mx = -INFINITY;
+        } else {
+          // G filter rows (kb == 1) share one slot and ONE barrier: every mbarrier wait costs the MMA warp
+          // ~100+ cycles, and at n_tile <= 64 those round trips, not the tensor pipe, bound the tile time
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            if (j < p.cout) {
-              float a = acc[j] + sbias[j];
-              if (p.relu) a = fmaxf(a, 0.f);
-              acc[j] = a;
-              mx = fmaxf(mx, a);
-            }
-          }
-          if (p.epilogue == IE_EPI_F32_SOFTMAX) {
-            if (p.y_aux) {
-              float* aux = p.y_aux + pix * p.cout;
-#pragma unroll
-              for (int j = 0; j < 64; ++j)
-                if (j < p.cout) aux[j] = acc[j];
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              if (j < p.cout) {
-                acc[j] = __expf(acc[j] - mx);
-                sum += acc[j];
-              }
-            }
-            const float inv = 1.f / sum;
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (j < p.cout) dst[j] = acc[j] * inv;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (j < p.cout) dst[j] = acc[j];
-          }
+          for (int g = 0; g < G; ++g)
+            tma_load_2d(a_base_ptr + stage * p.a_slot_bytes + g * p.a_box_bytes, &tm_a, &full_bar[stage], p.x_coff,
+                        r0 + p.dy_shift[g]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-    if (lane == 0) tma_store_wait<0>();   // all bulk stores complete before smem goes away
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, p.e.n_tile);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base_ptr));
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(base));
+    const uint32_t a_stride = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+    const uint32_t a_box = static_cast<uint32_t>(p.a_box_bytes) >> 4;
+    const uint32_t b_tile = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
+    const uint32_t b_tap = static_cast<uint32_t>(p.kb) * b_tile;      // distance between horizontal taps
+    mbar_wait(t.bres(), 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      uint32_t b_row = b_lo0;                                         // weights of filter row dy, block kb
+      for (int si = 0; si < stages_per_tile; ++si) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_slot_lo = a_lo0 + stage * a_stride;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int dx = 0; dx < NDX; ++dx) {
+              // tap (dy,dx) reads the box dx rows further down: +128 B (= +8) in the start address.  The
+              // hardware swizzles on absolute smem address bits, so a start that is not 1024-byte aligned
+              // needs no base-offset field (verified on B200: tools/try_resident.py)
+              const uint32_t a = a_slot_lo + g * a_box + dx * 8;
+              const uint32_t b = b_row + (g * NDX + dx) * b_tap;
+              umma_bf16_ss_lo(d_tmem, a, b, idesc, (g == 0 && dx == 0) ? (si != 0 ? 1u : 0u) : 1u);
+              umma_bf16_ss_lo(d_tmem, a + 2, b + 2, idesc, 1u);
+              umma_bf16_ss_lo(d_tmem, a + 4, b + 4, idesc, 1u);
+              umma_bf16_ss_lo(d_tmem, a + 6, b + 6, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (si == stages_per_tile - 1) umma_commit(&t.tfull()[buf]);
+        }
+        __syncwarp();
+        // G == 1: the weights of (dy, kb+1) follow (dy, kb) by one tile and those of (dy+1, 0) follow
+        // (dy, kb-1) by the remaining NDX-1 taps.  G == 3 (kb == 1): one batch per tile.
+        b_row += ((si + 1) % p.kb == 0) ? b_tile + (NDX - 1) * b_tap : b_tile;
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    epilogue_loop(p.e, &tm_y, t, tmem_base, warp, lane);
   }
 
-  // ---- teardown
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
@@ -320,25 +495,6 @@ int choose_n_tile(int cout, int epilogue) {
   return 64;
 }
 
-static int fill_taps(const ie_conv_desc* d, ConvKernelParams& p) {
-  const int wp = d->w + 2;
-  if (d->kh == 3 && d->kw == 3) {
-    p.ntaps = 9;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) p.tap_shift[i * 3 + j] = (i - 1) * wp + (j - 1);
-  } else if (d->kh == 2 && d->kw == 2) {
-    p.ntaps = 4;
-    for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 2; ++j) p.tap_shift[i * 2 + j] = i * wp + j;
-  } else if (d->kh == 1 && d->kw == 1) {
-    p.ntaps = 1;
-    p.tap_shift[0] = 0;
-  } else {
-    return -1;
-  }
-  return 0;
-}
-
 int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void* y_bf16, float* y_f32) {
   IE_REQUIRE(d && x && w, "conv: null descriptor / input / weights");
   IE_REQUIRE(d->n_img > 0 && d->h > 0 && d->w > 0, "conv: bad raster size %d x %d x %d", d->n_img, d->h, d->w);
@@ -349,6 +505,8 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
   IE_REQUIRE(d->cout > 0 && d->cout <= kMaxCout, "conv: cout=%d out of range", d->cout);
   IE_REQUIRE(d->hv >= 1 && d->hv <= d->h && d->wv >= 1 && d->wv <= d->w, "conv: bad valid extent %d x %d", d->hv, d->wv);
   IE_REQUIRE((long long)d->n_img * (d->h + 2) * (d->w + 2) < (1ll << 31) - 4096, "conv: raster too large for 32-bit rows");
+  IE_REQUIRE((d->kh == 3 && d->kw == 3) || (d->kh == 2 && d->kw == 2) || (d->kh == 1 && d->kw == 1),
+             "conv: unsupported kernel size %dx%d", d->kh, d->kw);
   if (d->epilogue == IE_EPI_BF16_RASTER) {
     IE_REQUIRE(y_bf16, "conv: y_bf16 is null");
     IE_REQUIRE(d->cout % 64 == 0, "conv: bf16 raster epilogue needs cout %% 64 == 0 (got %d)", d->cout);
@@ -356,66 +514,136 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
                "conv: bad output slice (coff %d, cout %d, pitch %d)", d->y_coff, d->cout, d->y_pitch);
   } else if (d->epilogue == IE_EPI_F32_NHWC || d->epilogue == IE_EPI_F32_SOFTMAX) {
     IE_REQUIRE(y_f32, "conv: y_f32 is null");
-    IE_REQUIRE(d->cout <= 64, "conv: fp32 epilogues need cout <= 64 (got %d)", d->cout);
+    IE_REQUIRE(d->cout <= 256, "conv: fp32 epilogues need cout <= 256 (got %d)", d->cout);
   } else {
     IE_REQUIRE(false, "conv: unknown epilogue %d", d->epilogue);
   }
   return IE_OK;
 }
 
+// Tuning / test hooks (not part of the documented ABI surface): force a main-loop flavour.
+static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident
+static int g_fuse_rows = 1;
+static int g_base_offset = 0;      // measured on B200: the 128B swizzle is a function of the absolute smem address,
+                                      // so row-shifted descriptor starts need NO base-offset field (setting it corrupts)
+
 }  // namespace ie
+
+extern "C" int ie_conv_set_mode(int mode, int flags) {
+  ie::g_force_mode = mode;
+  ie::g_base_offset = flags & 1;
+  ie::g_fuse_rows = (flags & 2) ? 0 : 1;
+  return IE_OK;
+}
 
 extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                                    void* y_bf16, float* y_f32, float* y_aux, void* stream) {
   using namespace ie;
   int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32);
   if (rc) return rc;
-  ConvKernelParams p{};
-  IE_REQUIRE(fill_taps(d, p) == 0, "conv: unsupported kernel size %dx%d", d->kh, d->kw);
   const long long R = (long long)d->n_img * (d->h + 2) * (d->w + 2);
-  p.R = (int)R;
-  p.plane = (d->h + 2) * (d->w + 2);
-  p.wp = d->w + 2;
-  p.hv = d->hv;
-  p.wv = d->wv;
-  p.kblocks_per_tap = d->cin / 64;
-  p.x_coff = d->x_coff;
-  p.cin = d->cin;
-  p.cout = d->cout;
-  p.n_tile = choose_n_tile(d->cout, d->epilogue);
-  p.n_tiles = (d->cout + p.n_tile - 1) / p.n_tile;
-  p.m_tiles = (int)((R + kBlockM - 1) / kBlockM);
-  p.y_coff = d->y_coff;
-  p.relu = d->relu;
-  p.epilogue = d->epilogue;
-  p.bias = bias;
-  p.y_f32 = y_f32;
-  p.y_aux = y_aux;
-  p.b_stage_bytes = ((p.n_tile * 128 + 1023) / 1024) * 1024;
-  const size_t max_smem = 227 * 1024;
-  int stages = kMaxStages;
-  while (stages > 2 && conv_smem_bytes(stages, p.b_stage_bytes) > max_smem) --stages;
-  p.stages = stages;
-  const size_t smem = conv_smem_bytes(stages, p.b_stage_bytes);
+  const int wp = d->w + 2;
+  EpiParams e{};
+  e.R = (int)R;
+  e.plane = (d->h + 2) * wp;
+  e.wp = wp;
+  e.hv = d->hv;
+  e.wv = d->wv;
+  e.cout = d->cout;
+  e.n_tile = choose_n_tile(d->cout, d->epilogue);
+  e.n_tiles = (d->cout + e.n_tile - 1) / e.n_tile;
+  e.m_tiles = (int)((R + kBlockM - 1) / kBlockM);
+  e.y_coff = d->y_coff;
+  e.relu = d->relu;
+  e.epilogue = d->epilogue;
+  e.bias = bias;
+  e.y_f32 = y_f32;
+  e.y_aux = y_aux;
+  const int ntaps = d->kh * d->kw;
+  const int ktot = ntaps * d->cin;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   CUtensorMap tm_a, tm_b, tm_y;
-  const int ktot = p.ntaps * d->cin;
-  rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tm_b, w_packed, (uint64_t)ktot, (uint64_t)(p.n_tiles * p.n_tile), (uint64_t)ktot, 64,
-                         (uint32_t)p.n_tile);
+  rc = make_tmap_2d_bf16(&tm_b, w_packed, (uint64_t)ktot, (uint64_t)(e.n_tiles * e.n_tile), (uint64_t)ktot, 64,
+                         (uint32_t)e.n_tile);
   if (rc) return rc;
   if (d->epilogue == IE_EPI_BF16_RASTER) {
     rc = make_tmap_2d_bf16(&tm_y, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 32);
     if (rc) return rc;
-  } else {
-    tm_y = tm_a;   // unused by the fp32 epilogues
   }
 
-  IE_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_igemm_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(tm_a, tm_b, tm_y, p);
+  // ---- resident-weights flavour: narrow layers whose whole weight matrix fits beside >= 3 A stages
+  const int b_res_bytes = ntaps * (d->cin / 64) * e.n_tile * 128;
+  const int box_rows = kBlockM + d->kw - 1;
+  int a_slot = ((box_rows * 128 + 1023) / 1024) * 1024;
+  const int res_room = (int)kMaxSmem - 1024 - kTailBytes - (b_res_bytes <= 200 * 1024 ? b_res_bytes : 200 * 1024);
+  const int fuse_rows = (d->kh == 3 && d->cin == 64 && g_fuse_rows) ? 3 : 1;      // whole 3x3x64 tile in one stage
+  const int a_box = a_slot;
+  a_slot *= fuse_rows;
+  const int res_stages = res_room > 0 ? res_room / a_slot : 0;
+  bool resident = e.n_tiles == 1 && e.n_tile <= 64 && b_res_bytes <= 160 * 1024 && res_stages >= (fuse_rows == 3 ? 2 : 3);
+  if (g_force_mode == 0) resident = false;
+  if (g_force_mode == 1)
+    IE_REQUIRE(e.n_tiles == 1 && b_res_bytes <= 200 * 1024 && res_stages >= 2,
+               "conv: resident mode forced but the weights do not fit");
+  if (g_force_mode == 1) resident = true;
+
+  const int grid_cap = sm_count();
+  if (resident) {
+    ResidentParams p{};
+    p.e = e;
+    p.ndy = d->kh;
+    p.ndx = d->kw;
+    for (int i = 0; i < d->kh; ++i) p.dy_shift[i] = (d->kh == 3) ? (i - 1) * wp - 1 : i * wp;
+    p.kb = d->cin / 64;
+    p.x_coff = d->x_coff;
+    p.cin = d->cin;
+    p.stages = res_stages > kMaxStages ? kMaxStages : res_stages;
+    p.box_rows = box_rows;
+    p.a_box_bytes = a_box;
+    p.a_slot_bytes = a_slot;
+    p.b_tile_bytes = e.n_tile * 128;
+    p.use_base_offset = g_base_offset;
+    rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, (uint32_t)box_rows);
+    if (rc) return rc;
+    if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
+    const size_t smem = 1024 + (size_t)b_res_bytes + (size_t)p.stages * a_slot + kTailBytes;
+    const int grid = e.m_tiles < grid_cap ? e.m_tiles : grid_cap;
+#define IE_LAUNCH_RES(NDX_, G_)                                                                                   \
+  do {                                                                                                            \
+    IE_CUDA(cudaFuncSetAttribute(conv_resident_kernel<NDX_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 (int)kMaxSmem));                                                                 \
+    conv_resident_kernel<NDX_, G_><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);                            \
+  } while (0)
+    if (d->kw == 3 && fuse_rows == 3) IE_LAUNCH_RES(3, 3);
+    else if (d->kw == 3) IE_LAUNCH_RES(3, 1);
+    else if (d->kw == 2) IE_LAUNCH_RES(2, 1);
+    else IE_LAUNCH_RES(1, 1);
+#undef IE_LAUNCH_RES
+    IE_LAUNCH_CHECK();
+    return IE_OK;
+  }
+
+  StreamParams p{};
+  p.e = e;
+  p.ntaps = ntaps;
+  for (int i = 0; i < d->kh; ++i)
+    for (int j = 0; j < d->kw; ++j)
+      p.tap_shift[i * d->kw + j] = (d->kh == 3) ? (i - 1) * wp + (j - 1) : i * wp + j;
+  p.kblocks_per_tap = d->cin / 64;
+  p.x_coff = d->x_coff;
+  p.cin = d->cin;
+  p.b_stage_bytes = ((e.n_tile * 128 + 1023) / 1024) * 1024;
+  int stages = (int)((kMaxSmem - 1024 - kTailBytes) / (kABytes + p.b_stage_bytes));
+  p.stages = stages > kMaxStages ? kMaxStages : stages;
+  rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
+  if (rc) return rc;
+  if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
+  const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + kTailBytes;
+  IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  const int tiles = e.m_tiles * e.n_tiles;
+  const int grid = tiles < grid_cap ? tiles : grid_cap;
+  conv_stream_kernel<<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

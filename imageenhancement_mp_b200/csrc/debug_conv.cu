@@ -64,7 +64,7 @@ __global__ void naive_conv_f32_kernel(const __nv_bfloat16* __restrict__ x, const
   int img, yy, xx;
   if (!naive_valid(p, r, img, yy, xx)) return;
   const long long pix = ((long long)img * p.hv + (yy - 1)) * p.wv + (xx - 1);
-  float v[64];
+  float v[256];
   float mx = -INFINITY;
   for (int co = 0; co < p.cout; ++co) {
     float a = naive_dot(x, w, p, r, co) + (bias ? bias[co] : 0.f);

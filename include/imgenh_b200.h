@@ -37,7 +37,7 @@ extern "C" {
 
 /* epilogue kinds for ie_conv2d_nhwc_bf16 */
 #define IE_EPI_BF16_RASTER 0 /* bias(+ReLU) -> bf16 raster slice (border rows zeroed)                    */
-#define IE_EPI_F32_NHWC 1    /* bias(+ReLU) -> fp32 [n][hv][wv][cout] (interior only), cout <= 64          */
+#define IE_EPI_F32_NHWC 1    /* bias(+ReLU) -> fp32 [n][hv][wv][cout] (interior only), cout <= 256         */
 #define IE_EPI_F32_SOFTMAX 2 /* as 1, then softmax over cout; y_aux (nullable) receives the logits        */
 
 typedef struct ie_conv_desc {
@@ -75,6 +75,10 @@ int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* ra
  * y_bf16 is used by IE_EPI_BF16_RASTER; y_f32 (and optional y_aux) by the fp32 epilogues.            */
 int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_bf16,
                         float* y_f32, float* y_aux, void* stream);
+
+/* Tuning / test hook: force the main-loop flavour of ie_conv2d_nhwc_bf16 (-1 auto, 0 streaming, 1 resident
+ * weights) and whether row-shifted smem descriptors carry the base-offset field.  Process-wide.        */
+int ie_conv_set_mode(int mode, int use_base_offset);
 
 /* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at
  * sizes the CPU oracle cannot reach).  Never called by the product path.                             */

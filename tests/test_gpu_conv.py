@@ -137,7 +137,7 @@ def test_conv_deep_k_vs_naive(cuda):
     assert_close_bf16(d1.data.float().cpu(), d2.data.float().cpu(), "tcgen05 vs naive, 2048->512 @26x26")
 
 
-@pytest.mark.parametrize("cout,softmax", [(10, True), (40, False), (16, True), (64, False)])
+@pytest.mark.parametrize("cout,softmax", [(10, True), (40, False), (16, True), (64, False), (80, False), (90, True)])
 def test_conv_f32_heads(cuda, cout, softmax):
     """The two small fp32 epilogues: coef conv + softmax (model_library.py:405-406) and layer3_3."""
     from imageenhancement_mp_b200 import ops
