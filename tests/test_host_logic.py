@@ -1,0 +1,120 @@
+"""Host-side logic on CPU: sharding, report aggregation / formatting, and the N>1 path of evaluate()
+with world_size-2 gloo processes (the per-batch numbers come from the oracle here; on GPUs they come
+from the fused metrics kernel - tests/test_gpu_model.py)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from imageenhancement_mp_b200 import data_utils as du
+from imageenhancement_mp_b200 import dist as idist
+from imageenhancement_mp_b200 import eval as ieval
+from imageenhancement_mp_b200 import synth
+
+T = 4
+
+
+def oracle_step_totals(model, xb, xt, burst_length):
+    """CPU stand-in for eval.gpu_step_totals: same additive totals layout, numbers from the oracle."""
+    recon = model(xb)
+    n = xb.shape[0]
+    tot = torch.zeros(burst_length + 6, dtype=torch.float64)
+    for i in range(n):
+        s = oracle.eval_step(recon[i:i + 1], xb[i:i + 1], xt[i:i + 1], burst_length)
+        tot[0] += s["psnr"]
+        for t in range(burst_length):
+            tot[1 + t] += s["psnr_perlayer"][t]
+        tot[burst_length + 1] += s["psnr_noise0"]
+        tot[burst_length + 2] += s["psnr_average"]
+        tot[burst_length + 3] += s["loss1"]
+        tot[burst_length + 4] += s["perlayer_loss"]
+        tot[burst_length + 5] += 1
+    return tot
+
+
+def fake_model(xb):
+    """Deterministic stand-in network: frame average + per-frame copies (shape [N,H,W,T+1])."""
+    burst = xb[..., :T]
+    return torch.cat([burst.mean(-1, keepdim=True), burst], dim=-1)
+
+
+def make_batches(nb, n, h, w):
+    return [synth.make_batch(n, h, w, seed=100 + i) for i in range(nb)]
+
+
+def reference_report(batches):
+    steps = [oracle.eval_step(fake_model(x), x, t, T) for x, t in batches]
+    return oracle.eval_report(steps, T)
+
+
+def test_shard_ranges_cover_exactly():
+    for n in (0, 1, 7, 8, 256):
+        for world in (1, 2, 3, 8):
+            spans = [idist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_single_process_report_matches_oracle_aggregation():
+    batches = make_batches(3, 4, 40, 48)
+    params = dict(synth.DEFAULT_PARAMS)
+    lines = []
+    rep = ieval.evaluate(fake_model, batches, params, step=7, out=lines.append, step_totals=oracle_step_totals)
+    ref = reference_report(batches)
+    for k in ieval.REPORT_KEYS:
+        assert rep[k] == pytest.approx(ref[k], rel=1e-6, abs=1e-6), k
+    assert rep["val_psnrnoshow0_unbiased"] == pytest.approx(ref["val_psnrnoshow0_unbiased"], rel=1e-6)
+    assert len(lines) == 8 and lines[1].startswith("epoch 7: val_deblur_loss = ")
+    assert [l.split(":")[1].split("=")[0].strip() for l in lines[1:]] == list(ieval.REPORT_KEYS)
+
+
+def test_totals_layout_roundtrip():
+    tot = torch.arange(T + 6, dtype=torch.float64) + 1
+    tot[-1] = 2
+    r = du.totals_to_report(tot, T)
+    assert r["psnr"] == 0.5 and r["psnr_perlayer"] == [1.0, 1.5, 2.0, 2.5] and r["count"] == 2
+    assert r["psnr_noise0"] == 3.0 and r["psnr_average"] == 3.5 and r["loss1"] == 4.0 and r["perlayer_loss"] == 4.5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    r, w, _ = idist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    batches = make_batches(3, 5, 40, 48)          # 5 images per batch: uneven 3/2 split across two ranks
+    rep = ieval.evaluate(fake_model, batches, dict(synth.DEFAULT_PARAMS), out=None, step_totals=oracle_step_totals)
+    q.put((rank, {k: rep[k] for k in ieval.REPORT_KEYS + ("count",)}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_evaluate_equals_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = reference_report(make_batches(3, 5, 40, 48))
+    for rank in (0, 1):
+        assert got[rank]["count"] == 15
+        for k in ieval.REPORT_KEYS:
+            assert got[rank][k] == pytest.approx(ref[k], rel=1e-6, abs=1e-6), (rank, k)

@@ -1,0 +1,147 @@
+"""Known-answer tests that pin the CPU oracle (no GPU).
+
+The reference has no tests; these are the analytic identities derivable from
+its own code, plus cross-checks between independent formulations inside the oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import model as omodel
+from oracle import preprocess as opre
+from imageenhancement_mp_b200 import synth, weights
+
+P = dict(synth.DEFAULT_PARAMS)
+
+
+def test_param_and_flop_counts_match_survey():
+    L = weights.simplemodel_layers(P)
+    W = weights.init_weights(L, scheme="zeros")
+    assert weights.count_params(W) == 50_447_218
+    per_px, per_img = weights.conv_flops(L, P, 0, 0)
+    assert per_px == 4_256_640 and per_img == 691_955_712
+    Lk = weights.basis_kpn_layers(dict(P, BURST_LENGTH=8, layer_type="dualparams"))
+    assert weights.count_params(weights.init_weights(Lk, scheme="zeros")) == 77_891_610    # 77.9 M
+
+
+def test_zero_weights_give_box_mean():
+    """Coef = 1/B and Bas = 1/(K*K*T) => frame t out = zero-padded 15x15 box mean (x T cancels 1/T)."""
+    W = weights.init_weights(weights.simplemodel_layers(P), scheme="zeros")
+    x, _ = synth.make_batch(2, 32, 40, P)
+    out, bas, ob = oracle.simplemodel_forward(W, P, x)
+    b = x[..., :4].permute(0, 3, 1, 2)
+    box = F.avg_pool2d(F.pad(b, (7, 7, 7, 7)), 15, 1).permute(0, 2, 3, 1)
+    assert torch.allclose(out[..., 1:], box, atol=1e-6)
+    assert torch.allclose(out[..., 0], box.mean(-1), atol=1e-6)
+    assert torch.allclose(bas, torch.full_like(bas, 1 / 900))
+
+
+def test_filter_is_a_partition_of_unity():
+    g = torch.Generator().manual_seed(3)
+    coef = torch.softmax(torch.randn(1, 24, 24, 10, generator=g), -1).double()
+    bas = omodel.basis_softmax(torch.randn(1, 15, 15, 40, generator=g).double(), 15, 4, 10)
+    ones = torch.ones(1, 24, 24, 4, dtype=torch.float64)
+    out = oracle.kpn_apply_literal(ones, coef, bas)
+    assert torch.allclose(out[:, 7:-7, 7:-7, 0], torch.ones(1, 10, 10, dtype=torch.float64), atol=1e-12)
+
+
+def test_literal_and_algebraic_filter_agree():
+    g = torch.Generator().manual_seed(4)
+    burst = torch.rand(2, 20, 28, 3, generator=g).double()
+    coef = torch.softmax(torch.randn(2, 20, 28, 7, generator=g), -1).double()
+    bas = omodel.basis_softmax(torch.randn(2, 15, 15, 21, generator=g).double(), 15, 3, 7)
+    a = oracle.kpn_apply_literal(burst, coef, bas)
+    b = oracle.kpn_apply_algebraic(burst, coef, bas)
+    assert float((a - b).abs().max()) < 1e-13
+
+
+def test_srgb_known_values():
+    v = oracle.sRGBforward(torch.tensor([0., .0031308, 1., 2.], dtype=torch.float64))
+    assert torch.allclose(v, torch.tensor([0., .040450, 1., 1 + 1.055 / 2.4], dtype=torch.float64), atol=2e-5)
+
+
+def test_psnr_constant_error_is_20db():
+    a = torch.rand(3, 30, 30, dtype=torch.float64)
+    assert abs(float(oracle.psnr_tf_batch(a + 0.1, a)) - 20.0) < 1e-9
+
+
+def test_invert_preproc_shapes_and_scaling():
+    img = torch.full((2, 40, 48), 0.25, dtype=torch.float64)
+    wl = torch.tensor([0.5, 1.0], dtype=torch.float64).view(2, 1, 1, 1)
+    out = oracle.invert_preproc(img, wl)
+    assert out.shape == (2, 24, 32)
+    assert torch.allclose(out[0], oracle.sRGBforward(torch.tensor(0.5, dtype=torch.float64)).expand(24, 32))
+    assert torch.allclose(out[1], oracle.sRGBforward(torch.tensor(0.25, dtype=torch.float64)).expand(24, 32))
+
+
+def test_gradient_loss_linear_ramp():
+    y, x = torch.meshgrid(torch.arange(12.), torch.arange(16.), indexing="ij")
+    a = (2 * x + 3 * y)[None]
+    z = torch.zeros_like(a)
+    # |d/dy| = 3/2, |d/dx| = 2/2 -> mean over both components = 1.25
+    assert abs(float(oracle.gradient_loss(a, z)) - 1.25) < 1e-6
+
+
+def test_fp32_and_fp64_forward_agree():
+    W = weights.init_weights(weights.simplemodel_layers(P), scheme="stress")
+    x, _ = synth.make_batch(1, 32, 32, P)
+    o32 = oracle.simplemodel_forward(W, P, x)[0]
+    W64 = {k: (w.double(), b.double()) for k, (w, b) in W.items()}
+    o64 = oracle.simplemodel_forward(W64, P, x.double())[0]
+    assert float((o32.double() - o64).abs().max()) < 2e-5
+
+
+def test_upsample_matches_manual_half_pixel():
+    x = torch.arange(6.).view(1, 2, 3, 1)
+    y = omodel.upsample_bilinear(x, 2)[0, :, :, 0]
+    # half-pixel centres: out[0] = in[0], out[1] = .75 in[0] + .25 in[1], ...
+    assert torch.allclose(y[0, :3], torch.tensor([0., 0.25, 0.75]))
+    assert torch.allclose(y[1, 0], torch.tensor(0.75))            # .75*0 + .25*3
+    legacy = omodel.upsample_bilinear(x, 2, legacy=True)[0, :, :, 0]
+    assert not torch.allclose(y, legacy)                          # the TF1 kernel differs (kept as a switch)
+
+
+def test_ssim_identities():
+    a = torch.rand(2, 40, 44)
+    assert torch.allclose(oracle.ssim(a, a), torch.ones(2, dtype=torch.float64), atol=1e-12)
+    b = (a + 0.2 * torch.randn(2, 40, 44)).clamp(0, 1)
+    s = oracle.ssim(a, b)
+    assert torch.all(s < 1) and torch.allclose(s, oracle.ssim(b, a))
+
+
+def test_preprocess_area_resize_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(1, 64, 96, 1, generator=g)
+    ours = opre.area_down(img, 4)[0, :, :, 0].numpy()
+    ref = cv2.resize(img[0, :, :, 0].numpy(), (24, 16), interpolation=cv2.INTER_AREA)
+    assert np.allclose(ours, ref, atol=1e-6)
+
+
+def test_preprocess_statistics_and_layout():
+    params = dict(P, height=16, width=16, BURST_LENGTH=3)
+    up, jit = 4, 16
+    hs = 16 * up + 2 * jit * up
+    src = torch.full((hs, hs, 1), 128, dtype=torch.uint8)
+    draws = {"crop0": (0, 0), "use_big": [True, False], "frame_off": [(3, 5), (1, 2)], "white_level": 0.5,
+             "sig_read": 0.01, "sig_shot": 0.05, "n_read": torch.zeros(16, 16, 3), "n_shot": torch.zeros(16, 16, 3)}
+    x, t = opre.preprocess_image(src, params, draws)
+    val = 0.5 * (128 / 255) ** 2.2
+    assert x.shape == (16, 16, 4) and t.shape == (16, 16, 2)
+    assert torch.allclose(x[..., :3], torch.full((16, 16, 3), val), atol=1e-6)
+    assert torch.allclose(x[..., 3], torch.full((16, 16), math.sqrt(0.01 ** 2 + val * 0.05 ** 2)), atol=1e-6)
+    assert torch.allclose(t[..., 1], torch.full((16, 16), 0.5))
+    assert opre.frame_origins(params, draws) == [(64, 64), (3, 5), (57, 58)]
+
+
+def test_eval_report_reproduces_leading_zero_bias():
+    steps = [{"loss1": 1.0, "perlayer_loss": 2.0, "psnr": 20.0, "psnr_perlayer": [30.0, 1, 1, 1],
+              "psnr_noise0": 10.0, "psnr_average": 12.0}] * 3
+    r = oracle.eval_report(steps, 4)
+    assert r["val_psnrnoshow0"] == pytest.approx(30.0 * 3 / 4)       # eval.py:136,193 start the list with [0]
+    assert r["val_psnrnoshow0_unbiased"] == pytest.approx(30.0)
+    assert r["val_total_loss"] == pytest.approx(3.0)
