@@ -36,7 +36,7 @@ SIGNATURES = {
     "ie_version": [],
     "ie_sm_count": [],
     "ie_pack_conv_weights": [_P, _I, _I, _I, _I, _I, _P, _P],
-    "ie_pack_input_im2col3x3": [_P, _I, _I, _I, _I, _P, _P],
+    "ie_pack_input_im2col3x3": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
     "ie_conv_set_mode": [_I, _I],
     "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
@@ -46,7 +46,7 @@ SIGNATURES = {
     "ie_broadcast_hw_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "ie_raster_to_nhwc_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "ie_softmax_taps_f32": [_P, _I, _I, _I, _P, _P],
-    "ie_kpn_apply_f32": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ie_kpn_apply_f32": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ie_mean_hw_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_invert_preproc_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P],
     "ie_eval_metrics_f32": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],

@@ -186,6 +186,60 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
       const int nch = (p.cout + 15) >> 4;
       const bool sm_mode = (p.epilogue == IE_EPI_F32_SOFTMAX);
       const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + (x - 1);
+      if (nch == 1) {
+        // <= 16 channels (the `coef` head): one TMEM read, everything in registers.  Valid pixels of a warp's
+        // 32 raster rows are consecutive in the NHWC output (the skipped border pixels have no output slot), so
+        // the rows are compacted through the warp's staging buffer and leave as fully coalesced 4-byte stores.
+        uint32_t v[16];
+        tmem_ld_x16(t_base, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        float a[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          a[j] = __uint_as_float(v[j]) + sbias[j];
+          if (p.relu) a[j] = fmaxf(a[j], 0.f);
+          if (j < p.cout) mx = fmaxf(mx, a[j]);
+        }
+        float e[16];
+        if (sm_mode) {
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            e[j] = (j < p.cout) ? __expf(a[j] - mx) : 0.f;
+            sum += e[j];
+          }
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) e[j] *= inv;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) e[j] = a[j];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (bal) {
+          const int rank = __popc(bal & ((1u << lane) - 1u));
+          const int nvalid = __popc(bal);
+          const long long pix_first = __shfl_sync(0xffffffffu, pix, __ffs(bal) - 1);
+          float* sf = reinterpret_cast<float*>(stg);
+          const int total = nvalid * p.cout;
+          for (int pass = 0; pass < ((sm_mode && p.y_aux) ? 2 : 1); ++pass) {
+            __syncwarp();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < p.cout) sf[rank * p.cout + j] = pass ? a[j] : e[j];
+            }
+            __syncwarp();
+            float* dst = (pass ? p.y_aux : p.y_f32) + pix_first * p.cout;
+            for (int i = lane; i < total; i += 32) dst[i] = sf[i];
+          }
+        }
+        continue;
+      }
       float* dst = p.y_f32 + pix * p.cout;
       float* aux = p.y_aux ? p.y_aux + pix * p.cout : nullptr;
       float mx = -INFINITY, inv = 1.f;

@@ -23,7 +23,7 @@ constexpr int kRowRegs = ((kPxPerThread + kMaxK - 1 + 3) / 4) * 4;   // 20
 
 template <int BC>
 __global__ void __launch_bounds__(256, 2)
-kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* __restrict__ coef,
+kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* __restrict__ coef, int Hc, int Wc,
                  const float* __restrict__ bas, float* __restrict__ out, int H, int W, int T, int K, int B,
                  int tiles_x, int tiles_y) {
   extern __shared__ float smem[];
@@ -51,6 +51,7 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
   const float* burst_img = burst + (long long)img * H * W * burst_pitch;
   const float* bas_img = bas + (long long)img * K * K * T * B;
   const long long pix_base = ((long long)img * H + py) * W + px;
+  const long long coef_base = ((long long)img * Hc + py) * Wc + px;
 
   for (int t = 0; t < T; ++t) {
     __syncthreads();
@@ -119,7 +120,7 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
 #pragma unroll
         for (int p = 0; p < kPxPerThread; ++p) {
           if (px + p < W) {
-            const float* cp = coef + (pix_base + p) * B + ch * BC;
+            const float* cp = coef + (coef_base + p) * B + ch * BC;
 #pragma unroll
             for (int b = 0; b < BC; ++b)
               if (ch * BC + b < B) res[p] = fmaf(__ldg(cp + b), g[p][b], res[p]);
@@ -146,13 +147,14 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
 
 }  // namespace ie
 
-extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, const float* bas, float* out,
-                                int n, int h, int w, int T, int K, int B, void* stream) {
+extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
+                                float* out, int n, int h, int w, int T, int K, int B, void* stream) {
   using namespace ie;
   IE_REQUIRE(burst && coef && bas && out, "kpn_apply: null pointer");
   IE_REQUIRE(n > 0 && h > 0 && w > 0 && T > 0 && B > 0, "kpn_apply: bad sizes");
   IE_REQUIRE(K >= 1 && K <= kMaxK && (K & 1), "kpn_apply: K must be odd and <= %d (got %d)", kMaxK, K);
   IE_REQUIRE(burst_pitch >= T, "kpn_apply: burst_pitch < T");
+  IE_REQUIRE(hc >= h && wc >= w, "kpn_apply: coef extent %dx%d smaller than the image %dx%d", hc, wc, h, w);
   const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
   const long long blocks = (long long)n * tiles_x * tiles_y;
   IE_REQUIRE(blocks < (1ll << 31), "kpn_apply: too many tiles");
@@ -166,11 +168,11 @@ extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ten) {
     IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpn_apply_kernel<10><<<(unsigned)blocks, 256, smem, st>>>(burst, burst_pitch, coef, bas, out, h, w, T, K, B,
+    kpn_apply_kernel<10><<<(unsigned)blocks, 256, smem, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w, T, K, B,
                                                              tiles_x, tiles_y);
   } else {
     IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpn_apply_kernel<8><<<(unsigned)blocks, 256, smem, st>>>(burst, burst_pitch, coef, bas, out, h, w, T, K, B,
+    kpn_apply_kernel<8><<<(unsigned)blocks, 256, smem, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w, T, K, B,
                                                             tiles_x, tiles_y);
   }
   IE_LAUNCH_CHECK();

@@ -33,78 +33,87 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int taps, in
 }
 
 // ------------------------------------------------------------------------------- input im2col
-// One thread per (raster row, 16-byte chunk): 8 consecutive k of the kvec*8-wide im2col row.
-__global__ void im2col3x3_kernel(const float* __restrict__ x, int n, int h, int w, int c, uint4* __restrict__ out,
-                                 long long rows, int kvec) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= rows * kvec) return;
-  const long long r = t / kvec;
-  const int chunk = (int)(t - r * kvec);
-  const int wp = w + 2, plane = (h + 2) * wp;
-  const int img = (int)(r / plane);
-  const int pr = (int)(r - (long long)img * plane);
-  const int y = pr / wp - 1, xx = pr % wp - 1;
+// grid = (ceil((w+2)*kvec / 256), h+2, n): blockIdx.y/z give the raster row and image, so no thread
+// divides a 64-bit index.  One thread per (padded x, 16-byte chunk) = 8 consecutive k of the im2col row;
+// the k -> (dy, dx, ch) split is a shared-memory table (c is a run-time value, 9*c <= 1024).
+// The source may be smaller than the raster (hs <= h, ws <= w): the rest reads as zero, which is how the
+// boundary pads 100x100 patches to the network stride without a padded copy of the input.
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int c, uint4* __restrict__ out, int kvec) {
+  __shared__ int s_off[1024];          // element offset of (dy, dx, ch) relative to the centre pixel
+  __shared__ signed char s_dy[1024], s_dx[1024];
+  const int ktot = 9 * c;
+  for (int k = threadIdx.x; k < kvec * 8; k += blockDim.x) {
+    int dy = 9, dx = 9, off = 0;       // dy = 9 marks the zero padding of k >= 9*c
+    if (k < ktot) {
+      const int tap = k / c, ch = k - tap * c;
+      dy = tap / 3 - 1; dx = tap % 3 - 1;
+      off = (dy * ws + dx) * c + ch;
+    }
+    s_off[k] = off; s_dy[k] = (signed char)dy; s_dx[k] = (signed char)dx;
+  }
+  __syncthreads();
+  const int wp = w + 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wp * kvec) return;
+  const int xp = idx / kvec, chunk = idx - xp * kvec;
+  const int yp = blockIdx.y, img = blockIdx.z;
+  const int y = yp - 1, xx = xp - 1;
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) f[e] = 0.f;
-  if (y >= 0 && y < h && xx >= 0 && xx < w) {
+  if (y >= 0 && y < hs && xx >= 0 && xx < ws) {
+    const float* centre = x + (((long long)img * hs + y) * ws + xx) * c;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = chunk * 8 + e;
-      if (k < 9 * c) {
-        const int tap = k / c, ch = k - tap * c;
-        const int sy = y + tap / 3 - 1, sx = xx + tap % 3 - 1;
-        if (sy >= 0 && sy < h && sx >= 0 && sx < w) f[e] = x[(((long long)img * h + sy) * w + sx) * c + ch];
-      }
+      const int sy = y + s_dy[k], sx = xx + s_dx[k];
+      if (sy >= 0 && sy < hs && sx >= 0 && sx < ws) f[e] = __ldg(centre + s_off[k]);
     }
   }
-  out[t] = pack8(f);
+  out[(((long long)img * (h + 2) + yp) * wp + xp) * kvec + chunk] = pack8(f);
 }
 
 // ------------------------------------------------------------------------------- max-pool 2x2
-__global__ void maxpool2_kernel(const uint4* __restrict__ x, int n, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
-                                uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const int ho = h >> 1, wo = w >> 1;
-  const long long total = (long long)n * (ho + 2) * (wo + 2) * cvec;
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int cv = (int)(t % cvec);
-  const long long ro = t / cvec;
-  const int wpo = wo + 2, plo = (ho + 2) * wpo;
-  const int img = (int)(ro / plo);
-  const int pr = (int)(ro - (long long)img * plo);
-  const int oy = pr / wpo, ox = pr % wpo;
+// grid = (ceil((wo+2)*cvec / 256), ho+2, n); one thread per (padded output x, 16-byte channel chunk).
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
+                uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+  const int ho = h >> 1, wo = w >> 1, wpo = wo + 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wpo * cvec) return;
+  const int ox = idx / cvec, cv = idx - ox * cvec;
+  const int oy = blockIdx.y, img = blockIdx.z;
   uint4 res = make_uint4(0, 0, 0, 0);
   if (oy >= 1 && oy <= ho && ox >= 1 && ox <= wo) {
     const int wpi = w + 2;
     const long long rin = ((long long)img * (h + 2) + (2 * oy - 1)) * wpi + (2 * ox - 1);
     const uint4* p = x + rin * x_pitch_v + x_coff_v + cv;
     float a[8], b[8], c[8], d[8], m[8];
-    unpack8(p[0], a);
-    unpack8(p[x_pitch_v], b);
-    unpack8(p[(long long)wpi * x_pitch_v], c);
-    unpack8(p[(long long)(wpi + 1) * x_pitch_v], d);
+    unpack8(__ldg(p), a);
+    unpack8(__ldg(p + x_pitch_v), b);
+    unpack8(__ldg(p + (long long)wpi * x_pitch_v), c);
+    unpack8(__ldg(p + (long long)(wpi + 1) * x_pitch_v), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
     res = pack8(m);
   }
+  const long long ro = ((long long)img * (ho + 2) + oy) * wpo + ox;
   y[ro * y_pitch_v + y_coff_v + cv] = res;
 }
 
 // ------------------------------------------------------------------------------- bilinear upsample
 // Half-pixel centres: src = (dst + 0.5)/s - 0.5; lower = max(floor(src),0), upper = min(ceil(src), size-1).
-__global__ void upsample_kernel(const uint4* __restrict__ x, int n, int h, int w, int cvec, int x_pitch_v,
-                                int x_coff_v, int s, uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const int ho = h * s, wo = w * s;
-  const long long total = (long long)n * (ho + 2) * (wo + 2) * cvec;
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int cv = (int)(t % cvec);
-  const long long ro = t / cvec;
-  const int wpo = wo + 2, plo = (ho + 2) * wpo;
-  const int img = (int)(ro / plo);
-  const int pr = (int)(ro - (long long)img * plo);
-  const int oy = pr / wpo - 1, ox = pr % wpo - 1;
+// grid = (ceil((wo+2)*cvec / 256), ho+2, n): the vertical taps / weights are block-uniform.
+__global__ void __launch_bounds__(256)
+upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v, int s,
+                uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+  const int ho = h * s, wo = w * s, wpo = wo + 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wpo * cvec) return;
+  const int oxp = idx / cvec, cv = idx - oxp * cvec;
+  const int oyp = blockIdx.y, img = blockIdx.z;
+  const int oy = oyp - 1, ox = oxp - 1;
   uint4 res = make_uint4(0, 0, 0, 0);
   if (oy >= 0 && oy < ho && ox >= 0 && ox < wo) {
     const float inv = 1.f / (float)s;
@@ -118,10 +127,10 @@ __global__ void upsample_kernel(const uint4* __restrict__ x, int n, int h, int w
     const long long base = (long long)img * (h + 2) * wpi;
     const uint4* p = x + x_coff_v + cv;
     float a[8], b[8], c[8], d[8], o[8];
-    unpack8(p[(base + (long long)(y0 + 1) * wpi + (x0 + 1)) * x_pitch_v], a);
-    unpack8(p[(base + (long long)(y0 + 1) * wpi + (x1 + 1)) * x_pitch_v], b);
-    unpack8(p[(base + (long long)(y1 + 1) * wpi + (x0 + 1)) * x_pitch_v], c);
-    unpack8(p[(base + (long long)(y1 + 1) * wpi + (x1 + 1)) * x_pitch_v], d);
+    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x0 + 1)) * x_pitch_v), a);
+    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x1 + 1)) * x_pitch_v), b);
+    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x0 + 1)) * x_pitch_v), c);
+    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x1 + 1)) * x_pitch_v), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float top = a[e] + (b[e] - a[e]) * lx;
@@ -130,6 +139,7 @@ __global__ void upsample_kernel(const uint4* __restrict__ x, int n, int h, int w
     }
     res = pack8(o);
   }
+  const long long ro = ((long long)img * (ho + 2) + oyp) * wpo + oxp;
   y[ro * y_pitch_v + y_coff_v + cv] = res;
 }
 
@@ -231,6 +241,15 @@ using namespace ie;
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Threads per block for a row of `total` work items: the fewest blocks of <= 256 threads, then the smallest
+// warp multiple that still covers the row (848 items -> 4 blocks of 224, not 4 x 256).
+static inline int row_block(long long total, int* blocks) {
+  const int nb = ie_ceil_div(total, 256);
+  const int per = ie_ceil_div(total, nb);
+  *blocks = nb;
+  return ((per + 31) / 32) * 32;
+}
+
 extern "C" int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, int ktot_pad,
                                     void* packed_bf16, void* stream) {
   IE_REQUIRE(hwio && packed_bf16, "pack_conv_weights: null pointer");
@@ -242,13 +261,17 @@ extern "C" int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, 
   return IE_OK;
 }
 
-extern "C" int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* raster_bf16, void* stream) {
+extern "C" int ie_pack_input_im2col3x3(const float* x, int n, int hs, int ws, int c, int h, int w, void* raster_bf16,
+                                       void* stream) {
   IE_REQUIRE(x && raster_bf16, "pack_input: null pointer");
   IE_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && 9 * c <= 1024, "pack_input: need 9*c <= 1024 (c=%d)", c);
-  const long long rows = (long long)n * (h + 2) * (w + 2);
+  IE_REQUIRE(hs > 0 && ws > 0 && hs <= h && ws <= w, "pack_input: source %dx%d must fit the %dx%d raster", hs, ws, h, w);
+  IE_REQUIRE(n <= 65535 && h + 2 <= 65535, "pack_input: grid too large");
   const int kvec = ((9 * c + 63) / 64) * 8;      // row width in 16-byte chunks: 9*c rounded up to 64 channels
-  im2col3x3_kernel<<<ie_ceil_div(rows * kvec, 256), 256, 0, S(stream)>>>(x, n, h, w, c,
-                                                                        static_cast<uint4*>(raster_bf16), rows, kvec);
+  int nb;
+  const int threads = row_block((long long)(w + 2) * kvec, &nb);
+  dim3 grid(nb, h + 2, n);
+  im2col3x3_kernel<<<grid, threads, 0, S(stream)>>>(x, hs, ws, h, w, c, static_cast<uint4*>(raster_bf16), kvec);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
@@ -264,10 +287,12 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "maxpool2: bad arguments (h %d, w %d)", h, w);
   if (int rc = check_slice("maxpool2(x)", c, x_pitch, x_coff)) return rc;
   if (int rc = check_slice("maxpool2(y)", c, y_pitch, y_coff)) return rc;
-  const long long total = (long long)n * (h / 2 + 2) * (w / 2 + 2) * (c / 8);
-  maxpool2_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(static_cast<const uint4*>(x), n, h, w, c / 8,
-                                                                 x_pitch / 8, x_coff / 8, static_cast<uint4*>(y),
-                                                                 y_pitch / 8, y_coff / 8);
+  IE_REQUIRE(n <= 65535 && h / 2 + 2 <= 65535, "maxpool2: grid too large");
+  int nb;
+  const int threads = row_block((long long)(w / 2 + 2) * (c / 8), &nb);
+  dim3 grid(nb, h / 2 + 2, n);
+  maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8,
+                                              static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
@@ -277,10 +302,12 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && scale >= 1, "upsample: bad arguments");
   if (int rc = check_slice("upsample(x)", c, x_pitch, x_coff)) return rc;
   if (int rc = check_slice("upsample(y)", c, y_pitch, y_coff)) return rc;
-  const long long total = (long long)n * (h * scale + 2) * (w * scale + 2) * (c / 8);
-  upsample_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(static_cast<const uint4*>(x), n, h, w, c / 8,
-                                                                 x_pitch / 8, x_coff / 8, scale,
-                                                                 static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
+  IE_REQUIRE(n <= 65535 && h * scale + 2 <= 65535, "upsample: grid too large");
+  int nb;
+  const int threads = row_block((long long)(w * scale + 2) * (c / 8), &nb);
+  dim3 grid(nb, h * scale + 2, n);
+  upsample_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8, scale,
+                                              static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

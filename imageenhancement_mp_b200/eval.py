@@ -7,6 +7,10 @@ batch instead of 3T+4 ``invert_preproc`` passes, running totals kept on the devi
 (the reference does a ``.numpy()`` sync for every number of every batch, :165-182), batches
 sharded over the ranks of a torchrun job and combined by ONE all-reduce at the end.
 
+Batches may live in (pinned) host memory: they are then staged to the device on a side stream, two
+slots deep, so the host->device copy of batch i+1 overlaps the forward of batch i - the reference's
+tf.data ``prefetch`` (data_utils.py:393) moved to where it matters on a GPU.
+
 Out of scope here: argparse CLI, checkpoint restore, TensorBoard writer,
 the ``.npz`` visualisation dump.
 """
@@ -27,6 +31,49 @@ def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length):
     n, h, w, _ = reconstructed.shape
     sums = du.eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length)   # :144-182
     return du.reduce_metric_sums(sums, h, w, burst_length)
+
+
+def staged_batches(val_batches, device, depth=2, pre_sharded=False):
+    """Yields each (sharded) batch as device tensors; host batches are copied on a side stream into
+    ``depth`` rotating device slots, one batch ahead of the consumer.  Device batches pass through."""
+    device = torch.device(device)
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+    slots = [None] * depth          # per slot: list of device buffers
+    released = [None] * depth       # event on `main`: the consumer is done with the slot
+
+    def stage(k, tensors):
+        if all(t.is_cuda for t in tensors):
+            return tensors, None
+        if slots[k] is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(slots[k], tensors)):
+            slots[k] = [torch.empty(t.shape, dtype=t.dtype, device=device) for t in tensors]
+            released[k] = torch.cuda.Event()
+            released[k].record(main)
+        copy.wait_event(released[k])
+        with torch.cuda.stream(copy):
+            for b, t in zip(slots[k], tensors):
+                b.copy_(t, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        return slots[k], ready
+
+    shard = (lambda b: list(b)) if pre_sharded else (lambda b: _dist.shard_batch(list(b)))
+    it = iter(val_batches)
+    k = 0
+    nxt = next(it, None)
+    staged = stage(k, shard(nxt)) if nxt is not None else None
+    while staged is not None:
+        cur, cur_k = staged, k
+        nxt = next(it, None)
+        k = (k + 1) % depth
+        staged = stage(k, shard(nxt)) if nxt is not None else None   # overlaps the step below
+        tensors, ready = cur
+        if ready is not None:
+            main.wait_event(ready)
+        yield tensors
+        if ready is not None:
+            released[cur_k] = torch.cuda.Event()
+            released[cur_k].record(main)
 
 
 def make_report(totals, num_batches, burst_length):
@@ -56,23 +103,38 @@ def format_report(report, step=1):
     return ['epoch %s: %s = %s' % (int(step), k, report[k]) for k in REPORT_KEYS]
 
 
-def evaluate(model, val_batches, params, step=1, out=print, step_totals=None):
-    """Validation loop.  val_batches yields (x_batch_burst [N,H,W,T+add], x_batch_truth [N,H,W,2]).
+def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, step_results=None, device=None,
+             pre_sharded=False):
+    """Validation loop.  val_batches yields (x_batch_burst [N,H,W,T+add], x_batch_truth [N,H,W,2]), on the
+    device or in (pinned) host memory.
 
-    Every rank of a torchrun job must iterate the same batches; each takes its contiguous slice.
+    Every rank of a torchrun job must iterate the same batches; each takes its contiguous slice
+    (``pre_sharded=True``: every rank is handed its own slice already, e.g. one loader per rank).
     ``step_totals(model, xb, xt, T)`` may be injected (CPU tests); default is the GPU path.
+    ``step_results``: optional list; every step's additive totals are appended to it as pinned host
+    tensors (asynchronous device->host copies, complete when evaluate returns) - the per-batch numbers
+    the reference reads with ``.numpy()`` at eval.py:165-182, without its per-batch stalls.
     Returns the report dict (identical on all ranks); rank 0 prints it through ``out``.
     """
     T = params["BURST_LENGTH"]
     fn = gpu_step_totals if step_totals is None else step_totals
     totals = None
     nb = 0
-    for x_batch_burst, x_batch_truth in val_batches:                               # eval.py:139
-        xb, xt = _dist.shard_batch([x_batch_burst, x_batch_truth])
+    if step_totals is None:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        batches = staged_batches(val_batches, device, pre_sharded=pre_sharded)
+    else:
+        batches = (list(b) if pre_sharded else _dist.shard_batch(list(b)) for b in val_batches)
+    for xb, xt in batches:                                                         # eval.py:139
         nb += 1
         if xb.shape[0] == 0:
             continue
         t = fn(model, xb, xt, T)
+        if step_results is not None:
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
+            host.copy_(t, non_blocking=True)
+            step_results.append(host)
         totals = t.clone() if totals is None else totals.add_(t)
     if totals is None:
         raise ValueError("evaluate: no validation data on this rank")

@@ -54,16 +54,8 @@ class _KpnModel:
     def _forward(self, inputs, taps=None, conv_fn="ie_conv2d_nhwc_bf16"):
         if not isinstance(inputs, torch.Tensor) or not inputs.is_cuda:
             raise ImgEnhError("inputs must be a CUDA torch.Tensor [N,H,W,T+add] (no CPU fallback)")
-        n, h, w, c = inputs.shape
-        s = self._engine.stride
-        hp, wp = -(-h // s) * s, -(-w // s) * s
-        x = inputs
-        if (hp, wp) != (h, w):
-            x = torch.nn.functional.pad(inputs, (0, 0, 0, wp - w, 0, hp - h))
-        out, bas, ob = self._engine.forward(x, taps=taps, conv_fn=conv_fn)
-        if (hp, wp) != (h, w):
-            out = out[:, :h, :w, :].contiguous()
-        return out, bas, ob
+        # sizes that are not multiples of the network stride are zero-padded implicitly by the engine
+        return self._engine.forward(inputs, taps=taps, conv_fn=conv_fn)
 
     def call(self, inputs):
         return self.__call__(inputs)

@@ -89,14 +89,16 @@ def im2col_width(c):
 
 
 def pack_input_im2col3x3(x, out=None):
-    """fp32 NHWC [n,h,w,c] -> Raster(n,h,w) with im2col_width(c) channels holding the 3x3xc neighbourhoods."""
+    """fp32 NHWC [n,hs,ws,c] -> Raster(n,h,w) with im2col_width(c) channels holding the 3x3xc neighbourhoods.
+
+    ``out`` may be larger than the source (h >= hs, w >= ws): the source is zero-padded at the bottom/right."""
     _lib.require_cuda(x)
-    n, h, w, c = x.shape
+    n, hs, ws, c = x.shape
     x = x.contiguous()
     if out is None:
-        out = new_raster(n, h, w, im2col_width(c), x.device)
-    assert out.pitch == im2col_width(c) and (out.n, out.h, out.w) == (n, h, w)
-    call("ie_pack_input_im2col3x3", ptr(x), n, h, w, c, ptr(out.data), stream())
+        out = new_raster(n, hs, ws, im2col_width(c), x.device)
+    assert out.pitch == im2col_width(c) and out.n == n and out.h >= hs and out.w >= ws
+    call("ie_pack_input_im2col3x3", ptr(x), n, hs, ws, c, out.h, out.w, ptr(out.data), stream())
     return out
 
 
@@ -182,9 +184,10 @@ def kpn_apply(x, T, coef, bas, out=None):
     _lib.require_cuda(x, coef, bas)
     n, h, w, pitch = x.shape
     K, B = bas.shape[1], bas.shape[-1]
+    hc, wc = coef.shape[1], coef.shape[2]          # >= (h, w): the network runs at the stride-padded size
     assert x.is_contiguous() and coef.is_contiguous() and bas.is_contiguous()
-    assert coef.shape == (n, h, w, B) and bas.shape == (n, K, K, T, B)
+    assert coef.shape[0] == n and coef.shape[3] == B and hc >= h and wc >= w and bas.shape == (n, K, K, T, B)
     if out is None:
         out = torch.empty(n, h, w, T + 1, dtype=torch.float32, device=x.device)
-    call("ie_kpn_apply_f32", ptr(x), pitch, ptr(coef), ptr(bas), ptr(out), n, h, w, T, K, B, stream())
+    call("ie_kpn_apply_f32", ptr(x), pitch, ptr(coef), hc, wc, ptr(bas), ptr(out), n, h, w, T, K, B, stream())
     return out

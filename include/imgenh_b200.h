@@ -66,10 +66,12 @@ int ie_sm_count(void);
 int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, int ktot_pad, void* packed_bf16,
                          void* stream);
 
-/* fp32 NHWC [n][h][w][c] -> bf16 raster [n*(h+2)*(w+2)][kpad], kpad = 9*c rounded up to a multiple of 64,
+/* fp32 NHWC [n][hs][ws][c] -> bf16 raster [n*(h+2)*(w+2)][kpad], kpad = 9*c rounded up to a multiple of 64,
  * holding each pixel's zero-padded 3x3xc neighbourhood, k = (i*3+j)*c + ch (rest zero): turns the first
- * conv (model_library.py:323/376, 196/235) into a 1x1 GEMM with K = kpad.                              */
-int ie_pack_input_im2col3x3(const float* x, int n, int h, int w, int c, void* raster_bf16, void* stream);
+ * conv (model_library.py:323/376, 196/235) into a 1x1 GEMM with K = kpad.  hs <= h, ws <= w: the source
+ * is implicitly zero-padded at the bottom/right to the raster size (the network-stride padding).       */
+int ie_pack_input_im2col3x3(const float* x, int n, int hs, int ws, int c, int h, int w, void* raster_bf16,
+                            void* stream);
 
 /* y = epilogue(conv(x, w) + bias).  w_packed from ie_pack_conv_weights with ktot_pad = kh*kw*cin.
  * y_bf16 is used by IE_EPI_BF16_RASTER; y_f32 (and optional y_aux) by the fp32 epilogues.            */
@@ -117,10 +119,11 @@ int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float*
 /* Filter synthesis + Convolve + Convolve_perlayer (model_library.py:439-451, 114-168), fused:
  *   out[n,y,x,1+t] = T * sum_b coef[n,y,x,b] * sum_{i,j} bas[n,i,j,t,b] * pad0(burst)[n,y+i-K/2,x+j-K/2,t]
  *   out[n,y,x,0]   = mean_t out[n,y,x,1+t]
- * burst: fp32 NHWC with `burst_pitch` channels per pixel (first T used); coef [n][h][w][B];
+ * burst: fp32 NHWC [n][h][w] with `burst_pitch` channels per pixel (first T used); coef [n][hc][wc][B]
+ * with hc >= h, wc >= w (the network runs at the stride-padded size; only the top-left h x w is read);
  * bas [n][K][K][T][B]; out [n][h][w][T+1].  The per-pixel kernels are never materialised.            */
-int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, const float* bas, float* out, int n,
-                     int h, int w, int T, int K, int B, void* stream);
+int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
+                     float* out, int n, int h, int w, int T, int K, int B, void* stream);
 
 /* ---- metrics (data_utils.py:24-164 as eval.py:139-182 calls them) --------------------------------- */
 

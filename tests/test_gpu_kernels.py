@@ -47,6 +47,21 @@ def test_im2col_first_layer(cuda):
     assert border_is_zero(dst)
 
 
+def test_im2col_implicit_stride_padding(cuda):
+    """A source smaller than the raster is zero-padded at the bottom/right (100x100 patches -> 104x104)."""
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 13, 21, 5, generator=g)
+    xp = F.pad(x, (0, 0, 0, 3, 0, 3))                                # -> 16 x 24
+    a = ops.pack_input_im2col3x3(x.to(cuda), ops.new_raster(2, 16, 24, 64, cuda))
+    b = ops.pack_input_im2col3x3(xp.to(cuda))
+    assert torch.equal(a.data, b.data)
+    full = b.data.float().view(2, 18, 26, 64)
+    assert bool((full[..., 45:] == 0).all()) and border_is_zero(b)
+    # centre tap (k = 4*5 .. 4*5+4) of an interior pixel is the pixel itself
+    assert torch.equal(full[:, 1:14, 1:22, 20:25].cpu(), bf16_round(x))
+
+
 def test_maxpool(cuda):
     from imageenhancement_mp_b200 import ops
     g = torch.Generator().manual_seed(2)
@@ -120,6 +135,17 @@ def test_kpn_apply_vs_literal(cuda, n, h, w, T, B):
     ref = oracle.kpn_apply_literal(x[..., :T].double(), coef.double(), bas.double())
     got = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda)).cpu()
     assert torch.allclose(got.double(), ref, atol=2e-6, rtol=1e-5)
+
+
+def test_kpn_apply_coef_at_padded_size(cuda):
+    """coef may be larger than the image (network runs at the stride-padded size): only the top-left is read."""
+    from imageenhancement_mp_b200 import ops
+    x, coef, bas = _kpn_inputs(2, 20, 28, 4, 10, 9)
+    ref = ops.kpn_apply(x.to(cuda), 4, coef.to(cuda), bas.to(cuda))
+    big = torch.rand(2, 24, 32, 10)
+    big[:, :20, :28] = coef
+    got = ops.kpn_apply(x.to(cuda), 4, big.to(cuda), bas.to(cuda))
+    assert torch.equal(got, ref)
 
 
 def test_kpn_apply_large_vs_algebraic(cuda):
