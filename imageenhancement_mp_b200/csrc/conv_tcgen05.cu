@@ -40,7 +40,8 @@ constexpr int kStgBytesPerWarp = 32 * 128;       // 32 rows x 64 bf16
 constexpr int kMaxCout = 1024;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator buffer
-constexpr int kTailBytes = 4 * kStgBytesPerWarp + kMaxCout * 4 + (2 * kMaxStages + 6) * 8 + 16;
+constexpr int kXchBytes = 2 * 4 * 2 * 32 * 4;     // wide-N epilogue: [half][warp][up/down][32] fp32 edge rows
+constexpr int kTailBytes = 4 * kStgBytesPerWarp + kMaxCout * 4 + (2 * kMaxStages + 6) * 8 + 16 + kXchBytes;
 constexpr size_t kMaxSmem = 227 * 1024;
 
 // Output-side description shared by both kernels.
@@ -72,6 +73,7 @@ struct SmemTail {
   __device__ uint64_t* tempty() const { return tfull() + 2; }              // [2]
   __device__ uint64_t* bres() const { return tempty() + 2; }               // [1] resident weights landed
   __device__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(bres() + 1); }
+  __device__ float* xch() const { return reinterpret_cast<float*>(bres() + 3); }   // 16 bytes after tmem_slot
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -541,6 +543,249 @@ conv_resident_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// =================================================================================================
+// Wide-N kernel: 3x3 convolutions with cout <= 64.
+//
+// At n_tile = 64 a 128x64x16 MMA needs 32 tensor cycles but reads 6 KB of operands from shared memory
+// (48 cycles at 128 B/clk), and every horizontal tap re-reads the same A rows: the narrow layers are bound by
+// shared-memory bandwidth, not by the tensor pipe.  Here the three horizontal taps become three 64-column
+// groups of ONE N = 192 accumulator,
+//     Z[r][dx*64 + co] = sum_dy sum_c X[r + (dy-1)*wp][c] * W[dy][dx][co][c],
+// so each A row block is read once per filter row (12 MMAs of 10 KB per 128 pixels instead of 36 of 6 KB,
+// tensor-bound at 96 cycles each), and the epilogue applies the horizontal shift on the OUTPUT side:
+//     Y[r][co] = Z[r-1][co] + Z[r][64 + co] + Z[r+1][128 + co]
+// with warp shuffles (row r lives in TMEM lane r, i.e. in thread r of the epilogue) plus a 2 KB shared-memory
+// exchange for the rows on warp boundaries.  Tiles therefore overlap by two rows (126 outputs per 128-row tile).
+// Weights: resident in smem when they fit (cin <= 128), else streamed with the A tiles.
+// =================================================================================================
+struct WideParams {
+  EpiParams e;
+  int dy_shift[3];       // raster-row shift of filter row dy: (dy-1)*wp
+  int kb;                // cin / 64
+  int x_coff;
+  int cin;
+  int stages;
+  int gw;                // accumulator columns per horizontal tap (64; 16..32 for the fp32 heads)
+  int b_tile_bytes;      // 3*gw*128: weights of one (filter row, channel block): [3*gw rows][64 k]
+  int a_slot_bytes;      // bytes per pipeline stage
+  int tile_rows;         // output rows per tile = 126
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
+__device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const CUtensorMap* tm_y32,
+                                                   const CUtensorMap* tm_y31, const SmemTail& t, uint32_t tmem_base,
+                                                   int warp, int lane) {
+  const EpiParams& p = wp_.e;
+  const int q = warp & 3;
+  const int m = q * 32 + lane;                 // row inside the 128-row tile = TMEM lane
+  uint8_t* stg = t.stg(warp - 2);
+  const float* sbias = t.bias();
+  float* xch = t.xch();
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const uint32_t use = static_cast<uint32_t>(it >> 1);
+    const int row0 = tile * wp_.tile_rows - 1;  // raster row of tile-local row 0
+    const int r = row0 + m;
+    const int rr = r < 0 ? 0 : r;
+    const int img = rr / p.plane;
+    const int pr = rr - img * p.plane;
+    const int y = pr / p.wp;
+    const int x = pr - y * p.wp;
+    const bool valid = (m >= 1) && (m <= wp_.tile_rows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) &&
+                       (x >= 1) && (x <= p.wv);
+    mbar_wait(&t.tfull()[buf], use & 1u);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+    uint32_t pk[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t z0[32], z1[32], z2[32];
+      tmem_ld_x32(t_base + c * 32, z0);
+      tmem_ld_x32(t_base + 64 + c * 32, z1);
+      tmem_ld_x32(t_base + 128 + c * 32, z2);
+      tmem_ld_wait();
+      if (c == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t.tempty()[buf]);
+      }
+      // rows on warp boundaries travel through shared memory
+      float* mine = xch + ((c * 4 + q) * 2) * 32;
+      if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mine[j] = __uint_as_float(z0[j]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mine[32 + j] = __uint_as_float(z2[j]);
+      }
+      epi_bar_sync();
+      const float* prev = xch + ((c * 4 + ((q + 3) & 3)) * 2) * 32;          // lane 31 of the warp below (rows m-1)
+      const float* next = xch + ((c * 4 + ((q + 1) & 3)) * 2 + 1) * 32;      // lane 0 of the warp above (rows m+1)
+      const float* bs = sbias + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);
+          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);
+          if (lane == 0) up = prev[j + e];        // q == 0: row m = 0 is never stored
+          if (lane == 31) dn = next[j + e];       // q == 3: row m = 127 is never stored
+          float a = up + __uint_as_float(z1[j + e]) + dn + bs[j + e];
+          if (p.relu) a = fmaxf(a, 0.f);
+          v[e] = a;
+        }
+        pk[c * 16 + (j >> 1)] = valid ? pack_bf16x2(v[0], v[1]) : 0u;
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+    // rows m = 0 and m = 127 belong to the neighbouring tiles: warps 0 and 3 store 31 rows; warp 0 shifts its
+    // rows up by one so that every TMA source starts on a 1024-byte boundary
+    const int srow = (q == 0) ? lane - 1 : lane;
+    if (srow >= 0) {
+      uint8_t* rowp = stg + srow * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (srow & 7)) << 4)) = val;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (q == 0) tma_store_2d(tm_y31, stg, p.y_coff, row0 + 1);
+      else if (q == 3) tma_store_2d(tm_y31, stg, p.y_coff, row0 + 96);
+      else tma_store_2d(tm_y32, stg, p.y_coff, row0 + q * 32);
+      tma_store_commit();
+    }
+  }
+  if (lane == 0) tma_store_wait<0>();
+}
+
+// RES: weights resident in smem.  G: filter rows per pipeline stage (3 needs RES and kb == 1).
+template <bool RES, int G>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_y32, const __grid_constant__ CUtensorMap tm_y31,
+                 const WideParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  const int b_res_bytes = RES ? 3 * p.kb * p.b_tile_bytes : 0;
+  uint8_t* a_base_ptr = base + b_res_bytes;
+  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.e.m_tiles;
+  const int stages_per_tile = 3 * p.kb / G;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y32);
+    tma_prefetch_desc(&tm_y31);
+  }
+  const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane);
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
+  const int piece = p.gw * 128;                    // one horizontal tap's weights: [gw rows][64 k]
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      if constexpr (RES) {
+        mbar_arrive_expect_tx(t.bres(), static_cast<uint32_t>(b_res_bytes));
+        for (int dy = 0; dy < 3; ++dy)
+          for (int kb = 0; kb < p.kb; ++kb)
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d(base + (dy * p.kb + kb) * p.b_tile_bytes + dx * piece, &tm_b, t.bres(),
+                          (dy * 3 + dx) * p.cin + kb * kBlockK, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * p.tile_rows - 1;
+        if constexpr (G == 3) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], 3u * kABytes);
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+            tma_load_2d(a_base_ptr + stage * p.a_slot_bytes + g * kABytes, &tm_a, &full_bar[stage], p.x_coff,
+                        row0 + p.dy_shift[g]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        } else {
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int kb = 0; kb < p.kb; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[stage], kABytes + (RES ? 0u : static_cast<uint32_t>(p.b_tile_bytes)));
+              uint8_t* a_dst = a_base_ptr + stage * p.a_slot_bytes;
+              tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row0 + p.dy_shift[dy]);
+              if constexpr (!RES) {
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+                  tma_load_2d(a_dst + kABytes + dx * piece, &tm_b, &full_bar[stage],
+                              (dy * 3 + dx) * p.cin + kb * kBlockK, 0);
+              }
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, 3 * p.gw);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base_ptr));
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(base));
+    const uint32_t a_stride = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+    const uint32_t b_tile = static_cast<uint32_t>(p.b_tile_bytes) >> 4;
+    if constexpr (RES) {
+      mbar_wait(t.bres(), 0);
+      tc_fence_after();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      for (int si = 0; si < stages_per_tile; ++si) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_slot_lo = a_lo0 + stage * a_stride;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const uint32_t a = a_slot_lo + g * (kABytes >> 4);
+            const uint32_t b = RES ? b_lo0 + (si * G + g) * b_tile : a_slot_lo + (kABytes >> 4);
+            umma_bf16_ss_lo(d_tmem, a, b, idesc, (g == 0) ? (si != 0 ? 1u : 0u) : 1u);
+            umma_bf16_ss_lo(d_tmem, a + 2, b + 2, idesc, 1u);
+            umma_bf16_ss_lo(d_tmem, a + 4, b + 4, idesc, 1u);
+            umma_bf16_ss_lo(d_tmem, a + 6, b + 6, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (si == stages_per_tile - 1) umma_commit(&t.tfull()[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    epilogue_wide_bf16(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // -------------------------------------------------------------------------------------------------
 int choose_n_tile(int cout, int epilogue) {
   if (epilogue != IE_EPI_BF16_RASTER) return ((cout + 15) / 16) * 16;
@@ -576,7 +821,7 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 }
 
 // Tuning / test hooks (not part of the documented ABI surface): force a main-loop flavour.
-static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident
+static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_base_offset = 0;      // measured on B200: the 128B swizzle is a function of the absolute smem address,
                                       // so row-shifted descriptor starts need NO base-offset field (setting it corrupts)
@@ -643,6 +888,52 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   if (g_force_mode == 1) resident = true;
 
   const int grid_cap = sm_count();
+
+  // ---- wide-N flavour: 3x3, cout <= 64 (one 64-column group per horizontal tap), bf16 raster output
+  bool wide = d->kh == 3 && d->kw == 3 && d->epilogue == IE_EPI_BF16_RASTER && e.n_tile == 64 && e.n_tiles == 1;
+  if (g_force_mode == 0 || g_force_mode == 1) wide = false;
+  if (g_force_mode == 2) IE_REQUIRE(wide, "conv: wide-N mode forced on an unsupported layer");
+  if (wide) {
+    WideParams p{};
+    p.e = e;
+    p.tile_rows = kBlockM - 2;
+    p.e.m_tiles = (int)((R + p.tile_rows - 1) / p.tile_rows);
+    for (int i = 0; i < 3; ++i) p.dy_shift[i] = (i - 1) * wp;
+    p.kb = d->cin / 64;
+    p.x_coff = d->x_coff;
+    p.cin = d->cin;
+    p.gw = 64;
+    p.b_tile_bytes = 3 * p.gw * 128;
+    const int w_bytes = 3 * p.kb * p.b_tile_bytes;
+    const bool res = w_bytes <= 150 * 1024;
+    const bool fuse = res && p.kb == 1;
+    p.a_slot_bytes = fuse ? 3 * kABytes : kABytes + (res ? 0 : p.b_tile_bytes);
+    int stages = ((int)kMaxSmem - 1024 - kTailBytes - (res ? w_bytes : 0)) / p.a_slot_bytes;
+    p.stages = stages > kMaxStages ? kMaxStages : stages;
+    IE_REQUIRE(p.stages >= 2, "conv: wide-N pipeline does not fit in shared memory");
+    CUtensorMap tm_y31;
+    rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tm_b, w_packed, (uint64_t)ktot, (uint64_t)64, (uint64_t)ktot, 64, (uint32_t)p.gw);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tm_y31, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 31);
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)(res ? w_bytes : 0) + (size_t)p.stages * p.a_slot_bytes + kTailBytes;
+    const int grid = p.e.m_tiles < grid_cap ? p.e.m_tiles : grid_cap;
+#define IE_LAUNCH_WIDE(RES_, G_)                                                                                  \
+  do {                                                                                                            \
+    IE_CUDA(cudaFuncSetAttribute(conv_wide_kernel<RES_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                 (int)kMaxSmem));                                                                 \
+    conv_wide_kernel<RES_, G_><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, tm_y31, p);                        \
+  } while (0)
+    if (fuse) IE_LAUNCH_WIDE(true, 3);
+    else if (res) IE_LAUNCH_WIDE(true, 1);
+    else IE_LAUNCH_WIDE(false, 1);
+#undef IE_LAUNCH_WIDE
+    IE_LAUNCH_CHECK();
+    return IE_OK;
+  }
+
   if (resident) {
     ResidentParams p{};
     p.e = e;

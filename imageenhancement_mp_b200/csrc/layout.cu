@@ -33,26 +33,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int taps, in
 }
 
 // ------------------------------------------------------------------------------- input im2col
-// grid = (ceil((w+2)*kvec / 256), h+2, n): blockIdx.y/z give the raster row and image, so no thread
-// divides a 64-bit index.  One thread per (padded x, 16-byte chunk) = 8 consecutive k of the im2col row;
-// the k -> (dy, dx, ch) split is a shared-memory table (c is a run-time value, 9*c <= 1024).
-// The source may be smaller than the raster (hs <= h, ws <= w): the rest reads as zero, which is how the
-// boundary pads 100x100 patches to the network stride without a padded copy of the input.
+// grid = (ceil((w+2)*kvec / threads), h+2, n): blockIdx.y/z give the raster row and image, so no thread
+// divides a 64-bit index.  One thread per (padded x, 16-byte chunk) = 8 consecutive k of the im2col row.
+// For filter row dy the 3*c values k = dy*3c + i are CONTIGUOUS in the source: row y+dy-1, floats
+// (x-1)*c + i, so no per-element tap arithmetic is needed.
+// The source may be smaller than the raster (hs <= h, ws <= w): it is implicitly zero-padded at the
+// bottom/right, which is how the boundary pads 100x100 patches to the network stride without a padded
+// copy of the input (pixels of the padding still see their real neighbours, exactly like a padded input).
 __global__ void __launch_bounds__(256)
 im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int c, uint4* __restrict__ out, int kvec) {
-  __shared__ int s_off[1024];          // element offset of (dy, dx, ch) relative to the centre pixel
-  __shared__ signed char s_dy[1024], s_dx[1024];
-  const int ktot = 9 * c;
-  for (int k = threadIdx.x; k < kvec * 8; k += blockDim.x) {
-    int dy = 9, dx = 9, off = 0;       // dy = 9 marks the zero padding of k >= 9*c
-    if (k < ktot) {
-      const int tap = k / c, ch = k - tap * c;
-      dy = tap / 3 - 1; dx = tap % 3 - 1;
-      off = (dy * ws + dx) * c + ch;
-    }
-    s_off[k] = off; s_dy[k] = (signed char)dy; s_dx[k] = (signed char)dx;
-  }
-  __syncthreads();
   const int wp = w + 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wp * kvec) return;
@@ -62,13 +51,19 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) f[e] = 0.f;
-  if (y >= 0 && y < hs && xx >= 0 && xx < ws) {
-    const float* centre = x + (((long long)img * hs + y) * ws + xx) * c;
+  if (y >= 0 && y < h && xx >= 0 && xx < w) {
+    const int c3 = 3 * c;
+    const float* img_base = x + (long long)img * hs * ws * c;
+    const int lo = (xx > 0) ? 0 : c;                         // i < lo: left neighbour outside the image
+    const int hi = (xx + 1 < ws) ? c3 : ((xx < ws) ? 2 * c : ((xx == ws) ? c : 0));   // i >= hi: right side outside
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = chunk * 8 + e;
-      const int sy = y + s_dy[k], sx = xx + s_dx[k];
-      if (sy >= 0 && sy < hs && sx >= 0 && sx < ws) f[e] = __ldg(centre + s_off[k]);
+      const int dy = (k >= c3) + (k >= 2 * c3);
+      const int i = k - dy * c3;
+      const int sy = y + dy - 1;
+      if (k < 3 * c3 && sy >= 0 && sy < hs && i >= lo && i < hi)
+        f[e] = __ldg(img_base + ((long long)sy * ws + (xx - 1)) * c + i);
     }
   }
   out[(((long long)img * (h + 2) + yp) * wp + xp) * kvec + chunk] = pack8(f);
@@ -141,6 +136,54 @@ upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
   }
   const long long ro = ((long long)img * (ho + 2) + oyp) * wpo + oxp;
   y[ro * y_pitch_v + y_coff_v + cv] = res;
+}
+
+// Scale 2: one thread per 2x2 OUTPUT block lying between four input pixels (i, j), (i, j+1), (i+1, j),
+// (i+1, j+1), i in [-1, h-1], j in [-1, w-1] with clamped indices: 4 loads and 4 unpacks per 4 outputs instead
+// of 16, and the blocks tile the padded output raster exactly (the out-of-image outputs of the edge blocks ARE
+// the zero border).  Same lerp expressions and weights (0.25 / 0.75) as the general kernel: bit-identical.
+__global__ void __launch_bounds__(256)
+upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
+                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (w + 1) * cvec) return;
+  const int jb = idx / cvec, cv = idx - jb * cvec;
+  const int j = jb - 1, i = (int)blockIdx.y - 1, img = blockIdx.z;
+  const int y0 = max(i, 0), y1 = min(i + 1, h - 1), x0 = max(j, 0), x1 = min(j + 1, w - 1);
+  const int wpi = w + 2;
+  const long long base = (long long)img * (h + 2) * wpi;
+  const uint4* p = x + x_coff_v + cv;
+  float a[8], b[8], c[8], d[8];
+  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x0 + 1)) * x_pitch_v), a);
+  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x1 + 1)) * x_pitch_v), b);
+  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x0 + 1)) * x_pitch_v), c);
+  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x1 + 1)) * x_pitch_v), d);
+  const int wo = 2 * w, ho = 2 * h, wpo = wo + 2;
+  // output pixel (2i+1+u, 2j+1+v), u, v in {0,1}; raster position = +1 in both coordinates
+  const long long ro = ((long long)img * (ho + 2) + (2 * i + 2)) * wpo + (2 * j + 2);
+  uint4* q = y + y_coff_v + cv;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float ly = u ? 0.75f : 0.25f;
+    const bool row_ok = (2 * i + 1 + u >= 0) && (2 * i + 1 + u < ho);
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const float lx = v ? 0.75f : 0.25f;
+      const bool ok = row_ok && (2 * j + 1 + v >= 0) && (2 * j + 1 + v < wo);
+      uint4 res = make_uint4(0, 0, 0, 0);
+      if (ok) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float top = a[e] + (b[e] - a[e]) * lx;
+          const float bot = c[e] + (d[e] - c[e]) * lx;
+          o[e] = top + (bot - top) * ly;
+        }
+        res = pack8(o);
+      }
+      q[(ro + (long long)u * wpo + v) * y_pitch_v] = res;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------- channel means
@@ -304,6 +347,14 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
   if (int rc = check_slice("upsample(y)", c, y_pitch, y_coff)) return rc;
   IE_REQUIRE(n <= 65535 && h * scale + 2 <= 65535, "upsample: grid too large");
   int nb;
+  if (scale == 2) {
+    const int threads = row_block((long long)(w + 1) * (c / 8), &nb);
+    dim3 grid(nb, h + 1, n);
+    upsample2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8,
+                                                     static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
+    IE_LAUNCH_CHECK();
+    return IE_OK;
+  }
   const int threads = row_block((long long)(w * scale + 2) * (c / 8), &nb);
   dim3 grid(nb, h * scale + 2, n);
   upsample_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8, scale,

@@ -85,6 +85,39 @@ def test_conv_bf16_vs_cpu(cuda, n, h, w, cin, cout, k):
     assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["stream", "resident", "wideN"])
+@pytest.mark.parametrize("n,h,w,cin", [(2, 16, 16, 64), (2, 24, 40, 128), (3, 40, 44, 64), (1, 20, 20, 640),
+                                       (5, 8, 8, 64)])
+def test_conv_narrow_flavours(cuda, mode, n, h, w, cin):
+    """Every main-loop flavour that can run a 3x3 cout=64 layer gives the same answer: streaming, resident
+    weights with row-shifted descriptors, and the wide-N kernel (horizontal taps as accumulator column groups,
+    shift applied in the epilogue; tiles overlap by two rows, so multi-tile and multi-image cases matter)."""
+    from imageenhancement_mp_b200 import ops, _lib, ImgEnhError
+    lib = _lib.load()
+    x, wt, b = make_case(n, h, w, cin, 64, 3, seed=21)
+    ref = bf16_round(ref_conv(x, wt, b, 3))
+    src = to_raster(x.to(cuda))
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    dst = ops.new_raster(n, h, w, 64, cuda)
+    dst.data.fill_(float("nan"))
+    lib.ie_conv_set_mode(mode, 0)
+    try:
+        try:
+            ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice())
+        except ImgEnhError:
+            if mode == 1 and cin > 128:
+                pytest.skip("weights do not fit in shared memory for the resident flavour")
+            raise
+        torch.cuda.synchronize()
+    finally:
+        lib.ie_conv_set_mode(-1, 0)
+    assert_close_bf16(ops.raster_to_nhwc(dst.slice()).cpu(), ref, f"flavour {mode} {cin}->64")
+    full = dst.data.float().view(n, h + 2, w + 2, 64)
+    mask = torch.ones(h + 2, w + 2, dtype=torch.bool, device=cuda)
+    mask[1:h + 1, 1:w + 1] = False
+    assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
+
+
 def test_conv_slices_and_concat(cuda):
     """Input read from a channel window, output written into a channel window (concat by slices)."""
     from imageenhancement_mp_b200 import ops
