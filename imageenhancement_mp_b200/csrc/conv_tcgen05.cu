@@ -73,7 +73,7 @@ struct SmemTail {
   __device__ uint64_t* tempty() const { return tfull() + 2; }              // [2]
   __device__ uint64_t* bres() const { return tempty() + 2; }               // [1] resident weights landed
   __device__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(bres() + 1); }
-  __device__ float* xch() const { return reinterpret_cast<float*>(bres() + 3); }   // 16 bytes after tmem_slot
+  __device__ float* xch() const { return reinterpret_cast<float*>(full() + 2 * kMaxStages + 8); }   // 16-byte aligned
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -150,31 +150,33 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
         uint32_t pk[32];
-        const float* bs = sbias + n0 + c * 64;
+        const uint32_t bs = smem_u32(sbias + n0 + c * 64);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __uint_as_float(v0[2 * j]) + bs[2 * j];
-          float b = __uint_as_float(v0[2 * j + 1]) + bs[2 * j + 1];
-          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          pk[j] = valid ? pack_bf16x2(a, b) : 0u;
+        for (int j = 0; j < 16; j += 2) {
+          const float4 bb = lds128(bs + j * 8);
+          float a0 = __uint_as_float(v0[2 * j]) + bb.x, a1 = __uint_as_float(v0[2 * j + 1]) + bb.y;
+          float a2 = __uint_as_float(v0[2 * j + 2]) + bb.z, a3 = __uint_as_float(v0[2 * j + 3]) + bb.w;
+          if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+          pk[j] = valid ? pack_bf16x2(a0, a1) : 0u;
+          pk[j + 1] = valid ? pack_bf16x2(a2, a3) : 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __uint_as_float(v1[2 * j]) + bs[32 + 2 * j];
-          float b = __uint_as_float(v1[2 * j + 1]) + bs[32 + 2 * j + 1];
-          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          pk[16 + j] = valid ? pack_bf16x2(a, b) : 0u;
+        for (int j = 0; j < 16; j += 2) {
+          const float4 bb = lds128(bs + 128 + j * 8);
+          float a0 = __uint_as_float(v1[2 * j]) + bb.x, a1 = __uint_as_float(v1[2 * j + 1]) + bb.y;
+          float a2 = __uint_as_float(v1[2 * j + 2]) + bb.z, a3 = __uint_as_float(v1[2 * j + 3]) + bb.w;
+          if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+          pk[16 + j] = valid ? pack_bf16x2(a0, a1) : 0u;
+          pk[16 + j + 1] = valid ? pack_bf16x2(a2, a3) : 0u;
         }
         // staging buffer must have been read by the previous TMA store
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B)
-        uint8_t* rowp = stg + lane * 128;
+        const uint32_t rowa = smem_u32(stg) + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = val;
-        }
+        for (int j = 0; j < 8; ++j)
+          sts128u(rowa + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -614,33 +616,38 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
         if (lane == 0) mbar_arrive(&t.tempty()[buf]);
       }
       // rows on warp boundaries travel through shared memory
-      float* mine = xch + ((c * 4 + q) * 2) * 32;
+      const uint32_t mine = smem_u32(xch + ((c * 4 + q) * 2) * 32);
       if (lane == 31) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mine[j] = __uint_as_float(z0[j]);
+        for (int j = 0; j < 32; j += 4) sts128u(mine + j * 4, z0[j], z0[j + 1], z0[j + 2], z0[j + 3]);
       }
       if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mine[32 + j] = __uint_as_float(z2[j]);
+        for (int j = 0; j < 32; j += 4) sts128u(mine + 128 + j * 4, z2[j], z2[j + 1], z2[j + 2], z2[j + 3]);
       }
       epi_bar_sync();
-      const float* prev = xch + ((c * 4 + ((q + 3) & 3)) * 2) * 32;          // lane 31 of the warp below (rows m-1)
-      const float* next = xch + ((c * 4 + ((q + 1) & 3)) * 2 + 1) * 32;      // lane 0 of the warp above (rows m+1)
-      const float* bs = sbias + c * 32;
+      // every lane loads the two edge rows (broadcast, no divergence) and lanes 0 / 31 select them
+      const uint32_t prev = smem_u32(xch + ((c * 4 + ((q + 3) & 3)) * 2) * 32);       // lane 31 of the warp below (row m-1)
+      const uint32_t next = smem_u32(xch + ((c * 4 + ((q + 1) & 3)) * 2 + 1) * 32);   // lane 0 of the warp above (row m+1)
+      const uint32_t bs = smem_u32(sbias + c * 32);
+      const bool first = (lane == 0), last = (lane == 31);
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float v[2];
+      for (int j = 0; j < 32; j += 4) {
+        const float4 pv = lds128(prev + j * 4), nx = lds128(next + j * 4), bb = lds128(bs + j * 4);
+        const float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, nxv[4] = {nx.x, nx.y, nx.z, nx.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float v[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < 4; ++e) {
           float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);
           float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);
-          if (lane == 0) up = prev[j + e];        // q == 0: row m = 0 is never stored
-          if (lane == 31) dn = next[j + e];       // q == 3: row m = 127 is never stored
-          float a = up + __uint_as_float(z1[j + e]) + dn + bs[j + e];
+          up = first ? pvv[e] : up;               // q == 0: row m = 0 is never stored
+          dn = last ? nxv[e] : dn;                // q == 3: row m = 127 is never stored
+          float a = up + __uint_as_float(z1[j + e]) + dn + bbv[e];
           if (p.relu) a = fmaxf(a, 0.f);
           v[e] = a;
         }
         pk[c * 16 + (j >> 1)] = valid ? pack_bf16x2(v[0], v[1]) : 0u;
+        pk[c * 16 + (j >> 1) + 1] = valid ? pack_bf16x2(v[2], v[3]) : 0u;
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -649,12 +656,10 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
     // rows up by one so that every TMA source starts on a 1024-byte boundary
     const int srow = (q == 0) ? lane - 1 : lane;
     if (srow >= 0) {
-      uint8_t* rowp = stg + srow * 128;
+      const uint32_t rowa = smem_u32(stg) + srow * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        *reinterpret_cast<uint4*>(rowp + ((j ^ (srow & 7)) << 4)) = val;
-      }
+      for (int j = 0; j < 8; ++j)
+        sts128u(rowa + ((j ^ (srow & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -890,8 +895,13 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   const int grid_cap = sm_count();
 
   // ---- wide-N flavour: 3x3, cout <= 64 (one 64-column group per horizontal tap), bf16 raster output
-  bool wide = d->kh == 3 && d->kw == 3 && d->epilogue == IE_EPI_BF16_RASTER && e.n_tile == 64 && e.n_tiles == 1;
+  const bool wide_ok = d->kh == 3 && d->kw == 3 && d->epilogue == IE_EPI_BF16_RASTER && e.n_tile == 64 && e.n_tiles == 1;
+  // measured on B200 (tools/conv_bench.py, 256 x 104^2): cin = 64 -> resident 213 us vs wide-N 251 us (its epilogue
+  // reads 3x the TMEM columns: 98 KB per tile at 64 B/clk); cin = 128 -> 507 vs 477 us; cin = 640 -> 870 (streaming
+  // N = 64) vs 491 us.  So wide-N takes over as soon as the main loop is long enough to hide the epilogue.
+  bool wide = wide_ok && d->cin > 64;
   if (g_force_mode == 0 || g_force_mode == 1) wide = false;
+  if (g_force_mode == 2) wide = wide_ok;
   if (g_force_mode == 2) IE_REQUIRE(wide, "conv: wide-N mode forced on an unsupported layer");
   if (wide) {
     WideParams p{};
