@@ -50,6 +50,7 @@ SIGNATURES = {
     "ie_mean_hw_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_invert_preproc_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P],
     "ie_eval_metrics_f32": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "ie_metric_totals_f64": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_sqdiff_sum_f32": [_P, _P, _I, _LL, _P, _P],
     "ie_img_loss_sums_f32": [_P, _P, _I, _I, _I, _P, _P],
     "ie_ssim_f32": [_P, _P, _I, _I, _I, _P, _P],

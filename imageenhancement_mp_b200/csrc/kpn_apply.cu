@@ -9,71 +9,103 @@
 //     out[..,0]   = sum_t out[..,1+t] / T                                            (model_library.py:134, 447)
 // so nothing per-pixel is ever stored.  fp32 on the CUDA cores: 2*K*K*T*B FLOP per pixel.
 //
-// Block = 16 x 16 threads, each thread owns 4 consecutive x -> 64 x 16 output pixels of one image.
-// Per frame: the (16+K-1) x (64+K-1) burst tile (zero padded) and the K*K*B basis slice sit in
-// shared memory; per filter row a thread pulls its 4+K-1 burst values with 128-bit loads and
-// every basis value is a warp-wide broadcast, giving 4*BC FFMA per 16-byte basis load.
+// Block = TX x TY threads (TX*TY <= 256, chosen on the host so that tiles cover the image with little waste:
+// 104-wide patches get TX = 26, one tile per row of tiles), each thread owns 4 consecutive x.  The burst tile
+// of ALL T frames (zero padded halo of K-1) and the whole K*K*T*B basis of the image are staged in shared
+// memory once (one barrier per block); per filter row a thread pulls its 4+K-1 burst values with 128-bit
+// loads and every basis value is a warp-wide broadcast, giving 4*BC FFMA per 16-byte basis load.
 #include "ie_common.cuh"
 
 namespace ie {
 
-constexpr int kTileW = 64, kTileH = 16, kPxPerThread = 4;
+constexpr int kPxPerThread = 4;
 constexpr int kMaxK = 15;
 constexpr int kRowRegs = ((kPxPerThread + kMaxK - 1 + 3) / 4) * 4;   // 20
+
+struct KpnTiling {
+  int tx, ty;            // threads per tile row / rows per tile
+  int tiles_x, tiles_y;
+  int sw, sh;            // smem tile pitch (floats, multiple of 4) and rows
+  int bpad;
+  int tp;                // frames staged per pass (all T when they fit)
+  size_t smem_bytes;
+};
 
 template <int BC>
 __global__ void __launch_bounds__(256, 2)
 kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* __restrict__ coef, int Hc, int Wc,
                  const float* __restrict__ bas, float* __restrict__ out, int H, int W, int T, int K, int B,
-                 int tiles_x, int tiles_y) {
+                 const KpnTiling tl) {
   extern __shared__ float smem[];
   const int halo = K - 1;
-  const int sw = ((kTileW + halo + 3) / 4) * 4 + 4;   // smem row pitch (floats), 16-byte multiple
-  const int sh = kTileH + halo;
-  const int nchunk = (B + BC - 1) / BC;
-  const int bpad = nchunk * BC;        // BC is a multiple of 4 or B%BC==0 with BC even -> see host
-  float* s_burst = smem;               // [sh][sw]
-  float* s_bas = smem + sh * sw;       // [K*K][bpad]
+  const int sw = tl.sw, sh = tl.sh, bpad = tl.bpad;
+  const int nchunk = bpad / BC;
+  const int tile_w = tl.tx * kPxPerThread;
+  const int TP = tl.tp;
+  float* s_burst = smem;                    // [TP][sh][sw]
+  float* s_bas = smem + TP * sh * sw;       // [TP][K*K][bpad]
 
   int bid = blockIdx.x;
-  const int tx_tile = bid % tiles_x; bid /= tiles_x;
-  const int ty_tile = bid % tiles_y;
-  const int img = bid / tiles_y;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int x0 = tx_tile * kTileW, y0 = ty_tile * kTileH;
+  const int tx_tile = bid % tl.tiles_x; bid /= tl.tiles_x;
+  const int ty_tile = bid % tl.tiles_y;
+  const int img = bid / tl.tiles_y;
+  const int ty = threadIdx.x / tl.tx, tx = threadIdx.x - ty * tl.tx;
+  const int x0 = tx_tile * tile_w, y0 = ty_tile * tl.ty;
   const int px = x0 + tx * kPxPerThread, py = y0 + ty;
   const int kpad = K / 2;
+  const bool active = ty < tl.ty;
 
+  const float* burst_img = burst + (long long)img * H * W * burst_pitch;
+  const float* bas_img = bas + (long long)img * K * K * T * B;
+
+  const long long pix_base = ((long long)img * H + py) * W + px;
+  const long long coef_base = ((long long)img * Hc + py) * Wc + px;
   float dsum[kPxPerThread];
 #pragma unroll
   for (int p = 0; p < kPxPerThread; ++p) dsum[p] = 0.f;
 
-  const float* burst_img = burst + (long long)img * H * W * burst_pitch;
-  const float* bas_img = bas + (long long)img * K * K * T * B;
-  const long long pix_base = ((long long)img * H + py) * W + px;
-  const long long coef_base = ((long long)img * Hc + py) * Wc + px;
-
-  for (int t = 0; t < T; ++t) {
-    __syncthreads();
-    // burst tile of frame t (zero outside the image = tf.pad at model_library.py:126)
-    for (int i = threadIdx.x; i < sh * sw; i += 256) {
-      const int ly = i / sw, lx = i - ly * sw;
-      const int gy = y0 + ly - kpad, gx = x0 + lx - kpad;
-      float v = 0.f;
-      if (lx < kTileW + halo && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = burst_img[((long long)gy * W + gx) * burst_pitch + t];
-      s_burst[i] = v;
+  for (int t0 = 0; t0 < T; t0 += TP) {
+  const int nt = min(TP, T - t0);
+  if (t0) __syncthreads();
+  // ---- stage the burst tile of frames [t0, t0+nt): a tile row is one contiguous run of (tile_w+halo)*pitch floats
+  {
+    const int run = (tile_w + halo) * burst_pitch;
+    const int gx0 = x0 - kpad;
+    for (int idx = threadIdx.x; idx < sh * run; idx += blockDim.x) {
+      const int ly = idx / run, e = idx - ly * run;
+      const int lx = e / burst_pitch, ch = e - lx * burst_pitch - t0;
+      if (ch >= 0 && ch < nt) {
+        const int gy = y0 + ly - kpad, gx = gx0 + lx;
+        float v = 0.f;                      // zero outside the image = tf.pad at model_library.py:126
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+          v = __ldg(burst_img + ((long long)gy * W + gx) * burst_pitch + t0 + ch);
+        s_burst[(ch * sh + ly) * sw + lx] = v;
+      }
     }
-    // basis slice of frame t: [tap][b] zero padded to bpad
-    for (int i = threadIdx.x; i < K * K * bpad; i += 256) {
-      const int tap = i / bpad, b = i - tap * bpad;
-      s_bas[i] = (b < B) ? bas_img[((long long)tap * T + t) * B + b] : 0.f;
+    // columns [tile_w+halo, sw) are read into registers (never used) by the 128-bit row loads: keep them finite
+    const int extra = sw - (tile_w + halo);
+    for (int idx = threadIdx.x; idx < nt * sh * extra; idx += blockDim.x) {
+      const int r = idx / extra, c = idx - r * extra;
+      s_burst[r * sw + tile_w + halo + c] = 0.f;
     }
-    __syncthreads();
+    // basis of the image: global [tap][t][b] -> smem [t][tap][bpad], zero padded
+    const int tb = T * B;
+    for (int idx = threadIdx.x; idx < K * K * nt * bpad; idx += blockDim.x) {
+      const int t = idx / (K * K * bpad), r = idx - t * (K * K * bpad);
+      const int tap = r / bpad, b = r - tap * bpad;
+      s_bas[idx] = (b < B) ? __ldg(bas_img + (long long)tap * tb + (t0 + t) * B + b) : 0.f;
+    }
+  }
+  __syncthreads();
+  if (!active) continue;
 
+  for (int tl_ = 0; tl_ < nt; ++tl_) {
+    const int t = t0 + tl_;
     float res[kPxPerThread];
 #pragma unroll
     for (int p = 0; p < kPxPerThread; ++p) res[p] = 0.f;
+    const float* sb_t = s_burst + (tl_ * sh + ty) * sw + tx * kPxPerThread;
+    const float* bas_t = s_bas + tl_ * K * K * bpad;
 
     for (int ch = 0; ch < nchunk; ++ch) {
       float g[kPxPerThread][BC];
@@ -84,13 +116,13 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
 
       for (int i = 0; i < K; ++i) {
         float row[kRowRegs];
-        const float4* rp = reinterpret_cast<const float4*>(s_burst + (ty + i) * sw + tx * kPxPerThread);
+        const float4* rp = reinterpret_cast<const float4*>(sb_t + i * sw);
 #pragma unroll
         for (int v = 0; v < kRowRegs / 4; ++v) {
           const float4 q = rp[v];
           row[4 * v] = q.x; row[4 * v + 1] = q.y; row[4 * v + 2] = q.z; row[4 * v + 3] = q.w;
         }
-        const float* bp = s_bas + (i * K) * bpad + ch * BC;
+        const float* bp = bas_t + (i * K) * bpad + ch * BC;
 #pragma unroll
         for (int j = 0; j < kMaxK; ++j) {
           if (j < K) {
@@ -138,11 +170,33 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
       }
     }
   }
-  if (py < H) {
+  }  // frame groups
+  if (active && py < H) {
 #pragma unroll
     for (int p = 0; p < kPxPerThread; ++p)
       if (px + p < W) out[(pix_base + p) * (T + 1)] = dsum[p];
   }
+}
+
+// Tiles: as few 128-px-wide columns of tiles as cover W, each an equal multiple of 4 px; rows balanced over H.
+static KpnTiling kpn_tiling(int h, int w, int T, int K, int B, int BC) {
+  KpnTiling t{};
+  t.tiles_x = (w + 127) / 128;
+  const int tile_w = (((w + t.tiles_x - 1) / t.tiles_x) + 3) / 4 * 4;
+  t.tx = tile_w / kPxPerThread;
+  int ty = 256 / t.tx;
+  t.tiles_y = (h + ty - 1) / ty;
+  t.ty = (h + t.tiles_y - 1) / t.tiles_y;
+  const int halo = K - 1;
+  t.sw = ((tile_w + halo + 3) / 4) * 4 + 4;
+  t.sh = t.ty + halo;
+  t.bpad = ((B + BC - 1) / BC) * BC;
+  // frames per pass: all of them if the block then still fits twice per SM, else as many as ~100 KB holds
+  const size_t per_frame = sizeof(float) * ((size_t)t.sh * t.sw + (size_t)K * K * t.bpad);
+  int tp = (int)((100 * 1024) / per_frame);
+  t.tp = tp < 1 ? 1 : (tp > T ? T : tp);
+  t.smem_bytes = per_frame * t.tp;
+  return t;
 }
 
 }  // namespace ie
@@ -155,25 +209,22 @@ extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float
   IE_REQUIRE(K >= 1 && K <= kMaxK && (K & 1), "kpn_apply: K must be odd and <= %d (got %d)", kMaxK, K);
   IE_REQUIRE(burst_pitch >= T, "kpn_apply: burst_pitch < T");
   IE_REQUIRE(hc >= h && wc >= w, "kpn_apply: coef extent %dx%d smaller than the image %dx%d", hc, wc, h, w);
-  const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
-  const long long blocks = (long long)n * tiles_x * tiles_y;
-  IE_REQUIRE(blocks < (1ll << 31), "kpn_apply: too many tiles");
-  const int halo = K - 1;
-  const int sw = ((kTileW + halo + 3) / 4) * 4 + 4, sh = kTileH + halo;
   const bool ten = (B % 10 == 0);
   const int BC = ten ? 10 : 8;
-  const int bpad = ((B + BC - 1) / BC) * BC;
-  const size_t smem = sizeof(float) * ((size_t)sh * sw + (size_t)K * K * bpad);
-  IE_REQUIRE(smem <= 200 * 1024, "kpn_apply: B=%d needs %zu bytes of shared memory", B, smem);
+  const KpnTiling tl = kpn_tiling(h, w, T, K, B, BC);
+  const long long blocks = (long long)n * tl.tiles_x * tl.tiles_y;
+  IE_REQUIRE(blocks < (1ll << 31), "kpn_apply: too many tiles");
+  IE_REQUIRE(tl.smem_bytes <= 200 * 1024, "kpn_apply: T=%d B=%d needs %zu bytes of shared memory", T, B, tl.smem_bytes);
+  const int threads = ((tl.tx * tl.ty + 31) / 32) * 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ten) {
-    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpn_apply_kernel<10><<<(unsigned)blocks, 256, smem, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w, T, K, B,
-                                                             tiles_x, tiles_y);
+    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes));
+    kpn_apply_kernel<10><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w,
+                                                                          T, K, B, tl);
   } else {
-    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpn_apply_kernel<8><<<(unsigned)blocks, 256, smem, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w, T, K, B,
-                                                            tiles_x, tiles_y);
+    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes));
+    kpn_apply_kernel<8><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w,
+                                                                         T, K, B, tl);
   }
   IE_LAUNCH_CHECK();
   return IE_OK;

@@ -83,80 +83,130 @@ __global__ void invert_preproc_kernel(const float* __restrict__ img, int pitch, 
 }
 
 // ------------------------------------------------------------------------------- fused eval metrics
-// Tile of 32 x 8 cropped pixels (+1 halo row/column for the forward differences).  For every pixel of
-// the haloed tile the error images d_k = sRGB(e_k/wl) - sRGB(gt/wl) go to shared memory, then each
-// interior thread accumulates d_k^2 and |d_k(y+1,x)-d_k(y,x)|/2 + |d_k(y,x+1)-d_k(y,x)|/2.
+// A block owns a 32-px-wide column strip of one image's cropped area over a range of rows and walks it in
+// sub-tiles of 8 rows (+1 halo row/column for the forward differences).  For every pixel of the haloed
+// sub-tile the error images d_k = sRGB(e_k/wl) - sRGB(gt/wl) go to shared memory, then each interior thread
+// accumulates d_k^2 and |d_k(y+1,x)-d_k(y,x)|/2 + |d_k(y,x+1)-d_k(y,x)|/2 in registers; ONE block reduction
+// and 2T+4 fp64 atomics per block at the end.  The kernel is bound by instruction issue (T+4 sRGB curves per
+// pixel), not by HBM: the curve uses the MUFU lg2/ex2 approximations (relative error < 1e-6).
 constexpr int kMT_W = 32, kMT_H = 8, kMaxT = 8;
+
+__device__ __forceinline__ float srgb_fast(float x) {
+  const float b = .0031308f, a = .055f, k0 = 12.92f;
+  const float gamma = 1.f / 2.4f;
+  const float k1 = (1.f + a) * gamma;
+  float l, e;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(x, b)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(gamma * l));
+  float r = (x < b) ? k0 * x : fmaf(1.f + a, e, -a);
+  if (x > 1.f) r = fmaf(k1, x, 1.f - k1);
+  return r;
+}
 
 __global__ void __launch_bounds__(256)
 eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ burst, int burst_pitch,
                     const float* __restrict__ truth, const float* __restrict__ wl, int h, int w, int T, int crop,
-                    int tiles_x, int tiles_y, double* __restrict__ sums) {
+                    int rows_per_block, double* __restrict__ sums) {
   __shared__ float s_d[kMaxT + 1][kMT_H + 1][kMT_W + 1];
-  int bid = blockIdx.x;
-  const int txi = bid % tiles_x; bid /= tiles_x;
-  const int tyi = bid % tiles_y;
-  const int n = bid / tiles_y;
+  const int n = blockIdx.z;
   const int hc = h - 2 * crop, wc = w - 2 * crop;
-  const int x0 = txi * kMT_W, y0 = tyi * kMT_H;
-  const float wln = wl[n];
+  const int x0 = blockIdx.x * kMT_W;
+  const int ys = blockIdx.y * rows_per_block, ye = min(ys + rows_per_block, hc);
+  const float inv_wl = 1.f / wl[n];
+  const float inv_T = 1.f / (float)T;
   const int nq = (T + 3) + (T + 1);
 
   float acc[2 * kMaxT + 4];
 #pragma unroll
   for (int q = 0; q < 2 * kMaxT + 4; ++q) acc[q] = 0.f;
 
-  for (int i = threadIdx.x; i < (kMT_H + 1) * (kMT_W + 1); i += 256) {
-    const int ly = i / (kMT_W + 1), lx = i - ly * (kMT_W + 1);
-    const int y = y0 + ly, x = x0 + lx;
-    const bool inside = (y < hc) && (x < wc);
-    const bool owner = inside && ly < kMT_H && lx < kMT_W;   // halo pixels are owned by the neighbouring tile
-    if (inside) {
-      const long long pix = ((long long)n * h + y + crop) * w + x + crop;
-      const float g = srgb_forward(truth[pix * 2] / wln);
-      const float* rp = recon + pix * (T + 1);
-      const float* bp = burst + pix * burst_pitch;
-      float bsum = 0.f;
+  for (int y0 = ys; y0 < ye; y0 += kMT_H) {
+    if (y0 != ys) __syncthreads();
+    for (int i = threadIdx.x; i < (kMT_H + 1) * (kMT_W + 1); i += 256) {
+      const int ly = i / (kMT_W + 1), lx = i - ly * (kMT_W + 1);
+      const int y = y0 + ly, x = x0 + lx;
+      const bool inside = (y < hc) && (x < wc);
+      // halo pixels are owned by the neighbouring tile / sub-tile
+      const bool owner = inside && ly < kMT_H && lx < kMT_W && y < ye;
+      if (inside) {
+        const long long pix = ((long long)n * h + y + crop) * w + x + crop;
+        const float g = srgb_fast(truth[pix * 2] * inv_wl);
+        const float* rp = recon + pix * (T + 1);
+        const float* bp = burst + pix * burst_pitch;
 #pragma unroll
-      for (int k = 0; k < kMaxT + 1; ++k) {
-        if (k <= T) {
-          const float d = srgb_forward(rp[k] / wln) - g;
-          s_d[k][ly][lx] = d;
-          if (owner) acc[k] += d * d;
+        for (int k = 0; k < kMaxT + 1; ++k) {
+          if (k <= T) {
+            const float d = srgb_fast(rp[k] * inv_wl) - g;
+            s_d[k][ly][lx] = d;
+            if (owner) acc[k] = fmaf(d, d, acc[k]);
+          }
         }
-      }
-      float b0 = 0.f;
+        if (owner) {
+          float b0 = 0.f, bsum = 0.f;
 #pragma unroll
-      for (int t = 0; t < kMaxT; ++t) {
-        if (t < T) {
-          const float v = bp[t];
-          if (t == 0) b0 = v;
-          bsum += v;
+          for (int t = 0; t < kMaxT; ++t) {
+            if (t < T) {
+              const float v = bp[t];
+              if (t == 0) b0 = v;
+              bsum += v;
+            }
+          }
+          const float d0 = srgb_fast(b0 * inv_wl) - g;                 // psnr_burst0, data_utils.py:152-154
+          const float da = srgb_fast((bsum * inv_T) * inv_wl) - g;     // psnr_average_f, :162-164
+          acc[T + 1] = fmaf(d0, d0, acc[T + 1]);
+          acc[T + 2] = fmaf(da, da, acc[T + 2]);
         }
-      }
-      if (owner) {
-        const float d0 = srgb_forward(b0 / wln) - g;              // psnr_burst0, data_utils.py:152-154
-        const float da = srgb_forward((bsum / (float)T) / wln) - g;  // psnr_average_f, :162-164
-        acc[T + 1] += d0 * d0;
-        acc[T + 2] += da * da;
       }
     }
-  }
-  __syncthreads();
-  {
-    const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
-    const int y = y0 + ly, x = x0 + lx;
-    if (y < hc - 1 && x < wc - 1) {
+    __syncthreads();
+    {
+      const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+      const int y = y0 + ly, x = x0 + lx;
+      if (y < ye && y < hc - 1 && x < wc - 1) {
 #pragma unroll
-      for (int k = 0; k < kMaxT + 1; ++k) {
-        if (k <= T) {
-          const float c = s_d[k][ly][lx];
-          acc[T + 3 + k] += .5f * fabsf(s_d[k][ly + 1][lx] - c) + .5f * fabsf(s_d[k][ly][lx + 1] - c);
+        for (int k = 0; k < kMaxT + 1; ++k) {
+          if (k <= T) {
+            const float c = s_d[k][ly][lx];
+            acc[T + 3 + k] += .5f * fabsf(s_d[k][ly + 1][lx] - c) + .5f * fabsf(s_d[k][ly][lx + 1] - c);
+          }
         }
       }
     }
   }
   block_accumulate<2 * kMaxT + 4>(acc, sums + (long long)n * nq, nq);
+}
+
+// ------------------------------------------------------------------------------- per-image sums -> totals
+// One block: psnr_k[n] = -10 log10(sums[n][k] / npx) (data_utils.py:118-119), loss_k[n] = mse + grad-L1
+// (:46-51); totals = [sum_n psnr_0..T+2, sum_n loss_0, sum_n sum_{k>=1} loss_k, n]  (fp64).
+__global__ void metric_totals_kernel(const double* __restrict__ sums, int n, int T, double npx, double ngr,
+                                     double* __restrict__ totals) {
+  const int nq = 2 * T + 4, nout = T + 6;
+  __shared__ double red[32][2 * kMaxT + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = 0; k < nout - 1; ++k) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double* s = sums + (long long)i * nq;
+      if (k < T + 3) {
+        acc += -10.0 * log10(s[k] / npx);
+      } else if (k == T + 3) {
+        acc += s[0] / npx + s[T + 3] / ngr;
+      } else {
+        for (int f = 1; f <= T; ++f) acc += s[f] / npx + s[T + 3 + f] / ngr;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp][k] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < nout - 1) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    totals[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) totals[nout - 1] = (double)n;
 }
 
 // ------------------------------------------------------------------------------- pair reductions
@@ -369,11 +419,29 @@ extern "C" int ie_eval_metrics_f32(const float* recon, const float* burst, int b
   IE_REQUIRE(recon && burst && truth && wl && sums, "eval_metrics: null pointer");
   IE_REQUIRE(n > 0 && T >= 1 && T <= kMaxT && burst_pitch >= T, "eval_metrics: bad T=%d (max %d)", T, kMaxT);
   IE_REQUIRE(crop >= 0 && h > 2 * crop + 1 && w > 2 * crop + 1, "eval_metrics: image %dx%d too small for crop %d", h, w, crop);
-  const int tiles_x = (w - 2 * crop + kMT_W - 1) / kMT_W, tiles_y = (h - 2 * crop + kMT_H - 1) / kMT_H;
-  const long long blocks = (long long)n * tiles_x * tiles_y;
-  IE_REQUIRE(blocks < (1ll << 31), "eval_metrics: too many tiles");
-  eval_metrics_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(recon, burst, burst_pitch, truth, wl, h, w, T, crop,
-                                                              tiles_x, tiles_y, sums);
+  const int hc = h - 2 * crop, wc = w - 2 * crop;
+  const int tiles_x = (wc + kMT_W - 1) / kMT_W;
+  // rows per block: a multiple of the 8-row sub-tile, as tall as still leaves ~4 blocks per SM in flight
+  const int sub = (hc + kMT_H - 1) / kMT_H;
+  long long want = 4ll * sm_count() / ((long long)tiles_x * n);
+  if (want < 1) want = 1;
+  if (want > sub) want = sub;
+  const int subs_per_block = (int)((sub + want - 1) / want);
+  const int rows_per_block = subs_per_block * kMT_H;
+  const int ysplit = (hc + rows_per_block - 1) / rows_per_block;
+  IE_REQUIRE(n <= 65535 && ysplit <= 65535, "eval_metrics: grid too large");
+  eval_metrics_kernel<<<dim3(tiles_x, ysplit, n), 256, 0, S(stream)>>>(recon, burst, burst_pitch, truth, wl, h, w, T, crop,
+                                                                       rows_per_block, sums);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_metric_totals_f64(const double* sums, int n, int h, int w, int T, int crop, double* totals,
+                                    void* stream) {
+  IE_REQUIRE(sums && totals && n > 0 && T >= 1 && T <= kMaxT, "metric_totals: bad arguments");
+  IE_REQUIRE(crop >= 0 && h > 2 * crop + 1 && w > 2 * crop + 1, "metric_totals: image %dx%d too small for crop %d", h, w, crop);
+  const double hc = h - 2 * crop, wc = w - 2 * crop;
+  metric_totals_kernel<<<1, 256, 0, S(stream)>>>(sums, n, T, hc * wc, (hc - 1) * (wc - 1) * 2, totals);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

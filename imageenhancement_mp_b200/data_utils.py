@@ -194,12 +194,11 @@ def reduce_metric_sums(sums, h, w, T):
     where loss_n = mse_n + gradl1_n; batch losses of the reference (global means over equal-size
     images) are these sums divided by n.
     """
-    hc, wc = h - 2 * LBUFF, w - 2 * LBUFF
-    npx, ngr = hc * wc, (hc - 1) * (wc - 1) * 2
-    psnr = -10.0 * torch.log10(sums[:, :T + 3] / npx)                 # data_utils.py:118-119
-    loss = sums[:, :T + 1] / npx + sums[:, T + 3:] / ngr              # data_utils.py:46-51
-    n = torch.full((1,), float(sums.shape[0]), dtype=torch.float64, device=sums.device)
-    return torch.cat([psnr.sum(0), loss[:, :1].sum(0), loss[:, 1:].sum().reshape(1), n])
+    _lib.require_cuda(sums)
+    assert sums.dtype == torch.float64 and sums.shape[1] == 2 * T + 4 and sums.is_contiguous()
+    tot = torch.empty(T + 6, dtype=torch.float64, device=sums.device)
+    call("ie_metric_totals_f64", ptr(sums), sums.shape[0], h, w, T, LBUFF, ptr(tot), stream())
+    return tot
 
 
 def totals_to_report(tot, T):

@@ -145,6 +145,12 @@ int ie_invert_preproc_f32(const float* img, int pitch, int coff, int nch, const 
 int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
                         const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream);
 
+/* Per-image sums of ie_eval_metrics_f32 -> the additive totals one eval step contributes (fp64, T+6 values):
+ *   [ sum_n psnr_deblur, sum_n psnr_frame_0..T-1, sum_n psnr_burst0, sum_n psnr_average,
+ *     sum_n loss_deblur_n, sum_n loss_perlayer_n, n ],  psnr = -10 log10(mse) (data_utils.py:118-119),
+ *   loss = mse + mean|grad diff| (:46-51).  This is the vector that is all-reduced across ranks.          */
+int ie_metric_totals_f64(const double* sums, int n, int h, int w, int T, int crop, double* totals, void* stream);
+
 /* psnr_tf_batch's inner reduction (data_utils.py:118-119): sums[n] += sum (a-b)^2 over `count` px.    */
 int ie_sqdiff_sum_f32(const float* a, const float* b, int n, long long count, double* sums, void* stream);
 
