@@ -208,6 +208,23 @@ def run_ours(args, cfg_name):
     ops.CONV_EVENTS = None
     report = du.totals_to_report(tot.cpu(), T)
 
+    if args.breakdown and rank == 0:
+        _lib.TRACE = []
+        for i in range(3):
+            step(*devb[i % NROT])
+        torch.cuda.synchronize()
+        agg = {}
+        for name, a, b in _lib.TRACE:
+            t = agg.setdefault(name, [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+        _lib.TRACE = None
+        tot = sum(v[1] for v in agg.values()) / 3
+        for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"breakdown: {name:34s} {cnt // 3:3d} launches/step {t / 3:8.3f} ms/step {100 * t / 3 / tot:5.1f}%", file=sys.stderr)
+        print(f"breakdown: sum of kernel times {tot:.3f} ms/step (events around every launch; includes launch gaps "
+              f"inside each bracket)", file=sys.stderr)
+
     # ---- end-to-end timing from pinned host buffers through the public API: eval.evaluate() stages every
     # batch host->device on a side stream (overlapping the previous step), runs forward + fused metrics, and
     # reads every step's metric totals back to pinned host memory (asynchronously; all complete at return)
@@ -281,6 +298,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="extra untimed pass: per-kernel CUDA-event times of one step, printed to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, args.config)

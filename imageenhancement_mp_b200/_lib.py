@@ -59,6 +59,7 @@ SIGNATURES = {
 
 _lib = None
 LAUNCHES = collections.Counter()      # C-ABI calls made (each enqueues exactly one kernel of ours)
+TRACE = None                          # set to a list to collect (name, start_event, end_event) per call (profiling)
 
 
 def load():
@@ -95,7 +96,14 @@ def stream():
 def call(name, *args):
     lib = load()
     LAUNCHES[name] += 1
-    rc = getattr(lib, name)(*args)
+    if TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        TRACE.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.ie_last_error().decode("utf-8", "replace")
         raise ImgEnhError(f"{name} failed ({rc}): {msg}")

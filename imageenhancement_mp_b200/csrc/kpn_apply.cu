@@ -31,14 +31,17 @@ struct KpnTiling {
   size_t smem_bytes;
 };
 
-template <int BC>
+// KK / BPAD: compile-time kernel size and basis pitch of the hot configuration (15, 10) - every basis load then
+// has an immediate offset and the tap loops carry no predicates; 0 = run-time values (any odd K <= 15, any B).
+template <int BC, int KK, int BPAD>
 __global__ void __launch_bounds__(256, 2)
 kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* __restrict__ coef, int Hc, int Wc,
-                 const float* __restrict__ bas, float* __restrict__ out, int H, int W, int T, int K, int B,
+                 const float* __restrict__ bas, float* __restrict__ out, int H, int W, int T, int K_rt, int B,
                  const KpnTiling tl) {
   extern __shared__ float smem[];
+  const int K = KK ? KK : K_rt;
   const int halo = K - 1;
-  const int sw = tl.sw, sh = tl.sh, bpad = tl.bpad;
+  const int sw = tl.sw, sh = tl.sh, bpad = BPAD ? BPAD : tl.bpad;
   const int nchunk = bpad / BC;
   const int tile_w = tl.tx * kPxPerThread;
   const int TP = tl.tp;
@@ -69,11 +72,13 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
   if (t0) __syncthreads();
   // ---- stage the burst tile of frames [t0, t0+nt): a tile row is one contiguous run of (tile_w+halo)*pitch floats
   {
+    // index splits use a float reciprocal (exact for these small non-negative ints) instead of integer division
     const int run = (tile_w + halo) * burst_pitch;
     const int gx0 = x0 - kpad;
+    const float inv_run = 1.f / (float)run, inv_pitch = 1.f / (float)burst_pitch;
     for (int idx = threadIdx.x; idx < sh * run; idx += blockDim.x) {
-      const int ly = idx / run, e = idx - ly * run;
-      const int lx = e / burst_pitch, ch = e - lx * burst_pitch - t0;
+      const int ly = (int)(((float)idx + 0.5f) * inv_run), e = idx - ly * run;
+      const int lx = (int)(((float)e + 0.5f) * inv_pitch), ch = e - lx * burst_pitch - t0;
       if (ch >= 0 && ch < nt) {
         const int gy = y0 + ly - kpad, gx = gx0 + lx;
         float v = 0.f;                      // zero outside the image = tf.pad at model_library.py:126
@@ -84,16 +89,26 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
     }
     // columns [tile_w+halo, sw) are read into registers (never used) by the 128-bit row loads: keep them finite
     const int extra = sw - (tile_w + halo);
+    const float inv_extra = 1.f / (float)extra;
     for (int idx = threadIdx.x; idx < nt * sh * extra; idx += blockDim.x) {
-      const int r = idx / extra, c = idx - r * extra;
+      const int r = (int)(((float)idx + 0.5f) * inv_extra), c = idx - r * extra;
       s_burst[r * sw + tile_w + halo + c] = 0.f;
     }
-    // basis of the image: global [tap][t][b] -> smem [t][tap][bpad], zero padded
+    // basis of the image: global [tap][T][B] (read in memory order) -> smem [t][tap][bpad]
     const int tb = T * B;
-    for (int idx = threadIdx.x; idx < K * K * nt * bpad; idx += blockDim.x) {
-      const int t = idx / (K * K * bpad), r = idx - t * (K * K * bpad);
-      const int tap = r / bpad, b = r - tap * bpad;
-      s_bas[idx] = (b < B) ? __ldg(bas_img + (long long)tap * tb + (t0 + t) * B + b) : 0.f;
+    const float inv_tb = 1.f / (float)tb, inv_b = 1.f / (float)B;
+    for (int idx = threadIdx.x; idx < K * K * tb; idx += blockDim.x) {
+      const int tap = (int)(((float)idx + 0.5f) * inv_tb), r = idx - tap * tb;
+      const int t = (int)(((float)r + 0.5f) * inv_b), b = r - t * B;
+      const int tl_ = t - t0;
+      if (tl_ >= 0 && tl_ < nt) s_bas[(tl_ * K * K + tap) * bpad + b] = __ldg(bas_img + idx);
+    }
+    if (bpad > B) {                          // zero the padding of the basis pitch
+      const int padw = bpad - B;
+      for (int idx = threadIdx.x; idx < nt * K * K * padw; idx += blockDim.x) {
+        const int r = idx / padw, c = idx - r * padw;
+        s_bas[r * bpad + B + c] = 0.f;
+      }
     }
   }
   __syncthreads();
@@ -124,8 +139,8 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
         }
         const float* bp = bas_t + (i * K) * bpad + ch * BC;
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j) {
-          if (j < K) {
+        for (int j = 0; j < (KK ? KK : kMaxK); ++j) {
+          if (KK || j < K) {
             float bv[BC];
             if constexpr (BC % 4 == 0) {
 #pragma unroll
@@ -217,15 +232,17 @@ extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float
   IE_REQUIRE(tl.smem_bytes <= 200 * 1024, "kpn_apply: T=%d B=%d needs %zu bytes of shared memory", T, B, tl.smem_bytes);
   const int threads = ((tl.tx * tl.ty + 31) / 32) * 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (ten) {
-    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes));
-    kpn_apply_kernel<10><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w,
-                                                                          T, K, B, tl);
-  } else {
-    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes));
-    kpn_apply_kernel<8><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(burst, burst_pitch, coef, hc, wc, bas, out, h, w,
-                                                                         T, K, B, tl);
-  }
+#define IE_LAUNCH_KPN(BC_, KK_, BPAD_)                                                                              \
+  do {                                                                                                                \
+    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<BC_, KK_, BPAD_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)tl.smem_bytes));                                                                \
+    kpn_apply_kernel<BC_, KK_, BPAD_><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(                              \
+        burst, burst_pitch, coef, hc, wc, bas, out, h, w, T, K, B, tl);                                               \
+  } while (0)
+  if (ten && K == 15 && B == 10) IE_LAUNCH_KPN(10, 15, 10);      // eval.py defaults (K=15, B=10)
+  else if (ten) IE_LAUNCH_KPN(10, 0, 0);
+  else IE_LAUNCH_KPN(8, 0, 0);
+#undef IE_LAUNCH_KPN
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -53,17 +53,33 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
   for (int e = 0; e < 8; ++e) f[e] = 0.f;
   if (y >= 0 && y < h && xx >= 0 && xx < w) {
     const int c3 = 3 * c;
-    const float* img_base = x + (long long)img * hs * ws * c;
     const int lo = (xx > 0) ? 0 : c;                         // i < lo: left neighbour outside the image
     const int hi = (xx + 1 < ws) ? c3 : ((xx < ws) ? 2 * c : ((xx == ws) ? c : 0));   // i >= hi: right side outside
+    // this chunk's 8 values span at most two filter rows: dy0 = first, switch to dy0+1 at k == (dy0+1)*c3
+    const int k0 = chunk * 8;
+    const int dy0 = (k0 >= c3) + (k0 >= 2 * c3);
+    const float* centre = x + (((long long)img * hs + y) * ws + (xx - 1)) * c;      // (y, x-1, ch 0)
+    const float* r0 = centre + (long long)(dy0 - 1) * ws * c - dy0 * c3;              // + k gives the element
+    const float* r1 = r0 + (long long)ws * c - c3;
+    const bool ok0 = (y + dy0 - 1 >= 0) && (y + dy0 - 1 < hs);
+    const bool ok1 = (y + dy0 >= 0) && (y + dy0 < hs) && (dy0 < 2);
+    const int sw_k = (dy0 + 1) * c3;                          // first k of the next filter row
+    if (c3 >= 8) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = chunk * 8 + e;
-      const int dy = (k >= c3) + (k >= 2 * c3);
-      const int i = k - dy * c3;
-      const int sy = y + dy - 1;
-      if (k < 3 * c3 && sy >= 0 && sy < hs && i >= lo && i < hi)
-        f[e] = __ldg(img_base + ((long long)sy * ws + (xx - 1)) * c + i);
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        const bool second = k >= sw_k;
+        const int i = k - (second ? sw_k : dy0 * c3);
+        const bool ok = (second ? ok1 : ok0) && i >= lo && i < hi && k < 3 * c3;
+        if (ok) f[e] = __ldg((second ? r1 : r0) + k);
+      }
+    } else {                                                  // c <= 2: a chunk may span all three filter rows
+      for (int e = 0; e < 8; ++e) {
+        const int k = k0 + e;
+        const int dy = (k >= c3) + (k >= 2 * c3);
+        const int i = k - dy * c3, sy = y + dy - 1;
+        if (k < 3 * c3 && sy >= 0 && sy < hs && i >= lo && i < hi) f[e] = __ldg(centre + (long long)(dy - 1) * ws * c + i);
+      }
     }
   }
   out[(((long long)img * (h + 2) + yp) * wp + xp) * kvec + chunk] = pack8(f);

@@ -47,19 +47,24 @@ def test_im2col_first_layer(cuda):
     assert border_is_zero(dst)
 
 
-def test_im2col_implicit_stride_padding(cuda):
+@pytest.mark.parametrize("c", [5, 2, 3, 9])
+def test_im2col_implicit_stride_padding(cuda, c):
     """A source smaller than the raster is zero-padded at the bottom/right (100x100 patches -> 104x104)."""
     from imageenhancement_mp_b200 import ops
     g = torch.Generator().manual_seed(2)
-    x = torch.rand(2, 13, 21, 5, generator=g)
+    x = torch.rand(2, 13, 21, c, generator=g)
     xp = F.pad(x, (0, 0, 0, 3, 0, 3))                                # -> 16 x 24
-    a = ops.pack_input_im2col3x3(x.to(cuda), ops.new_raster(2, 16, 24, 64, cuda))
+    kw = ops.im2col_width(c)
+    a = ops.pack_input_im2col3x3(x.to(cuda), ops.new_raster(2, 16, 24, kw, cuda))
     b = ops.pack_input_im2col3x3(xp.to(cuda))
     assert torch.equal(a.data, b.data)
-    full = b.data.float().view(2, 18, 26, 64)
-    assert bool((full[..., 45:] == 0).all()) and border_is_zero(b)
-    # centre tap (k = 4*5 .. 4*5+4) of an interior pixel is the pixel itself
-    assert torch.equal(full[:, 1:14, 1:22, 20:25].cpu(), bf16_round(x))
+    full = b.data.float().view(2, 18, 26, kw)
+    assert bool((full[..., 9 * c:] == 0).all()) and border_is_zero(b)
+    # every tap of an interior pixel is the corresponding (zero-padded) neighbour
+    ref = F.pad(xp, (0, 0, 1, 1, 1, 1))
+    for tap in range(9):
+        i, j = divmod(tap, 3)
+        assert torch.equal(full[:, 1:17, 1:25, tap * c:(tap + 1) * c].cpu(), bf16_round(ref[:, i:i + 16, j:j + 24]))
 
 
 def test_maxpool(cuda):
