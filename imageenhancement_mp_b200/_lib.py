@@ -37,6 +37,7 @@ SIGNATURES = {
     "ie_sm_count": [],
     "ie_pack_conv_weights": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_pack_input_im2col3x3": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ie_conv_first_layer_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P],
     "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
     "ie_conv_set_mode": [_I, _I],
     "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],

@@ -81,11 +81,12 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 }
 
 // One-time CTA setup common to both kernels; returns the TMEM base address.
-__device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams& e, int stages, int warp, int lane) {
-  for (int i = threadIdx.x; i < kMaxCout; i += kThreads) t.bias()[i] = (i < e.cout && e.bias) ? e.bias[i] : 0.f;
+__device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams& e, int stages, int warp, int lane,
+                                              uint32_t full_count = 1) {
+  for (int i = threadIdx.x; i < kMaxCout; i += blockDim.x) t.bias()[i] = (i < e.cout && e.bias) ? e.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&t.full()[s], 1);
+      mbar_init(&t.full()[s], full_count);
       mbar_init(&t.empty()[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -791,6 +792,129 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// =================================================================================================
+// First layer: Conv2D(64, 3, 'same', relu) on the raw fp32 NHWC input (model_library.py:323/376, 196/235)
+// with the im2col fused into the kernel.  K = 9*C <= 64 is one 64-wide K block, so a tile is ONE stage of four
+// MMAs; there is no bf16 im2col raster in HBM (368 MB written + read back at 256 x 104^2).  Four extra
+// "builder" warps (one thread per tile row) gather each pixel's 3x3xC neighbourhood - three runs of 3*C
+// contiguous floats - straight from the input, convert to bf16 and write the 128-byte swizzled A row that TMA
+// would have written; generic-proxy writes are made visible to the tensor core with fence.proxy.async.
+// The source may be smaller than the raster (implicit zero padding to the network stride, see im2col).
+// =================================================================================================
+struct FirstParams {
+  EpiParams e;
+  const float* x;
+  int hs, ws;            // source size
+  int stages;
+};
+constexpr int kFirstThreads = 320;   // warp 0: weights, warp 1: MMA, warps 2-5: epilogue, warps 6-9: builders
+
+template <int C>
+__global__ void __launch_bounds__(kFirstThreads, 1)
+conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_y, const FirstParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  constexpr int kWBytes = 64 * 128;                       // [64 cout][64 k] bf16
+  uint8_t* a_base_ptr = base + kWBytes;
+  SmemTail t{a_base_ptr + p.stages * kABytes};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.e.m_tiles;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+  }
+  const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane, 4);
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(t.bres(), kWBytes);
+      tma_load_2d(base, &tm_b, t.bres(), 0, 0);
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, 64);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base_ptr));
+    const uint32_t b_lo = umma_desc_lo(smem_u32(base));
+    mbar_wait(t.bres(), 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+        const uint32_t a = a_lo0 + stage * (kABytes >> 4);
+        umma_bf16_ss_lo(d_tmem, a, b_lo, idesc, 0u);
+        umma_bf16_ss_lo(d_tmem, a + 2, b_lo + 2, idesc, 1u);
+        umma_bf16_ss_lo(d_tmem, a + 4, b_lo + 4, idesc, 1u);
+        umma_bf16_ss_lo(d_tmem, a + 6, b_lo + 6, idesc, 1u);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&t.tfull()[buf]);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp < 6) {
+    epilogue_loop(p.e, &tm_y, t, tmem_base, warp, lane);
+  } else {
+    // ================================ A-tile builders ==============================
+    const int row_local = (warp - 6) * 32 + lane;
+    constexpr int C3 = 3 * C;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int r = tile * kBlockM + row_local;
+      const int img = r / p.e.plane;
+      const int pr = r - img * p.e.plane;
+      const int yp = pr / p.e.wp;
+      const int y = yp - 1, x = pr - yp * p.e.wp - 1;
+      const bool interior = (r < p.e.R) && (y >= 0) && (y < p.e.hv) && (x >= 0) && (x < p.e.wv);
+      const float* centre = p.x + ((static_cast<long long>(img) * p.hs + y) * p.ws + (x - 1)) * C;   // (y, x-1, 0)
+      bool rowok[3], colok[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        rowok[d] = interior && (y + d - 1 >= 0) && (y + d - 1 < p.hs);
+        colok[d] = (x + d - 1 >= 0) && (x + d - 1 < p.ws);
+      }
+      float v[64];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        v[k] = 0.f;
+        if (k < 9 * C) {
+          constexpr int dummy = 0; (void)dummy;
+          const int dy = k / C3, i = k % C3, g = i / C;
+          if (rowok[dy] && colok[g]) v[k] = __ldg(centre + (dy - 1) * p.ws * C + i);
+        }
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      const uint32_t rowa = smem_u32(a_base_ptr + stage * kABytes) + row_local * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128u(rowa + ((j ^ (row_local & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // -------------------------------------------------------------------------------------------------
 int choose_n_tile(int cout, int epilogue) {
   if (epilogue != IE_EPI_BF16_RASTER) return ((cout + 15) / 16) * 16;
@@ -999,6 +1123,55 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   const int tiles = e.m_tiles * e.n_tiles;
   const int grid = tiles < grid_cap ? tiles : grid_cap;
   conv_stream_kernel<<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, int c, int h, int w, const void* w_packed,
+                                       const float* bias, int cout, int relu, void* y_bf16, int y_pitch, int y_coff,
+                                       void* stream) {
+  using namespace ie;
+  IE_REQUIRE(x && w_packed && y_bf16, "conv_first: null pointer");
+  IE_REQUIRE(n > 0 && hs > 0 && ws > 0 && hs <= h && ws <= w, "conv_first: source %dx%d must fit the %dx%d raster", hs, ws, h, w);
+  IE_REQUIRE(c == 3 || c == 5, "conv_first: fused first layer is built for 3 or 5 input channels (got %d); use "
+                               "ie_pack_input_im2col3x3 + ie_conv2d_nhwc_bf16", c);
+  IE_REQUIRE(cout == 64, "conv_first: cout must be 64 (got %d)", cout);
+  IE_REQUIRE(y_coff % 64 == 0 && y_coff + cout <= y_pitch && y_pitch % 8 == 0, "conv_first: bad output slice");
+  const long long R = (long long)n * (h + 2) * (w + 2);
+  IE_REQUIRE(R < (1ll << 31) - 4096, "conv_first: raster too large for 32-bit rows");
+  FirstParams p{};
+  p.e.R = (int)R;
+  p.e.plane = (h + 2) * (w + 2);
+  p.e.wp = w + 2;
+  p.e.hv = h;
+  p.e.wv = w;
+  p.e.cout = cout;
+  p.e.n_tile = 64;
+  p.e.n_tiles = 1;
+  p.e.m_tiles = (int)((R + kBlockM - 1) / kBlockM);
+  p.e.y_coff = y_coff;
+  p.e.relu = relu;
+  p.e.epilogue = IE_EPI_BF16_RASTER;
+  p.e.bias = bias;
+  p.x = x;
+  p.hs = hs;
+  p.ws = ws;
+  p.stages = 6;
+  CUtensorMap tm_b, tm_y;
+  int rc = make_tmap_2d_bf16(&tm_b, w_packed, 64, 64, 64, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm_y, y_bf16, (uint64_t)y_pitch, (uint64_t)R, (uint64_t)y_pitch, 64, 32);
+  if (rc) return rc;
+  const size_t smem = 1024 + 64 * 128 + (size_t)p.stages * kABytes + kTailBytes;
+  const int grid = p.e.m_tiles < sm_count() ? p.e.m_tiles : sm_count();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c == 5) {
+    IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    conv_first_kernel<5><<<grid, kFirstThreads, smem, st>>>(tm_b, tm_y, p);
+  } else {
+    IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    conv_first_kernel<3><<<grid, kFirstThreads, smem, st>>>(tm_b, tm_y, p);
+  }
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -90,7 +90,6 @@ class Engine:
         p = {}
         chans = dict(A["downs"])
         # encoder rasters per level l (resolution h >> l)
-        p["in0"] = R(h, w, self.k0)
         p["x0"] = R(h, w, 64)
         up_in = {}                                   # channels entering each coef up block
         prev = 1024
@@ -154,8 +153,15 @@ class Engine:
                 taps[name] = ops.raster_to_nhwc(dst)[:, :hv, :wv]
 
         # ---- encoder (model_library.py:376-386 / 235-244)
-        ops.pack_input_im2col3x3(x, p["in0"])
-        conv("layer0", p["in0"].slice(), p["x0"].slice(), k=1)
+        if c in ops.FIRST_LAYER_FUSED_CHANNELS and conv_fn == "ie_conv2d_nhwc_bf16":
+            ops.conv_first_layer(x, W["layer0"], Bv["layer0"], p["x0"].slice())        # im2col fused in-kernel
+            if taps is not None:
+                taps["layer0"] = ops.raster_to_nhwc(p["x0"].slice())
+        else:
+            if "in0" not in p:
+                p["in0"] = ops.new_raster(n, h, w, self.k0, self.device)
+            ops.pack_input_im2col3x3(x, p["in0"])
+            conv("layer0", p["in0"].slice(), p["x0"].slice(), k=1)
         cur = p["x0"].slice()
         up_in = {}
         prev = 1024

@@ -102,6 +102,26 @@ def pack_input_im2col3x3(x, out=None):
     return out
 
 
+FIRST_LAYER_FUSED_CHANNELS = (3, 5)
+
+
+def conv_first_layer(x, w_packed, bias, dst: Slice, relu=True):
+    """Conv2D(64, 3, 'same') on the raw fp32 NHWC input with the im2col fused into the kernel (c in 3, 5)."""
+    _lib.require_cuda(x)
+    n, hs, ws, c = x.shape
+    r = dst.r
+    assert x.is_contiguous() and r.n == n and r.h >= hs and r.w >= ws and w_packed.shape == (64, 64)
+    e0 = e1 = None
+    if CONV_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    call("ie_conv_first_layer_f32", ptr(x), n, hs, ws, c, r.h, r.w, ptr(w_packed), ptr(bias), dst.c, int(relu),
+         ptr(r.data), r.pitch, dst.coff, stream())
+    if e0 is not None:
+        e1.record()
+        CONV_EVENTS.append((e0, e1))
+
+
 def _desc(src: Slice, kh, kw, cout, relu, epilogue, dst: Slice | None, valid=None):
     r = src.r
     hv, wv = (r.h, r.w) if valid is None else valid

@@ -47,6 +47,30 @@ def test_im2col_first_layer(cuda):
     assert border_is_zero(dst)
 
 
+@pytest.mark.parametrize("c,n,hs,ws,h,w", [(5, 2, 16, 24, 16, 24), (3, 3, 13, 21, 16, 24), (5, 7, 100, 100, 104, 104)])
+def test_first_layer_fused_im2col(cuda, c, n, hs, ws, h, w):
+    """conv_first_kernel (im2col built in-kernel by the builder warps) == im2col raster + 1x1 GEMM, bit for bit,
+    and == Conv2D(64, 3, 'same', relu) of the (zero-padded) input (model_library.py:323, 376)."""
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = bf16_round(torch.rand(n, hs, ws, c, generator=g))
+    wt = bf16_round(torch.randn(3, 3, c, 64, generator=g) * 0.2)
+    b = torch.randn(64, generator=g) * 0.1
+    wp = ops.pack_conv_weights(wt.to(cuda), ktot_pad=64)
+    fused = ops.new_raster(n, h, w, 128, cuda)
+    fused.data.fill_(float("nan"))
+    ops.conv_first_layer(x.to(cuda), wp, b.to(cuda), fused.slice(64, 64))
+    src = ops.pack_input_im2col3x3(x.to(cuda), ops.new_raster(n, h, w, 64, cuda))
+    two = ops.new_raster(n, h, w, 64, cuda)
+    ops.conv2d(src.slice(), wp, b.to(cuda), two.slice(), k=1)
+    torch.cuda.synchronize()
+    assert torch.equal(fused.data[:, 64:], two.data)
+    assert bool(torch.isnan(fused.data[:, :64]).all())          # wrote only its slice
+    ref = omodel.conv2d_relu(F.pad(x, (0, 0, 0, w - ws, 0, h - hs)), (wt, b), "same")
+    got = ops.raster_to_nhwc(fused.slice(64, 64)).cpu()
+    assert torch.allclose(got, bf16_round(ref), atol=2e-2, rtol=2 ** -7)
+
+
 @pytest.mark.parametrize("c", [5, 2, 3, 9])
 def test_im2col_implicit_stride_padding(cuda, c):
     """A source smaller than the raster is zero-padded at the bottom/right (100x100 patches -> 104x104)."""
