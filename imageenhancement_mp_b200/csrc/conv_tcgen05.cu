@@ -47,8 +47,8 @@ constexpr size_t kMaxSmem = 227 * 1024;
 // Output-side description shared by both kernels.
 struct EpiParams {
   int R;             // raster rows
-  int plane;         // (h+2)*(w+2)
-  int wp;            // w+2
+  int plane;         // (h+1)*(w+1)
+  int wp;            // w+1
   int hv, wv;        // valid output extent
   int cout;
   int n_tile;
@@ -131,7 +131,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
     const int pr = r - img * p.plane;
     const int y = pr / p.wp;
     const int x = pr - y * p.wp;
-    const bool valid = (r < p.R) && (y >= 1) && (y <= p.hv) && (x >= 1) && (x <= p.wv);
+    const bool valid = (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
 
     mbar_wait(&tfull_bar[buf], use & 1u);
     tc_fence_after();
@@ -190,7 +190,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
       // them 16 TMEM columns at a time; the softmax re-reads TMEM instead of holding them in registers.
       const int nch = (p.cout + 15) >> 4;
       const bool sm_mode = (p.epilogue == IE_EPI_F32_SOFTMAX);
-      const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + (x - 1);
+      const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + x;
       if (nch == 1) {
         // <= 16 channels (the `coef` head): one TMEM read, everything in registers.  Valid pixels of a warp's
         // 32 raster rows are consecutive in the NHWC output (the skipped border pixels have no output slot), so
@@ -599,7 +599,7 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
     const int y = pr / p.wp;
     const int x = pr - y * p.wp;
     const bool valid = (m >= 1) && (m <= wp_.tile_rows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) &&
-                       (x >= 1) && (x <= p.wv);
+                       (x < p.wv);
     mbar_wait(&t.tfull()[buf], use & 1u);
     tc_fence_after();
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
@@ -876,7 +876,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
       const int img = r / p.e.plane;
       const int pr = r - img * p.e.plane;
       const int yp = pr / p.e.wp;
-      const int y = yp - 1, x = pr - yp * p.e.wp - 1;
+      const int y = yp - 1, x = pr - yp * p.e.wp;
       const bool interior = (r < p.e.R) && (y >= 0) && (y < p.e.hv) && (x >= 0) && (x < p.e.wv);
       const float* centre = p.x + ((static_cast<long long>(img) * p.hs + y) * p.ws + (x - 1)) * C;   // (y, x-1, 0)
       bool rowok[3], colok[3];
@@ -932,7 +932,7 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
   IE_REQUIRE(d->x_pitch % 8 == 0, "conv: x_pitch must be a multiple of 8");
   IE_REQUIRE(d->cout > 0 && d->cout <= kMaxCout, "conv: cout=%d out of range", d->cout);
   IE_REQUIRE(d->hv >= 1 && d->hv <= d->h && d->wv >= 1 && d->wv <= d->w, "conv: bad valid extent %d x %d", d->hv, d->wv);
-  IE_REQUIRE((long long)d->n_img * (d->h + 2) * (d->w + 2) < (1ll << 31) - 4096, "conv: raster too large for 32-bit rows");
+  IE_REQUIRE((long long)d->n_img * (d->h + 1) * (d->w + 1) < (1ll << 31) - 4096, "conv: raster too large for 32-bit rows");
   IE_REQUIRE((d->kh == 3 && d->kw == 3) || (d->kh == 2 && d->kw == 2) || (d->kh == 1 && d->kw == 1),
              "conv: unsupported kernel size %dx%d", d->kh, d->kw);
   if (d->epilogue == IE_EPI_BF16_RASTER) {
@@ -969,11 +969,11 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   using namespace ie;
   int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32);
   if (rc) return rc;
-  const long long R = (long long)d->n_img * (d->h + 2) * (d->w + 2);
-  const int wp = d->w + 2;
+  const long long R = (long long)d->n_img * (d->h + 1) * (d->w + 1);
+  const int wp = d->w + 1;
   EpiParams e{};
   e.R = (int)R;
-  e.plane = (d->h + 2) * wp;
+  e.plane = (d->h + 1) * wp;
   e.wp = wp;
   e.hv = d->hv;
   e.wv = d->wv;
@@ -1137,12 +1137,12 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
                                "ie_pack_input_im2col3x3 + ie_conv2d_nhwc_bf16", c);
   IE_REQUIRE(cout == 64, "conv_first: cout must be 64 (got %d)", cout);
   IE_REQUIRE(y_coff % 64 == 0 && y_coff + cout <= y_pitch && y_pitch % 8 == 0, "conv_first: bad output slice");
-  const long long R = (long long)n * (h + 2) * (w + 2);
+  const long long R = (long long)n * (h + 1) * (w + 1);
   IE_REQUIRE(R < (1ll << 31) - 4096, "conv_first: raster too large for 32-bit rows");
   FirstParams p{};
   p.e.R = (int)R;
-  p.e.plane = (h + 2) * (w + 2);
-  p.e.wp = w + 2;
+  p.e.plane = (h + 1) * (w + 1);
+  p.e.wp = w + 1;
   p.e.hv = h;
   p.e.wv = w;
   p.e.cout = cout;

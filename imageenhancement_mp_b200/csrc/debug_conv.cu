@@ -38,7 +38,7 @@ __device__ bool naive_valid(const NaiveParams& p, long long r, int& img, int& y,
   const int pr = (int)(r - (long long)img * p.plane);
   y = pr / p.wp;
   x = pr - y * p.wp;
-  return y >= 1 && y <= p.hv && x >= 1 && x <= p.wv;
+  return y >= 1 && y <= p.hv && x < p.wv;
 }
 
 __global__ void naive_conv_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
@@ -63,7 +63,7 @@ __global__ void naive_conv_f32_kernel(const __nv_bfloat16* __restrict__ x, const
   if (r >= p.R) return;
   int img, yy, xx;
   if (!naive_valid(p, r, img, yy, xx)) return;
-  const long long pix = ((long long)img * p.hv + (yy - 1)) * p.wv + (xx - 1);
+  const long long pix = ((long long)img * p.hv + (yy - 1)) * p.wv + xx;
   float v[256];
   float mx = -INFINITY;
   for (int co = 0; co < p.cout; ++co) {
@@ -92,7 +92,7 @@ extern "C" int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const
   using namespace ie;
   if (int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32)) return rc;
   NaiveParams p{};
-  const int wp = d->w + 2;
+  const int wp = d->w + 1;
   if (d->kh == 3 && d->kw == 3) {
     p.ntaps = 9;
     for (int i = 0; i < 3; ++i)
@@ -106,8 +106,8 @@ extern "C" int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const
   } else {
     IE_REQUIRE(false, "debug conv: unsupported kernel size");
   }
-  p.R = (long long)d->n_img * (d->h + 2) * wp;
-  p.plane = (d->h + 2) * wp;
+  p.R = (long long)d->n_img * (d->h + 1) * wp;
+  p.plane = (d->h + 1) * wp;
   p.wp = wp;
   p.hv = d->hv; p.wv = d->wv;
   p.cin = d->cin; p.x_pitch = d->x_pitch; p.x_coff = d->x_coff;

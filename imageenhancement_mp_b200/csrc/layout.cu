@@ -33,7 +33,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int taps, in
 }
 
 // ------------------------------------------------------------------------------- input im2col
-// grid = (ceil((w+2)*kvec / threads), h+2, n): blockIdx.y/z give the raster row and image, so no thread
+// grid = (ceil((w+1)*kvec / threads), h+1, n): blockIdx.y/z give the raster row and image, so no thread
 // divides a 64-bit index.  One thread per (padded x, 16-byte chunk) = 8 consecutive k of the im2col row.
 // For filter row dy the 3*c values k = dy*3c + i are CONTIGUOUS in the source: row y+dy-1, floats
 // (x-1)*c + i, so no per-element tap arithmetic is needed.
@@ -42,12 +42,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ hwio, int taps, in
 // copy of the input (pixels of the padding still see their real neighbours, exactly like a padded input).
 __global__ void __launch_bounds__(256)
 im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int c, uint4* __restrict__ out, int kvec) {
-  const int wp = w + 2;
+  const int wp = w + 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wp * kvec) return;
   const int xp = idx / kvec, chunk = idx - xp * kvec;
   const int yp = blockIdx.y, img = blockIdx.z;
-  const int y = yp - 1, xx = xp - 1;
+  const int y = yp - 1, xx = xp;                          // raster row 0 / column w are the shared zero border
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) f[e] = 0.f;
@@ -82,23 +82,23 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
       }
     }
   }
-  out[(((long long)img * (h + 2) + yp) * wp + xp) * kvec + chunk] = pack8(f);
+  out[(((long long)img * (h + 1) + yp) * wp + xp) * kvec + chunk] = pack8(f);
 }
 
 // ------------------------------------------------------------------------------- max-pool 2x2
-// grid = (ceil((wo+2)*cvec / 256), ho+2, n); one thread per (padded output x, 16-byte channel chunk).
+// grid = (ceil((wo+1)*cvec / 256), ho+1, n); one thread per (padded output x, 16-byte channel chunk).
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const int ho = h >> 1, wo = w >> 1, wpo = wo + 2;
+  const int ho = h >> 1, wo = w >> 1, wpo = wo + 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wpo * cvec) return;
   const int ox = idx / cvec, cv = idx - ox * cvec;
   const int oy = blockIdx.y, img = blockIdx.z;
   uint4 res = make_uint4(0, 0, 0, 0);
-  if (oy >= 1 && oy <= ho && ox >= 1 && ox <= wo) {
-    const int wpi = w + 2;
-    const long long rin = ((long long)img * (h + 2) + (2 * oy - 1)) * wpi + (2 * ox - 1);
+  if (oy >= 1 && oy <= ho && ox < wo) {
+    const int wpi = w + 1;
+    const long long rin = ((long long)img * (h + 1) + (2 * oy - 1)) * wpi + 2 * ox;
     const uint4* p = x + rin * x_pitch_v + x_coff_v + cv;
     float a[8], b[8], c[8], d[8], m[8];
     unpack8(__ldg(p), a);
@@ -109,22 +109,22 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
     for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
     res = pack8(m);
   }
-  const long long ro = ((long long)img * (ho + 2) + oy) * wpo + ox;
+  const long long ro = ((long long)img * (ho + 1) + oy) * wpo + ox;
   y[ro * y_pitch_v + y_coff_v + cv] = res;
 }
 
 // ------------------------------------------------------------------------------- bilinear upsample
 // Half-pixel centres: src = (dst + 0.5)/s - 0.5; lower = max(floor(src),0), upper = min(ceil(src), size-1).
-// grid = (ceil((wo+2)*cvec / 256), ho+2, n): the vertical taps / weights are block-uniform.
+// grid = (ceil((wo+1)*cvec / 256), ho+1, n): the vertical taps / weights are block-uniform.
 __global__ void __launch_bounds__(256)
 upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v, int s,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const int ho = h * s, wo = w * s, wpo = wo + 2;
+  const int ho = h * s, wo = w * s, wpo = wo + 1;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wpo * cvec) return;
   const int oxp = idx / cvec, cv = idx - oxp * cvec;
   const int oyp = blockIdx.y, img = blockIdx.z;
-  const int oy = oyp - 1, ox = oxp - 1;
+  const int oy = oyp - 1, ox = oxp;
   uint4 res = make_uint4(0, 0, 0, 0);
   if (oy >= 0 && oy < ho && ox >= 0 && ox < wo) {
     const float inv = 1.f / (float)s;
@@ -134,14 +134,14 @@ upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
     const int y0 = max((int)fy, 0), y1 = min((int)ceilf(sy), h - 1);
     const int x0 = max((int)fx, 0), x1 = min((int)ceilf(sx), w - 1);
     const float ly = sy - fy, lx = sx - fx;
-    const int wpi = w + 2;
-    const long long base = (long long)img * (h + 2) * wpi;
+    const int wpi = w + 1;
+    const long long base = (long long)img * (h + 1) * wpi;
     const uint4* p = x + x_coff_v + cv;
     float a[8], b[8], c[8], d[8], o[8];
-    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x0 + 1)) * x_pitch_v), a);
-    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x1 + 1)) * x_pitch_v), b);
-    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x0 + 1)) * x_pitch_v), c);
-    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x1 + 1)) * x_pitch_v), d);
+    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x0) * x_pitch_v), a);
+    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x1) * x_pitch_v), b);
+    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x0) * x_pitch_v), c);
+    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x1) * x_pitch_v), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float top = a[e] + (b[e] - a[e]) * lx;
@@ -150,7 +150,7 @@ upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
     }
     res = pack8(o);
   }
-  const long long ro = ((long long)img * (ho + 2) + oyp) * wpo + oxp;
+  const long long ro = ((long long)img * (ho + 1) + oyp) * wpo + oxp;
   y[ro * y_pitch_v + y_coff_v + cv] = res;
 }
 
@@ -166,17 +166,18 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
   const int jb = idx / cvec, cv = idx - jb * cvec;
   const int j = jb - 1, i = (int)blockIdx.y - 1, img = blockIdx.z;
   const int y0 = max(i, 0), y1 = min(i + 1, h - 1), x0 = max(j, 0), x1 = min(j + 1, w - 1);
-  const int wpi = w + 2;
-  const long long base = (long long)img * (h + 2) * wpi;
+  const int wpi = w + 1;
+  const long long base = (long long)img * (h + 1) * wpi;
   const uint4* p = x + x_coff_v + cv;
   float a[8], b[8], c[8], d[8];
-  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x0 + 1)) * x_pitch_v), a);
-  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + (x1 + 1)) * x_pitch_v), b);
-  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x0 + 1)) * x_pitch_v), c);
-  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + (x1 + 1)) * x_pitch_v), d);
-  const int wo = 2 * w, ho = 2 * h, wpo = wo + 2;
-  // output pixel (2i+1+u, 2j+1+v), u, v in {0,1}; raster position = +1 in both coordinates
-  const long long ro = ((long long)img * (ho + 2) + (2 * i + 2)) * wpo + (2 * j + 2);
+  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x0) * x_pitch_v), a);
+  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x1) * x_pitch_v), b);
+  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x0) * x_pitch_v), c);
+  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x1) * x_pitch_v), d);
+  const int wo = 2 * w, ho = 2 * h, wpo = wo + 1;
+  // output pixel (oy, ox) = (2i+1+u, 2j+1+v), u, v in {0,1}; raster position (oy + 1, ox): oy = -1 is the
+  // shared zero row, ox = wo the shared zero column; oy = ho and ox = -1 have no slot
+  const long long ro = ((long long)img * (ho + 1) + (2 * i + 2)) * wpo + (2 * j + 1);
   uint4* q = y + y_coff_v + cv;
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
@@ -186,6 +187,7 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
     for (int v = 0; v < 2; ++v) {
       const float lx = v ? 0.75f : 0.25f;
       const bool ok = row_ok && (2 * j + 1 + v >= 0) && (2 * j + 1 + v < wo);
+      if (2 * i + 1 + u >= ho || 2 * j + 1 + v < 0) continue;       // outside the raster
       uint4 res = make_uint4(0, 0, 0, 0);
       if (ok) {
         float o[8];
@@ -208,8 +210,8 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
                                     float* __restrict__ mean, int c, float scale) {
   const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int cb = blockIdx.x, img = blockIdx.y;
-  const int wp = w + 2;
-  const long long base = (long long)img * (h + 2) * wp;
+  const int wp = w + 1;
+  const long long base = (long long)img * (h + 1) * wp;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -217,7 +219,7 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
   for (int pix = blockIdx.z * 32 + pl; pix < npix; pix += gridDim.z * 32) {
     const int yy = pix / w, xx = pix - yy * w;
     float f[8];
-    unpack8(x[(base + (long long)(yy + 1) * wp + (xx + 1)) * x_pitch_v + x_coff_v + cb * 8 + vl], f);
+    unpack8(x[(base + (long long)(yy + 1) * wp + xx) * x_pitch_v + x_coff_v + cb * 8 + vl], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += f[e];
   }
@@ -235,17 +237,17 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
 
 __global__ void broadcast_kernel(const float* __restrict__ vec, int n, int kh, int kw, int cvec, int c,
                                  uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const long long total = (long long)n * (kh + 2) * (kw + 2) * cvec;
+  const long long total = (long long)n * (kh + 1) * (kw + 1) * cvec;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int cv = (int)(t % cvec);
   const long long ro = t / cvec;
-  const int wp = kw + 2, pl = (kh + 2) * wp;
+  const int wp = kw + 1, pl = (kh + 1) * wp;
   const int img = (int)(ro / pl);
   const int pr = (int)(ro - (long long)img * pl);
   const int oy = pr / wp, ox = pr % wp;
   uint4 res = make_uint4(0, 0, 0, 0);
-  if (oy >= 1 && oy <= kh && ox >= 1 && ox <= kw) {
+  if (oy >= 1 && oy <= kh && ox < kw) {
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = vec[(long long)img * c + cv * 8 + e];
@@ -264,7 +266,7 @@ __global__ void raster_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int n
   const int xx = (int)(pix % w);
   const int yy = (int)((pix / w) % h);
   const int img = (int)(pix / ((long long)w * h));
-  const long long r = ((long long)img * (h + 2) + yy + 1) * (w + 2) + xx + 1;
+  const long long r = ((long long)img * (h + 1) + yy + 1) * (w + 1) + xx;
   y[t] = __bfloat162float(x[r * x_pitch + x_coff + ch]);
 }
 
@@ -325,11 +327,11 @@ extern "C" int ie_pack_input_im2col3x3(const float* x, int n, int hs, int ws, in
   IE_REQUIRE(x && raster_bf16, "pack_input: null pointer");
   IE_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && 9 * c <= 1024, "pack_input: need 9*c <= 1024 (c=%d)", c);
   IE_REQUIRE(hs > 0 && ws > 0 && hs <= h && ws <= w, "pack_input: source %dx%d must fit the %dx%d raster", hs, ws, h, w);
-  IE_REQUIRE(n <= 65535 && h + 2 <= 65535, "pack_input: grid too large");
+  IE_REQUIRE(n <= 65535 && h + 1 <= 65535, "pack_input: grid too large");
   const int kvec = ((9 * c + 63) / 64) * 8;      // row width in 16-byte chunks: 9*c rounded up to 64 channels
   int nb;
-  const int threads = row_block((long long)(w + 2) * kvec, &nb);
-  dim3 grid(nb, h + 2, n);
+  const int threads = row_block((long long)(w + 1) * kvec, &nb);
+  dim3 grid(nb, h + 1, n);
   im2col3x3_kernel<<<grid, threads, 0, S(stream)>>>(x, hs, ws, h, w, c, static_cast<uint4*>(raster_bf16), kvec);
   IE_LAUNCH_CHECK();
   return IE_OK;
@@ -348,8 +350,8 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
   if (int rc = check_slice("maxpool2(y)", c, y_pitch, y_coff)) return rc;
   IE_REQUIRE(n <= 65535 && h / 2 + 2 <= 65535, "maxpool2: grid too large");
   int nb;
-  const int threads = row_block((long long)(w / 2 + 2) * (c / 8), &nb);
-  dim3 grid(nb, h / 2 + 2, n);
+  const int threads = row_block((long long)(w / 2 + 1) * (c / 8), &nb);
+  dim3 grid(nb, h / 2 + 1, n);
   maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8,
                                               static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
   IE_LAUNCH_CHECK();
@@ -371,8 +373,8 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
     IE_LAUNCH_CHECK();
     return IE_OK;
   }
-  const int threads = row_block((long long)(w * scale + 2) * (c / 8), &nb);
-  dim3 grid(nb, h * scale + 2, n);
+  const int threads = row_block((long long)(w * scale + 1) * (c / 8), &nb);
+  dim3 grid(nb, h * scale + 1, n);
   upsample_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8, scale,
                                               static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
   IE_LAUNCH_CHECK();
@@ -403,7 +405,7 @@ extern "C" int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int
                                     void* stream) {
   IE_REQUIRE(vec && y && n > 0 && kh > 0 && kw > 0, "broadcast: bad arguments");
   if (int rc = check_slice("broadcast(y)", c, y_pitch, y_coff)) return rc;
-  const long long total = (long long)n * (kh + 2) * (kw + 2) * (c / 8);
+  const long long total = (long long)n * (kh + 1) * (kw + 1) * (c / 8);
   broadcast_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(vec, n, kh, kw, c / 8, c, static_cast<uint4*>(y),
                                                                   y_pitch / 8, y_coff / 8);
   IE_LAUNCH_CHECK();

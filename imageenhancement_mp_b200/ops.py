@@ -1,7 +1,8 @@
 """Python-level wrappers of the C ABI, operating on torch CUDA tensors.
 
-A ``Raster`` is the library's activation container: bf16 ``[n*(h+2)*(w+2), pitch]`` with a
-one-pixel zero border per image (see include/imgenh_b200.h).  ``Slice`` is a channel window
+A ``Raster`` is the library's activation container: bf16 ``[n*(h+1)*(w+1), pitch]``, every image
+preceded by one zero row and every image row followed by one zero pixel (a shared one-pixel
+border, see include/imgenh_b200.h).  ``Slice`` is a channel window
 of a raster - how the reference's ``layers.concatenate([up, skip])``
 (/root/reference/model_library.py:96) is expressed without a copy.
 """
@@ -44,7 +45,7 @@ class Raster:
 
     @property
     def rows(self):
-        return self.n * (self.h + 2) * (self.w + 2)
+        return self.n * (self.h + 1) * (self.w + 1)
 
     def slice(self, coff=0, c=None):
         return Slice(self, coff, self.pitch - coff if c is None else c)
@@ -59,7 +60,7 @@ class Slice:
 
 def new_raster(n, h, w, c, device):
     # torch.empty: every row (borders included) is written by the producing kernel
-    return Raster(torch.empty(n * (h + 2) * (w + 2), c, dtype=torch.bfloat16, device=device), n, h, w)
+    return Raster(torch.empty(n * (h + 1) * (w + 1), c, dtype=torch.bfloat16, device=device), n, h, w)
 
 
 def conv_n_tile(cout, epilogue):

@@ -14,11 +14,15 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
  *   - return 0 on success, <0 on error; ie_last_error() gives the message for this thread.
  *
- * Activation layout ("raster"): bf16, NHWC, each image stored with a one-pixel zero border:
- *   rows = n_img * (h+2) * (w+2), row r = (n*(h+2) + y)*(w+2) + x, `pitch` channels per row.
- *   A k x k 'same' convolution tap is then a constant row shift of this 2-D [rows][pitch]
- *   matrix, so TMA fetches every tap with a plain 2-D box and the zero border supplies the
- *   padding.  Channel slices (coff, c) of a wider raster are how concatenation is expressed.
+ * Activation layout ("raster"): bf16, NHWC, with a SHARED one-pixel zero border: every image is preceded by
+ *   one zero row and every image row is followed by one zero pixel,
+ *   rows = n_img * (h+1) * (w+1), pixel (n, y, x) at row r = (n*(h+1) + y + 1)*(w+1) + x, `pitch` channels per row.
+ *   The zero pixel ending row y is also the left neighbour of row y+1, the zero row of image n+1 is also the
+ *   bottom border of image n, and rows before the first / after the last image do not exist (TMA fills
+ *   out-of-range rows with zeros).  A k x k 'same' convolution tap is then a constant row shift of this 2-D
+ *   [rows][pitch] matrix, so TMA fetches every tap with a plain 2-D box and the border supplies the padding -
+ *   at (h+1)(w+1)/(hw) - 1 extra rows (8 % at 26x26) instead of 16 % for a full border.
+ *   Channel slices (coff, c) of a wider raster are how concatenation is expressed.
  */
 #ifndef IMGENH_B200_H
 #define IMGENH_B200_H
@@ -41,7 +45,7 @@ extern "C" {
 #define IE_EPI_F32_SOFTMAX 2 /* as 1, then softmax over cout; y_aux (nullable) receives the logits        */
 
 typedef struct ie_conv_desc {
-  int32_t n_img, h, w; /* interior size of the INPUT raster (rows = n_img*(h+2)*(w+2))                   */
+  int32_t n_img, h, w; /* interior size of the INPUT raster (rows = n_img*(h+1)*(w+1))                   */
   int32_t hv, wv;      /* valid OUTPUT extent inside the same raster geometry: (h,w) for 'same',
                           (h-1,w-1) for the 2x2 'valid' conv; everything outside is written as zero      */
   int32_t kh, kw;      /* 3x3 ('same', centred), 2x2 ('valid', taps at +0/+1) or 1x1                     */
@@ -66,7 +70,7 @@ int ie_sm_count(void);
 int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, int ktot_pad, void* packed_bf16,
                          void* stream);
 
-/* fp32 NHWC [n][hs][ws][c] -> bf16 raster [n*(h+2)*(w+2)][kpad], kpad = 9*c rounded up to a multiple of 64,
+/* fp32 NHWC [n][hs][ws][c] -> bf16 raster [n*(h+1)*(w+1)][kpad], kpad = 9*c rounded up to a multiple of 64,
  * holding each pixel's zero-padded 3x3xc neighbourhood, k = (i*3+j)*c + ch (rest zero): turns the first
  * conv (model_library.py:323/376, 196/235) into a 1x1 GEMM with K = kpad.  hs <= h, ws <= w: the source
  * is implicitly zero-padded at the bottom/right to the raster size (the network-stride padding).       */

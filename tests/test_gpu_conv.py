@@ -16,7 +16,7 @@ def to_raster(x):
     """fp32 NHWC (cuda) -> ops.Raster with a zero border."""
     from imageenhancement_mp_b200 import ops
     n, h, w, c = x.shape
-    data = F.pad(x, (0, 0, 1, 1, 1, 1)).reshape(-1, c).to(torch.bfloat16).contiguous()
+    data = F.pad(x, (0, 0, 0, 1, 1, 0)).reshape(-1, c).to(torch.bfloat16).contiguous()   # zero row above, zero pixel right
     return ops.Raster(data, n, h, w)
 
 
@@ -78,10 +78,10 @@ def test_conv_bf16_vs_cpu(cuda, n, h, w, cin, cout, k):
         got = got[:, :h - 1, :w - 1]
     assert_close_bf16(got, ref, f"conv {k}x{k} {cin}->{cout}")
     # the zero border (and everything outside the valid extent) must be exactly zero
-    full = dst.data.float().view(n, h + 2, w + 2, cout)
+    full = dst.data.float().view(n, h + 1, w + 1, cout)
     hv, wv = (h - 1, w - 1) if k == 2 else (h, w)
-    mask = torch.ones(h + 2, w + 2, dtype=torch.bool, device=cuda)
-    mask[1:hv + 1, 1:wv + 1] = False
+    mask = torch.ones(h + 1, w + 1, dtype=torch.bool, device=cuda)
+    mask[1:hv + 1, 0:wv] = False
     assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
 
 
@@ -112,9 +112,9 @@ def test_conv_narrow_flavours(cuda, mode, n, h, w, cin):
     finally:
         lib.ie_conv_set_mode(-1, 0)
     assert_close_bf16(ops.raster_to_nhwc(dst.slice()).cpu(), ref, f"flavour {mode} {cin}->64")
-    full = dst.data.float().view(n, h + 2, w + 2, 64)
-    mask = torch.ones(h + 2, w + 2, dtype=torch.bool, device=cuda)
-    mask[1:h + 1, 1:w + 1] = False
+    full = dst.data.float().view(n, h + 1, w + 1, 64)
+    mask = torch.ones(h + 1, w + 1, dtype=torch.bool, device=cuda)
+    mask[1:h + 1, 0:w] = False
     assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
 
 
