@@ -18,11 +18,10 @@
 
 namespace ie {
 
-constexpr int kPxPerThread = 4;
 constexpr int kMaxK = 15;
-constexpr int kRowRegs = ((kPxPerThread + kMaxK - 1 + 3) / 4) * 4;   // 20
 
 struct KpnTiling {
+  int px;                // consecutive x per thread (4 or 8)
   int tx, ty;            // threads per tile row / rows per tile
   int tiles_x, tiles_y;
   int sw, sh;            // smem tile pitch (floats, multiple of 4) and rows
@@ -33,12 +32,13 @@ struct KpnTiling {
 
 // KK / BPAD: compile-time kernel size and basis pitch of the hot configuration (15, 10) - every basis load then
 // has an immediate offset and the tap loops carry no predicates; 0 = run-time values (any odd K <= 15, any B).
-template <int BC, int KK, int BPAD>
-__global__ void __launch_bounds__(256, 2)
+template <int BC, int KK, int BPAD, int kPxPerThread>
+__global__ void __launch_bounds__(256, kPxPerThread == 4 ? 2 : 1)
 kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* __restrict__ coef, int Hc, int Wc,
                  const float* __restrict__ bas, float* __restrict__ out, int H, int W, int T, int K_rt, int B,
                  const KpnTiling tl) {
   extern __shared__ float smem[];
+  constexpr int kRowRegs = ((kPxPerThread + kMaxK - 1 + 3) / 4) * 4;   // 20 / 24
   const int K = KK ? KK : K_rt;
   const int halo = K - 1;
   const int sw = tl.sw, sh = tl.sh, bpad = BPAD ? BPAD : tl.bpad;
@@ -123,42 +123,34 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
     const float* bas_t = s_bas + tl_ * K * K * bpad;
 
     for (int ch = 0; ch < nchunk; ++ch) {
-      float g[kPxPerThread][BC];
+      // accumulators as fp32 PAIRS over the basis index: Blackwell's packed FFMA2 (fma.rn.f32x2) does two
+      // IEEE fp32 FMAs per issue slot - a scalar FFMA stream tops out at half the FP32 lanes on sm_100.
+      float2 g[kPxPerThread][BC / 2];
 #pragma unroll
       for (int p = 0; p < kPxPerThread; ++p)
 #pragma unroll
-        for (int b = 0; b < BC; ++b) g[p][b] = 0.f;
+        for (int b = 0; b < BC / 2; ++b) g[p][b] = make_float2(0.f, 0.f);
 
       for (int i = 0; i < K; ++i) {
-        float row[kRowRegs];
+        float2 row[kRowRegs];               // every burst value duplicated into both halves of a pair
         const float4* rp = reinterpret_cast<const float4*>(sb_t + i * sw);
 #pragma unroll
         for (int v = 0; v < kRowRegs / 4; ++v) {
           const float4 q = rp[v];
-          row[4 * v] = q.x; row[4 * v + 1] = q.y; row[4 * v + 2] = q.z; row[4 * v + 3] = q.w;
+          row[4 * v] = make_float2(q.x, q.x); row[4 * v + 1] = make_float2(q.y, q.y);
+          row[4 * v + 2] = make_float2(q.z, q.z); row[4 * v + 3] = make_float2(q.w, q.w);
         }
         const float* bp = bas_t + (i * K) * bpad + ch * BC;
 #pragma unroll
         for (int j = 0; j < (KK ? KK : kMaxK); ++j) {
           if (KK || j < K) {
-            float bv[BC];
-            if constexpr (BC % 4 == 0) {
+            float2 bv[BC / 2];
 #pragma unroll
-              for (int v = 0; v < BC / 4; ++v) {
-                const float4 q = *reinterpret_cast<const float4*>(bp + j * bpad + 4 * v);
-                bv[4 * v] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
-              }
-            } else {
-#pragma unroll
-              for (int v = 0; v < BC / 2; ++v) {
-                const float2 q = *reinterpret_cast<const float2*>(bp + j * bpad + 2 * v);
-                bv[2 * v] = q.x; bv[2 * v + 1] = q.y;
-              }
-            }
+            for (int v = 0; v < BC / 2; ++v) bv[v] = *reinterpret_cast<const float2*>(bp + j * bpad + 2 * v);
 #pragma unroll
             for (int p = 0; p < kPxPerThread; ++p)
 #pragma unroll
-              for (int b = 0; b < BC; ++b) g[p][b] = fmaf(row[j + p], bv[b], g[p][b]);
+              for (int b = 0; b < BC / 2; ++b) g[p][b] = __ffma2_rn(row[j + p], bv[b], g[p][b]);
           }
         }
       }
@@ -170,7 +162,7 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
             const float* cp = coef + (coef_base + p) * B + ch * BC;
 #pragma unroll
             for (int b = 0; b < BC; ++b)
-              if (ch * BC + b < B) res[p] = fmaf(__ldg(cp + b), g[p][b], res[p]);
+              if (ch * BC + b < B) res[p] = fmaf(__ldg(cp + b), (b & 1) ? g[p][b >> 1].y : g[p][b >> 1].x, res[p]);
           }
         }
       }
@@ -194,12 +186,15 @@ kpn_apply_kernel(const float* __restrict__ burst, int burst_pitch, const float* 
 }
 
 // Tiles: as few 128-px-wide columns of tiles as cover W, each an equal multiple of 4 px; rows balanced over H.
-static KpnTiling kpn_tiling(int h, int w, int T, int K, int B, int BC) {
+static KpnTiling kpn_tiling(int h, int w, int T, int K, int B, int BC, int px) {
   KpnTiling t{};
-  t.tiles_x = (w + 127) / 128;
-  const int tile_w = (((w + t.tiles_x - 1) / t.tiles_x) + 3) / 4 * 4;
-  t.tx = tile_w / kPxPerThread;
+  t.px = px;
+  const int max_tile_w = 32 * px;
+  t.tiles_x = (w + max_tile_w - 1) / max_tile_w;
+  const int tile_w = (((w + t.tiles_x - 1) / t.tiles_x) + px - 1) / px * px;
+  t.tx = tile_w / px;
   int ty = 256 / t.tx;
+  if (ty > 32) ty = 32;
   t.tiles_y = (h + ty - 1) / ty;
   t.ty = (h + t.tiles_y - 1) / t.tiles_y;
   const int halo = K - 1;
@@ -226,22 +221,25 @@ extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float
   IE_REQUIRE(hc >= h && wc >= w, "kpn_apply: coef extent %dx%d smaller than the image %dx%d", hc, wc, h, w);
   const bool ten = (B % 10 == 0);
   const int BC = ten ? 10 : 8;
-  const KpnTiling tl = kpn_tiling(h, w, T, K, B, BC);
+  const bool hot = ten && K == 15 && B == 10;                 // eval.py defaults (K=15, B=10)
+  const int px = 4;      // 8 px per thread (one block of 8 warps per SM) measured slower on B200: 1.94 vs 1.38 ms at cfg2
+  const KpnTiling tl = kpn_tiling(h, w, T, K, B, BC, px);
   const long long blocks = (long long)n * tl.tiles_x * tl.tiles_y;
   IE_REQUIRE(blocks < (1ll << 31), "kpn_apply: too many tiles");
   IE_REQUIRE(tl.smem_bytes <= 200 * 1024, "kpn_apply: T=%d B=%d needs %zu bytes of shared memory", T, B, tl.smem_bytes);
   const int threads = ((tl.tx * tl.ty + 31) / 32) * 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define IE_LAUNCH_KPN(BC_, KK_, BPAD_)                                                                              \
+#define IE_LAUNCH_KPN(BC_, KK_, BPAD_, PX_)                                                                         \
   do {                                                                                                                \
-    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<BC_, KK_, BPAD_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+    IE_CUDA(cudaFuncSetAttribute(kpn_apply_kernel<BC_, KK_, BPAD_, PX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)tl.smem_bytes));                                                                \
-    kpn_apply_kernel<BC_, KK_, BPAD_><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(                              \
+    kpn_apply_kernel<BC_, KK_, BPAD_, PX_><<<(unsigned)blocks, threads, tl.smem_bytes, st>>>(                         \
         burst, burst_pitch, coef, hc, wc, bas, out, h, w, T, K, B, tl);                                               \
   } while (0)
-  if (ten && K == 15 && B == 10) IE_LAUNCH_KPN(10, 15, 10);      // eval.py defaults (K=15, B=10)
-  else if (ten) IE_LAUNCH_KPN(10, 0, 0);
-  else IE_LAUNCH_KPN(8, 0, 0);
+  if (hot && px == 8) IE_LAUNCH_KPN(10, 15, 10, 8);
+  else if (hot) IE_LAUNCH_KPN(10, 15, 10, 4);
+  else if (ten) IE_LAUNCH_KPN(10, 0, 0, 4);
+  else IE_LAUNCH_KPN(8, 0, 0, 4);
 #undef IE_LAUNCH_KPN
   IE_LAUNCH_CHECK();
   return IE_OK;

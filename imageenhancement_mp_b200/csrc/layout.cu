@@ -388,7 +388,7 @@ extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int
   if (int rc = check_slice("channel_mean(x)", c, x_pitch, x_coff)) return rc;
   IE_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
   const int npix = h * w;
-  int splits = (2 * sm_count() + (c / 64) * n - 1) / ((c / 64) * n);
+  int splits = (8 * sm_count() + (c / 64) * n - 1) / ((c / 64) * n);       // >= 8 blocks per SM in flight
   const int max_splits = (npix + 31) / 32;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
