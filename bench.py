@@ -145,7 +145,7 @@ def run_reference(args, cfg_name):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------- GPU arm
@@ -287,10 +287,23 @@ def run_ours(args, cfg_name):
         v, dt, cores = cpu_oracle_rate(sample_n, h, w, params, W)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{sample_n} images of {h}x{w}, forward + eval metrics, one pass ({dt:.1f} s)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line of the contract, written to the real stdout (see main: fd 1 is parked on stderr while
+    the benchmark runs, because NCCL prints its version banner to stdout from C)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

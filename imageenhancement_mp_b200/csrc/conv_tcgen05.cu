@@ -674,6 +674,112 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
   if (lane == 0) tma_store_wait<0>();
 }
 
+
+// Epilogue of the wide-N kernel for the small fp32 heads (cout <= 16, gw = 16: the `coef` conv + softmax,
+// model_library.py:405-406).  Same horizontal combine as above on 16-column groups, then the single-chunk
+// fp32 path of epilogue_loop: softmax in registers, rows compacted through the staging buffer, coalesced stores.
+__device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const SmemTail& t, uint32_t tmem_base,
+                                                  int warp, int lane) {
+  const EpiParams& p = wp_.e;
+  const int q = warp & 3;
+  const int m = q * 32 + lane;
+  float* sf = reinterpret_cast<float*>(t.stg(warp - 2));
+  const float* sbias = t.bias();
+  float* xch = t.xch();
+  const bool sm_mode = (p.epilogue == IE_EPI_F32_SOFTMAX);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const uint32_t use = static_cast<uint32_t>(it >> 1);
+    const int row0 = tile * wp_.tile_rows - 1;
+    const int r = row0 + m;
+    const int rr = r < 0 ? 0 : r;
+    const int img = rr / p.plane;
+    const int pr = rr - img * p.plane;
+    const int y = pr / p.wp;
+    const int x = pr - y * p.wp;
+    const bool valid = (m >= 1) && (m <= wp_.tile_rows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
+    const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + x;
+    mbar_wait(&t.tfull()[buf], use & 1u);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+    uint32_t z0[16], z1[16], z2[16];
+    tmem_ld_x16(t_base, z0);
+    tmem_ld_x16(t_base + 16, z1);
+    tmem_ld_x16(t_base + 32, z2);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t.tempty()[buf]);
+    const int par = it & 1;                                   // exchange buffers alternate between tiles
+    const uint32_t mine = smem_u32(xch + ((par * 4 + q) * 2) * 32);
+    if (lane == 31) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) sts128u(mine + j * 4, z0[j], z0[j + 1], z0[j + 2], z0[j + 3]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) sts128u(mine + 128 + j * 4, z2[j], z2[j + 1], z2[j + 2], z2[j + 3]);
+    }
+    epi_bar_sync();
+    const uint32_t prev = smem_u32(xch + ((par * 4 + ((q + 3) & 3)) * 2) * 32);
+    const uint32_t next = smem_u32(xch + ((par * 4 + ((q + 1) & 3)) * 2 + 1) * 32);
+    const uint32_t bs = smem_u32(sbias);
+    const bool first = (lane == 0), last = (lane == 31);
+    float a[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 pv = lds128(prev + j * 4), nx = lds128(next + j * 4), bb = lds128(bs + j * 4);
+      const float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, nxv[4] = {nx.x, nx.y, nx.z, nx.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);
+        float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);
+        up = first ? pvv[e] : up;
+        dn = last ? nxv[e] : dn;
+        float v = up + __uint_as_float(z1[j + e]) + dn + bbv[e];
+        if (p.relu) v = fmaxf(v, 0.f);
+        a[j + e] = v;
+        if (j + e < p.cout) mx = fmaxf(mx, v);
+      }
+    }
+    float e_[16];
+    if (sm_mode) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        e_[j] = (j < p.cout) ? __expf(a[j] - mx) : 0.f;
+        sum += e_[j];
+      }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) e_[j] *= inv;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) e_[j] = a[j];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (bal) {
+      const int rank = __popc(bal & ((1u << lane) - 1u));
+      const int nvalid = __popc(bal);
+      const long long pix_first = __shfl_sync(0xffffffffu, pix, __ffs(bal) - 1);
+      const int total = nvalid * p.cout;
+      for (int pass = 0; pass < ((sm_mode && p.y_aux) ? 2 : 1); ++pass) {
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < p.cout) sf[rank * p.cout + j] = pass ? a[j] : e_[j];
+        }
+        __syncwarp();
+        float* dst = (pass ? p.y_aux : p.y_f32) + pix_first * p.cout;
+        for (int i = lane; i < total; i += 32) dst[i] = sf[i];
+      }
+    }
+  }
+}
+
 // RES: weights resident in smem.  G: filter rows per pipeline stage (3 needs RES and kb == 1).
 template <bool RES, int G>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -783,8 +889,10 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
+  } else if (p.e.epilogue == IE_EPI_BF16_RASTER) {
     epilogue_wide_bf16(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
+  } else {
+    epilogue_wide_f32(p, t, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -1023,9 +1131,11 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   // measured on B200 (tools/conv_bench.py, 256 x 104^2): cin = 64 -> resident 213 us vs wide-N 251 us (its epilogue
   // reads 3x the TMEM columns: 98 KB per tile at 64 B/clk); cin = 128 -> 507 vs 477 us; cin = 640 -> 870 (streaming
   // N = 64) vs 491 us.  So wide-N takes over as soon as the main loop is long enough to hide the epilogue.
-  bool wide = wide_ok && d->cin > 64;
+  // small fp32 heads (cout <= 16): three 16-column groups, N = 48 - a third of the A reads of the N = 16 resident path
+  const bool wide_f32 = d->kh == 3 && d->kw == 3 && d->epilogue != IE_EPI_BF16_RASTER && d->cout <= 16 && d->cin <= 128;
+  bool wide = (wide_ok && d->cin > 64) || wide_f32;
   if (g_force_mode == 0 || g_force_mode == 1) wide = false;
-  if (g_force_mode == 2) wide = wide_ok;
+  if (g_force_mode == 2) wide = wide_ok || wide_f32;
   if (g_force_mode == 2) IE_REQUIRE(wide, "conv: wide-N mode forced on an unsupported layer");
   if (wide) {
     WideParams p{};
@@ -1036,7 +1146,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     p.kb = d->cin / 64;
     p.x_coff = d->x_coff;
     p.cin = d->cin;
-    p.gw = 64;
+    p.gw = wide_f32 ? 16 : 64;
     p.b_tile_bytes = 3 * p.gw * 128;
     const int w_bytes = 3 * p.kb * p.b_tile_bytes;
     const bool res = w_bytes <= 150 * 1024;
@@ -1048,10 +1158,15 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     CUtensorMap tm_y31;
     rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tm_b, w_packed, (uint64_t)ktot, (uint64_t)64, (uint64_t)ktot, 64, (uint32_t)p.gw);
+    rc = make_tmap_2d_bf16(&tm_b, w_packed, (uint64_t)ktot, (uint64_t)p.gw, (uint64_t)ktot, 64, (uint32_t)p.gw);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tm_y31, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 31);
-    if (rc) return rc;
+    if (wide_f32) {
+      tm_y = tm_a;                      // unused by the fp32 epilogue
+      tm_y31 = tm_a;
+    } else {
+      rc = make_tmap_2d_bf16(&tm_y31, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 31);
+      if (rc) return rc;
+    }
     const size_t smem = 1024 + (size_t)(res ? w_bytes : 0) + (size_t)p.stages * p.a_slot_bytes + kTailBytes;
     const int grid = p.e.m_tiles < grid_cap ? p.e.m_tiles : grid_cap;
 #define IE_LAUNCH_WIDE(RES_, G_)                                                                                  \
