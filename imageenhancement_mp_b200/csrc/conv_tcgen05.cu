@@ -34,14 +34,20 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // bf16 elements = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kThreads2 = 320;       // + warps 6-9: a second epilogue set (narrow layers: the epilogue is the critical path)
 constexpr int kMaxStages = 8;
 constexpr int kStgBytesPerWarp = 32 * 128;       // 32 rows x 64 bf16
 constexpr int kMaxCout = 1024;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator buffer
 constexpr int kXchBytes = 2 * 4 * 2 * 32 * 4;     // wide-N epilogue: [half][warp][up/down][32] fp32 edge rows
-constexpr int kTailBytes = 4 * kStgBytesPerWarp + kMaxCout * 4 + (2 * kMaxStages + 6) * 8 + 16 + kXchBytes;
+// tail of the dynamic smem for `nsets` epilogue sets (4 warps each): staging + bias + barriers + exchange rows
+constexpr int tail_bytes(int nsets) {
+  return nsets * 4 * kStgBytesPerWarp + kMaxCout * 4 + (2 * kMaxStages + 6) * 8 + 16 + nsets * kXchBytes;
+}
+constexpr int kTailBytes = tail_bytes(1);
+constexpr int kTailBytes2 = tail_bytes(2);
 constexpr size_t kMaxSmem = 227 * 1024;
 
 // Output-side description shared by both kernels.
@@ -65,9 +71,12 @@ struct EpiParams {
 // Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
 struct SmemTail {
   uint8_t* p;
+  int nsets = 1;         // epilogue sets (4 warps each)
   __device__ uint8_t* stg(int warp) const { return p + warp * kStgBytesPerWarp; }
-  __device__ float* bias() const { return reinterpret_cast<float*>(p + 4 * kStgBytesPerWarp); }
-  __device__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(p + 4 * kStgBytesPerWarp + kMaxCout * 4); }
+  __device__ float* bias() const { return reinterpret_cast<float*>(p + nsets * 4 * kStgBytesPerWarp); }
+  __device__ uint64_t* full() const {
+    return reinterpret_cast<uint64_t*>(p + nsets * 4 * kStgBytesPerWarp + kMaxCout * 4);
+  }
   __device__ uint64_t* empty() const { return full() + kMaxStages; }
   __device__ uint64_t* tfull() const { return empty() + kMaxStages; }     // [2]
   __device__ uint64_t* tempty() const { return tfull() + 2; }              // [2]
@@ -108,8 +117,11 @@ __device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams
 
 // Epilogue warps (4 warps, one TMEM lane quadrant each): walk the CTA's tiles and drain the accumulator
 // buffers as the MMA warp completes them.
+// With two sets (warps 2-5 and 6-9) set s takes the CTA's tiles it = s, s+2, ... and therefore always drains TMEM
+// buffer s: the sets never touch the same tile, staging buffer or barrier phase.
 __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensorMap* tm_y, const SmemTail& t,
                                               uint32_t tmem_base, int warp, int lane) {
+  const int set = (warp - 2) >> 2;
   const int q = warp & 3;                      // TMEM lane quadrant this warp may read
   const int row_in_tile = q * 32 + lane;
   uint8_t* stg = t.stg(warp - 2);
@@ -117,8 +129,8 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
   uint64_t* tfull_bar = t.tfull();
   uint64_t* tempty_bar = t.tempty();
   const int num_tiles = p.m_tiles * p.n_tiles;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+  int it = set;
+  for (int tile = blockIdx.x + set * gridDim.x; tile < num_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
     const int m_tile = tile / p.n_tiles;
     const int n_idx = tile - m_tile * p.n_tiles;
     const int r0 = m_tile * kBlockM;
@@ -428,7 +440,7 @@ struct ResidentParams {
 // NDX = horizontal taps; G = filter rows fused into one pipeline stage (G = 3 needs kb == 1: the whole
 // 3x3x64 tile is then ONE stage of 36 MMAs per barrier round trip).
 template <int NDX, int G>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads2, 1)
 conv_resident_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_y, const ResidentParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -436,7 +448,7 @@ conv_resident_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const int ntaps = p.ndy * p.ndx;
   const int b_bytes = ntaps * p.kb * p.b_tile_bytes;      // resident weights, [tap][kb][n_tile x 64]
   uint8_t* a_base_ptr = base + b_bytes;
-  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes};
+  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes, 2};
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.e.m_tiles;                      // single N tile
@@ -573,9 +585,10 @@ struct WideParams {
   int b_tile_bytes;      // 3*gw*128: weights of one (filter row, channel block): [3*gw rows][64 k]
   int a_slot_bytes;      // bytes per pipeline stage
   int tile_rows;         // output rows per tile = 126
+  int nsets;             // epilogue sets in use (1: warps 6-9 idle, 16 KB more smem for the pipeline)
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }
 
 // Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
 __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const CUtensorMap* tm_y32,
@@ -586,9 +599,10 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
   const int m = q * 32 + lane;                 // row inside the 128-row tile = TMEM lane
   uint8_t* stg = t.stg(warp - 2);
   const float* sbias = t.bias();
-  float* xch = t.xch();
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+  const int set = (warp - 2) >> 2;
+  float* xch = t.xch() + set * (kXchBytes / 4);
+  int it = set;
+  for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
     const int buf = it & 1;
     const uint32_t use = static_cast<uint32_t>(it >> 1);
     const int row0 = tile * wp_.tile_rows - 1;  // raster row of tile-local row 0
@@ -626,7 +640,7 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
 #pragma unroll
         for (int j = 0; j < 32; j += 4) sts128u(mine + 128 + j * 4, z2[j], z2[j + 1], z2[j + 2], z2[j + 3]);
       }
-      epi_bar_sync();
+      epi_bar_sync(set);
       // every lane loads the two edge rows (broadcast, no divergence) and lanes 0 / 31 select them
       const uint32_t prev = smem_u32(xch + ((c * 4 + ((q + 3) & 3)) * 2) * 32);       // lane 31 of the warp below (row m-1)
       const uint32_t next = smem_u32(xch + ((c * 4 + ((q + 1) & 3)) * 2 + 1) * 32);   // lane 0 of the warp above (row m+1)
@@ -685,10 +699,11 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
   const int m = q * 32 + lane;
   float* sf = reinterpret_cast<float*>(t.stg(warp - 2));
   const float* sbias = t.bias();
-  float* xch = t.xch();
+  const int set = (warp - 2) >> 2;
+  float* xch = t.xch() + set * (kXchBytes / 4);
   const bool sm_mode = (p.epilogue == IE_EPI_F32_SOFTMAX);
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+  int it = set, local = 0;
+  for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets, ++local) {
     const int buf = it & 1;
     const uint32_t use = static_cast<uint32_t>(it >> 1);
     const int row0 = tile * wp_.tile_rows - 1;
@@ -711,7 +726,7 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&t.tempty()[buf]);
-    const int par = it & 1;                                   // exchange buffers alternate between tiles
+    const int par = local & 1;                                // exchange buffers alternate between this set's tiles
     const uint32_t mine = smem_u32(xch + ((par * 4 + q) * 2) * 32);
     if (lane == 31) {
 #pragma unroll
@@ -721,7 +736,7 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
 #pragma unroll
       for (int j = 0; j < 16; j += 4) sts128u(mine + 128 + j * 4, z2[j], z2[j + 1], z2[j + 2], z2[j + 3]);
     }
-    epi_bar_sync();
+    epi_bar_sync(set);
     const uint32_t prev = smem_u32(xch + ((par * 4 + ((q + 3) & 3)) * 2) * 32);
     const uint32_t next = smem_u32(xch + ((par * 4 + ((q + 1) & 3)) * 2 + 1) * 32);
     const uint32_t bs = smem_u32(sbias);
@@ -782,7 +797,7 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
 
 // RES: weights resident in smem.  G: filter rows per pipeline stage (3 needs RES and kb == 1).
 template <bool RES, int G>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads2, 1)
 conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_y32, const __grid_constant__ CUtensorMap tm_y31,
                  const WideParams p) {
@@ -790,7 +805,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint8_t* base = align1024(smem_raw);
   const int b_res_bytes = RES ? 3 * p.kb * p.b_tile_bytes : 0;
   uint8_t* a_base_ptr = base + b_res_bytes;
-  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes};
+  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes, p.nsets};
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.e.m_tiles;
@@ -889,6 +904,8 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
+  } else if (warp >= 2 + 4 * p.nsets) {
+    // second epilogue set not in use
   } else if (p.e.epilogue == IE_EPI_BF16_RASTER) {
     epilogue_wide_bf16(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
   } else {
@@ -1060,6 +1077,8 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 // Tuning / test hooks (not part of the documented ABI surface): force a main-loop flavour.
 static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
+static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
+                                     // epilogue sets, bit 2 one filter row per stage even when cin = 64
 static int g_base_offset = 0;      // measured on B200: the 128B swizzle is a function of the absolute smem address,
                                       // so row-shifted descriptor starts need NO base-offset field (setting it corrupts)
 
@@ -1069,6 +1088,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_force_mode = mode;
   ie::g_base_offset = flags & 1;
   ie::g_fuse_rows = (flags & 2) ? 0 : 1;
+  ie::g_wide_flags = (flags >> 2) & 7;
   return IE_OK;
 }
 
@@ -1112,7 +1132,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   const int b_res_bytes = ntaps * (d->cin / 64) * e.n_tile * 128;
   const int box_rows = kBlockM + d->kw - 1;
   int a_slot = ((box_rows * 128 + 1023) / 1024) * 1024;
-  const int res_room = (int)kMaxSmem - 1024 - kTailBytes - (b_res_bytes <= 200 * 1024 ? b_res_bytes : 200 * 1024);
+  const int res_room = (int)kMaxSmem - 1024 - kTailBytes2 - (b_res_bytes <= 200 * 1024 ? b_res_bytes : 200 * 1024);
   const int fuse_rows = (d->kh == 3 && d->cin == 64 && g_fuse_rows) ? 3 : 1;      // whole 3x3x64 tile in one stage
   const int a_box = a_slot;
   a_slot *= fuse_rows;
@@ -1128,12 +1148,13 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
 
   // ---- wide-N flavour: 3x3, cout <= 64 (one 64-column group per horizontal tap), bf16 raster output
   const bool wide_ok = d->kh == 3 && d->kw == 3 && d->epilogue == IE_EPI_BF16_RASTER && e.n_tile == 64 && e.n_tiles == 1;
-  // measured on B200 (tools/conv_bench.py, 256 x 104^2): cin = 64 -> resident 213 us vs wide-N 251 us (its epilogue
-  // reads 3x the TMEM columns: 98 KB per tile at 64 B/clk); cin = 128 -> 507 vs 477 us; cin = 640 -> 870 (streaming
-  // N = 64) vs 491 us.  So wide-N takes over as soon as the main loop is long enough to hide the epilogue.
+  // measured on B200 (tools/conv_bench.py, 256 x 104^2, us; resident = row-shifted descriptors at N = 64):
+  //   cin  64: resident 206, wide-N 200 (two epilogue sets; 251 with one: the epilogue reads 3x the TMEM columns)
+  //   cin 128: resident 527, wide-N 370 (weights resident, one epilogue set -> 3 A stages)
+  //   cin 640: streaming N = 64 870, wide-N 417 (weights streamed with the A tiles)
   // small fp32 heads (cout <= 16): three 16-column groups, N = 48 - a third of the A reads of the N = 16 resident path
   const bool wide_f32 = d->kh == 3 && d->kw == 3 && d->epilogue != IE_EPI_BF16_RASTER && d->cout <= 16 && d->cin <= 128;
-  bool wide = (wide_ok && d->cin > 64) || wide_f32;
+  bool wide = wide_ok || wide_f32;
   if (g_force_mode == 0 || g_force_mode == 1) wide = false;
   if (g_force_mode == 2) wide = wide_ok || wide_f32;
   if (g_force_mode == 2) IE_REQUIRE(wide, "conv: wide-N mode forced on an unsupported layer");
@@ -1149,10 +1170,15 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     p.gw = wide_f32 ? 16 : 64;
     p.b_tile_bytes = 3 * p.gw * 128;
     const int w_bytes = 3 * p.kb * p.b_tile_bytes;
-    const bool res = w_bytes <= 150 * 1024;
-    const bool fuse = res && p.kb == 1;
+    const bool res = w_bytes <= 150 * 1024 && !(g_wide_flags & 1);
+    const bool fuse = res && p.kb == 1 && !(g_wide_flags & 4);
     p.a_slot_bytes = fuse ? 3 * kABytes : kABytes + (res ? 0 : p.b_tile_bytes);
-    int stages = ((int)kMaxSmem - 1024 - kTailBytes - (res ? w_bytes : 0)) / p.a_slot_bytes;
+    // two epilogue sets when the main loop of a tile is short (one channel block); deeper layers hide the epilogue
+    // anyway and need the 16 KB for pipeline stages (measured: 128->64 resident 378 us with one set, 487 with two)
+    p.nsets = (p.kb == 1) ? 2 : 1;
+    if (g_wide_flags & 2) p.nsets = 3 - p.nsets;
+    const int tail = tail_bytes(p.nsets);
+    int stages = ((int)kMaxSmem - 1024 - tail - (res ? w_bytes : 0)) / p.a_slot_bytes;
     p.stages = stages > kMaxStages ? kMaxStages : stages;
     IE_REQUIRE(p.stages >= 2, "conv: wide-N pipeline does not fit in shared memory");
     CUtensorMap tm_y31;
@@ -1167,13 +1193,13 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
       rc = make_tmap_2d_bf16(&tm_y31, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 31);
       if (rc) return rc;
     }
-    const size_t smem = 1024 + (size_t)(res ? w_bytes : 0) + (size_t)p.stages * p.a_slot_bytes + kTailBytes;
+    const size_t smem = 1024 + (size_t)(res ? w_bytes : 0) + (size_t)p.stages * p.a_slot_bytes + tail;
     const int grid = p.e.m_tiles < grid_cap ? p.e.m_tiles : grid_cap;
 #define IE_LAUNCH_WIDE(RES_, G_)                                                                                  \
   do {                                                                                                            \
     IE_CUDA(cudaFuncSetAttribute(conv_wide_kernel<RES_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                  (int)kMaxSmem));                                                                 \
-    conv_wide_kernel<RES_, G_><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, tm_y31, p);                        \
+    conv_wide_kernel<RES_, G_><<<grid, kThreads2, smem, st>>>(tm_a, tm_b, tm_y, tm_y31, p);                        \
   } while (0)
     if (fuse) IE_LAUNCH_WIDE(true, 3);
     else if (res) IE_LAUNCH_WIDE(true, 1);
@@ -1201,13 +1227,13 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, (uint32_t)box_rows);
     if (rc) return rc;
     if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
-    const size_t smem = 1024 + (size_t)b_res_bytes + (size_t)p.stages * a_slot + kTailBytes;
+    const size_t smem = 1024 + (size_t)b_res_bytes + (size_t)p.stages * a_slot + kTailBytes2;
     const int grid = e.m_tiles < grid_cap ? e.m_tiles : grid_cap;
 #define IE_LAUNCH_RES(NDX_, G_)                                                                                   \
   do {                                                                                                            \
     IE_CUDA(cudaFuncSetAttribute(conv_resident_kernel<NDX_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                  (int)kMaxSmem));                                                                 \
-    conv_resident_kernel<NDX_, G_><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);                            \
+    conv_resident_kernel<NDX_, G_><<<grid, kThreads2, smem, st>>>(tm_a, tm_b, tm_y, p);                            \
   } while (0)
     if (d->kw == 3 && fuse_rows == 3) IE_LAUNCH_RES(3, 3);
     else if (d->kw == 3) IE_LAUNCH_RES(3, 1);

@@ -22,9 +22,10 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default="")
     ap.add_argument("--mode", type=int, default=-1, help="-1 auto, 0 stream, 1 resident, 2 wide-N (forced)")
+    ap.add_argument("--flags", type=int, default=0, help="ie_conv_set_mode flags (4: wide streams weights, 8: one epilogue set)")
     a = ap.parse_args()
     dev = torch.device("cuda")
-    _lib.load().ie_conv_set_mode(a.mode, 0)
+    _lib.load().ie_conv_set_mode(a.mode, a.flags)
     out = []
     for name, div, cin, cout, k, epi in LAYERS:
         if a.only and a.only not in name:
