@@ -933,7 +933,7 @@ struct FirstParams {
   int hs, ws;            // source size
   int stages;
 };
-constexpr int kFirstThreads = 320;   // warp 0: weights, warp 1: MMA, warps 2-5: epilogue, warps 6-9: builders
+constexpr int kFirstThreads = 448;   // warp 0: weights, warp 1: MMA, warps 2-5: epilogue, warps 6-13: two builder sets
 
 template <int C>
 __global__ void __launch_bounds__(kFirstThreads, 1)
@@ -992,11 +992,15 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
     epilogue_loop(p.e, &tm_y, t, tmem_base, warp, lane);
   } else {
     // ================================ A-tile builders ==============================
-    const int row_local = (warp - 6) * 32 + lane;
+    // two sets of four warps; set s builds the CTA's tiles it = s, s+2, ... into stage it % stages (a single warp
+    // per scheduler cannot hide the latency of its 45 gathers, exactly like the epilogue)
+    const int bset = (warp - 6) >> 2;
+    const int row_local = ((warp - 6) & 3) * 32 + lane;
     constexpr int C3 = 3 * C;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = bset;
+    for (int tile = blockIdx.x + bset * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int stage = it % p.stages;
+      const uint32_t phase = static_cast<uint32_t>(it / p.stages) & 1u;
       const int r = tile * kBlockM + row_local;
       const int img = r / p.e.plane;
       const int pr = r - img * p.e.plane;
@@ -1031,7 +1035,6 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
-      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   }
 
