@@ -48,6 +48,16 @@ CONFIGS = {
 }
 
 
+def read_conv_traffic(cfg_name):
+    """DRAM bytes of the conv launches of one step, from the committed ncu capture (profiles/r*_conv_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
+    if cfg_name != "cfg2" or not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get("conv_dram_bytes_per_step"), os.path.relpath(files[-1], ROOT)
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -263,6 +273,7 @@ def run_ours(args, cfg_name):
     per_px, per_img = weights.conv_flops(layers, params, hp, wp)
     conv_flops_step = nb * (per_px * hp * wp + per_img)     # per rank, at the computed (padded) size
     achieved = conv_flops_step * args.steps / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, traffic_src = read_conv_traffic(cfg_name)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -275,9 +286,12 @@ def run_ours(args, cfg_name):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(res[0].numel() * 8),
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
-        "roofline": {"kernel": "conv_igemm_kernel (all %d launches per step)" % (n_conv // max(args.steps, 1)),
+        "roofline": {"kernel": "tcgen05 conv kernels: conv_stream / conv_wide / conv_resident / conv_first "
+                               "(all %d launches of a step; achieved and traffic are per step)" % (n_conv // max(args.steps, 1)),
                      "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                     "traffic_note": ("DRAM bytes (read+write) of the same launches of one step, ncu --set full: " + traffic_src)
+                     if traffic_src else "no ncu capture for this config",
                      "peak_source": peaks["source"] + " sustained bf16", "frac_of_burst": achieved / peaks["bf16_burst"],
                      "conv_ms_per_step": conv_ms / args.steps, "conv_tflop_per_step": conv_flops_step / 1e12},
         "quality": {"psnr": report["psnr"], "psnr_noise0": report["psnr_noise0"], "psnr_average": report["psnr_average"]},

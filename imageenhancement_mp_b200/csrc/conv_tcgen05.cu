@@ -1110,8 +1110,15 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   e.wv = d->wv;
   e.cout = d->cout;
   e.n_tile = choose_n_tile(d->cout, d->epilogue);
-  e.n_tiles = (d->cout + e.n_tile - 1) / e.n_tile;
   e.m_tiles = (int)((R + kBlockM - 1) / kBlockM);
+  // small rasters (the per-image basis branch: 256 images x 2x2 px = 18 M tiles): trade N-tile width for CTAs
+  // until the grid covers the SMs - a 2048->512 layer on 36 CTAs ran 102 us with 112 SMs idle
+  if (d->epilogue == IE_EPI_BF16_RASTER) {
+    while (e.n_tile > 64 && d->cout % (e.n_tile / 2) == 0 &&
+           (long long)e.m_tiles * ((d->cout + e.n_tile - 1) / e.n_tile) * 2 <= sm_count())
+      e.n_tile /= 2;
+  }
+  e.n_tiles = (d->cout + e.n_tile - 1) / e.n_tile;
   e.y_coff = d->y_coff;
   e.relu = d->relu;
   e.epilogue = d->epilogue;

@@ -157,7 +157,19 @@ upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
 // Scale 2: one thread per 2x2 OUTPUT block lying between four input pixels (i, j), (i, j+1), (i+1, j),
 // (i+1, j+1), i in [-1, h-1], j in [-1, w-1] with clamped indices: 4 loads and 4 unpacks per 4 outputs instead
 // of 16, and the blocks tile the padded output raster exactly (the out-of-image outputs of the edge blocks ARE
-// the zero border).  Same lerp expressions and weights (0.25 / 0.75) as the general kernel: bit-identical.
+// the zero border).  Same lerp formula and weights (0.25 / 0.75) as the general kernel, on fp32 pairs (FFMA2).
+__device__ __forceinline__ void unpack8_pairs(const uint4& v, float2 (&f)[4]) {
+  f[0] = make_float2(bf16_lo(v.x), bf16_hi(v.x));
+  f[1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
+  f[2] = make_float2(bf16_lo(v.z), bf16_hi(v.z));
+  f[3] = make_float2(bf16_lo(v.w), bf16_hi(v.w));
+}
+// a + (b - a) * l on fp32 pairs: two packed FFMA2 (sm_100 fma.rn.f32x2) per pair
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 l) {
+  const float2 d = __ffma2_rn(a, make_float2(-1.f, -1.f), b);
+  return __ffma2_rn(d, l, a);
+}
+
 __global__ void __launch_bounds__(256)
 upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
                  uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
@@ -169,35 +181,41 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
   const int wpi = w + 1;
   const long long base = (long long)img * (h + 1) * wpi;
   const uint4* p = x + x_coff_v + cv;
-  float a[8], b[8], c[8], d[8];
-  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x0) * x_pitch_v), a);
-  unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x1) * x_pitch_v), b);
-  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x0) * x_pitch_v), c);
-  unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x1) * x_pitch_v), d);
+  float2 a[4], b[4], c[4], d[4];
+  unpack8_pairs(__ldg(p + (base + (long long)(y0 + 1) * wpi + x0) * x_pitch_v), a);
+  unpack8_pairs(__ldg(p + (base + (long long)(y0 + 1) * wpi + x1) * x_pitch_v), b);
+  unpack8_pairs(__ldg(p + (base + (long long)(y1 + 1) * wpi + x0) * x_pitch_v), c);
+  unpack8_pairs(__ldg(p + (base + (long long)(y1 + 1) * wpi + x1) * x_pitch_v), d);
   const int wo = 2 * w, ho = 2 * h, wpo = wo + 1;
   // output pixel (oy, ox) = (2i+1+u, 2j+1+v), u, v in {0,1}; raster position (oy + 1, ox): oy = -1 is the
   // shared zero row, ox = wo the shared zero column; oy = ho and ox = -1 have no slot
   const long long ro = ((long long)img * (ho + 1) + (2 * i + 2)) * wpo + (2 * j + 1);
   uint4* q = y + y_coff_v + cv;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const float ly = u ? 0.75f : 0.25f;
-    const bool row_ok = (2 * i + 1 + u >= 0) && (2 * i + 1 + u < ho);
+  for (int v = 0; v < 2; ++v) {
+    const int ox = 2 * j + 1 + v;
+    if (ox < 0) continue;                                   // left of the raster
+    const float lxs = v ? 0.75f : 0.25f;
+    const float2 lx = make_float2(lxs, lxs);
+    float2 top[4], bot[4];
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const float lx = v ? 0.75f : 0.25f;
-      const bool ok = row_ok && (2 * j + 1 + v >= 0) && (2 * j + 1 + v < wo);
-      if (2 * i + 1 + u >= ho || 2 * j + 1 + v < 0) continue;       // outside the raster
+    for (int e = 0; e < 4; ++e) {
+      top[e] = lerp2(a[e], b[e], lx);
+      bot[e] = lerp2(c[e], d[e], lx);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int oy = 2 * i + 1 + u;
+      if (oy >= ho) continue;                               // below the raster
       uint4 res = make_uint4(0, 0, 0, 0);
-      if (ok) {
-        float o[8];
+      if (oy >= 0 && ox < wo) {
+        const float lys = u ? 0.75f : 0.25f;
+        const float2 ly = make_float2(lys, lys);
+        float2 o[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float top = a[e] + (b[e] - a[e]) * lx;
-          const float bot = c[e] + (d[e] - c[e]) * lx;
-          o[e] = top + (bot - top) * ly;
-        }
-        res = pack8(o);
+        for (int e = 0; e < 4; ++e) o[e] = lerp2(top[e], bot[e], ly);
+        res = make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y), pack_bf16x2(o[2].x, o[2].y),
+                         pack_bf16x2(o[3].x, o[3].y));
       }
       q[(ro + (long long)u * wpo + v) * y_pitch_v] = res;
     }

@@ -261,6 +261,59 @@ __global__ void img_loss_sums_kernel(const float* __restrict__ a, const float* _
   block_accumulate<2>(acc, sums, 2);
 }
 
+// Vectorised variant (w % 4 == 0, 16-byte aligned rows): a thread owns 4 consecutive x and walks kLossRows
+// rows downwards, carrying the difference row it just loaded as the "current" row of the next step, so every
+// element is loaded once (+1 halo row per strip, +1 scalar per row for the x+1 neighbour of the last lane).
+constexpr int kLossRows = 16;
+__global__ void __launch_bounds__(128)
+img_loss_sums_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
+                         double* __restrict__ sums) {
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;      // group of 4 pixels
+  const int x = xq * 4;
+  const int y0 = blockIdx.y * kLossRows;
+  const long long img = (long long)blockIdx.z * h * w;
+  float acc[2] = {0.f, 0.f};
+  if (x < w) {
+    const float* pa = a + img + x;
+    const float* pb = b + img + x;
+    const bool has_right = x + 4 < w;
+    auto load = [&](int y, float (&d)[5]) {
+      const float4 va = __ldcs(reinterpret_cast<const float4*>(pa + (long long)y * w));
+      const float4 vb = __ldcs(reinterpret_cast<const float4*>(pb + (long long)y * w));
+      d[0] = va.x - vb.x; d[1] = va.y - vb.y; d[2] = va.z - vb.z; d[3] = va.w - vb.w;
+      d[4] = has_right ? __ldg(pa + (long long)y * w + 4) - __ldg(pb + (long long)y * w + 4) : 0.f;
+    };
+    float cur[5], nxt[5];
+    load(y0, cur);
+    const int yend = min(y0 + kLossRows, h);
+    for (int y = y0; y < yend; ++y) {
+      const bool has_below = y + 1 < h;
+      if (has_below) load(y + 1, nxt);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[0] = fmaf(cur[e], cur[e], acc[0]);
+        if (has_below && x + e < w - 1) acc[1] += .5f * fabsf(nxt[e] - cur[e]) + .5f * fabsf(cur[e + 1] - cur[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 5; ++e) cur[e] = nxt[e];
+    }
+  }
+  // 128-thread block: reduce with the 256-thread helper's layout (upper warps contribute zeros)
+  __shared__ float red[4][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float s = warp_sum(acc[q]);
+    if (lane == 0) red[warp][q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const double s = (double)red[0][threadIdx.x] + (double)red[1][threadIdx.x] + (double)red[2][threadIdx.x] +
+                     (double)red[3][threadIdx.x];
+    atomicAdd(&sums[threadIdx.x], s);
+  }
+}
+
 // ------------------------------------------------------------------------------- SSIM (extension)
 // Output tile 64 x 32 (VALID): input 74 x 42.  Horizontal 11-tap pass with 8 outputs per thread
 // (sliding window in registers) over the five moments a, b, a^2, b^2, ab, then the vertical pass.
@@ -460,6 +513,14 @@ extern "C" int ie_sqdiff_sum_f32(const float* a, const float* b, int n, long lon
 extern "C" int ie_img_loss_sums_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream) {
   IE_REQUIRE(a && b && sums && n > 0 && h > 1 && w > 1, "img_loss_sums: bad arguments");
   const long long total = (long long)n * h * w;
+  const bool vec = (w % 4 == 0) && (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) &&
+                   n <= 65535 && (h + kLossRows - 1) / kLossRows <= 65535;
+  if (vec) {
+    dim3 grid(ie_ceil_div(w / 4, 128), (h + kLossRows - 1) / kLossRows, n);
+    img_loss_sums_vec_kernel<<<grid, 128, 0, S(stream)>>>(a, b, h, w, sums);
+    IE_LAUNCH_CHECK();
+    return IE_OK;
+  }
   long long gx = (total + 255) / 256;
   if (gx > 8ll * sm_count()) gx = 8ll * sm_count();
   img_loss_sums_kernel<<<(unsigned)gx, 256, 0, S(stream)>>>(a, b, h, w, total, sums);

@@ -105,19 +105,20 @@ def test_maxpool(cuda):
     assert border_is_zero(dst)
 
 
-@pytest.mark.parametrize("scale,h,w", [(2, 5, 7), (8, 2, 2), (2, 1, 1)])
+@pytest.mark.parametrize("scale,h,w", [(2, 5, 7), (8, 2, 2), (2, 1, 1), (2, 13, 13)])
 def test_upsample_bilinear(cuda, scale, h, w):
     from imageenhancement_mp_b200 import ops
     g = torch.Generator().manual_seed(3)
     x = bf16_round(torch.randn(2, h, w, 64, generator=g))
     src = to_raster(x.to(cuda))
     dst = ops.new_raster(2, h * scale, w * scale, 128, cuda)
-    dst.data.zero_()
+    dst.data.fill_(float("nan"))
     ops.upsample_bilinear(src.slice(), dst.slice(0, 64), scale)
     got = ops.raster_to_nhwc(dst.slice(0, 64)).cpu()
     ref = omodel.upsample_bilinear(x, scale)
     assert torch.allclose(got, ref, atol=2e-2, rtol=2 ** -7)
-    assert border_is_zero(dst)
+    assert border_is_zero(ops.Raster(dst.data[:, :64].contiguous(), dst.n, dst.h, dst.w))   # every border entry written
+    assert bool(torch.isnan(dst.data[:, 64:]).all())                                          # nothing outside the slice
 
 
 def test_channel_mean_and_broadcast(cuda):
@@ -228,6 +229,17 @@ def test_reference_api_metrics(cuda):
     lay = du.invert_deblur_layer(rc, wn)
     assert lay.shape == (3, 24, 40 * T)
     assert torch.allclose(lay.cpu().double(), oracle.invert_deblur_layer(recon.double(), wn_ref), atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 37, 52), (2, 19, 23), (1, 16, 4), (2, 65, 516)])
+def test_basic_img_loss_shapes(cuda, n, h, w):
+    """basic_img_loss / gradient_loss (data_utils.py:37-51): vectorised (w % 4 == 0) and scalar kernels, edge sizes."""
+    from imageenhancement_mp_b200 import data_utils as du
+    g = torch.Generator().manual_seed(h * w)
+    a, b = torch.rand(n, h, w, generator=g), torch.rand(n, h, w, generator=g)
+    rel = lambda p, q: abs(float(p) - float(q)) / max(abs(float(q)), 1e-12)
+    assert rel(du.basic_img_loss(a.to(cuda), b.to(cuda)), oracle.basic_img_loss(a.double(), b.double())) < 1e-5
+    assert rel(du.gradient_loss(a.to(cuda), b.to(cuda)), oracle.gradient_loss(a.double(), b.double())) < 1e-5
 
 
 @pytest.mark.parametrize("n,h,w,T", [(3, 40, 56, 4), (2, 104, 104, 4), (1, 33, 49, 2), (2, 100, 100, 8)])
