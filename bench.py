@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: megapixels/s enhanced (Simplemodel forward + PSNR/SSIM-style eval metrics).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg1|cfg2|cfg3|cfg4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic input: model forward
@@ -45,6 +45,7 @@ CONFIGS = {
     "cfg1": (32, 100, 100, "configs[0]: 32x100x100x5 patches (reference CPU case)"),
     "cfg2": (256, 100, 100, "configs[1]: batch 256 of 100x100 patches, bf16 trunk"),
     "cfg3": (8, 720, 1280, "configs[2]: 1280x720 images, micro-batch 8 per step per GPU"),
+    "cfg4": (1, 2448, 3264, "configs[3]: 3264x2448 photos, one image per step per GPU (8-way image-sharded at N=8)"),
 }
 
 

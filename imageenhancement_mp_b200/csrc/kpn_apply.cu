@@ -244,3 +244,69 @@ extern "C" int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Convolve / cus_convolve / Convolve_perlayer with MATERIALISED per-pixel filters
+// (model_library.py:114-168), for callers that build `filts` themselves.  One warp per pixel: the lanes
+// stride over the pixel's K*K*T contiguous filter taps (coalesced 128-byte reads - the kernel is bound by the
+// 4*K*K*T bytes of filter per pixel), the burst neighbourhood comes from L1/L2.
+//   out[n,y,x,0]   = sum_{i,j,t} pad0(burst)[n,y+i-K/2,x+j-K/2,t] * filts[n,y,x,i,j,t]          (Convolve)
+//   out[n,y,x,1+t] = T * sum_{i,j} pad0(burst)[n,y+i-K/2,x+j-K/2,t] * filts[n,y,x,i,j,t]        (Convolve_perlayer)
+// -------------------------------------------------------------------------------------------------
+namespace ie {
+constexpr int kConvMaxT = 8;
+__global__ void __launch_bounds__(256)
+convolve_filts_kernel(const float* __restrict__ burst, int burst_pitch, const float* __restrict__ filts,
+                      float* __restrict__ out, long long npix, int H, int W, int T, int K) {
+  const long long pix = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int lane = threadIdx.x & 31;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const long long img = pix / ((long long)W * H);
+  const int taps = K * K * T, kpad = K / 2;
+  const float* f = filts + pix * taps;
+  const float* b = burst + img * H * W * burst_pitch;
+  float acc[kConvMaxT];
+#pragma unroll
+  for (int t = 0; t < kConvMaxT; ++t) acc[t] = 0.f;
+  for (int e = lane; e < taps; e += 32) {
+    const int ij = e / T, t = e - ij * T;
+    const int i = ij / K, j = ij - i * K;
+    const int gy = y + i - kpad, gx = x + j - kpad;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const float v = __ldcs(f + e) * __ldg(b + ((long long)gy * W + gx) * burst_pitch + t);
+#pragma unroll
+      for (int k = 0; k < kConvMaxT; ++k)
+        if (k == t) acc[k] += v;
+    }
+  }
+  float total = 0.f;
+#pragma unroll
+  for (int t = 0; t < kConvMaxT; ++t) {
+    if (t < T) {
+      float s = acc[t];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      total += s;
+      if (lane == 0) out[pix * (T + 1) + 1 + t] = s * (float)T;
+    }
+  }
+  if (lane == 0) out[pix * (T + 1)] = total;
+}
+}  // namespace ie
+
+extern "C" int ie_convolve_filts_f32(const float* burst, int burst_pitch, const float* filts, float* out, int n, int h,
+                                     int w, int T, int K, void* stream) {
+  using namespace ie;
+  IE_REQUIRE(burst && filts && out, "convolve_filts: null pointer");
+  IE_REQUIRE(n > 0 && h > 0 && w > 0 && T >= 1 && T <= kConvMaxT, "convolve_filts: bad sizes (T=%d, max %d)", T, kConvMaxT);
+  IE_REQUIRE(K >= 1 && (K & 1) && K <= 31 && burst_pitch >= T, "convolve_filts: bad K=%d / burst_pitch=%d", K, burst_pitch);
+  const long long npix = (long long)n * h * w;
+  const long long blocks = (npix + 7) / 8;
+  IE_REQUIRE(blocks < (1ll << 31), "convolve_filts: too many pixels");
+  convolve_filts_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(burst, burst_pitch, filts, out,
+                                                                                         npix, h, w, T, K);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}

@@ -84,3 +84,42 @@ class Basis_kpn(_KpnModel):
     def __call__(self, inputs, **kw):
         out, bas, _ = self._forward(inputs, **kw)
         return out, bas                              # :295
+
+
+class Convolve:
+    """model_library.py:114-135: per-pixel filtering with materialised filters, summed over the frames.
+
+    ``Convolve(K)(img_stack [N,H,W,T], filts [N,H,W,K,K,T]) -> [N,H,W]``.  The models of this package never
+    materialise ``filts`` (they call the fused ``ops.kpn_apply``); this layer exists for drop-in callers."""
+
+    def __init__(self, final_K, name='convolve', **kwargs):
+        self.final_K = final_K
+        self.name = name
+
+    def __call__(self, img_stack, filts):
+        from . import ops
+        return ops.convolve_filts(img_stack, filts, self.final_K)[..., 0]
+
+    call = __call__
+
+
+def cus_convolve(img_stack, filts, final_K):
+    """model_library.py:136-152 (the functional twin of ``Convolve.call``)."""
+    return Convolve(final_K)(img_stack, filts)
+
+
+class Convolve_perlayer:
+    """model_library.py:153-168: the same filter applied frame by frame, each scaled by the number of frames.
+
+    ``Convolve_perlayer(K, T)(conv_stack [N,H,W,T], filts [N,H,W,K,K,T]) -> [N,H,W,T]``."""
+
+    def __init__(self, final_K, burst_length, name='convolve_perlayer', **kwargs):
+        self.final_K = final_K
+        self.burst_length = burst_length
+        self.name = name
+
+    def __call__(self, conv_stack, filts):
+        from . import ops
+        return ops.convolve_filts(conv_stack, filts, self.final_K)[..., 1:]
+
+    call = __call__

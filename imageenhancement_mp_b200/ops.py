@@ -212,3 +212,16 @@ def kpn_apply(x, T, coef, bas, out=None):
         out = torch.empty(n, h, w, T + 1, dtype=torch.float32, device=x.device)
     call("ie_kpn_apply_f32", ptr(x), pitch, ptr(coef), hc, wc, ptr(bas), ptr(out), n, h, w, T, K, B, stream())
     return out
+
+
+def convolve_filts(img_stack, filts, K):
+    """Materialised-filter path (model_library.py:114-168): img_stack [n,h,w,T], filts [n,h,w,K,K,T] (or flattened
+    [n,h,w,K*K*T]) -> [n,h,w,T+1]: channel 0 = Convolve, channels 1.. = Convolve_perlayer."""
+    _lib.require_cuda(img_stack, filts)
+    n, h, w, T = img_stack.shape
+    x = img_stack.contiguous().float()
+    f = filts.contiguous().float()
+    assert f.numel() == n * h * w * K * K * T, "filts must hold K*K*T taps per pixel"
+    out = torch.empty(n, h, w, T + 1, dtype=torch.float32, device=x.device)
+    call("ie_convolve_filts_f32", ptr(x), T, ptr(f), ptr(out), n, h, w, T, K, stream())
+    return out

@@ -135,6 +135,14 @@ int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float*
 int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
                      float* out, int n, int h, int w, int T, int K, int B, void* stream);
 
+/* Convolve / cus_convolve / Convolve_perlayer (model_library.py:114-168) with MATERIALISED filters, for callers
+ * that build `filts` [n][h][w][K][K][T] themselves (the models never do - they use ie_kpn_apply_f32):
+ *   out[n,y,x,0]   = sum_{i,j,t} pad0(burst)[n,y+i-K/2,x+j-K/2,t] * filts[n,y,x,i,j,t]        (Convolve.call)
+ *   out[n,y,x,1+t] = T * sum_{i,j} pad0(burst)[..,t] * filts[n,y,x,i,j,t]                     (Convolve_perlayer.call)
+ * burst: fp32 NHWC with `burst_pitch` channels per pixel (first T used); out [n][h][w][T+1].             */
+int ie_convolve_filts_f32(const float* burst, int burst_pitch, const float* filts, float* out, int n, int h, int w,
+                          int T, int K, void* stream);
+
 /* ---- metrics (data_utils.py:24-164 as eval.py:139-182 calls them) --------------------------------- */
 
 /* mean over H,W of channel `coff` of an fp32 NHWC tensor: white level of eval.py:144-145. out [n].    */

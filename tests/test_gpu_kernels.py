@@ -189,6 +189,23 @@ def test_kpn_apply_large_vs_algebraic(cuda):
     assert torch.allclose(got1[:, 7:-7, 7:-7, 0], torch.ones(2, 90, 90), atol=1e-5)
 
 
+@pytest.mark.parametrize("n,h,w,T,K", [(2, 12, 20, 4, 15), (1, 9, 7, 3, 5), (1, 17, 33, 8, 15)])
+def test_convolve_layers_with_materialised_filters(cuda, n, h, w, T, K):
+    """Convolve / cus_convolve / Convolve_perlayer (model_library.py:114-168) against the oracle's literal restatement."""
+    from imageenhancement_mp_b200 import model_library as ml
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(n, h, w, T, generator=g)
+    filts = torch.randn(n, h, w, K, K, T, generator=g) / (K * K * T)
+    ref = omodel.convolve(imgs.double(), filts.double(), K)
+    ref_pl = omodel.convolve_perlayer(imgs.double(), filts.double(), K)
+    got = ml.Convolve(K)(imgs.to(cuda), filts.to(cuda)).cpu()
+    got_pl = ml.Convolve_perlayer(K, T)(imgs.to(cuda), filts.to(cuda)).cpu()
+    assert got.shape == (n, h, w) and got_pl.shape == (n, h, w, T)
+    assert torch.allclose(got.double(), ref, atol=2e-6, rtol=1e-5)
+    assert torch.allclose(got_pl.double(), ref_pl, atol=2e-6, rtol=1e-5)
+    assert torch.equal(ml.cus_convolve(imgs.to(cuda), filts.to(cuda), K).cpu(), got)
+
+
 # ------------------------------------------------------------------ metrics
 def _metric_inputs(n, h, w, T, seed):
     x, truth = synth.make_batch(n, h, w, {"BURST_LENGTH": T}, seed=seed)
