@@ -1,0 +1,60 @@
+"""GPU end-to-end: eval.evaluate() (the validation loop + report of the reference's eval.py:139-195) against the
+oracle's per-batch eval_step + eval_report, from pinned HOST batches (staged on a side stream) and from device
+batches, including eval.py's own defaults (batch 1 of 32x32, T=4, singlestd)."""
+import pytest
+import torch
+
+import oracle
+from imageenhancement_mp_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_report(W, params, batches):
+    T = params["BURST_LENGTH"]
+    steps = []
+    for x, t in batches:
+        h, w = x.shape[1:3]
+        xp, _ = synth.pad_to_multiple(x, 8)
+        out = oracle.simplemodel_forward(W, params, xp)[0][:, :h, :w]
+        steps.append(oracle.eval_step(out, x, t, T))
+    return oracle.eval_report(steps, T)
+
+
+@pytest.mark.parametrize("where", ["pinned_host", "device"])
+@pytest.mark.parametrize("nb,n,h,w", [(3, 4, 40, 48), (4, 1, 32, 32), (2, 3, 100, 100)])
+def test_evaluate_matches_oracle_report(cuda, where, nb, n, h, w):
+    from imageenhancement_mp_b200 import eval as ieval, model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    batches = [synth.make_batch(n, h, w, params, seed=50 + i) for i in range(nb)]
+    ref = oracle_report(W, params, batches)
+    model = ml.Simplemodel(params, weights=W)
+    if where == "device":
+        fed = [(x.to(cuda), t.to(cuda)) for x, t in batches]
+    else:
+        fed = [(x.pin_memory(), t.pin_memory()) for x, t in batches]
+    lines, per_step = [], []
+    rep = ieval.evaluate(model, fed, params, step=3, out=lines.append, step_results=per_step)
+    assert rep["count"] == nb * n and len(per_step) == nb
+    assert abs(rep["val_psnr"] - ref["val_psnr"]) <= 0.05                    # north-star PSNR tolerance (dB)
+    assert abs(rep["val_psnrburst0"] - ref["val_psnrburst0"]) <= 1e-3         # no network involved: fp32 kernels
+    assert abs(rep["val_psnraverage"] - ref["val_psnraverage"]) <= 1e-3
+    assert abs(rep["val_psnrnoshow0"] - ref["val_psnrnoshow0"]) <= 0.05
+    assert abs(rep["val_psnrnoshow0_unbiased"] - ref["val_psnrnoshow0_unbiased"]) <= 0.05
+    for k in ("val_deblur_loss", "val_perlayer_loss", "val_total_loss"):
+        assert abs(rep[k] - ref[k]) <= 2e-3 * max(1.0, abs(ref[k])), k
+    assert len(lines) == 8 and lines[1].startswith("epoch 3: val_deblur_loss = ")
+    # the per-step totals (asynchronous D2H copies into pinned memory) add up to the final totals
+    tot = torch.stack([p.double() for p in per_step]).sum(0)
+    assert float(tot[-1]) == nb * n
+    assert abs(float(tot[0]) / float(tot[-1]) - rep["val_psnr"]) <= 1e-9
+
+
+def test_evaluate_rejects_cpu_model_inputs(cuda):
+    from imageenhancement_mp_b200 import model_library as ml, ImgEnhError
+    params = dict(synth.DEFAULT_PARAMS)
+    model = ml.Simplemodel(params)
+    x, _ = synth.make_batch(1, 32, 32, params)
+    with pytest.raises(ImgEnhError):
+        model(x)                       # CPU tensor straight into the model: no fallback
