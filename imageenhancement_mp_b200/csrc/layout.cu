@@ -86,31 +86,62 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
 }
 
 // ------------------------------------------------------------------------------- max-pool 2x2
-// grid = (ceil((wo+1)*cvec / 256), ho+1, n); one thread per (padded output x, 16-byte channel chunk).
+// block = 256 threads = cvb channel chunks (16 B each) x 256/cvb pixel lanes; grid = (cvec/cvb, row groups, n).
+// A block walks the padded output pixels of its rows; consecutive threads touch consecutive channel chunks
+// (512-byte runs).  Optionally the per-image channel SUMS of the INPUT are accumulated on the way (each input
+// pixel belongs to exactly one 2x2 window): this is the GlobalAveragePooling2D of Poolskip
+// (model_library.py:110) on the very tensor the pool reads, so the basis branch needs no second pass over it.
+constexpr int kPoolRows = 2;           // padded output rows per block
 __global__ void __launch_bounds__(256)
-maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
-                uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const int ho = h >> 1, wo = w >> 1, wpo = wo + 1;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= wpo * cvec) return;
-  const int ox = idx / cvec, cv = idx - ox * cvec;
-  const int oy = blockIdx.y, img = blockIdx.z;
-  uint4 res = make_uint4(0, 0, 0, 0);
-  if (oy >= 1 && oy <= ho && ox < wo) {
-    const int wpi = w + 1;
-    const long long rin = ((long long)img * (h + 1) + (2 * oy - 1)) * wpi + 2 * ox;
-    const uint4* p = x + rin * x_pitch_v + x_coff_v + cv;
-    float a[8], b[8], c[8], d[8], m[8];
-    unpack8(__ldg(p), a);
-    unpack8(__ldg(p + x_pitch_v), b);
-    unpack8(__ldg(p + (long long)wpi * x_pitch_v), c);
-    unpack8(__ldg(p + (long long)(wpi + 1) * x_pitch_v), d);
+maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, int x_pitch_v, int x_coff_v,
+                uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale) {
+  const int ho = h >> 1, wo = w >> 1, wpo = wo + 1, wpi = w + 1;
+  const int cl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
+  const int cv = blockIdx.x * cvb + cl;
+  const int img = blockIdx.z;
+  const int oy0 = blockIdx.y * kPoolRows;
+  const int rows = min(kPoolRows, ho + 1 - oy0);
+  float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
-    res = pack8(m);
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (cv < cvec) {
+    for (int p = pl; p < rows * wpo; p += npl) {
+      const int ry = p / wpo, ox = p - ry * wpo;
+      const int oy = oy0 + ry;
+      uint4 res = make_uint4(0, 0, 0, 0);
+      if (oy >= 1 && ox < wo) {
+        const long long rin = ((long long)img * (h + 1) + (2 * oy - 1)) * wpi + 2 * ox;
+        const uint4* q = x + rin * x_pitch_v + x_coff_v + cv;
+        float a[8], b[8], c[8], d[8], m[8];
+        unpack8(__ldg(q), a);
+        unpack8(__ldg(q + x_pitch_v), b);
+        unpack8(__ldg(q + (long long)wpi * x_pitch_v), c);
+        unpack8(__ldg(q + (long long)(wpi + 1) * x_pitch_v), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
+          acc[e] += (a[e] + b[e]) + (c[e] + d[e]);
+        }
+        res = pack8(m);
+      }
+      const long long ro = ((long long)img * (ho + 1) + oy) * wpo + ox;
+      y[ro * y_pitch_v + y_coff_v + cv] = res;
+    }
   }
-  const long long ro = ((long long)img * (ho + 1) + oy) * wpo + ox;
-  y[ro * y_pitch_v + y_coff_v + cv] = res;
+  if (chan_sum == nullptr) return;
+  __shared__ float red[256][9];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  // thread t < cvb*8 owns channel (t / 8 -> chunk, t % 8 -> element) and sums over the pixel lanes
+  const int t = threadIdx.x;
+  if (t < cvb * 8) {
+    const int chunk = t >> 3, e = t & 7;
+    float s = 0.f;
+    for (int l = 0; l < npl; ++l) s += red[l * cvb + chunk][e];
+    const int ch = (blockIdx.x * cvb + chunk) * 8 + e;
+    if (blockIdx.x * cvb + chunk < cvec) atomicAdd(&chan_sum[(long long)img * cvec * 8 + ch], s * scale);
+  }
 }
 
 // ------------------------------------------------------------------------------- bilinear upsample
@@ -362,16 +393,20 @@ static int check_slice(const char* who, int c, int pitch, int coff) {
 }
 
 extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y,
-                                     int y_pitch, int y_coff, void* stream) {
+                                     int y_pitch, int y_coff, float* chan_mean, void* stream) {
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "maxpool2: bad arguments (h %d, w %d)", h, w);
   if (int rc = check_slice("maxpool2(x)", c, x_pitch, x_coff)) return rc;
   if (int rc = check_slice("maxpool2(y)", c, y_pitch, y_coff)) return rc;
-  IE_REQUIRE(n <= 65535 && h / 2 + 2 <= 65535, "maxpool2: grid too large");
-  int nb;
-  const int threads = row_block((long long)(w / 2 + 1) * (c / 8), &nb);
-  dim3 grid(nb, h / 2 + 1, n);
-  maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8,
-                                              static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
+  const int cvec = c / 8;
+  const int cvb = cvec < 32 ? cvec : 32;
+  const int row_groups = (h / 2 + 1 + kPoolRows - 1) / kPoolRows;
+  IE_REQUIRE(n <= 65535 && row_groups <= 65535, "maxpool2: grid too large");
+  if (chan_mean) IE_CUDA(cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
+  dim3 grid(ie_ceil_div(cvec, cvb), row_groups, n);
+  const int threads = (256 / cvb) * cvb;
+  maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, cvec, cvb, x_pitch / 8, x_coff / 8,
+                                                  static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, chan_mean,
+                                                  1.f / ((float)h * (float)w));
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -168,11 +168,14 @@ class Engine:
         for name, cout, skip in A["coef_ups"]:
             up_in[skip] = prev
             prev = cout
+        basis_skips = {skip for _, _, skip, _, _ in A["basis_ups"]}
+        skip_means = {}
         for dname, cch in A["downs"]:
             conv(dname + ".conv2d1", cur, p[dname + ".c1"].slice())
             skip = p["cat." + dname].slice(up_in[dname], cch)
             conv(dname + ".conv2d2", p[dname + ".c1"].slice(), skip)
-            ops.maxpool2(skip, p[dname + ".pool"].slice())
+            # the pool also yields the channel means of the skip it reads, if the basis branch wants them (Poolskip)
+            skip_means[dname] = ops.maxpool2(skip, p[dname + ".pool"].slice(), want_mean=dname in basis_skips)
             cur = p[dname + ".pool"].slice()
         for bname in A["bottleneck"]:
             conv(bname, cur, p[bname].slice())
@@ -199,7 +202,7 @@ class Engine:
             cat = p["bcat." + name]
             cin_up = cur.c
             ops.upsample_bilinear(cur, cat.slice(0, cin_up), s)          # Upblock.upsampling :94
-            skip_mean = ops.channel_mean(p["cat." + skip].slice(up_in[skip], chans[skip]))   # Poolskip :110
+            skip_mean = skip_means[skip]                                  # Poolskip :110, from the max-pool kernel
             ops.broadcast_hw(skip_mean, cat.slice(cin_up, chans[skip]))  # tile :112, concat :96
             conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
             conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())

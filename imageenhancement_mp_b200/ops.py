@@ -156,11 +156,14 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
     return (y, aux) if softmax else y
 
 
-def maxpool2(src: Slice, dst: Slice):
+def maxpool2(src: Slice, dst: Slice, want_mean=False):
+    """MaxPooling2D(2,2); with ``want_mean`` also returns the per-image channel means [n, c] of the INPUT slice."""
     r = src.r
     assert (dst.r.n, dst.r.h, dst.r.w) == (r.n, r.h // 2, r.w // 2) and dst.c == src.c
+    mean = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device) if want_mean else None
     call("ie_maxpool2_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff,
-         ptr(dst.r.data), dst.r.pitch, dst.coff, stream())
+         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), stream())
+    return mean
 
 
 def upsample_bilinear(src: Slice, dst: Slice, scale):

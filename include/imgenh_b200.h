@@ -99,9 +99,11 @@ int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const void* w_pa
 
 /* ---- layout glue of the U-Net (bandwidth kernels) ------------------------------------------------- */
 
-/* MaxPooling2D(2,2) (model_library.py:74): raster (h,w) slice -> raster (h/2,w/2) slice, border zeroed. */
+/* MaxPooling2D(2,2) (model_library.py:74): raster (h,w) slice -> raster (h/2,w/2) slice, border zeroed.
+ * chan_mean (nullable, [n][c] fp32): also receives the per-image channel means of the INPUT slice - the
+ * GlobalAveragePooling2D of Poolskip (model_library.py:110) on the tensor the pool reads anyway.         */
 int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y, int y_pitch,
-                          int y_coff, void* stream);
+                          int y_coff, float* chan_mean, void* stream);
 
 /* UpSampling2D(scale, 'bilinear') half-pixel centres (model_library.py:92) written straight into a
  * channel slice of the consumer's concat raster (model_library.py:96); border zeroed.               */

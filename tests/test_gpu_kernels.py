@@ -97,12 +97,18 @@ def test_maxpool(cuda):
     src = to_raster(x.to(cuda))
     dst = ops.new_raster(3, 6, 10, 128, cuda)
     dst.data.fill_(5.0)
-    ops.maxpool2(src.slice(64, 64), dst.slice(64, 64))
+    assert ops.maxpool2(src.slice(64, 64), dst.slice(64, 64)) is None
     got = ops.raster_to_nhwc(dst.slice(64, 64)).cpu()
     assert torch.equal(got, omodel.maxpool2(x[..., 64:128]))
     assert torch.all(dst.data[:, :64] == 5.0)
     dst.data[:, :64] = 0
     assert border_is_zero(dst)
+    # fused Poolskip statistics: per-image channel means of the INPUT slice (GlobalAveragePooling2D, model_library.py:110)
+    for coff, c in ((0, 192), (64, 128), (128, 64)):
+        d2 = ops.new_raster(3, 6, 10, c, cuda)
+        mean = ops.maxpool2(src.slice(coff, c), d2.slice(), want_mean=True)
+        assert torch.equal(ops.raster_to_nhwc(d2.slice()).cpu(), omodel.maxpool2(x[..., coff:coff + c]))
+        assert torch.allclose(mean.cpu(), x[..., coff:coff + c].mean(dim=(1, 2)), atol=1e-5, rtol=1e-5)
 
 
 @pytest.mark.parametrize("scale,h,w", [(2, 5, 7), (8, 2, 2), (2, 1, 1), (2, 13, 13)])
