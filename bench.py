@@ -284,6 +284,8 @@ def run_ours(args, cfg_name):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "batch_per_gpu": nb, "global_batch": nb * world, "image": [h, w],
                    "computed_at": [hp, wp], "channels": T + 1, "net": "Simplemodel T=4 K=15 B=10 singlestd, glorot init",
+                   "precision": "bf16 operands / fp32 accumulation in the convolutions, fp32 softmaxes and metrics, "
+                                "TF32 operands / fp32 accumulation in the per-pixel filter",
                    "parallelism": f"image-sharded x{world}",
                    "l2": f"{NROT} input batches rotated ({NROT * h2d_bytes >> 20} MiB) and >300 MB of activations per layer: inputs larger than L2"},
         "clocks": clocks,

@@ -137,6 +137,12 @@ int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float*
 int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
                      float* out, int n, int h, int w, int T, int K, int B, void* stream);
 
+/* Same contract on the tensor cores (warp-level TF32 MMA, fp32 accumulate) for K = 15, B <= 16, T <= 4: burst and
+ * basis are rounded to TF32 (10-bit mantissa), so the result differs from ie_kpn_apply_f32 by < 2^-10 of the
+ * pixel range - inside the path's tolerance (max-abs 1e-2 on [0,1] pixels), ~2.5x faster.                 */
+int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
+                      float* out, int n, int h, int w, int T, int K, int B, void* stream);
+
 /* Convolve / cus_convolve / Convolve_perlayer (model_library.py:114-168) with MATERIALISED filters, for callers
  * that build `filts` [n][h][w][K][K][T] themselves (the models never do - they use ie_kpn_apply_f32):
  *   out[n,y,x,0]   = sum_{i,j,t} pad0(burst)[n,y+i-K/2,x+j-K/2,t] * filts[n,y,x,i,j,t]        (Convolve.call)

@@ -172,6 +172,26 @@ def test_kpn_apply_vs_literal(cuda, n, h, w, T, B):
     assert torch.allclose(got.double(), ref, atol=2e-6, rtol=1e-5)
 
 
+@pytest.mark.parametrize("n,h,w,T,B", [(2, 16, 24, 4, 10), (1, 40, 72, 2, 10), (3, 104, 104, 4, 10), (1, 21, 150, 3, 16),
+                                       (1, 200, 300, 1, 7)])
+def test_kpn_apply_tf32_tensor_core_variant(cuda, n, h, w, T, B):
+    """The mma.sync TF32 variant: same contract; operands rounded to a 10-bit mantissa, fp32 accumulation.  Stated
+    bound: the output is a convex combination of burst pixels, so |err| <= 2^-10 * max|burst| (observed ~1e-4)."""
+    from imageenhancement_mp_b200 import ops
+    x, coef, bas = _kpn_inputs(n, h, w, T, B, 11)
+    ref = oracle.kpn_apply_algebraic(x[..., :T].double(), coef.double(), bas.double())
+    got = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda), precision="tf32").cpu()
+    err = float((got.double() - ref).abs().max())
+    assert err <= 2.0 ** -10 * float(x.abs().max()) * 1.05, err
+    f32 = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda)).cpu()
+    assert float((got - f32).abs().max()) <= 1e-3
+    # partition of unity survives the rounding of the basis to within its TF32 resolution
+    ones = torch.ones_like(x).to(cuda)
+    got1 = ops.kpn_apply(ones, T, coef.to(cuda), bas.to(cuda), precision="tf32").cpu()
+    if h > 14 and w > 14:
+        assert float((got1[:, 7:-7, 7:-7, 0] - 1).abs().max()) <= 1e-3
+
+
 def test_kpn_apply_coef_at_padded_size(cuda):
     """coef may be larger than the image (network runs at the stride-padded size): only the top-left is read."""
     from imageenhancement_mp_b200 import ops
