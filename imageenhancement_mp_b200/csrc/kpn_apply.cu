@@ -335,7 +335,8 @@ extern "C" int ie_convolve_filts_f32(const float* burst, int burst_pitch, const 
 // =================================================================================================
 namespace ie {
 
-constexpr int kTfK = 15, kTfRing = 4 + kTfK - 1, kTfTileW = 128, kTfSw = kTfTileW + kTfK - 1 + 6;   // 18 rows, pitch 148
+// ring: the 4 rows of the group being filtered + halo; pitch 144 floats
+constexpr int kTfK = 15, kTfRing = 4 + kTfK - 1, kTfTileW = 128, kTfSw = kTfTileW + kTfK - 1 + 2;
 constexpr int kTfMaxT = 4;
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -350,10 +351,101 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// 4-byte asynchronous global->shared copy; src_bytes = 0 zero-fills (tf.pad, model_library.py:126)
+__device__ __forceinline__ void cp_async4_tf(float* smem_dst, const float* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+               "r"(src_bytes)
+               : "memory");
+}
+
 struct KpnTfParams {
   int H, W, Hc, Wc, T, B, burst_pitch;
   int col_tiles, row_splits, rows_per_block;
 };
+
+// One output row segment of MT 16-px M tiles, all frames: the body of a warp's work in a row group.
+template <int MT>
+__device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag, const float* __restrict__ s_ring,
+                                             const float* __restrict__ coef, float* __restrict__ out,
+                                             const KpnTfParams& P, int img, int y, int xpx, int s0, int xw, int lane) {
+  const int T = P.T, B = P.B, W = P.W;
+  const int g = lane >> 2, c = lane & 3;
+  const float fT = (float)T;
+  float dsum[MT][2];
+  float cf[MT][2][4];                       // coef[px][2c, 2c+1, 8+2c, 9+2c] of this thread's 2*MT pixels
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    dsum[m][0] = dsum[m][1] = 0.f;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int px = xpx + 16 * m + g + 8 * hrow;
+      const float* cp = coef + (((long long)img * P.Hc + y) * P.Wc + (px < W ? px : 0)) * B;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = (q >> 1) * 8 + 2 * c + (q & 1);
+        cf[m][hrow][q] = (px < W && b < B) ? __ldg(cp + b) : 0.f;
+      }
+    }
+  }
+  for (int t = 0; t < T; ++t) {
+    float acc[MT][2][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][nt][e] = 0.f;
+    const float2* bf_t = s_bfrag + (t * kTfK) * 128 + lane;
+    const float* ring_t = s_ring + t * kTfRing * kTfSw + xw + g + c;
+    for (int i = 0; i < kTfK; ++i) {
+      int sl = s0 + i;
+      if (sl >= kTfRing) sl -= kTfRing;
+      const float* rp = ring_t + sl * kTfSw;
+      uint32_t w[4 * MT + 2];
+#pragma unroll
+      for (int q = 0; q < 4 * MT + 2; ++q) w[q] = __float_as_uint(rp[4 * q]);            // already rounded to TF32
+      const float2 b00 = bf_t[(i * 4 + 0) * 32], b01 = bf_t[(i * 4 + 1) * 32];   // ks 0: nt 0, 1
+      const float2 b10 = bf_t[(i * 4 + 2) * 32], b11 = bf_t[(i * 4 + 3) * 32];   // ks 1: nt 0, 1
+      // A[r][k] = row[16 m + r + 8 ks + k]:  a0 (g, c), a1 (g+8, c), a2 (g, c+4), a3 (g+8, c+4).
+      // All 2*MT accumulators of K step 0 first, then K step 1: dependent MMAs are 2*MT issues apart.
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        mma_tf32(acc[m][0], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b00.x), __float_as_uint(b00.y));
+        mma_tf32(acc[m][1], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b01.x), __float_as_uint(b01.y));
+      }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        mma_tf32(acc[m][0], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b10.x), __float_as_uint(b10.y));
+        mma_tf32(acc[m][1], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b11.x), __float_as_uint(b11.y));
+      }
+    }
+    // mix with the per-pixel coefficients: thread holds G[px][2c, 2c+1] (nt 0) and G[px][8+2c, 9+2c] (nt 1)
+    // for px = 16 m + g (e = 0, 1) and 16 m + g + 8 (e = 2, 3); the 4 lanes of a row add up through shuffles
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int px = xpx + 16 * m + g + 8 * hrow;
+        float s = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) s = fmaf(cf[m][hrow][nt * 2 + e], acc[m][nt][2 * hrow + e], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (c == 0 && px < W) out[(((long long)img * P.H + y) * W + px) * (T + 1) + 1 + t] = s * fT;
+        dsum[m][hrow] += s;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int px = xpx + 16 * m + g + 8 * hrow;
+      if (c == 0 && px < W) out[(((long long)img * P.H + y) * W + px) * (T + 1)] = dsum[m][hrow];
+    }
+}
 
 __global__ void __launch_bounds__(256, 2)
 kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__ coef, const float* __restrict__ bas,
@@ -372,123 +464,82 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
   if (yb0 >= H) return;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, c = lane & 3;
   const float* burst_img = burst + (long long)img * H * W * P.burst_pitch;
   const float* bas_img = bas + (long long)img * kTfK * kTfK * T * B;
 
   // ---- basis -> B fragments (once per block).  Fragment (t, i, ks, nt), lane (g, c):
   //      b0 = Bas[i][j = 8 ks + c][t][n = 8 nt + g],  b1 = Bas[i][j = 8 ks + c + 4][t][n]   (zero for j >= 15, n >= B)
-  for (int idx = threadIdx.x; idx < T * kTfK * 2 * 2 * 32; idx += blockDim.x) {
-    const int l = idx & 31, nt = (idx >> 5) & 1, ks = (idx >> 6) & 1;
-    const int ti = idx >> 7, i = ti % kTfK, t = ti / kTfK;
-    const int n = nt * 8 + (l >> 2), j0 = ks * 8 + (l & 3), j1 = j0 + 4;
-    float b0 = 0.f, b1 = 0.f;
-    if (n < B) {
-      if (j0 < kTfK) b0 = __ldg(bas_img + ((long long)(i * kTfK + j0) * T + t) * B + n);
-      if (j1 < kTfK) b1 = __ldg(bas_img + ((long long)(i * kTfK + j1) * T + t) * B + n);
+  // The image's basis [tap][t][b] is read in memory order (coalesced) and scattered to its fragment slot.
+  {
+    float* bf = reinterpret_cast<float*>(s_bfrag);
+    for (int idx = threadIdx.x; idx < T * kTfK * 2 * 2 * 32 * 2; idx += blockDim.x) bf[idx] = 0.f;
+    __syncthreads();
+    const int tb = T * B;
+    const float inv_tb = 1.f / (float)tb, inv_b = 1.f / (float)B;
+    for (int idx = threadIdx.x; idx < kTfK * kTfK * tb; idx += blockDim.x) {
+      const int tap = (int)(((float)idx + 0.5f) * inv_tb), r = idx - tap * tb;
+      const int t = (int)(((float)r + 0.5f) * inv_b), n = r - t * B;
+      const int i = tap / kTfK, j = tap - i * kTfK;
+      const int ks = j >> 3, cpos = j & 7, cc = cpos & 3, half = cpos >> 2;
+      const int nt = n >> 3, gg = n & 7;
+      bf[(((((t * kTfK + i) * 2 + ks) * 2 + nt) * 32) + gg * 4 + cc) * 2 + half] = to_tf32(__ldg(bas_img + idx));
     }
-    s_bfrag[idx] = make_float2(to_tf32(b0), to_tf32(b1));
   }
 
-  // stages burst rows [gy0, gy1) of every frame into the ring (slot = (gy + 7) mod 18), zero outside the image
+  // stages burst rows [gy0, gy1) of every frame into the ring (slot = (gy + 7) mod 18), rounded to TF32, zero outside
+  // the image.  (cp.async into a deeper ring was tried: the copy cannot round, and cvt.rna.tf32 is a 4-instruction
+  // sequence on sm_100 - converting the A fragments at load time cost more than the latency it hid.)
   auto stage_rows = [&](int gy0, int gy1) {
     const int run = (kTfTileW + kTfK - 1) * P.burst_pitch;
     const float inv_run = 1.f / (float)run, inv_pitch = 1.f / (float)P.burst_pitch;
     const int nrows = gy1 - gy0;
-    for (int idx = threadIdx.x; idx < nrows * run; idx += blockDim.x) {
-      const int r = (int)(((float)idx + 0.5f) * inv_run), e = idx - r * run;
-      const int lx = (int)(((float)e + 0.5f) * inv_pitch), ch = e - lx * P.burst_pitch;
-      if (ch < T) {
-        const int gy = gy0 + r, gx = x0 - kTfK / 2 + lx;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(burst_img + ((long long)gy * W + gx) * P.burst_pitch + ch);
-        s_ring[(ch * kTfRing + (gy + kTfK / 2) % kTfRing) * kTfSw + lx] = to_tf32(v);
+    // four independent loads in flight per thread before the first conversion / store
+    for (int idx0 = threadIdx.x; idx0 < nrows * run; idx0 += 4 * blockDim.x) {
+      float v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * blockDim.x;
+        v[u] = 0.f;
+        dst[u] = -1;
+        if (idx < nrows * run) {
+          const int r = (int)(((float)idx + 0.5f) * inv_run), e = idx - r * run;
+          const int lx = (int)(((float)e + 0.5f) * inv_pitch), ch = e - lx * P.burst_pitch;
+          if (ch < T) {
+            const int gy = gy0 + r, gx = x0 - kTfK / 2 + lx;
+            dst[u] = (ch * kTfRing + (gy + kTfK / 2) % kTfRing) * kTfSw + lx;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v[u] = __ldg(burst_img + ((long long)gy * W + gx) * P.burst_pitch + ch);
+          }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u] >= 0) s_ring[dst[u]] = to_tf32(v[u]);
     }
   };
-  // the 6 pad columns of every ring row are read by the A loads of the last M tile (never used for a valid pixel)
-  for (int idx = threadIdx.x; idx < T * kTfRing * 6; idx += blockDim.x)
-    s_ring[(idx / 6) * kTfSw + kTfTileW + kTfK - 1 + idx % 6] = 0.f;
+  // the 2 pad columns of every ring row are read by the A loads of the last M tile (never used for a valid pixel)
+  for (int idx = threadIdx.x; idx < T * kTfRing * 2; idx += blockDim.x)
+    s_ring[(idx / 2) * kTfSw + kTfTileW + kTfK - 1 + idx % 2] = 0.f;
 
   const int wr = warp >> 1;                  // row of the group this warp filters
   const int xw = (warp & 1) * 64;            // its 64-px half of the tile
-  const float fT = (float)T;
+  const int mt = min(4, (W - x0 - xw + 15) >> 4);                         // M tiles of this warp that hold real pixels
 
   for (int yg = yb0; yg < yb1; yg += 4) {
     __syncthreads();                                                      // previous group done with the ring
     if (yg == yb0) stage_rows(yg - kTfK / 2, yg + 4 + kTfK / 2);
     else stage_rows(yg + kTfK / 2, yg + 4 + kTfK / 2);                    // 4 new rows
     __syncthreads();
-
     const int y = yg + wr;
+    if (y >= yb1) continue;
     const int s0 = y % kTfRing;                                           // slot of burst row y - 7 (filter row 0)
-    float dsum[4][2];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) dsum[m][0] = dsum[m][1] = 0.f;
-
-    const int mt = min(4, (W - x0 - xw + 15) >> 4);                       // M tiles of this warp that hold real pixels
-    if (y < yb1 && mt > 0) {
-      for (int t = 0; t < T; ++t) {
-        float acc[4][2][4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[m][nt][e] = 0.f;
-        const float2* bf_t = s_bfrag + (t * kTfK) * 128 + lane;
-        const float* ring_t = s_ring + t * kTfRing * kTfSw + xw + g + c;
-        for (int i = 0; i < kTfK; ++i) {
-          int sl = s0 + i;
-          if (sl >= kTfRing) sl -= kTfRing;
-          const float* rp = ring_t + sl * kTfSw;
-          uint32_t w[18];
-#pragma unroll
-          for (int q = 0; q < 18; ++q) w[q] = __float_as_uint(rp[4 * q]);
-          const float2 b00 = bf_t[(i * 4 + 0) * 32], b01 = bf_t[(i * 4 + 1) * 32];   // ks 0: nt 0, 1
-          const float2 b10 = bf_t[(i * 4 + 2) * 32], b11 = bf_t[(i * 4 + 3) * 32];   // ks 1: nt 0, 1
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (m >= mt) break;                                           // warp-uniform
-            // A[r][k] = row[16 m + r + 8 ks + k]:  a0 (g, c), a1 (g+8, c), a2 (g, c+4), a3 (g+8, c+4)
-            mma_tf32(acc[m][0], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b00.x), __float_as_uint(b00.y));
-            mma_tf32(acc[m][1], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b01.x), __float_as_uint(b01.y));
-            mma_tf32(acc[m][0], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b10.x), __float_as_uint(b10.y));
-            mma_tf32(acc[m][1], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b11.x), __float_as_uint(b11.y));
-          }
-        }
-        // mix with the per-pixel coefficients: thread holds G[px][2c, 2c+1] (nt 0) and G[px][8+2c, 9+2c] (nt 1)
-        // for px = 16 m + g (e = 0, 1) and 16 m + g + 8 (e = 2, 3); the 4 lanes of a row add up through shuffles
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-#pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow) {
-            const int px = x0 + xw + 16 * m + g + 8 * hrow;
-            float s = 0.f;
-            if (px < W) {
-              const float* cp = coef + (((long long)img * P.Hc + y) * P.Wc + px) * B;
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int b = nt * 8 + 2 * c + e;
-                  if (b < B) s = fmaf(__ldg(cp + b), acc[m][nt][2 * hrow + e], s);
-                }
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (c == 0 && px < W) out[(((long long)img * H + y) * W + px) * (T + 1) + 1 + t] = s * fT;
-            dsum[m][hrow] += s;
-          }
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-          const int px = x0 + xw + 16 * m + g + 8 * hrow;
-          if (c == 0 && px < W) out[(((long long)img * H + y) * W + px) * (T + 1)] = dsum[m][hrow];
-        }
+    // the warp's 64 px as two halves of 2 M tiles: the per-pixel coefficients of a half stay in registers across
+    // the frames (they were re-loaded per frame at first: a third of the stall samples were their latency)
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int m_left = mt - 2 * half;                                   // warp-uniform
+      if (m_left >= 2) kpn_tf32_row<2>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xw + 32 * half, s0, xw + 32 * half, lane);
+      else if (m_left == 1) kpn_tf32_row<1>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xw + 32 * half, s0, xw + 32 * half, lane);
     }
   }
 }
@@ -506,11 +557,12 @@ extern "C" int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const floa
   KpnTfParams P{};
   P.H = h; P.W = w; P.Hc = hc; P.Wc = wc; P.T = T; P.B = B; P.burst_pitch = burst_pitch;
   P.col_tiles = (w + kTfTileW - 1) / kTfTileW;
-  // blocks: one per (image, 128-px column) if that already fills the GPU twice over, else split the rows too
+  // blocks: ~4 per SM so that the last wave is short, but at least 4 row groups each (the basis fragments and the
+  // 14 halo rows are staged once per block)
   const long long base = (long long)n * P.col_tiles;
   const int groups = (h + 3) / 4;
-  long long splits = (2ll * sm_count() + base - 1) / base;
-  if (splits > groups / 4) splits = groups / 4;          // at least 4 row groups per block (the basis is staged per block)
+  long long splits = (4ll * sm_count() + base - 1) / base;
+  if (splits > groups / 4) splits = groups / 4;
   if (splits < 1) splits = 1;
   P.rows_per_block = (int)(((groups + splits - 1) / splits) * 4);
   P.row_splits = (h + P.rows_per_block - 1) / P.rows_per_block;

@@ -181,10 +181,13 @@ def test_kpn_apply_tf32_tensor_core_variant(cuda, n, h, w, T, B):
     x, coef, bas = _kpn_inputs(n, h, w, T, B, 11)
     ref = oracle.kpn_apply_algebraic(x[..., :T].double(), coef.double(), bas.double())
     got = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda), precision="tf32").cpu()
-    err = float((got.double() - ref).abs().max())
-    assert err <= 2.0 ** -10 * float(x.abs().max()) * 1.05, err
+    # channel 0 is a convex combination of burst pixels: |err| <= 2^-10 max|burst| (two operands rounded to 2^-11
+    # each); the per-frame channels carry the reference's factor T (model_library.py:164) on a partial sum
+    bound = 2.0 ** -10 * float(x.abs().max()) * 1.05
+    assert float((got[..., 0].double() - ref[..., 0]).abs().max()) <= bound
+    assert float((got[..., 1:].double() - ref[..., 1:]).abs().max()) <= T * bound
     f32 = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda)).cpu()
-    assert float((got - f32).abs().max()) <= 1e-3
+    assert float((got - f32).abs().max()) <= T * bound
     # partition of unity survives the rounding of the basis to within its TF32 resolution
     ones = torch.ones_like(x).to(cuda)
     got1 = ops.kpn_apply(ones, T, coef.to(cuda), bas.to(cuda), precision="tf32").cpu()
