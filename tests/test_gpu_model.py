@@ -42,6 +42,23 @@ def run_pair(cuda, arch, params, n, h, w, scheme, seed=1234, conv_fn="ie_conv2d_
     return res_g, taps_g, (out_o,) + tuple(res_o[1:]), taps_o, x, truth
 
 
+def test_small_batches_replay_a_cuda_graph(cuda):
+    """Launch-bound inputs (eval.py's default: one 32x32 patch) go through a captured CUDA graph: same bits as the
+    eager launch sequence, and later calls with new data of the same shape reuse the graph."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    model = ml.Simplemodel(params, weights=W)
+    eager = ml.Simplemodel(dict(params, graph_max_pixels=0), weights=W)
+    for seed in (1, 2, 3):
+        x, _ = synth.make_batch(1, 32, 32, params, seed=seed)
+        a = model(x.to(cuda))
+        b = eager(x.to(cuda))
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+    assert len(model._engine._graphs) == 1 and len(eager._engine._graphs) == 0
+
+
 def test_filter_precision_switch(cuda):
     """filter_precision='fp32' routes the per-pixel filter through the CUDA-core kernel; the default (tensor-core
     TF32 kernel) differs from it by far less than the path's tolerance."""
