@@ -69,7 +69,11 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region.
+
+    nvidia-smi needs up to a second to enumerate an 8-GPU box before its first line: `wait_first` blocks until a
+    sample has arrived, and `mark()` remembers where the timed region starts so that only samples taken under load
+    are summarised (all samples if the region was too short to catch one)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -77,26 +81,39 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
+        self.lines = []
+        self.start_at = 0
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception:
             self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line)
+        threading.Thread(target=pump, daemon=True).start()
+
+    def wait_first(self, timeout=8.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.start_at = len(self.lines)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.12)                       # one more sampling period: the last line covers the end of the region
         self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
+        lines = self.lines[self.start_at:] or self.lines
         sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
+        for line in lines:
             f = [s.strip() for s in line.split(",")]
             if len(f) < 9:
                 continue
@@ -202,11 +219,15 @@ def run_ours(args, cfg_name):
             torch.cuda.synchronize()
 
     # ---- resident-input timing
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(*devb[i % NROT])
+    if rank == 0:
+        sampler.wait_first()
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     _lib.LAUNCHES.clear()
     ops.CONV_EVENTS = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,7 +279,7 @@ def run_ours(args, cfg_name):
     sync_all()
     e2e_ms = e0.elapsed_time(e1)
     assert len(res) == args.steps and abs(e2e_report["count"] - world * nb * args.steps) < 0.5
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms, e2e_ms, conv_ms], dtype=torch.float64, device=dev)
     if world > 1:
