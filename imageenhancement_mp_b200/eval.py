@@ -25,11 +25,23 @@ REPORT_KEYS = ("val_deblur_loss", "val_perlayer_loss", "val_total_loss", "val_ps
                "val_psnrburst0", "val_psnraverage")
 
 
-def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length):
-    """Forward + fused metrics for one (local) batch -> additive fp64 totals on the device."""
-    reconstructed = model(x_batch_burst)[0]                                       # eval.py:143
+def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None):
+    """Forward + fused metrics for one (local) batch -> additive fp64 totals on the device.
+
+    ``vis``: optional dict of lists receiving the reference's visualisation arrays for this batch (eval.py:164-169):
+    invert_gt, invert_deblur, invert_perlayer, Basis, originbasis (numpy, one device->host copy each)."""
+    res = model(x_batch_burst)                                                    # eval.py:143
+    reconstructed = res[0]
     n, h, w, _ = reconstructed.shape
     sums = du.eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length)   # :144-182
+    if vis is not None:
+        wl = du.white_level_of(x_batch_truth)                                     # :144-145
+        vis["invert_gt"].append(du.invert_preproc(x_batch_truth[..., 0], wl).cpu().numpy())         # :146-147
+        vis["invert_deblur"].append(du.invert_preproc(reconstructed[..., 0], wl).cpu().numpy())     # :148-149
+        vis["invert_perlayer"].append(du.invert_deblur_layer(reconstructed, wl).cpu().numpy())      # :158
+        vis["Basis"].append(res[1].cpu().numpy())
+        if len(res) > 2:
+            vis["originbasis"].append(res[2].cpu().numpy())
     return du.reduce_metric_sums(sums, h, w, burst_length)
 
 
@@ -104,7 +116,7 @@ def format_report(report, step=1):
 
 
 def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, step_results=None, device=None,
-             pre_sharded=False):
+             pre_sharded=False, visualization=False, dump_path=None):
     """Validation loop.  val_batches yields (x_batch_burst [N,H,W,T+add], x_batch_truth [N,H,W,2]), on the
     device or in (pinned) host memory.
 
@@ -114,10 +126,18 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
     ``step_results``: optional list; every step's additive totals are appended to it as pinned host
     tensors (asynchronous device->host copies, complete when evaluate returns) - the per-batch numbers
     the reference reads with ``.numpy()`` at eval.py:165-182, without its per-batch stalls.
+    ``visualization`` (eval.py:41 ``--visualization``): also collect invert_gt / invert_deblur / invert_perlayer /
+    Basis / originbasis of every local batch and write them with ``np.savez`` like eval.py:201-207 (to ``dump_path``,
+    default ``data<time>.npz``; with several ranks every rank writes ``<stem>.rank<r>.npz`` for its shard).
     Returns the report dict (identical on all ranks); rank 0 prints it through ``out``.
     """
     T = params["BURST_LENGTH"]
-    fn = gpu_step_totals if step_totals is None else step_totals
+    vis = {k: [] for k in ("invert_gt", "invert_deblur", "invert_perlayer", "Basis", "originbasis")} \
+        if (visualization and step_totals is None) else None
+    if step_totals is not None:
+        fn = step_totals
+    else:
+        fn = lambda m, xb, xt, T_: gpu_step_totals(m, xb, xt, T_, vis=vis)
     totals = None
     nb = 0
     if step_totals is None:
@@ -140,6 +160,14 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
         raise ValueError("evaluate: no validation data on this rank")
     _dist.all_reduce_totals(totals)                                                # the one exchange step
     report = make_report(totals.cpu(), nb, T)                                      # the one D2H copy
+    if vis is not None:
+        import datetime
+        import numpy as np
+        path = dump_path or ("data" + datetime.datetime.now().strftime("%Y%m%d-%H%M%S") + ".npz")
+        if _dist.world() > 1:
+            path = (path[:-4] if path.endswith(".npz") else path) + ".rank%d.npz" % _dist.rank()
+        np.savez(path, **{k: np.stack(v) for k, v in vis.items() if v})            # eval.py:201-207
+        report["dump_path"] = path
     if _dist.rank() == 0 and out is not None:
         out('-----------------------------validation resule for %d------------------------------' % int(report["count"]))
         for line in format_report(report, step):

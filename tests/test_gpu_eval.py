@@ -51,6 +51,30 @@ def test_evaluate_matches_oracle_report(cuda, where, nb, n, h, w):
     assert abs(float(tot[0]) / float(tot[-1]) - rep["val_psnr"]) <= 1e-9
 
 
+def test_evaluate_visualization_dump(cuda, tmp_path):
+    """--visualization (eval.py:41,164-169,201-207): the .npz holds the same five arrays, one entry per batch."""
+    import numpy as np
+    from imageenhancement_mp_b200 import eval as ieval, model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    batches = [synth.make_batch(2, 32, 40, params, seed=70 + i) for i in range(2)]
+    model = ml.Simplemodel(params, weights=W)
+    path = str(tmp_path / "dump.npz")
+    rep = ieval.evaluate(model, [(x.to(cuda), t.to(cuda)) for x, t in batches], params, out=None,
+                         visualization=True, dump_path=path)
+    z = np.load(rep["dump_path"])
+    assert sorted(z.files) == ["Basis", "invert_deblur", "invert_gt", "invert_perlayer", "originbasis"]
+    assert z["invert_gt"].shape == (2, 2, 16, 24) and z["invert_perlayer"].shape == (2, 2, 16, 24 * 4)
+    assert z["Basis"].shape == (2, 2, 15, 15, 4, 10) and z["originbasis"].shape == (2, 2, 15, 15, 40)
+    x, t = batches[1]
+    wl = t[..., 1:2].double().mean(dim=(1, 2), keepdim=True)
+    ref_gt = oracle.invert_preproc(t[..., 0].double(), wl)
+    assert np.allclose(z["invert_gt"][1], ref_gt.numpy(), atol=2e-6, rtol=1e-5)
+    out = oracle.simplemodel_forward(W, params, x)[0]
+    # bf16 trunk error amplified by 1/white_level and the sRGB slope (12.92 near black): compare the mean
+    assert np.abs(z["invert_deblur"][1] - oracle.invert_preproc(out[..., 0].double(), wl).numpy()).mean() <= 5e-3
+
+
 def test_evaluate_rejects_cpu_model_inputs(cuda):
     from imageenhancement_mp_b200 import model_library as ml, ImgEnhError
     params = dict(synth.DEFAULT_PARAMS)
