@@ -57,6 +57,7 @@ SIGNATURES = {
     "ie_sqdiff_sum_f32": [_P, _P, _I, _LL, _P, _P],
     "ie_img_loss_sums_f32": [_P, _P, _I, _I, _I, _P, _P],
     "ie_ssim_f32": [_P, _P, _I, _I, _I, _P, _P],
+    "ie_preprocess_u8_rng": [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P, C.c_ulonglong, _I, _I, _I, _I, _P, _P, _P],
     "ie_preprocess_u8": [_P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
 }
 

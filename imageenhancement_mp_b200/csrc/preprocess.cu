@@ -6,12 +6,35 @@
 
 namespace ie {
 
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): counter-based, so the normals of
+// element i depend only on (seed, i) - reproducible across grids, ranks and the numpy oracle (oracle/preprocess.py).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f; }
+// two standard normals for element `idx`: Box-Muller on (u0,u1) and (u2,u3)
+__device__ __forceinline__ void normal_pair(unsigned long long seed, unsigned long long idx, float& z0, float& z1) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float two_pi = 6.283185307179586f;
+  z0 = sqrtf(-2.f * logf(u01(c[0]))) * cosf(two_pi * u01(c[1]));
+  z1 = sqrtf(-2.f * logf(u01(c[2]))) * cosf(two_pi * u01(c[3]));
+}
+
 __global__ void __launch_bounds__(256)
 preprocess_u8_kernel(const uint8_t* __restrict__ src, int hs, int ws, int c, const int32_t* __restrict__ org, int up,
                      float degamma, const float* __restrict__ wl, const float* __restrict__ sig_read,
                      const float* __restrict__ sig_shot, const float* __restrict__ n_read,
-                     const float* __restrict__ n_shot, int layer_type, int h, int w, int T, float* __restrict__ x,
-                     float* __restrict__ truth, long long total) {
+                     const float* __restrict__ n_shot, unsigned long long seed, int use_rng, int layer_type, int h,
+                     int w, int T, float* __restrict__ x, float* __restrict__ truth, long long total) {
   __shared__ float lut[256];   // (v/255)^degamma has 256 possible values (data_utils.py:213)
   lut[threadIdx.x] = powf((float)threadIdx.x / 255.f, degamma);
   __syncthreads();
@@ -48,6 +71,10 @@ preprocess_u8_kernel(const uint8_t* __restrict__ src, int hs, int ws, int c, con
     if (n_read != nullptr && n_shot != nullptr) {
       const long long ni = t * T + f;
       v = tr + sqrtf(tr) * ss * n_shot[ni] + sr * n_read[ni];       // :463-465
+    } else if (use_rng) {
+      float zs, zr;                                                 // tf.random.normal x2 of add_read_shot_tf, on device
+      normal_pair(seed, (unsigned long long)(t * T + f), zs, zr);
+      v = tr + sqrtf(tr) * ss * zs + sr * zr;
     }
     xo[f] = v;
     if (f == 0) {
@@ -77,7 +104,23 @@ extern "C" int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c
   IE_REQUIRE((n_read == nullptr) == (n_shot == nullptr), "preprocess_u8: give both noise tensors or neither");
   const long long total = (long long)n * h * w;
   preprocess_u8_kernel<<<ie_ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, n_read, n_shot, layer_type, h, w, T, x, truth, total);
+      src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, n_read, n_shot, 0ull, 0, layer_type, h, w, T, x, truth, total);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_preprocess_u8_rng(const uint8_t* src, int n, int hs, int ws, int c, const int32_t* org, int up,
+                                    float degamma, const float* wl, const float* sig_read, const float* sig_shot,
+                                    unsigned long long seed, int layer_type, int h, int w, int T, float* x, float* truth,
+                                    void* stream) {
+  using namespace ie;
+  IE_REQUIRE(src && org && wl && sig_read && sig_shot && x && truth, "preprocess_u8_rng: null pointer");
+  IE_REQUIRE(n > 0 && hs > 0 && ws > 0 && c > 0 && up >= 1 && h > 0 && w > 0 && T >= 1, "preprocess_u8_rng: bad sizes");
+  IE_REQUIRE(layer_type >= 0 && layer_type <= 2, "preprocess_u8_rng: layer_type must be 0, 1 or 2");
+  const long long total = (long long)n * h * w;
+  preprocess_u8_kernel<<<ie_ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, nullptr, nullptr, seed, 1, layer_type, h, w, T, x, truth,
+      total);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -225,12 +225,13 @@ def eval_metrics(reconstructed, x_batch_burst, x_batch_truth, burst_length):
 
 
 # ------------------------------------------------------------------ preprocessing
-def preprocess_image(src_u8, org, params, white_level, sig_read, sig_shot, n_read=None, n_shot=None):
+def preprocess_image(src_u8, org, params, white_level, sig_read, sig_shot, n_read=None, n_shot=None, seed=None):
     """Batched arithmetic of DataLoader.preprocess_image (data_utils.py:198-265).
 
     src_u8 [N,Hs,Ws,C] uint8 CUDA; org [N,T,2] int32 crop origins (y,x) per frame in source pixels
     (see oracle.preprocess.frame_origins for how the reference's nested crops map to them);
-    white_level / sig_read / sig_shot [N] fp32; n_read / n_shot [N,h,w,T] standard normals or None.
+    white_level / sig_read / sig_shot [N] fp32; n_read / n_shot [N,h,w,T] standard normals or None;
+    ``seed`` (int, instead of the noise tensors): draw the normals on the device (Philox4x32-10 + Box-Muller).
     Returns (x [N,h,w,T+add], truth [N,h,w,2]) like the reference's (noisy++sig, truth++white_level).
     """
     _lib.require_cuda(src_u8, org, white_level, sig_read, sig_shot)
@@ -246,6 +247,12 @@ def preprocess_image(src_u8, org, params, white_level, sig_read, sig_shot, n_rea
     f = lambda t: t.contiguous().float()
     nr = f(n_read) if n_read is not None else None
     ns = f(n_shot) if n_shot is not None else None
+    if seed is not None:
+        assert nr is None and ns is None, "give either the noise tensors or a seed"
+        call("ie_preprocess_u8_rng", ptr(src_u8.contiguous()), n, hs, ws, c, ptr(org.contiguous()), up,
+             float(params["degamma"]), ptr(f(white_level)), ptr(f(sig_read)), ptr(f(sig_shot)), int(seed) & (2 ** 64 - 1),
+             lt, h, w, T, ptr(x), ptr(truth), stream())
+        return x, truth
     call("ie_preprocess_u8", ptr(src_u8.contiguous()), n, hs, ws, c, ptr(org.contiguous()), up,
          float(params["degamma"]), ptr(f(white_level)), ptr(f(sig_read)), ptr(f(sig_shot)), ptr(nr), ptr(ns), lt,
          h, w, T, ptr(x), ptr(truth), stream())

@@ -201,6 +201,14 @@ int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c, const int
                      const float* n_shot, int layer_type, int h, int w, int T, float* x, float* truth,
                      void* stream);
 
+/* Same, with the read / shot noise normals of add_read_shot_tf (data_utils.py:462-466) drawn ON THE DEVICE:
+ * Philox4x32-10 keyed by `seed`, counter = element index ((n*h + y)*w + x)*T + t, Box-Muller; element-wise
+ * reproducible (numpy restatement: oracle/preprocess.py::philox_normals).  The reference draws from TF's RNG
+ * stream, which is not reproducible outside TF: the distribution is the contract, not the bits.               */
+int ie_preprocess_u8_rng(const uint8_t* src, int n, int hs, int ws, int c, const int32_t* org, int up, float degamma,
+                         const float* wl, const float* sig_read, const float* sig_shot, unsigned long long seed,
+                         int layer_type, int h, int w, int T, float* x, float* truth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,3 +89,32 @@ def frame_origins(params, draws):
         base = 0 if draws["use_big"][k] else delta_up
         out.append((cy + base + oy, cx + base + ox))
     return out
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw - SC'11, Random123) on numpy uint64 arrays holding 32-bit values."""
+    import numpy as np
+    c = [np.asarray(v, dtype=np.uint64) for v in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return c
+
+
+def philox_normals(seed, count):
+    """numpy restatement of the device noise generator (csrc/preprocess.cu): Philox4x32-10 keyed by ``seed``,
+    counter = element index, Box-Muller on (u0,u1) -> z_shot and (u2,u3) -> z_read.  Returns two float32 arrays."""
+    import numpy as np
+    idx = np.arange(count, dtype=np.uint64)
+    zero = np.zeros(count, np.uint64)
+    c = philox4x32_10(idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), zero, zero,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u = [((v >> np.uint64(8)).astype(np.float64) * 2.0 ** -24 + 2.0 ** -25) for v in c]
+    z_shot = np.sqrt(-2.0 * np.log(u[0])) * np.cos(2.0 * np.pi * u[1])
+    z_read = np.sqrt(-2.0 * np.log(u[2])) * np.cos(2.0 * np.pi * u[3])
+    return z_shot.astype(np.float32), z_read.astype(np.float32)

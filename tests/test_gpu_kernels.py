@@ -360,3 +360,29 @@ def test_preprocess(cuda, layer_type, color):
                                  f(wl), f(sr), f(ss), torch.stack(nr).to(cuda), torch.stack(ns).to(cuda))
     assert torch.allclose(gx.cpu().double(), torch.stack(xs), atol=2e-6, rtol=2e-5)
     assert torch.allclose(gt.cpu().double(), torch.stack(ts), atol=2e-6, rtol=2e-5)
+
+
+def test_preprocess_device_noise_matches_numpy_philox(cuda):
+    """ie_preprocess_u8_rng: the normals drawn on the device (Philox4x32-10 + Box-Muller) are the ones the numpy
+    restatement produces, element by element - so the noisy burst equals the explicit-noise kernel fed with them."""
+    from oracle import preprocess as opre
+    from imageenhancement_mp_b200 import data_utils as du
+    params = dict(synth.DEFAULT_PARAMS, height=20, width=28, BURST_LENGTH=4, layer_type="singlestd")
+    N, T, up = 3, 4, 4
+    g = torch.Generator().manual_seed(9)
+    hs, ws = 20 * up + 40, 28 * up + 24
+    src = torch.randint(0, 256, (N, hs, ws, 1), generator=g, dtype=torch.uint8).to(cuda)
+    org = torch.randint(0, 20, (N, T, 2), generator=g, dtype=torch.int32).to(cuda)
+    wl = torch.tensor([0.3, 0.7, 1.0], device=cuda)
+    sr = torch.tensor([0.01, 0.003, 0.02], device=cuda)
+    ss = torch.tensor([0.05, 0.02, 0.09], device=cuda)
+    seed = 0x1234_5678_9abc
+    x_rng, t_rng = du.preprocess_image(src, org, params, wl, sr, ss, seed=seed)
+    zs, zr = opre.philox_normals(seed, N * 20 * 28 * T)
+    n_shot = torch.from_numpy(zs).view(N, 20, 28, T).to(cuda)
+    n_read = torch.from_numpy(zr).view(N, 20, 28, T).to(cuda)
+    x_exp, t_exp = du.preprocess_image(src, org, params, wl, sr, ss, n_read=n_read, n_shot=n_shot)
+    assert torch.equal(t_rng, t_exp)
+    assert torch.allclose(x_rng, x_exp, atol=2e-6, rtol=1e-5)
+    clean, _ = du.preprocess_image(src, org, params, wl, sr, ss)
+    assert float((x_rng[..., :T] - clean[..., :T]).abs().max()) > 1e-3          # noise really was added

@@ -145,3 +145,20 @@ def test_eval_report_reproduces_leading_zero_bias():
     assert r["val_psnrnoshow0"] == pytest.approx(30.0 * 3 / 4)       # eval.py:136,193 start the list with [0]
     assert r["val_psnrnoshow0_unbiased"] == pytest.approx(30.0)
     assert r["val_total_loss"] == pytest.approx(3.0)
+
+
+def test_philox4x32_10_known_answers():
+    """The device noise generator is Philox4x32-10; its numpy restatement against the Random123 known-answer vectors
+    (kat_vectors: philox4x32 10 rounds)."""
+    from oracle import preprocess as opre
+    got = [int(v[0]) for v in opre.philox4x32_10([0], [0], [0], [0], 0, 0)]
+    assert got == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    got = [int(v[0]) for v in opre.philox4x32_10([f], [f], [f], [f], f, f)]
+    assert got == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    got = [int(v[0]) for v in opre.philox4x32_10([0x243f6a88], [0x85a308d3], [0x13198a2e], [0x03707344], 0xa4093822, 0x299f31d0)]
+    assert got == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    zs, zr = opre.philox_normals(1234, 200000)
+    assert abs(float(zs.mean())) < 0.01 and abs(float(zs.std()) - 1) < 0.01
+    assert abs(float(zr.mean())) < 0.01 and abs(float(zr.std()) - 1) < 0.01
+    assert abs(float((zs * zr).mean())) < 0.01
