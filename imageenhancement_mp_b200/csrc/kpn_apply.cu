@@ -359,7 +359,8 @@ __device__ __forceinline__ void cp_async4_tf(float* smem_dst, const float* gsrc,
 }
 
 struct KpnTfParams {
-  int H, W, Hc, Wc, T, B, burst_pitch;
+  int H, W, Hc, Wc, T, B, burst_pitch;   // T = frames handled by this launch
+  int t0, Ttot, accumulate;              // first frame, frames of the burst, add the frame sum to out[...,0]
   int col_tiles, row_splits, rows_per_block;
 };
 
@@ -370,7 +371,7 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
                                              const KpnTfParams& P, int img, int y, int xpx, int s0, int xw, int lane) {
   const int T = P.T, B = P.B, W = P.W;
   const int g = lane >> 2, c = lane & 3;
-  const float fT = (float)T;
+  const float fT = (float)P.Ttot;
   float dsum[MT][2];
   float cf[MT][2][4];                       // coef[px][2c, 2c+1, 8+2c, 9+2c] of this thread's 2*MT pixels
 #pragma unroll
@@ -433,7 +434,7 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
           for (int e = 0; e < 2; ++e) s = fmaf(cf[m][hrow][nt * 2 + e], acc[m][nt][2 * hrow + e], s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (c == 0 && px < W) out[(((long long)img * P.H + y) * W + px) * (T + 1) + 1 + t] = s * fT;
+        if (c == 0 && px < W) out[(((long long)img * P.H + y) * W + px) * (P.Ttot + 1) + 1 + P.t0 + t] = s * fT;
         dsum[m][hrow] += s;
       }
     }
@@ -443,7 +444,10 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int px = xpx + 16 * m + g + 8 * hrow;
-      if (c == 0 && px < W) out[(((long long)img * P.H + y) * W + px) * (T + 1)] = dsum[m][hrow];
+      if (c == 0 && px < W) {
+        float* o0 = out + (((long long)img * P.H + y) * W + px) * (P.Ttot + 1);
+        *o0 = P.accumulate ? *o0 + dsum[m][hrow] : dsum[m][hrow];
+      }
     }
 }
 
@@ -465,7 +469,7 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* burst_img = burst + (long long)img * H * W * P.burst_pitch;
-  const float* bas_img = bas + (long long)img * kTfK * kTfK * T * B;
+  const float* bas_img = bas + (long long)img * kTfK * kTfK * P.Ttot * B;
 
   // ---- basis -> B fragments (once per block).  Fragment (t, i, ks, nt), lane (g, c):
   //      b0 = Bas[i][j = 8 ks + c][t][n = 8 nt + g],  b1 = Bas[i][j = 8 ks + c + 4][t][n]   (zero for j >= 15, n >= B)
@@ -474,7 +478,7 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
     float* bf = reinterpret_cast<float*>(s_bfrag);
     for (int idx = threadIdx.x; idx < T * kTfK * 2 * 2 * 32 * 2; idx += blockDim.x) bf[idx] = 0.f;
     __syncthreads();
-    const int tb = T * B;
+    const int tb = T * B;                      // this launch's frames [t0, t0+T) are contiguous within a tap
     const float inv_tb = 1.f / (float)tb, inv_b = 1.f / (float)B;
     for (int idx = threadIdx.x; idx < kTfK * kTfK * tb; idx += blockDim.x) {
       const int tap = (int)(((float)idx + 0.5f) * inv_tb), r = idx - tap * tb;
@@ -482,7 +486,8 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
       const int i = tap / kTfK, j = tap - i * kTfK;
       const int ks = j >> 3, cpos = j & 7, cc = cpos & 3, half = cpos >> 2;
       const int nt = n >> 3, gg = n & 7;
-      bf[(((((t * kTfK + i) * 2 + ks) * 2 + nt) * 32) + gg * 4 + cc) * 2 + half] = to_tf32(__ldg(bas_img + idx));
+      bf[(((((t * kTfK + i) * 2 + ks) * 2 + nt) * 32) + gg * 4 + cc) * 2 + half] =
+          to_tf32(__ldg(bas_img + ((long long)tap * P.Ttot + P.t0) * B + r));
     }
   }
 
@@ -505,10 +510,11 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
         if (idx < nrows * run) {
           const int r = (int)(((float)idx + 0.5f) * inv_run), e = idx - r * run;
           const int lx = (int)(((float)e + 0.5f) * inv_pitch), ch = e - lx * P.burst_pitch;
-          if (ch < T) {
+          if (ch < T) {                       // (channels t0 + ch of the pixel are read below)
             const int gy = gy0 + r, gx = x0 - kTfK / 2 + lx;
             dst[u] = (ch * kTfRing + (gy + kTfK / 2) % kTfRing) * kTfSw + lx;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v[u] = __ldg(burst_img + ((long long)gy * W + gx) * P.burst_pitch + ch);
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+              v[u] = __ldg(burst_img + ((long long)gy * W + gx) * P.burst_pitch + P.t0 + ch);
           }
         }
       }
@@ -551,11 +557,11 @@ extern "C" int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const floa
   using namespace ie;
   IE_REQUIRE(burst && coef && bas && out, "kpn_apply_tf32: null pointer");
   IE_REQUIRE(n > 0 && h > 0 && w > 0, "kpn_apply_tf32: bad sizes");
-  IE_REQUIRE(K == kTfK && B >= 1 && B <= 16 && T >= 1 && T <= kTfMaxT,
-             "kpn_apply_tf32: built for K = 15, B <= 16, T <= %d (got K=%d B=%d T=%d); use ie_kpn_apply_f32", kTfMaxT, K, B, T);
+  IE_REQUIRE(K == kTfK && B >= 1 && B <= 16 && T >= 1 && T <= 2 * kTfMaxT,
+             "kpn_apply_tf32: built for K = 15, B <= 16, T <= %d (got K=%d B=%d T=%d); use ie_kpn_apply_f32", 2 * kTfMaxT, K, B, T);
   IE_REQUIRE(burst_pitch >= T && hc >= h && wc >= w, "kpn_apply_tf32: bad pitch / coef extent");
   KpnTfParams P{};
-  P.H = h; P.W = w; P.Hc = hc; P.Wc = wc; P.T = T; P.B = B; P.burst_pitch = burst_pitch;
+  P.H = h; P.W = w; P.Hc = hc; P.Wc = wc; P.B = B; P.burst_pitch = burst_pitch; P.Ttot = T;
   P.col_tiles = (w + kTfTileW - 1) / kTfTileW;
   // blocks: ~4 per SM so that the last wave is short, but at least 4 row groups each (the basis fragments and the
   // 14 halo rows are staged once per block)
@@ -568,9 +574,16 @@ extern "C" int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const floa
   P.row_splits = (h + P.rows_per_block - 1) / P.rows_per_block;
   const long long blocks = base * P.row_splits;
   IE_REQUIRE(blocks < (1ll << 31), "kpn_apply_tf32: too many blocks");
-  const size_t smem = sizeof(float) * ((size_t)T * kTfK * 2 * 2 * 32 * 2 + (size_t)T * kTfRing * kTfSw);
-  IE_CUDA(cudaFuncSetAttribute(kpn_apply_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kpn_apply_tf32_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(burst, coef, bas, out, P);
+  // the basis fragments of 4 frames fill the shared memory: longer bursts run as two passes over the frames, the
+  // second adding its frame sum to out[...,0]
+  for (int t0 = 0; t0 < T; t0 += kTfMaxT) {
+    P.t0 = t0;
+    P.T = (T - t0 < kTfMaxT) ? T - t0 : kTfMaxT;
+    P.accumulate = t0 > 0;
+    const size_t smem = sizeof(float) * ((size_t)P.T * kTfK * 2 * 2 * 32 * 2 + (size_t)P.T * kTfRing * kTfSw);
+    IE_CUDA(cudaFuncSetAttribute(kpn_apply_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kpn_apply_tf32_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(burst, coef, bas, out, P);
+  }
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -62,7 +62,7 @@ class Engine:
             raise ImgEnhError("Kernel_size must be 15: the basis branch emits 15x15 kernels (model_library.py:364)")
         self.device = torch.device(device)
         # per-pixel filter: "tf32" = tensor-core kernel (operands rounded to a 10-bit mantissa, fp32 accumulation,
-        # |err| <= 2^-10 of the pixel range) where it applies (K=15, B<=16, T<=4), "fp32" = CUDA-core kernel (1e-5)
+        # |err| <= 2^-10 of the pixel range) where it applies (K=15, B<=16, T<=8), "fp32" = CUDA-core kernel (1e-5)
         self.filter_precision = params.get("filter_precision", "tf32")
         if self.filter_precision not in ("tf32", "fp32"):
             raise ImgEnhError("filter_precision must be 'tf32' or 'fp32'")

@@ -173,12 +173,13 @@ def test_kpn_apply_vs_literal(cuda, n, h, w, T, B):
 
 
 @pytest.mark.parametrize("n,h,w,T,B", [(2, 16, 24, 4, 10), (1, 40, 72, 2, 10), (3, 104, 104, 4, 10), (1, 21, 150, 3, 16),
-                                       (1, 200, 300, 1, 7)])
+                                       (1, 200, 300, 1, 7), (2, 64, 64, 8, 10), (1, 33, 47, 6, 12)])
 def test_kpn_apply_tf32_tensor_core_variant(cuda, n, h, w, T, B):
     """The mma.sync TF32 variant: same contract; operands rounded to a 10-bit mantissa, fp32 accumulation.  Stated
     bound: the output is a convex combination of burst pixels, so |err| <= 2^-10 * max|burst| (observed ~1e-4)."""
     from imageenhancement_mp_b200 import ops
     x, coef, bas = _kpn_inputs(n, h, w, T, B, 11)
+    x = torch.cat([x, torch.rand(n, h, w, 1)], -1) if T > 4 else x      # T+2 channels: the pitch is not T+1
     ref = oracle.kpn_apply_algebraic(x[..., :T].double(), coef.double(), bas.double())
     got = ops.kpn_apply(x.to(cuda), T, coef.to(cuda), bas.to(cuda), precision="tf32").cpu()
     # channel 0 is a convex combination of burst pixels: |err| <= 2^-10 max|burst| (two operands rounded to 2^-11
