@@ -303,8 +303,8 @@ def run_ours(args, cfg_name):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": desc, "batch_per_gpu": nb, "global_batch": nb * world, "image": [h, w],
-                   "computed_at": [hp, wp], "channels": T + 1, "net": "Simplemodel T=4 K=15 B=10 singlestd, glorot init",
+        "config": {"workload": desc, "images_per_gpu_per_step": nb, "images_per_step": nb * world, "image": [h, w],
+                   "computed_at": [hp, wp], "channels": T + 1, "network": "Simplemodel T=4 K=15 B=10 singlestd, glorot init",
                    "precision": "bf16 operands / fp32 accumulation in the convolutions, fp32 softmaxes and metrics, "
                                 "TF32 operands / fp32 accumulation in the per-pixel filter",
                    "parallelism": f"image-sharded x{world}",
