@@ -162,3 +162,35 @@ def test_philox4x32_10_known_answers():
     assert abs(float(zs.mean())) < 0.01 and abs(float(zs.std()) - 1) < 0.01
     assert abs(float(zr.mean())) < 0.01 and abs(float(zr.std()) - 1) < 0.01
     assert abs(float((zs * zr).mean())) < 0.01
+
+
+def test_conv_pool_resize_against_independent_implementations():
+    """The TensorFlow semantics the oracle ASSUMES, cross-checked against independent
+    implementations of the same published definitions that exist in this image: scipy's correlate2d for
+    Conv2D(..., 'same') / 'valid' (cross-correlation, symmetric zero padding), a numpy block-max for
+    MaxPooling2D(2,2), OpenCV's half-pixel-centre INTER_LINEAR for UpSampling2D('bilinear') and scipy's softmax."""
+    import cv2
+    import numpy as np
+    from scipy.signal import correlate2d
+    from scipy.special import softmax
+    from oracle import model as omodel
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 9, 11, 3, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, 3, 4, generator=g, dtype=torch.float64)
+    b = torch.randn(4, generator=g, dtype=torch.float64)
+    for padding, mode in (("same", "same"), ("valid", "valid")):
+        got = omodel.conv2d_relu(x, (w, b), padding)[0].numpy()
+        ref = np.stack([sum(correlate2d(x[0, :, :, ci].numpy(), w[:, :, ci, co].numpy(), mode=mode, boundary="fill")
+                            for ci in range(3)) + float(b[co]) for co in range(4)], axis=-1)
+        assert np.allclose(got, np.maximum(ref, 0), atol=1e-12)
+    xp = torch.randn(2, 6, 8, 5, generator=g, dtype=torch.float64)
+    blocks = xp.numpy().reshape(2, 3, 2, 4, 2, 5).max(axis=(2, 4))
+    assert np.array_equal(omodel.maxpool2(xp).numpy(), blocks)
+    xu = torch.rand(1, 5, 7, 3, generator=g, dtype=torch.float32)
+    for s in (2, 8):
+        ref = cv2.resize(xu[0].numpy(), (7 * s, 5 * s), interpolation=cv2.INTER_LINEAR)
+        assert np.allclose(omodel.upsample_bilinear(xu, s)[0].numpy(), ref, atol=1e-5)
+    ob = torch.randn(2, 15, 15, 40, generator=g, dtype=torch.float64)
+    bas = omodel.basis_softmax(ob, 15, 4, 10)                                   # softmax over the 900 taps per basis
+    ref = softmax(ob.numpy().reshape(2, 900, 10), axis=1).reshape(2, 15, 15, 4, 10)
+    assert np.allclose(bas.numpy(), ref, atol=1e-14)
