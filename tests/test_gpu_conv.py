@@ -199,3 +199,32 @@ def test_conv_rejects_bad_descriptors(cuda):
     wp = torch.zeros(64, 9 * 96, dtype=torch.bfloat16, device=cuda)
     with pytest.raises(ImgEnhError):
         ops.conv2d(src.slice(), wp, None, dst.slice())
+
+
+def test_conv_random_shape_sweep_vs_naive(cuda):
+    """Randomised layer shapes through every dispatch path (streaming at three N tiles, resident, wide-N resident /
+    streaming, adaptive N tile on small rasters) against the CUDA-core validation kernel."""
+    import random
+    from imageenhancement_mp_b200 import ops
+    rnd = random.Random(7)
+    for trial in range(24):
+        cin = rnd.choice([64, 64, 128, 192, 320, 640])
+        cout = rnd.choice([64, 64, 128, 192, 256, 512])
+        k = rnd.choice([3, 3, 3, 1, 2])
+        n = rnd.choice([1, 2, 5])
+        h, w = rnd.randint(2, 40), rnd.randint(2, 44)
+        if k == 2 and (h < 2 or w < 2):
+            continue
+        x, wt, b = make_case(n, h, w, cin, cout, k, seed=100 + trial)
+        src = to_raster(x.to(cuda))
+        wp = ops.pack_conv_weights(wt.to(cuda))
+        bias = b.to(cuda)
+        valid = (h - 1, w - 1) if k == 2 else None
+        d1 = ops.new_raster(n, h, w, cout, cuda)
+        d2 = ops.new_raster(n, h, w, cout, cuda)
+        d1.data.fill_(float("nan"))
+        ops.conv2d(src.slice(), wp, bias, d1.slice(), k=k, valid=valid)
+        ops.conv2d(src.slice(), wp, bias, d2.slice(), k=k, valid=valid, fn="ie_debug_conv2d_naive")
+        torch.cuda.synchronize()
+        assert not torch.isnan(d1.data).any(), f"trial {trial}: unwritten output ({n},{h},{w},{cin}->{cout},k{k})"
+        assert_close_bf16(d1.data.float().cpu(), d2.data.float().cpu(), f"trial {trial}: ({n},{h},{w},{cin}->{cout},k{k})")
