@@ -32,7 +32,6 @@ namespace ie {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // bf16 elements = 128 bytes = one swizzle row
-constexpr int kUmmaK = 16;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kThreads = 192;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kThreads2 = 320;       // + warps 6-9: a second epilogue set (narrow layers: the epilogue is the critical path)
@@ -434,7 +433,6 @@ struct ResidentParams {
   int a_box_bytes;       // box_rows*128 rounded up to 1024
   int a_slot_bytes;      // G boxes
   int b_tile_bytes;      // n_tile*128
-  int use_base_offset;   // descriptor base-offset field = (start >> 7) & 7 for row-shifted starts
 };
 
 // NDX = horizontal taps; G = filter rows fused into one pipeline stage (G = 3 needs kb == 1: the whole
@@ -1082,14 +1080,13 @@ static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
-static int g_base_offset = 0;      // measured on B200: the 128B swizzle is a function of the absolute smem address,
-                                      // so row-shifted descriptor starts need NO base-offset field (setting it corrupts)
+// (measured on B200: the 128B swizzle is a function of the absolute smem address, so row-shifted descriptor starts
+//  need NO base-offset field - setting it corrupts; the experiment lived behind flag bit 0, now unused)
 
 }  // namespace ie
 
 extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_force_mode = mode;
-  ie::g_base_offset = flags & 1;
   ie::g_fuse_rows = (flags & 2) ? 0 : 1;
   ie::g_wide_flags = (flags >> 2) & 7;
   return IE_OK;
@@ -1233,7 +1230,6 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     p.a_box_bytes = a_box;
     p.a_slot_bytes = a_slot;
     p.b_tile_bytes = e.n_tile * 128;
-    p.use_base_offset = g_base_offset;
     rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, (uint32_t)box_rows);
     if (rc) return rc;
     if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;

@@ -89,8 +89,9 @@ int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_pack
                         float* y_f32, float* y_aux, void* stream);
 
 /* Tuning / test hook: force the main-loop flavour of ie_conv2d_nhwc_bf16 (-1 auto, 0 streaming, 1 resident
- * weights) and whether row-shifted smem descriptors carry the base-offset field.  Process-wide.        */
-int ie_conv_set_mode(int mode, int use_base_offset);
+ * weights, 2 wide-N).  flags: bit 1 one filter row per stage in the resident kernel, bit 2 wide-N streams its
+ * weights, bit 3 flip the number of epilogue warp sets, bit 4 one filter row per stage in wide-N.  Process-wide. */
+int ie_conv_set_mode(int mode, int flags);
 
 /* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at
  * sizes the CPU oracle cannot reach).  Never called by the product path.                             */
