@@ -84,12 +84,12 @@ __global__ void invert_preproc_kernel(const float* __restrict__ img, int pitch, 
 
 // ------------------------------------------------------------------------------- fused eval metrics
 // A block owns a 32-px-wide column strip of one image's cropped area over a range of rows and walks it in
-// sub-tiles of 8 rows (+1 halo row/column for the forward differences).  For every pixel of the haloed
+// sub-tiles of 32 rows (+1 halo row/column for the forward differences).  For every pixel of the haloed
 // sub-tile the error images d_k = sRGB(e_k/wl) - sRGB(gt/wl) go to shared memory, then each interior thread
 // accumulates d_k^2 and |d_k(y+1,x)-d_k(y,x)|/2 + |d_k(y,x+1)-d_k(y,x)|/2 in registers; ONE block reduction
 // and 2T+4 fp64 atomics per block at the end.  The kernel is bound by instruction issue (T+4 sRGB curves per
 // pixel), not by HBM: the curve uses the MUFU lg2/ex2 approximations (relative error < 1e-6).
-constexpr int kMT_W = 32, kMT_H = 8, kMaxT = 8;
+constexpr int kMT_W = 32, kMT_H = 32, kMaxT = 8;     // sub-tile: 32 x 32 px, 4 rows per thread (+1 halo row / column)
 
 __device__ __forceinline__ float srgb_fast(float x) {
   const float b = .0031308f, a = .055f, k0 = 12.92f;
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256)
 eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ burst, int burst_pitch,
                     const float* __restrict__ truth, const float* __restrict__ wl, int h, int w, int T, int crop,
                     int rows_per_block, double* __restrict__ sums) {
-  __shared__ float s_d[kMaxT + 1][kMT_H + 1][kMT_W + 1];
+  extern __shared__ float s_d[];                       // [T+1][kMT_H+1][kMT_W+1]
+  constexpr int SW = kMT_W + 1, SH = kMT_H + 1;
   const int n = blockIdx.z;
   const int hc = h - 2 * crop, wc = w - 2 * crop;
   const int x0 = blockIdx.x * kMT_W;
@@ -116,16 +117,19 @@ eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ b
   const float inv_T = 1.f / (float)T;
   const int nq = (T + 3) + (T + 1);
 
+  // statically indexed accumulators (a run-time T in the index would push the array to local memory):
+  // acc[k] squared error of e_k, acc[9] burst0, acc[10] burst mean, acc[11 + k] gradient L1 of e_k
   float acc[2 * kMaxT + 4];
 #pragma unroll
   for (int q = 0; q < 2 * kMaxT + 4; ++q) acc[q] = 0.f;
 
   for (int y0 = ys; y0 < ye; y0 += kMT_H) {
     if (y0 != ys) __syncthreads();
-    for (int i = threadIdx.x; i < (kMT_H + 1) * (kMT_W + 1); i += 256) {
-      const int ly = i / (kMT_W + 1), lx = i - ly * (kMT_W + 1);
+    // 33 x 33 pixel evaluations by 256 threads: 4 full passes + a 65-pixel tail (6 % halo overhead)
+    for (int i = threadIdx.x; i < SH * SW; i += 256) {
+      const int ly = i / SW, lx = i - ly * SW;
       const int y = y0 + ly, x = x0 + lx;
-      const bool inside = (y < hc) && (x < wc);
+      const bool inside = (y < hc) && (x < wc) && (y <= ye);         // the row at ye is only the halo of row ye-1
       // halo pixels are owned by the neighbouring tile / sub-tile
       const bool owner = inside && ly < kMT_H && lx < kMT_W && y < ye;
       if (inside) {
@@ -137,7 +141,7 @@ eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ b
         for (int k = 0; k < kMaxT + 1; ++k) {
           if (k <= T) {
             const float d = srgb_fast(rp[k] * inv_wl) - g;
-            s_d[k][ly][lx] = d;
+            s_d[(k * SH + ly) * SW + lx] = d;
             if (owner) acc[k] = fmaf(d, d, acc[k]);
           }
         }
@@ -153,27 +157,54 @@ eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ b
           }
           const float d0 = srgb_fast(b0 * inv_wl) - g;                 // psnr_burst0, data_utils.py:152-154
           const float da = srgb_fast((bsum * inv_T) * inv_wl) - g;     // psnr_average_f, :162-164
-          acc[T + 1] = fmaf(d0, d0, acc[T + 1]);
-          acc[T + 2] = fmaf(da, da, acc[T + 2]);
+          acc[kMaxT + 1] = fmaf(d0, d0, acc[kMaxT + 1]);
+          acc[kMaxT + 2] = fmaf(da, da, acc[kMaxT + 2]);
         }
       }
     }
     __syncthreads();
     {
-      const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
-      const int y = y0 + ly, x = x0 + lx;
-      if (y < ye && y < hc - 1 && x < wc - 1) {
+      const int lx = threadIdx.x & 31;
+      const int x = x0 + lx;
 #pragma unroll
-        for (int k = 0; k < kMaxT + 1; ++k) {
-          if (k <= T) {
-            const float c = s_d[k][ly][lx];
-            acc[T + 3 + k] += .5f * fabsf(s_d[k][ly + 1][lx] - c) + .5f * fabsf(s_d[k][ly][lx + 1] - c);
+      for (int r = 0; r < kMT_H / 8; ++r) {
+        const int ly = (threadIdx.x >> 5) + 8 * r;
+        const int y = y0 + ly;
+        if (y < ye && y < hc - 1 && x < wc - 1) {
+#pragma unroll
+          for (int k = 0; k < kMaxT + 1; ++k) {
+            if (k <= T) {
+              const float c = s_d[(k * SH + ly) * SW + lx];
+              acc[kMaxT + 3 + k] += .5f * fabsf(s_d[(k * SH + ly + 1) * SW + lx] - c) + .5f * fabsf(s_d[(k * SH + ly) * SW + lx + 1] - c);
+            }
           }
         }
       }
     }
   }
-  block_accumulate<2 * kMaxT + 4>(acc, sums + (long long)n * nq, nq);
+  // block reduction; static slot q -> output index: k -> k, 9 -> T+1, 10 -> T+2, 11+k -> T+3+k
+  __shared__ float red[8][2 * kMaxT + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 2 * kMaxT + 4; ++q) {
+    const float v = warp_sum(acc[q]);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kMaxT + 4) {
+    const int q = threadIdx.x;
+    int dst = -1;
+    if (q <= kMaxT) dst = (q <= T) ? q : -1;
+    else if (q == kMaxT + 1) dst = T + 1;
+    else if (q == kMaxT + 2) dst = T + 2;
+    else dst = (q - kMaxT - 3 <= T) ? T + 3 + (q - kMaxT - 3) : -1;
+    if (dst >= 0) {
+      double v = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) v += (double)red[wq][q];
+      atomicAdd(&sums[(long long)n * nq + dst], v);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------- per-image sums -> totals
@@ -483,8 +514,10 @@ extern "C" int ie_eval_metrics_f32(const float* recon, const float* burst, int b
   const int rows_per_block = subs_per_block * kMT_H;
   const int ysplit = (hc + rows_per_block - 1) / rows_per_block;
   IE_REQUIRE(n <= 65535 && ysplit <= 65535, "eval_metrics: grid too large");
-  eval_metrics_kernel<<<dim3(tiles_x, ysplit, n), 256, 0, S(stream)>>>(recon, burst, burst_pitch, truth, wl, h, w, T, crop,
-                                                                       rows_per_block, sums);
+  const size_t smem = sizeof(float) * (size_t)(T + 1) * (kMT_H + 1) * (kMT_W + 1);
+  IE_CUDA(cudaFuncSetAttribute(eval_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  eval_metrics_kernel<<<dim3(tiles_x, ysplit, n), 256, smem, S(stream)>>>(recon, burst, burst_pitch, truth, wl, h, w, T,
+                                                                          crop, rows_per_block, sums);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
