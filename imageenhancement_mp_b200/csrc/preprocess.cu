@@ -38,14 +38,15 @@ preprocess_u8_kernel(const uint8_t* __restrict__ src, int hs, int ws, int c, con
   __shared__ float lut[256];   // (v/255)^degamma has 256 possible values (data_utils.py:213)
   lut[threadIdx.x] = powf((float)threadIdx.x / 255.f, degamma);
   __syncthreads();
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int px = (int)(t % w);
-  const int py = (int)((t / w) % h);
-  const int n = (int)(t / ((long long)w * h));
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y, n = blockIdx.z;
+  if (px >= w) return;
+  const long long t = ((long long)n * h + py) * w + px;
+  (void)total;
   const int add = layer_type == 1 ? 1 : (layer_type == 2 ? 2 : 0);
   const float wln = wl[n], sr = sig_read[n], ss = sig_shot[n];
   const uint8_t* img = src + (long long)n * hs * ws * c;
+  const bool img_aligned = (reinterpret_cast<uintptr_t>(img) & 3) == 0;
   const float inv_area = 1.f / (float)(up * up);
   float* xo = x + t * (T + add);
   float noisy0 = 0.f;
@@ -53,6 +54,22 @@ preprocess_u8_kernel(const uint8_t* __restrict__ src, int hs, int ws, int c, con
     const int oy = org[((long long)n * T + f) * 2] + py * up;
     const int ox = org[((long long)n * T + f) * 2 + 1] + px * up;
     float csum = 0.f;
+    // fast path (the reference defaults: upscale 4, grey source): the 4x4 window is inside the image -> per row one
+    // unaligned 4-byte fetch assembled from two aligned words (funnel shift), no per-sample bounds checks
+    const long long first = (long long)oy * ws + ox;
+    if (up == 4 && c == 1 && oy >= 0 && oy + 4 <= hs && ox >= 0 && ox + 4 <= ws &&
+        (((long long)(oy + 3) * ws + ox) & ~3ll) + 8 <= (long long)hs * ws && img_aligned) {
+      float s = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 4; ++dy) {
+        const long long off = first + (long long)dy * ws;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (off & ~3ll));
+        const uint32_t lo = __ldg(wp), hi = __ldg(wp + 1);
+        const uint32_t v = __funnelshift_r(lo, hi, 8 * (int)(off & 3));
+        s += (lut[v & 255u] + lut[(v >> 8) & 255u]) + (lut[(v >> 16) & 255u] + lut[v >> 24]);
+      }
+      csum = s * inv_area;
+    } else
     for (int ch = 0; ch < c; ++ch) {          // AREA mean per channel, then channel mean (:459, :220)
       float s = 0.f;
       for (int dy = 0; dy < up; ++dy) {
@@ -103,7 +120,8 @@ extern "C" int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c
   IE_REQUIRE(layer_type >= 0 && layer_type <= 2, "preprocess_u8: layer_type must be 0 (empty), 1 (singlestd), 2 (dualparams)");
   IE_REQUIRE((n_read == nullptr) == (n_shot == nullptr), "preprocess_u8: give both noise tensors or neither");
   const long long total = (long long)n * h * w;
-  preprocess_u8_kernel<<<ie_ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  IE_REQUIRE(n <= 65535 && h <= 65535, "preprocess_u8: grid too large");
+  preprocess_u8_kernel<<<dim3(ie_ceil_div(w, 256), h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, n_read, n_shot, 0ull, 0, layer_type, h, w, T, x, truth, total);
   IE_LAUNCH_CHECK();
   return IE_OK;
@@ -118,7 +136,8 @@ extern "C" int ie_preprocess_u8_rng(const uint8_t* src, int n, int hs, int ws, i
   IE_REQUIRE(n > 0 && hs > 0 && ws > 0 && c > 0 && up >= 1 && h > 0 && w > 0 && T >= 1, "preprocess_u8_rng: bad sizes");
   IE_REQUIRE(layer_type >= 0 && layer_type <= 2, "preprocess_u8_rng: layer_type must be 0, 1 or 2");
   const long long total = (long long)n * h * w;
-  preprocess_u8_kernel<<<ie_ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  IE_REQUIRE(n <= 65535 && h <= 65535, "preprocess_u8_rng: grid too large");
+  preprocess_u8_kernel<<<dim3(ie_ceil_div(w, 256), h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, nullptr, nullptr, seed, 1, layer_type, h, w, T, x, truth,
       total);
   IE_LAUNCH_CHECK();
