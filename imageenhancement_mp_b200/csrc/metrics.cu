@@ -365,37 +365,22 @@ img_loss_sums_vec_kernel(const float* __restrict__ a, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------- SSIM (extension)
-// Output tile 64 x 32 (VALID): input 74 x 42.  Horizontal 11-tap pass with 8 outputs per thread
-// (sliding window in registers) over the five moments a, b, a^2, b^2, ab, then the vertical pass.
-constexpr int kSW = 64, kSH = 32, kSR = 5, kSTaps = 11;
-constexpr int kSInW = kSW + 2 * kSR, kSInH = kSH + 2 * kSR;      // 74 x 42
-constexpr int kSInPitch = 76;
+// tf.image.ssim semantics: 11-tap Gaussian (sigma 1.5) window, VALID, K1 = .01, K2 = .03, max_val 1.
+constexpr int kSR = 5, kSTaps = 11;
 
-__global__ void __launch_bounds__(256)
-ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, int tiles_x, int tiles_y,
-            double* __restrict__ sums) {
-  extern __shared__ float sm[];
-  float* s_a = sm;                                 // [42][76]
-  float* s_b = s_a + kSInH * kSInPitch;            // [42][76]
-  float* s_m = s_b + kSInH * kSInPitch;            // [5][42][64]
-  int bid = blockIdx.x;
-  const int txi = bid % tiles_x; bid /= tiles_x;
-  const int tyi = bid % tiles_y;
-  const int n = bid / tiles_y;
+// Streaming SSIM: a thread owns one output COLUMN of a 128-column strip and walks down the rows.  Per input row it
+// filters its 11 horizontal neighbours (coalesced loads through L1: lane i reads x+i .. x+i+10) into the five moments
+// (a, b, a^2, b^2, ab) as fp32 pairs (FFMA2), pushes them into an 11-row window held in REGISTERS, and once the window
+// is full produces one output row with the vertical pass.  No shared memory, no barriers, no horizontal halo work;
+// vertical halo = 10 rows per kSsimRows outputs.
+constexpr int kSsimRows = 128;
+__global__ void __launch_bounds__(128)
+ssim_stream_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, double* __restrict__ sums) {
+  const int n = blockIdx.z;
   const int ho = h - 2 * kSR, wo = w - 2 * kSR;
-  const int x0 = txi * kSW, y0 = tyi * kSH;
-  const float* pa = a + (long long)n * h * w;
-  const float* pb = b + (long long)n * h * w;
-  for (int i = threadIdx.x; i < kSInH * kSInPitch; i += 256) {
-    const int ly = i / kSInPitch, lx = i - ly * kSInPitch;
-    const int y = y0 + ly, x = x0 + lx;
-    float va = 0.f, vb = 0.f;
-    if (lx < kSInW && y < h && x < w) { va = pa[(long long)y * w + x]; vb = pb[(long long)y * w + x]; }
-    s_a[i] = va;
-    s_b[i] = vb;
-  }
-  __syncthreads();
-  // normalised 11-tap Gaussian, sigma 1.5 (tf.image.ssim's _fspecial_gauss)
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;            // output column
+  const int y0 = blockIdx.y * kSsimRows;                          // first output row of this block
+  const int y1 = min(y0 + kSsimRows, ho);
   float g[kSTaps];
   {
     float gs = 0.f;
@@ -408,84 +393,62 @@ ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int
 #pragma unroll
     for (int k = 0; k < kSTaps; ++k) g[k] /= gs;
   }
-  // horizontal: work item = (row, group of 8 columns)
-  for (int item = threadIdx.x; item < kSInH * (kSW / 8); item += 256) {
-    const int ly = item / (kSW / 8), gx = (item - ly * (kSW / 8)) * 8;
-    float ra[8 + 2 * kSR + 2], rb[8 + 2 * kSR + 2];
-    const float4* qa = reinterpret_cast<const float4*>(s_a + ly * kSInPitch + gx);
-    const float4* qb = reinterpret_cast<const float4*>(s_b + ly * kSInPitch + gx);
-#pragma unroll
-    for (int v = 0; v < 5; ++v) {
-      const float4 u = qa[v], z = qb[v];
-      ra[4 * v] = u.x; ra[4 * v + 1] = u.y; ra[4 * v + 2] = u.z; ra[4 * v + 3] = u.w;
-      rb[4 * v] = z.x; rb[4 * v + 1] = z.y; rb[4 * v + 2] = z.z; rb[4 * v + 3] = z.w;
-    }
-    float m[5][8];
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
-#pragma unroll
-      for (int p = 0; p < 8; ++p) m[q][p] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8 + 2 * kSR; ++k) {
-      const float va = ra[k], vb = rb[k];
-      const float aa = va * va, bb = vb * vb, ab = va * vb;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int tap = k - p;
-        if (tap >= 0 && tap < kSTaps) {
-          m[0][p] = fmaf(g[tap], va, m[0][p]);
-          m[1][p] = fmaf(g[tap], vb, m[1][p]);
-          m[2][p] = fmaf(g[tap], aa, m[2][p]);
-          m[3][p] = fmaf(g[tap], bb, m[3][p]);
-          m[4][p] = fmaf(g[tap], ab, m[4][p]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      float4* dst = reinterpret_cast<float4*>(s_m + (q * kSInH + ly) * kSW + gx);
-      dst[0] = make_float4(m[q][0], m[q][1], m[q][2], m[q][3]);
-      dst[1] = make_float4(m[q][4], m[q][5], m[q][6], m[q][7]);
-    }
-  }
-  __syncthreads();
-  // vertical: thread = (column, group of 8 rows)
-  float acc[1] = {0.f};
-  {
-    const int lx = threadIdx.x & 63, gy = (threadIdx.x >> 6) * 8;
-    float m[5][8];
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
-#pragma unroll
-      for (int p = 0; p < 8; ++p) m[q][p] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8 + 2 * kSR; ++k) {
-      float v[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) v[q] = s_m[(q * kSInH + gy + k) * kSW + lx];
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int tap = k - p;
-        if (tap >= 0 && tap < kSTaps) {
-#pragma unroll
-          for (int q = 0; q < 5; ++q) m[q][p] = fmaf(g[tap], v[q], m[q][p]);
-        }
-      }
-    }
+  float acc = 0.f;
+  if (x < wo) {
+    const float* pa = a + (long long)n * h * w + x;
+    const float* pb = b + (long long)n * h * w + x;
+    // vertical window: hm[r] = horizontally filtered moments of input row (current - r)
+    float2 w_ab[kSTaps], w_sq[kSTaps];
+    float w_x[kSTaps];
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+    // input rows y0 .. y1 + 9; output row (yi - 10) is complete after input row yi
+    for (int yi0 = y0; yi0 < y1 + 2 * kSR; yi0 += kSTaps) {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int y = y0 + gy + p, x = x0 + lx;
-      if (y < ho && x < wo) {
-        const float mu_a = m[0][p], mu_b = m[1][p];
-        const float num0 = 2.f * mu_a * mu_b, den0 = mu_a * mu_a + mu_b * mu_b;
-        const float lum = (num0 + c1) / (den0 + c1);
-        const float cs = (2.f * m[4][p] - num0 + c2) / (m[2][p] + m[3][p] - den0 + c2);
-        acc[0] += lum * cs;
+      for (int slot = 0; slot < kSTaps; ++slot) {                  // the window rotates by one slot per input row
+        const int yi = yi0 + slot;
+        if (yi < y1 + 2 * kSR) {
+          const float* ra = pa + (long long)yi * w;
+          const float* rb = pb + (long long)yi * w;
+          float2 m_ab = make_float2(0.f, 0.f), m_sq = make_float2(0.f, 0.f);
+          float m_x = 0.f;
+#pragma unroll
+          for (int k = 0; k < kSTaps; ++k) {
+            const float va = __ldg(ra + k), vb = __ldg(rb + k);
+            const float2 gg = make_float2(g[k], g[k]);
+            m_ab = __ffma2_rn(gg, make_float2(va, vb), m_ab);
+            m_sq = __ffma2_rn(gg, make_float2(va * va, vb * vb), m_sq);
+            m_x = fmaf(g[k], va * vb, m_x);
+          }
+          w_ab[slot] = m_ab; w_sq[slot] = m_sq; w_x[slot] = m_x;
+          const int yo = yi - 2 * kSR;
+          if (yo >= y0) {
+            // vertical pass: input row yi - r sits in slot (slot - r) mod 11 and takes tap 10 - r
+            float2 v_ab = make_float2(0.f, 0.f), v_sq = make_float2(0.f, 0.f);
+            float v_x = 0.f;
+#pragma unroll
+            for (int r = 0; r < kSTaps; ++r) {
+              const int sl = (slot - r + kSTaps) % kSTaps;           // compile-time
+              const float2 gg = make_float2(g[kSTaps - 1 - r], g[kSTaps - 1 - r]);
+              v_ab = __ffma2_rn(gg, w_ab[sl], v_ab);
+              v_sq = __ffma2_rn(gg, w_sq[sl], v_sq);
+              v_x = fmaf(g[kSTaps - 1 - r], w_x[sl], v_x);
+            }
+            const float mu_a = v_ab.x, mu_b = v_ab.y;
+            const float num0 = 2.f * mu_a * mu_b, den0 = mu_a * mu_a + mu_b * mu_b;
+            const float lum = (num0 + c1) / (den0 + c1);
+            const float cs = (2.f * v_x - num0 + c2) / (v_sq.x + v_sq.y - den0 + c2);
+            acc += lum * cs;
+          }
+        }
       }
     }
   }
-  block_accumulate<1>(acc, sums + n, 1);
+  // 128-thread block reduction
+  __shared__ float red[4];
+  const float s = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&sums[n], (double)red[0] + (double)red[1] + (double)red[2] + (double)red[3]);
 }
 
 }  // namespace ie
@@ -590,12 +553,10 @@ extern "C" int ie_img_loss_sums_f32(const float* a, const float* b, int n, int h
 
 extern "C" int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream) {
   IE_REQUIRE(a && b && sums && n > 0 && h >= kSTaps && w >= kSTaps, "ssim: images must be at least 11x11");
-  const int tiles_x = (w - 2 * kSR + kSW - 1) / kSW, tiles_y = (h - 2 * kSR + kSH - 1) / kSH;
-  const long long blocks = (long long)n * tiles_x * tiles_y;
-  IE_REQUIRE(blocks < (1ll << 31), "ssim: too many tiles");
-  const size_t smem = sizeof(float) * (2 * kSInH * kSInPitch + 5 * kSInH * kSW);
-  IE_CUDA(cudaFuncSetAttribute(ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ssim_kernel<<<(unsigned)blocks, 256, smem, S(stream)>>>(a, b, h, w, tiles_x, tiles_y, sums);
+  const int ho = h - 2 * kSR, wo = w - 2 * kSR;
+  const int gy = (ho + kSsimRows - 1) / kSsimRows;
+  IE_REQUIRE(n <= 65535 && gy <= 65535, "ssim: grid too large");
+  ssim_stream_kernel<<<dim3(ie_ceil_div(wo, 128), gy, n), 128, 0, S(stream)>>>(a, b, h, w, sums);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
