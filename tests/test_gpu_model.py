@@ -183,3 +183,28 @@ def test_no_cpu_fallback(cuda):
     m = ml.Simplemodel(params, weights=W)
     with pytest.raises(ImgEnhError):
         m(torch.zeros(1, 32, 32, 5))
+
+
+def test_full_size_batch_is_image_independent(cuda):
+    """BASELINE configs[1] at full size (256 patches of 100x100): every image of the batch gets the result it gets
+    alone - the size-independent property that catches cross-image leaks through the shared-border raster, the
+    overlapping wide-N tiles, the persistent tile loops and the per-image pooled statistics."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    model = ml.Simplemodel(params, weights=W)
+    x, _ = synth.make_batch(256, 100, 100, params, seed=77)
+    xd = x.to(cuda)
+    out, bas, ob = model(xd)
+    assert out.shape == (256, 100, 100, 5) and bool(torch.isfinite(out).all())
+    for i in (0, 1, 127, 200, 255):
+        o1, b1, ob1 = model(xd[i:i + 1].contiguous())
+        # the per-image channel means are accumulated with atomics (summation order varies): allow fp32 noise
+        assert float((ob1[0] - ob[i]).abs().max()) <= 2e-4 * float(ob[i].abs().max())
+        assert float((b1[0] - bas[i]).abs().max()) <= 1e-5
+        assert float((o1[0] - out[i]).abs().max()) <= 2e-4
+    # partition of unity at full size: both softmaxes sum to one, so a constant burst stays constant >= 7 px inside
+    xc = xd.clone()
+    xc[..., :4] = 0.5
+    oc = model(xc)[0]
+    assert float((oc[:, 7:-7, 7:-7, 0] - 0.5).abs().max()) <= 2e-3
