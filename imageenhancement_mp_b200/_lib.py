@@ -41,9 +41,9 @@ SIGNATURES = {
     "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
     "ie_conv_set_mode": [_I, _I],
     "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
-    "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P],
+    "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _P],
     "ie_upsample_bilinear_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
-    "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _LL, _P],
     "ie_broadcast_hw_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "ie_raster_to_nhwc_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "ie_softmax_taps_f32": [_P, _I, _I, _I, _P, _P],

@@ -94,7 +94,8 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
 constexpr int kPoolRows = 2;           // padded output rows per block
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, int x_pitch_v, int x_coff_v,
-                uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale) {
+                uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale,
+                int stat_y0, int stat_y1) {
   const int ho = h >> 1, wo = w >> 1, wpo = wo + 1, wpi = w + 1;
   const int cl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
   const int cv = blockIdx.x * cvb + cl;
@@ -118,9 +119,11 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
         unpack8(__ldg(q + (long long)wpi * x_pitch_v), c);
         unpack8(__ldg(q + (long long)(wpi + 1) * x_pitch_v), d);
 #pragma unroll
+        // statistics only over input rows [stat_y0, stat_y1) (both even): a spatial shard leaves its halo out
+        const bool in_stats = (2 * (oy - 1) >= stat_y0) && (2 * (oy - 1) < stat_y1);
         for (int e = 0; e < 8; ++e) {
           m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
-          acc[e] += (a[e] + b[e]) + (c[e] + d[e]);
+          if (in_stats) acc[e] += (a[e] + b[e]) + (c[e] + d[e]);
         }
         res = pack8(m);
       }
@@ -256,7 +259,7 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
 // ------------------------------------------------------------------------------- channel means
 // block = 256 threads = 32 pixel lanes x 8 vector lanes (64 channels); grid = (c/64, n, splits).
 __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, int x_pitch_v, int x_coff_v,
-                                    float* __restrict__ mean, int c, float scale) {
+                                    float* __restrict__ mean, int c, float scale, int y0, int y1) {
   const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int cb = blockIdx.x, img = blockIdx.y;
   const int wp = w + 1;
@@ -264,9 +267,9 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  const int npix = h * w;
+  const int npix = (y1 - y0) * w;                      // rows [y0, y1) only (a spatial shard leaves its halo out)
   for (int pix = blockIdx.z * 32 + pl; pix < npix; pix += gridDim.z * 32) {
-    const int yy = pix / w, xx = pix - yy * w;
+    const int yr = pix / w, xx = pix - yr * w, yy = y0 + yr;
     float f[8];
     unpack8(x[(base + (long long)(yy + 1) * wp + xx) * x_pitch_v + x_coff_v + cb * 8 + vl], f);
 #pragma unroll
@@ -393,7 +396,8 @@ static int check_slice(const char* who, int c, int pitch, int coff) {
 }
 
 extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y,
-                                     int y_pitch, int y_coff, float* chan_mean, void* stream) {
+                                     int y_pitch, int y_coff, float* chan_mean, int stat_y0, int stat_y1,
+                                     long long stat_count, void* stream) {
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "maxpool2: bad arguments (h %d, w %d)", h, w);
   if (int rc = check_slice("maxpool2(x)", c, x_pitch, x_coff)) return rc;
   if (int rc = check_slice("maxpool2(y)", c, y_pitch, y_coff)) return rc;
@@ -404,9 +408,13 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
   if (chan_mean) IE_CUDA(cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
   dim3 grid(ie_ceil_div(cvec, cvb), row_groups, n);
   const int threads = (256 / cvb) * cvb;
+  if (stat_y1 <= 0) { stat_y0 = 0; stat_y1 = h; }
+  if (stat_count <= 0) stat_count = (long long)h * w;
+  IE_REQUIRE(stat_y0 >= 0 && stat_y1 <= h && stat_y0 % 2 == 0 && stat_y1 % 2 == 0 && stat_y0 < stat_y1,
+             "maxpool2: bad statistics row range [%d, %d)", stat_y0, stat_y1);
   maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, cvec, cvb, x_pitch / 8, x_coff / 8,
                                                   static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, chan_mean,
-                                                  1.f / ((float)h * (float)w));
+                                                  1.f / (float)stat_count, stat_y0, stat_y1);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
@@ -435,12 +443,15 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
 }
 
 extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff,
-                                         float* mean, void* stream) {
+                                         float* mean, int y0, int y1, long long count, void* stream) {
   IE_REQUIRE(x && mean && n > 0 && h > 0 && w > 0, "channel_mean: bad arguments");
   IE_REQUIRE(c % 64 == 0, "channel_mean: c must be a multiple of 64 (got %d)", c);
   if (int rc = check_slice("channel_mean(x)", c, x_pitch, x_coff)) return rc;
   IE_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
-  const int npix = h * w;
+  if (y1 <= 0) { y0 = 0; y1 = h; }
+  if (count <= 0) count = (long long)h * w;
+  IE_REQUIRE(y0 >= 0 && y1 <= h && y0 < y1, "channel_mean: bad row range [%d, %d)", y0, y1);
+  const int npix = (y1 - y0) * w;
   int splits = (8 * sm_count() + (c / 64) * n - 1) / ((c / 64) * n);       // >= 8 blocks per SM in flight
   const int max_splits = (npix + 31) / 32;
   if (splits > max_splits) splits = max_splits;
@@ -449,7 +460,7 @@ extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int
   IE_REQUIRE(n <= 65535, "channel_mean: n too large");
   dim3 grid(c / 64, n, splits);
   channel_mean_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, x_pitch / 8, x_coff / 8, mean,
-                                                  c, 1.f / (float)npix);
+                                                  c, 1.f / (float)count, y0, y1);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

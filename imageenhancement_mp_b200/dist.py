@@ -71,3 +71,30 @@ def all_reduce_totals(totals):
 def barrier():
     if world() > 1:
         dist.barrier()
+
+
+# ------------------------------------------------------------------ spatial sharding of one large image
+SPATIAL_HALO = 72      # receptive-field radius of the coefficient path (~70 px) rounded up to the network stride
+
+
+def spatial_shards(height, world_, stride=8, halo=SPATIAL_HALO):
+    """Row bands of ONE image for ``world_`` ranks: a list of dicts
+    ``own=(a, b)`` rows of the image the rank owns, ``slab=(s0, s1)`` rows it must read (own + halo, clipped to the
+    image), ``own_in_slab=(a - s0, b - s0)``.  All numbers are multiples of ``stride``."""
+    assert height % stride == 0 and halo % stride == 0
+    units = height // stride
+    base, rem = divmod(units, world_)
+    out, a = [], 0
+    for r in range(world_):
+        b = a + (base + (1 if r < rem else 0)) * stride
+        s0, s1 = max(0, a - halo), min(height, b + halo)
+        out.append(dict(own=(a, b), slab=(s0, s1), own_in_slab=(a - s0, b - s0)))
+        a = b
+    return out
+
+
+def all_reduce_sum(t):
+    """SUM all-reduce of a CUDA tensor, in place, stream-ordered; identity for a single process."""
+    if world() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t

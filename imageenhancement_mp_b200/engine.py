@@ -158,7 +158,7 @@ class Engine:
         return tuple(o.clone() for o in outs)               # the graph's output buffers are overwritten by the next replay
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x, taps=None, conv_fn="ie_conv2d_nhwc_bf16"):
+    def forward(self, x, taps=None, conv_fn="ie_conv2d_nhwc_bf16", shard=None):
         """x: fp32 NHWC [n,hs,ws,T+add] on CUDA.  The network runs at (h, w) = (hs, ws) rounded up to the
         network stride; the zero padding at the bottom/right (what the boundary does for the 100x100 patches
         of BASELINE.json) is implicit in the first and last kernels - no padded copy is made.
@@ -166,6 +166,12 @@ class Engine:
         Returns (output [n,hs,ws,T+1], Bas [n,K,K,T,B], originbasis [n,K,K,T*B]), all fp32.
         ``taps``: optional dict filled with fp32 copies of intermediates (parity tests).
         ``conv_fn``: tests may route every convolution through the naive validation kernel.
+        ``shard``: spatial sharding of ONE large image over several ranks (dist.spatial_shards).  ``x`` is then this
+        rank's slab (its rows plus a halo): dict(own=(r0, r1) rows of the slab this rank owns, total_rows=H of the
+        whole image, reduce=callable).  The per-image pooled statistics that feed the basis branch
+        (model_library.py:409-411, 421) are taken over the owned rows only, scaled by the whole image's pixel count and
+        handed to ``reduce`` (an all-reduce SUM over the ranks) before the basis branch runs - the one exchange step
+        spatial sharding needs.  The output covers the whole slab; rows outside ``own`` are halo (discard them).
         """
         if not x.is_cuda:
             raise ImgEnhError("input must be a CUDA tensor (no CPU fallback)")
@@ -177,6 +183,17 @@ class Engine:
         x = x.contiguous().float()
         A, W, Bv = self.arch, self.wp, self.bias
         p = self._plan(n, h, w)
+        if shard is not None:
+            r0, r1 = shard["own"]
+            if r0 % st or r1 % st or not (0 <= r0 < r1 <= h) or shard["total_rows"] % st:
+                raise ImgEnhError(f"spatial shard rows {r0}:{r1} / {shard['total_rows']} must be multiples of {st}")
+
+        def stat_rows(level):
+            """(rows, count) of the pooled statistics of a tensor at resolution 1/2^level."""
+            if shard is None:
+                return None, 0
+            r0, r1 = shard["own"]
+            return (r0 >> level, r1 >> level), (shard["total_rows"] >> level) * (w >> level)
         chans = dict(A["downs"])
         dnames = [d for d, _ in A["downs"]]
 
@@ -204,12 +221,14 @@ class Engine:
             prev = cout
         basis_skips = {skip for _, _, skip, _, _ in A["basis_ups"]}
         skip_means = {}
-        for dname, cch in A["downs"]:
+        for level, (dname, cch) in enumerate(A["downs"]):
             conv(dname + ".conv2d1", cur, p[dname + ".c1"].slice())
             skip = p["cat." + dname].slice(up_in[dname], cch)
             conv(dname + ".conv2d2", p[dname + ".c1"].slice(), skip)
             # the pool also yields the channel means of the skip it reads, if the basis branch wants them (Poolskip)
-            skip_means[dname] = ops.maxpool2(skip, p[dname + ".pool"].slice(), want_mean=dname in basis_skips)
+            rows, count = stat_rows(level)
+            skip_means[dname] = ops.maxpool2(skip, p[dname + ".pool"].slice(), want_mean=dname in basis_skips,
+                                             rows=rows, count=count)
             cur = p[dname + ".pool"].slice()
         for bname in A["bottleneck"]:
             conv(bname, cur, p[bname].slice())
@@ -229,7 +248,20 @@ class Engine:
         coef, logits = ops.conv2d_f32(cur, W["coef"], Bv["coef"], self.B, softmax=True,
                                       want_logits=taps is not None, fn=conv_fn)
         # ---- basis branch (model_library.py:409-438 / 258-281)
-        gavg = ops.channel_mean(bott)                                    # :409-410
+        rows, count = stat_rows(len(A["downs"]))
+        gavg = ops.channel_mean(bott, rows=rows, count=count)            # :409-410
+        if shard is not None:
+            # the exchange step of spatial sharding: partial means (already divided by the global pixel count) of the
+            # bottleneck and of every pooled skip, summed over the ranks
+            names = [d for d in dnames if skip_means.get(d) is not None]
+            packed = torch.cat([gavg] + [skip_means[d] for d in names], dim=1)
+            packed = shard["reduce"](packed)
+            gavg = packed[:, :gavg.shape[1]].contiguous()
+            off = gavg.shape[1]
+            for d in names:
+                cd = skip_means[d].shape[1]
+                skip_means[d] = packed[:, off:off + cd].contiguous()
+                off += cd
         ops.broadcast_hw(gavg, p["seed"].slice())
         cur = p["seed"].slice()
         for name, cout, skip, k, s in A["basis_ups"]:

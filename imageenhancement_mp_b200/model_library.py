@@ -62,6 +62,18 @@ class _KpnModel:
     def call(self, inputs):
         return self.__call__(inputs)
 
+    def call_spatial_shard(self, x_slab, shard, total_rows, reduce=None):
+        """One rank's part of a spatially sharded forward of ONE large image.
+
+        ``x_slab``: rows ``shard["slab"]`` of the image(s) [N, s1-s0, W, T+add]; ``shard`` from ``dist.spatial_shards``;
+        ``reduce``: SUM all-reduce over the ranks (default ``dist.all_reduce_sum``: NCCL under torchrun).
+        Returns (output of the owned rows [N, b-a, W, T+1], Bas, originbasis) - Bas is identical on every rank."""
+        from . import dist as _dist
+        a, b = shard["own_in_slab"]
+        out, bas, ob = self._engine.forward(
+            x_slab, shard=dict(own=(a, b), total_rows=total_rows, reduce=reduce or _dist.all_reduce_sum))
+        return out[:, a:b].contiguous(), bas, ob
+
 
 class Simplemodel(_KpnModel):
     """model_library.py:306-452."""

@@ -156,13 +156,15 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
     return (y, aux) if softmax else y
 
 
-def maxpool2(src: Slice, dst: Slice, want_mean=False):
-    """MaxPooling2D(2,2); with ``want_mean`` also returns the per-image channel means [n, c] of the INPUT slice."""
+def maxpool2(src: Slice, dst: Slice, want_mean=False, rows=None, count=0):
+    """MaxPooling2D(2,2); with ``want_mean`` also returns the per-image channel means [n, c] of the INPUT slice
+    (over input rows ``rows`` = (y0, y1) and divided by ``count`` pixels when given: spatial shards)."""
     r = src.r
     assert (dst.r.n, dst.r.h, dst.r.w) == (r.n, r.h // 2, r.w // 2) and dst.c == src.c
     mean = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device) if want_mean else None
+    y0, y1 = rows if rows is not None else (0, 0)
     call("ie_maxpool2_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff,
-         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), stream())
+         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), y0, y1, int(count), stream())
     return mean
 
 
@@ -173,11 +175,13 @@ def upsample_bilinear(src: Slice, dst: Slice, scale):
          ptr(dst.r.data), dst.r.pitch, dst.coff, stream())
 
 
-def channel_mean(src: Slice, out=None):
+def channel_mean(src: Slice, out=None, rows=None, count=0):
     r = src.r
     if out is None:
         out = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device)
-    call("ie_channel_mean_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(out), stream())
+    y0, y1 = rows if rows is not None else (0, 0)
+    call("ie_channel_mean_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(out), y0, y1, int(count),
+         stream())
     return out
 
 

@@ -208,3 +208,31 @@ def test_full_size_batch_is_image_independent(cuda):
     xc[..., :4] = 0.5
     oc = model(xc)[0]
     assert float((oc[:, 7:-7, 7:-7, 0] - 0.5).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("H,W_,world", [(256, 96, 2), (320, 64, 3)])
+def test_spatial_sharding_matches_the_unsharded_forward(cuda, H, W_, world):
+    """ONE image cut into row bands (72-row halos) with the pooled statistics summed across the bands - emulated on
+    one GPU: every band is run twice, once to collect its partial statistics and once with the global sum, which is
+    what the all-reduce over the ranks delivers (tools/spatial_shard_check.py runs the real NCCL version)."""
+    from imageenhancement_mp_b200 import dist as idist, model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    model = ml.Simplemodel(params, weights=W)
+    x, _ = synth.make_batch(1, H, W_, params, seed=5)
+    xd = x.to(cuda)
+    ref_out, ref_bas, ref_ob = model(xd)
+    shards = idist.spatial_shards(H, world)
+    partial = []
+    for sh in shards:
+        s0, s1 = sh["slab"]
+        model.call_spatial_shard(xd[:, s0:s1].contiguous(), sh, H, reduce=lambda t: (partial.append(t.clone()), t)[1])
+    total = torch.stack(partial).sum(0)
+    for sh in shards:
+        s0, s1 = sh["slab"]
+        a, b = sh["own"]
+        out, bas, ob = model.call_spatial_shard(xd[:, s0:s1].contiguous(), sh, H, reduce=lambda t: t.copy_(total))
+        assert out.shape == (1, b - a, W_, 5)
+        assert float((ob - ref_ob).abs().max()) <= 2e-4 * float(ref_ob.abs().max())
+        assert float((bas - ref_bas).abs().max()) <= 1e-5
+        assert float((out - ref_out[:, a:b]).abs().max()) <= 2e-4, (a, b)

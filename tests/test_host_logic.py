@@ -60,6 +60,20 @@ def test_shard_ranges_cover_exactly():
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
 
 
+def test_spatial_shards_tile_the_image():
+    for H in (2448, 720, 256, 64):
+        for world in (1, 2, 3, 8):
+            sh = idist.spatial_shards(H, world)
+            assert sh[0]["own"][0] == 0 and sh[-1]["own"][1] == H
+            for i, d in enumerate(sh):
+                a, b = d["own"]; s0, s1 = d["slab"]
+                assert a % 8 == 0 and b % 8 == 0 and s0 % 8 == 0 and s1 % 8 == 0 and s0 <= a <= b <= s1
+                assert s0 == max(0, a - idist.SPATIAL_HALO) and s1 == min(H, b + idist.SPATIAL_HALO)
+                assert d["own_in_slab"] == (a - s0, b - s0)
+                if i:
+                    assert sh[i - 1]["own"][1] == a
+
+
 def test_single_process_report_matches_oracle_aggregation():
     batches = make_batches(3, 4, 40, 48)
     params = dict(synth.DEFAULT_PARAMS)
