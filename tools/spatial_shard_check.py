@@ -32,12 +32,12 @@ e1.record(); torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / a.reps], device=dev)
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-# gather the bands on rank 0
+# gather the bands on rank 0 (bands may differ by one stride in height: broadcast each from its owner)
 bands = [torch.empty(1, d["own"][1] - d["own"][0], a.w, 5, device=dev) for d in idist.spatial_shards(a.h, world)]
+bands[rank].copy_(out)
 if world > 1:
-    dist.all_gather(bands, out) if len({b.shape for b in bands}) == 1 else [dist.broadcast(b, src=i) if i != rank else b.copy_(out) or dist.broadcast(b, src=i) for i, b in enumerate(bands)]
-else:
-    bands[0].copy_(out)
+    for i, b in enumerate(bands):
+        dist.broadcast(b, src=i)
 if rank == 0:
     full = torch.cat(bands, dim=1)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
