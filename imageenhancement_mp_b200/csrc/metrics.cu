@@ -4,6 +4,7 @@
 // 3T+4 separate invert_preproc calls.  Plus an SSIM extension (tf.image.ssim semantics).
 // fp32 arithmetic per pixel, fp64 for everything that is accumulated across pixels.
 #include "ie_common.cuh"
+#include "ie_ptx.cuh"
 
 namespace ie {
 
@@ -226,6 +227,233 @@ eval_metrics_kernel(const float* __restrict__ recon, const float* __restrict__ b
   }
 }
 
+// ------------------------------------------------------------------------------- fused eval metrics, row-streaming
+// Same contract as eval_metrics_kernel, organised for the HBM roofline.  The three tensors are interleaved NHWC
+// (recon T+1 floats per pixel, burst `burst_pitch`, truth 2), so a per-pixel thread reads them with a 20-byte lane
+// stride.  Here a block owns a strip of (warps x 31) columns and walks down its rows in batches of `rb` rows:
+//   stage A  every row segment is ONE contiguous run of floats -> lane r of warp 0 moves row r of the next batch with
+//            three 1-D TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier): no per-thread
+//            copy instructions (a 16-byte cp.async version spent more issue slots on index math than stage B on the
+//            curves), fully coalesced, and batch i+1 is in flight while batch i is processed - DRAM latency is hidden
+//            by the two-buffer pipeline, not by occupancy;
+//   stage B  thread = pixel column: reads its pixel from shared memory (lane stride C floats: conflict-free for odd
+//            C), evaluates the T+4 sRGB curves, squares the errors, takes the horizontal forward difference from the
+//            right neighbour with a warp shuffle (warps overlap by one column, lane 31 is halo only) and the vertical
+//            one from the previous row's errors kept in registers.
+// Row segments start at arbitrary float offsets: the copy starts at the enclosing 16-byte boundary and the pixel data
+// sit `mis` floats into the shared-memory row.  Requires 16-byte aligned base pointers (else the tile kernel above).
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One row segment of `len` floats starting at element `s` of `base` (which holds `total` floats) is copied from the
+// enclosing 16-byte boundary.  plan(): the aligned start and the float count of the bulk copy; a tail that would cross
+// the end of the tensor (< 16 bytes, last row of the last image only) is moved with plain loads here, BEFORE the
+// lane's mbarrier arrive releases them.
+struct RowCopy {
+  long long a0;
+  int nfl;
+  __device__ __forceinline__ void plan(float* sdst, const float* __restrict__ base, long long total, long long s, int len) {
+    a0 = s & ~3ll;
+    nfl = (((int)(s - a0) + len + 3) >> 2) << 2;
+    if (a0 + nfl > total) {
+      const int keep = (int)((total - a0) & ~3ll);
+      for (int i = keep; a0 + i < total; ++i) sdst[i] = base[a0 + i];
+      nfl = keep;
+    }
+    if (nfl < 0) nfl = 0;
+  }
+  __device__ __forceinline__ uint32_t bytes() const { return (uint32_t)nfl * 4u; }
+  __device__ __forceinline__ void go(float* sdst, const float* __restrict__ base, uint64_t* bar) const {
+    if (nfl > 0) bulk_g2s(sdst, base + a0, bytes(), bar);
+  }
+};
+
+// sRGBforward(x * inv_wl) - data_utils.py:24-36 on the white-level-normalised value - with the scale folded in:
+// power segment on max(x, b*wl) as ex2(gamma*lg2(x) + gamma*lg2(inv_wl)); the linear toe is min(k0*x', power) (the
+// power curve is concave and meets the toe at b, so the toe is the smaller one exactly where x' < b); x' > 1 selects
+// the tangent.  MUFU lg2/ex2: relative error < 1e-6.
+struct SrgbScaled {
+  float b_wl, gl, k0i, k1i, c1;
+  __device__ __forceinline__ explicit SrgbScaled(float inv_wl) {
+    const float gamma = 1.f / 2.4f, k1 = 1.055f * gamma;
+    b_wl = .0031308f / inv_wl;
+    gl = gamma * log2f(inv_wl);
+    k0i = 12.92f * inv_wl;
+    k1i = k1 * inv_wl;
+    c1 = 1.f - k1;
+  }
+  __device__ __forceinline__ float operator()(float x, float wl_) const {
+    float l, e;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(x, b_wl)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(1.f / 2.4f, l, gl)));
+    float r = fminf(k0i * x, fmaf(1.055f, e, -.055f));
+    if (x > wl_) r = fmaf(k1i, x, c1);
+    return r;
+  }
+};
+
+template <int TT>
+__global__ void __launch_bounds__(128)
+eval_metrics_rows_kernel(const float* __restrict__ recon, const float* __restrict__ burst, int burst_pitch,
+                         const float* __restrict__ truth, const float* __restrict__ wl, int n_img, int h, int w,
+                         int T_rt, int crop, int rows_per_block, int rb, double* __restrict__ sums) {
+  extern __shared__ float4 s_dyn4[];
+  float* sm = reinterpret_cast<float*>(s_dyn4);
+  __shared__ uint64_t full[2];
+  const int T = TT ? TT : T_rt;
+  const int C = T + 1;
+  const int nwarps = blockDim.x >> 5;
+  const int two = nwarps * 31;                                  // output columns of the block
+  const int n = blockIdx.z;
+  const int hc = h - 2 * crop, wc = w - 2 * crop;
+  const int x0 = blockIdx.x * two;
+  const int ys = blockIdx.y * rows_per_block, ye = min(ys + rows_per_block, hc);
+  const int ylast = min(ye, hc - 1);                            // row ye is only the vertical halo of row ye - 1
+  const int nrows_total = ylast - ys + 1;
+  const float wl_n = wl[n];
+  const float inv_wl = 1.f / wl_n;
+  const float inv_T = 1.f / (float)T;
+  const SrgbScaled curve(inv_wl);
+
+  // shared-memory rows: strides in floats (multiples of 4); +6 = up to 3 floats of misalignment at either end
+  const int st_rc = (((two + 1) * C + 6) >> 2) << 2, st_tr = (((two + 1) * 2 + 6) >> 2) << 2,
+            st_bu = ((two * burst_pitch + 6) >> 2) << 2;
+  const int buf_floats = rb * (st_rc + st_tr + st_bu);
+  const int px_h = min(two + 1, w - (x0 + crop));               // pixels of the row that exist (incl. right halo)
+  const int px_b = min(two, w - (x0 + crop));
+  const long long npix_all = (long long)n_img * h * w;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], rb);
+    mbar_init(&full[1], rb);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // warp 0, lane r: row r of the batch (every lane < rb arrives once per batch, rows that do not exist with 0 bytes)
+  auto issue = [&](int batch) {
+    const int r = threadIdx.x;
+    if (r < rb) {
+      const int yb = ys + batch * rb;
+      float* b = sm + (batch & 1) * buf_floats;
+      uint64_t* bar = &full[batch & 1];
+      const int y = yb + r;
+      if (y <= ylast) {
+        const long long pix0 = ((long long)n * h + y + crop) * w + x0 + crop;
+        const bool need_burst = y < ye;                          // the halo row needs no burst
+        float* d_rc = b + r * st_rc;
+        float* d_tr = b + rb * st_rc + r * st_tr;
+        float* d_bu = b + rb * (st_rc + st_tr) + r * st_bu;
+        RowCopy c_rc, c_tr, c_bu;
+        c_rc.plan(d_rc, recon, npix_all * C, pix0 * C, px_h * C);
+        c_tr.plan(d_tr, truth, npix_all * 2, pix0 * 2, px_h * 2);
+        c_bu.nfl = 0;
+        if (need_burst) c_bu.plan(d_bu, burst, npix_all * burst_pitch, pix0 * burst_pitch, px_b * burst_pitch);
+        mbar_arrive_expect_tx(bar, c_rc.bytes() + c_tr.bytes() + c_bu.bytes());
+        c_rc.go(d_rc, recon, bar);
+        c_tr.go(d_tr, truth, bar);
+        c_bu.go(d_bu, burst, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+  };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = warp * 31 + lane;
+  const int x = x0 + lx;
+  const bool col_own = (lane < 31) && (x < wc);
+  const bool col_grad = (lane < 31) && (x < wc - 1);
+
+  float sq[kMaxT + 1], gr[kMaxT + 1], prev[kMaxT + 1];
+  float sq_b0 = 0.f, sq_avg = 0.f;
+#pragma unroll
+  for (int k = 0; k <= kMaxT; ++k) { sq[k] = 0.f; gr[k] = 0.f; prev[k] = 0.f; }
+
+  const int nbatch = (nrows_total + rb - 1) / rb;
+  issue(0);
+  for (int bi = 0; bi < nbatch; ++bi) {
+    if (bi + 1 < nbatch) issue(bi + 1);
+    mbar_wait(&full[bi & 1], (bi >> 1) & 1);
+    const float* b = sm + (bi & 1) * buf_floats;
+    const int yb = ys + bi * rb;
+    const int nr = min(rb, ylast - yb + 1);
+    for (int r = 0; r < nr; ++r) {
+      const int y = yb + r;
+      const long long pix0 = ((long long)n * h + y + crop) * w + x0 + crop;
+      const int mis_rc = (int)((pix0 * C) & 3), mis_tr = (int)((pix0 * 2) & 3), mis_bu = (int)((pix0 * burst_pitch) & 3);
+      const float* rc = b + r * st_rc + mis_rc + lx * C;
+      const float* tr = b + rb * st_rc + r * st_tr + mis_tr + lx * 2;
+      const float* bu = b + rb * (st_rc + st_tr) + r * st_bu + mis_bu + lx * burst_pitch;
+      const bool row_own = y < ye;                              // uniform
+      const bool own = col_own && row_own;
+      const bool hval = col_grad && row_own && (y < hc - 1);
+      const bool vval = col_grad && (y > ys);
+      const float g = curve(tr[0], wl_n);
+#pragma unroll
+      for (int k = 0; k <= kMaxT; ++k) {
+        if (k <= T) {
+          const float c = curve(rc[k], wl_n) - g;
+          const float cr = __shfl_down_sync(0xffffffffu, c, 1);
+          if (own) sq[k] = fmaf(c, c, sq[k]);
+          if (hval) gr[k] += fabsf(cr - c);
+          if (vval) gr[k] += fabsf(c - prev[k]);
+          prev[k] = c;
+        }
+      }
+      if (own) {
+        float b0 = 0.f, bsum = 0.f;
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t) {
+          if (t < T) {
+            const float v = bu[t];
+            if (t == 0) b0 = v;
+            bsum += v;
+          }
+        }
+        const float d0 = curve(b0, wl_n) - g;                        // psnr_burst0, data_utils.py:152-154
+        const float da = curve(bsum * inv_T, wl_n) - g;              // psnr_average_f, :162-164
+        sq_b0 = fmaf(d0, d0, sq_b0);
+        sq_avg = fmaf(da, da, sq_avg);
+      }
+    }
+    __syncthreads();                                            // the buffer is refilled by the next iteration's issue
+  }
+
+  // block reduction: slot q -> output index: k -> k, 9 -> T+1, 10 -> T+2, 11+k -> T+3+k (gradient sums carry 1/2)
+  __shared__ float red[4][2 * kMaxT + 4];
+#pragma unroll
+  for (int q = 0; q < 2 * kMaxT + 4; ++q) {
+    float v;
+    if (q <= kMaxT) v = sq[q];
+    else if (q == kMaxT + 1) v = sq_b0;
+    else if (q == kMaxT + 2) v = sq_avg;
+    else v = gr[q - kMaxT - 3];
+    v = warp_sum(v);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kMaxT + 4) {
+    const int q = threadIdx.x;
+    const int nq = 2 * T + 4;
+    int dst = -1;
+    double scale = 1.0;
+    if (q <= kMaxT) dst = (q <= T) ? q : -1;
+    else if (q == kMaxT + 1) dst = T + 1;
+    else if (q == kMaxT + 2) dst = T + 2;
+    else { dst = (q - kMaxT - 3 <= T) ? T + 3 + (q - kMaxT - 3) : -1; scale = 0.5; }
+    if (dst >= 0) {
+      double v = 0.0;
+      for (int wq = 0; wq < nwarps; ++wq) v += (double)red[wq][q];
+      atomicAdd(&sums[(long long)n * nq + dst], v * scale);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- per-image sums -> totals
 // One block: psnr_k[n] = -10 log10(sums[n][k] / npx) (data_utils.py:118-119), loss_k[n] = mse + grad-L1
 // (:46-51); totals = [sum_n psnr_0..T+2, sum_n loss_0, sum_n sum_{k>=1} loss_k, n]  (fp64).
@@ -314,7 +542,7 @@ __global__ void img_loss_sums_kernel(const float* __restrict__ a, const float* _
 // Vectorised variant (w % 4 == 0, 16-byte aligned rows): a thread owns 4 consecutive x and walks kLossRows
 // rows downwards, carrying the difference row it just loaded as the "current" row of the next step, so every
 // element is loaded once (+1 halo row per strip, +1 scalar per row for the x+1 neighbour of the last lane).
-constexpr int kLossRows = 16;
+constexpr int kLossRows = 32;
 __global__ void __launch_bounds__(128)
 img_loss_sums_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w,
                          double* __restrict__ sums) {
@@ -333,19 +561,21 @@ img_loss_sums_vec_kernel(const float* __restrict__ a, const float* __restrict__ 
       d[0] = va.x - vb.x; d[1] = va.y - vb.y; d[2] = va.z - vb.z; d[3] = va.w - vb.w;
       d[4] = has_right ? __ldg(pa + (long long)y * w + 4) - __ldg(pb + (long long)y * w + 4) : 0.f;
     };
-    float cur[5], nxt[5];
-    load(y0, cur);
+    // rows y+1 and y+2 are in flight while row y is consumed (two loads of latency per thread hidden)
+    float cur[5], nxt[5], nn[5];
     const int yend = min(y0 + kLossRows, h);
+    load(y0, cur);
+    if (y0 + 1 < h) load(y0 + 1, nxt);
     for (int y = y0; y < yend; ++y) {
       const bool has_below = y + 1 < h;
-      if (has_below) load(y + 1, nxt);
+      if (y + 2 < h && y + 2 <= yend) load(y + 2, nn);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         acc[0] = fmaf(cur[e], cur[e], acc[0]);
         if (has_below && x + e < w - 1) acc[1] += .5f * fabsf(nxt[e] - cur[e]) + .5f * fabsf(cur[e + 1] - cur[e]);
       }
 #pragma unroll
-      for (int e = 0; e < 5; ++e) cur[e] = nxt[e];
+      for (int e = 0; e < 5; ++e) { cur[e] = nxt[e]; nxt[e] = nn[e]; }
     }
   }
   // 128-thread block: reduce with the 256-thread helper's layout (upper warps contribute zeros)
@@ -488,12 +718,59 @@ extern "C" int ie_invert_preproc_f32(const float* img, int pitch, int coff, int 
   return IE_OK;
 }
 
+// Tuning knobs of the row-streaming kernel (tools/metric_sweep.py sweeps them; 0 = default).
+static int g_em_rb = 0, g_em_warps = 0, g_em_legacy = 0;
+extern "C" int ie_eval_metrics_tune(int rows_per_batch, int warps, int legacy) {
+  g_em_rb = rows_per_batch; g_em_warps = warps; g_em_legacy = legacy;
+  return IE_OK;
+}
+
+template <int TT>
+static int launch_eval_metrics_rows(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                                    const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream) {
+  const int hc = h - 2 * crop, wc = w - 2 * crop;
+  int nwarps = g_em_warps;
+  if (nwarps < 1 || nwarps > 4) {                              // narrowest block that wastes the fewest thread columns
+    long long best = -1;
+    for (int cand = 4; cand >= 2; --cand) {
+      const long long cols = (long long)((wc + cand * 31 - 1) / (cand * 31)) * cand * 32;
+      if (best < 0 || cols < best) { best = cols; nwarps = cand; }
+    }
+  }
+  const int two = nwarps * 31;
+  const int tiles_x = (wc + two - 1) / two;
+  const int rb = g_em_rb > 0 ? g_em_rb : 2;
+  long long ysplit = 32ll * sm_count() / ((long long)tiles_x * n);
+  if (ysplit < 1) ysplit = 1;
+  int rows_per_block = (int)((hc + ysplit - 1) / ysplit);
+  if (rows_per_block < 16) rows_per_block = 16;
+  if (rows_per_block > hc) rows_per_block = hc;
+  const int gy = (hc + rows_per_block - 1) / rows_per_block;
+  IE_REQUIRE(n <= 65535 && gy <= 65535, "eval_metrics: grid too large");
+  const int C = T + 1;
+  const int st = 4 * ((((two + 1) * C + 6) >> 2) + (((two + 1) * 2 + 6) >> 2) + ((two * burst_pitch + 6) >> 2));
+  const size_t smem = sizeof(float) * 2 * (size_t)rb * st;
+  IE_REQUIRE(smem <= 200 * 1024, "eval_metrics: burst_pitch %d needs %zu bytes of shared memory", burst_pitch, smem);
+  IE_CUDA(cudaFuncSetAttribute(eval_metrics_rows_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  eval_metrics_rows_kernel<TT><<<dim3(tiles_x, gy, n), nwarps * 32, smem, S(stream)>>>(
+      recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, rows_per_block, rb, sums);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
 extern "C" int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
                                    const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream) {
   IE_REQUIRE(recon && burst && truth && wl && sums, "eval_metrics: null pointer");
   IE_REQUIRE(n > 0 && T >= 1 && T <= kMaxT && burst_pitch >= T, "eval_metrics: bad T=%d (max %d)", T, kMaxT);
   IE_REQUIRE(crop >= 0 && h > 2 * crop + 1 && w > 2 * crop + 1, "eval_metrics: image %dx%d too small for crop %d", h, w, crop);
   const int hc = h - 2 * crop, wc = w - 2 * crop;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(recon) | reinterpret_cast<uintptr_t>(burst) |
+                         reinterpret_cast<uintptr_t>(truth)) & 15) == 0;
+  if (aligned && !g_em_legacy && burst_pitch <= 2 * kMaxT + 2) {
+    if (T == 4) return launch_eval_metrics_rows<4>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, stream);
+    if (T == 8) return launch_eval_metrics_rows<8>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, stream);
+    return launch_eval_metrics_rows<0>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, stream);
+  }
   const int tiles_x = (wc + kMT_W - 1) / kMT_W;
   // rows per block: a multiple of the 8-row sub-tile, as tall as still leaves ~4 blocks per SM in flight
   const int sub = (hc + kMT_H - 1) / kMT_H;

@@ -108,7 +108,209 @@ preprocess_u8_kernel(const uint8_t* __restrict__ src, int hs, int ws, int c, con
   }
 }
 
+// ------------------------------------------------------------------------------- 4 px per thread (reference defaults)
+// upscale 4, grey source, w % 4 == 0, T in {4, 8}: a thread owns FOUR consecutive output pixels, i.e. per frame and
+// source row one run of 16 source bytes.  What bounded the per-pixel kernel above was the de-gamma LUT: 64 lookups per
+// output pixel at random addresses (3.5-way bank conflicts on average) and 32 scalar 4-byte fetches.  Here
+//   * the LUT is replicated 32x with a 256-byte entry stride (64 KB, half used): lane l only ever reads bank l ->
+//     conflict-free, and ONE byte-permute builds the address  sample * 256 + lane * 4  from the packed word;
+//   * the 16 bytes come from two aligned 128-bit loads; the run's byte offset inside them is the same for all threads
+//     of a row (thread stride = 16 bytes), so the word selection runs on warp-uniform predicates (11 selects + 4 funnel shifts);
+//   * noise inputs and both outputs move as 128-bit vectors (4 px x T, 4 px x (T+add), 4 px x 2 floats are contiguous).
+// Summation order is that of the kernel above (bit-identical truth); the noise terms use MUFU.SQRT (~1 ulp).
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// lut_b = table base (bytes); lane4 = lane * 4.  One PRMT builds the byte offset  b * 256 + lane * 4  of sample b.
+__device__ __forceinline__ float lut1(const char* lut_b, uint32_t off) { return *reinterpret_cast<const float*>(lut_b + off); }
+__device__ __forceinline__ float lut4(const char* lut_b, uint32_t lane4, uint32_t v) {
+  const float a = lut1(lut_b, __byte_perm(v, lane4, 0x5504));
+  const float b = lut1(lut_b, __byte_perm(v, lane4, 0x5514));
+  const float c = lut1(lut_b, __byte_perm(v, lane4, 0x5524));
+  const float d = lut1(lut_b, __byte_perm(v, lane4, 0x5534));
+  return (a + b) + (c + d);
+}
+// The 16 bytes at byte offset `mis` of the 32-byte window (lo, hi): two select stages pick the 5 words they span
+// (11 selects on 2 warp-uniform predicates; a 4-way switch was if-converted into 4 x 4 predicated funnel shifts).
+__device__ __forceinline__ void row16(const uint4& lo, const uint4& hi, int mis, const char* lut_b, uint32_t lane4,
+                                      float (&s)[4]) {
+  const bool s2 = (mis & 8) != 0, s1 = (mis & 4) != 0;
+  const int sh = (mis & 3) * 8;
+  const uint32_t t0 = s2 ? lo.z : lo.x, t1 = s2 ? lo.w : lo.y, t2 = s2 ? hi.x : lo.z, t3 = s2 ? hi.y : lo.w,
+                 t4 = s2 ? hi.z : hi.x, t5 = s2 ? hi.w : hi.y;
+  const uint32_t u0 = s1 ? t1 : t0, u1 = s1 ? t2 : t1, u2 = s1 ? t3 : t2, u3 = s1 ? t4 : t3, u4 = s1 ? t5 : t4;
+  s[0] += lut4(lut_b, lane4, __funnelshift_r(u0, u1, sh));
+  s[1] += lut4(lut_b, lane4, __funnelshift_r(u1, u2, sh));
+  s[2] += lut4(lut_b, lane4, __funnelshift_r(u2, u3, sh));
+  s[3] += lut4(lut_b, lane4, __funnelshift_r(u3, u4, sh));
+}
+
+// Border quads (a window leaves the source): per-sample bounds checks, zero padding of make_first_truth (:436-438).
+__device__ __noinline__ float4 box16_clipped(const uint8_t* __restrict__ img, int hs, int ws, int oy, int ox,
+                                             const char* lut_b, uint32_t lane4) {
+  float s[4];
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    float a = 0.f;
+#pragma unroll 1
+    for (int dy = 0; dy < 4; ++dy) {
+      const int sy = oy + dy;
+      if (sy < 0 || sy >= hs) continue;
+#pragma unroll 1
+      for (int dx = 0; dx < 4; ++dx) {
+        const int sx = ox + p * 4 + dx;
+        if (sx < 0 || sx >= ws) continue;
+        a += lut1(lut_b, ((uint32_t)img[(long long)sy * ws + sx] << 8) + lane4);
+      }
+    }
+    s[p] = a;
+  }
+  return make_float4(s[0], s[1], s[2], s[3]);
+}
+
+template <int T, int ADD, bool RNG>
+__global__ void __launch_bounds__(256)
+preprocess_u8_quad_kernel(const uint8_t* __restrict__ src, int hs, int ws, const int32_t* __restrict__ org,
+                          float degamma, const float* __restrict__ wl, const float* __restrict__ sig_read,
+                          const float* __restrict__ sig_shot, const float* __restrict__ n_read,
+                          const float* __restrict__ n_shot, unsigned long long seed, int n_img, int h, int w,
+                          float* __restrict__ x, float* __restrict__ truth) {
+  extern __shared__ float lutr[];                                // [256][64]: entry b, copy l at float b * 64 + l (l < 32)
+  {
+    const float v = powf((float)threadIdx.x / 255.f, degamma);
+    const int l = threadIdx.x & 31;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) lutr[threadIdx.x * 64 + ((l + j) & 31)] = v;
+  }
+  __syncthreads();
+  const char* lut_b = reinterpret_cast<const char*>(lutr);
+  const uint32_t lane4 = (threadIdx.x & 31) * 4;
+  constexpr int CH = T + ADD;
+  const int n = blockIdx.z;
+  const float wln = wl[n], sr = sig_read[n], ss = sig_shot[n];
+  const long long img_off = (long long)n * hs * ws;
+  const long long src_total = (long long)n_img * hs * ws;
+  const int qw = w >> 2;
+  const int nquads = h * qw;
+  const float inv_area = 1.f / 16.f;
+  int oys[T], oxs[T];
+#pragma unroll
+  for (int f = 0; f < T; ++f) {
+    oys[f] = org[((long long)n * T + f) * 2];
+    oxs[f] = org[((long long)n * T + f) * 2 + 1];
+  }
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += gridDim.x * blockDim.x) {
+    const int py = q / qw, px = (q - py * qw) * 4;
+    const long long t0 = ((long long)n * h + py) * w + px;
+    float xv[4 * CH], tv[8];
+    float4 nsv[T], nrv[T];                                       // noise of the quad: element p * T + f
+    const bool have_noise = !RNG && (n_read != nullptr) && (n_shot != nullptr);
+    if (have_noise) {
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        nsv[j] = __ldcs(reinterpret_cast<const float4*>(n_shot + t0 * T) + j);
+        nrv[j] = __ldcs(reinterpret_cast<const float4*>(n_read + t0 * T) + j);
+      }
+    }
+    const float* nsf = reinterpret_cast<const float*>(nsv);
+    const float* nrf = reinterpret_cast<const float*>(nrv);
+#pragma unroll
+    for (int f = 0; f < T; ++f) {
+      const int oy = oys[f] + py * 4, ox = oxs[f] + px * 4;
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      const long long off_last = img_off + (long long)(oy + 3) * ws + ox;
+      if (oy >= 0 && oy + 4 <= hs && ox >= 0 && ox + 16 <= ws && (off_last & ~15ll) + 32 <= src_total) {
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) {
+          const long long off = img_off + (long long)(oy + dy) * ws + ox;
+          const uint4* p16 = reinterpret_cast<const uint4*>(src + (off & ~15ll));
+          const uint4 lo = __ldg(p16), hi = __ldg(p16 + 1);
+          row16(lo, hi, (int)(off & 15), lut_b, lane4, s);
+        }
+      } else {
+        const float4 b = box16_clipped(src + img_off, hs, ws, oy, ox, lut_b, lane4);
+        s[0] = b.x; s[1] = b.y; s[2] = b.z; s[3] = b.w;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float csum = s[p] * inv_area;
+        const float tr = wln * (csum / 1.f);                     // :230 (grey source: channel mean of one channel)
+        float v = tr;
+        if (have_noise) {
+          v = tr + sqrt_approx(tr) * ss * nsf[p * T + f] + sr * nrf[p * T + f];   // :463-465
+        } else if (RNG) {
+          float zs, zr;
+          normal_pair(seed, (unsigned long long)((t0 + p) * T + f), zs, zr);
+          v = tr + sqrt_approx(tr) * ss * zs + sr * zr;
+        }
+        xv[p * CH + f] = v;
+        if (f == 0) { tv[2 * p] = tr; tv[2 * p + 1] = wln; }     // :248-252
+      }
+    }
+    if (ADD == 1) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) xv[p * CH + T] = sqrt_approx(sr * sr + fmaxf(0.f, xv[p * CH]) * ss * ss);   // :256
+    } else if (ADD == 2) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { xv[p * CH + T] = sr; xv[p * CH + T + 1] = ss; }                     // :257
+    }
+    float4* xo = reinterpret_cast<float4*>(x + t0 * CH);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) __stcs(xo + j, make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]));
+    float4* to = reinterpret_cast<float4*>(truth + t0 * 2);
+    __stcs(to, make_float4(tv[0], tv[1], tv[2], tv[3]));
+    __stcs(to + 1, make_float4(tv[4], tv[5], tv[6], tv[7]));
+  }
+}
+
+static int g_pre_legacy = 0;
+template <int T, int ADD>
+static int launch_quad(const uint8_t* src, int n, int hs, int ws, const int32_t* org, float degamma, const float* wl,
+                       const float* sig_read, const float* sig_shot, const float* n_read, const float* n_shot,
+                       unsigned long long seed, int use_rng, int h, int w, float* x, float* truth, cudaStream_t st) {
+  const size_t smem = 256 * 64 * sizeof(float);
+  auto kern = use_rng ? preprocess_u8_quad_kernel<T, ADD, true> : preprocess_u8_quad_kernel<T, ADD, false>;
+  IE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long nquads = (long long)h * (w / 4);
+  long long gx = (nquads + 255) / 256;
+  const long long cap = (12ll * sm_count() + n - 1) / n;       // the 32 KB table is built once per block: few, long blocks
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  kern<<<dim3((unsigned)gx, 1, n), 256, smem, st>>>(src, hs, ws, org, degamma, wl, sig_read, sig_shot, n_read, n_shot, seed,
+                                                    n, h, w, x, truth);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+// Returns 1 if the quad kernel took the call, 0 if the caller must use the general kernel, <0 on error.
+static int try_quad(const uint8_t* src, int n, int hs, int ws, int c, const int32_t* org, int up, float degamma,
+                    const float* wl, const float* sig_read, const float* sig_shot, const float* n_read,
+                    const float* n_shot, unsigned long long seed, int use_rng, int layer_type, int h, int w, int T,
+                    float* x, float* truth, cudaStream_t st) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(x) |
+                       reinterpret_cast<uintptr_t>(truth) | reinterpret_cast<uintptr_t>(n_read) |
+                       reinterpret_cast<uintptr_t>(n_shot);
+  if (g_pre_legacy || up != 4 || c != 1 || (w & 3) || (al & 15) || (long long)h * (w / 4) > 0x7fffffffll) return 0;
+  int rc = 0;
+#define IE_QUAD(TT, AA)                                                                                              \
+  if (T == TT && layer_type == AA) {                                                                                 \
+    rc = launch_quad<TT, AA>(src, n, hs, ws, org, degamma, wl, sig_read, sig_shot, n_read, n_shot, seed, use_rng, h, \
+                             w, x, truth, st);                                                                       \
+    return rc == IE_OK ? 1 : rc;                                                                                     \
+  }
+  IE_QUAD(4, 0) IE_QUAD(4, 1) IE_QUAD(4, 2) IE_QUAD(8, 0) IE_QUAD(8, 1) IE_QUAD(8, 2)
+#undef IE_QUAD
+  return 0;
+}
+
 }  // namespace ie
+
+extern "C" int ie_preprocess_tune(int legacy) {
+  ie::g_pre_legacy = legacy;
+  return IE_OK;
+}
 
 extern "C" int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c, const int32_t* org, int up,
                                 float degamma, const float* wl, const float* sig_read, const float* sig_shot,
@@ -121,6 +323,11 @@ extern "C" int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c
   IE_REQUIRE((n_read == nullptr) == (n_shot == nullptr), "preprocess_u8: give both noise tensors or neither");
   const long long total = (long long)n * h * w;
   IE_REQUIRE(n <= 65535 && h <= 65535, "preprocess_u8: grid too large");
+  {
+    const int q = try_quad(src, n, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, n_read, n_shot, 0ull, 0,
+                           layer_type, h, w, T, x, truth, static_cast<cudaStream_t>(stream));
+    if (q != 0) return q < 0 ? q : IE_OK;
+  }
   preprocess_u8_kernel<<<dim3(ie_ceil_div(w, 256), h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, n_read, n_shot, 0ull, 0, layer_type, h, w, T, x, truth, total);
   IE_LAUNCH_CHECK();
@@ -137,6 +344,11 @@ extern "C" int ie_preprocess_u8_rng(const uint8_t* src, int n, int hs, int ws, i
   IE_REQUIRE(layer_type >= 0 && layer_type <= 2, "preprocess_u8_rng: layer_type must be 0, 1 or 2");
   const long long total = (long long)n * h * w;
   IE_REQUIRE(n <= 65535 && h <= 65535, "preprocess_u8_rng: grid too large");
+  {
+    const int q = try_quad(src, n, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, nullptr, nullptr, seed, 1,
+                           layer_type, h, w, T, x, truth, static_cast<cudaStream_t>(stream));
+    if (q != 0) return q < 0 ? q : IE_OK;
+  }
   preprocess_u8_kernel<<<dim3(ie_ceil_div(w, 256), h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, hs, ws, c, org, up, degamma, wl, sig_read, sig_shot, nullptr, nullptr, seed, 1, layer_type, h, w, T, x, truth,
       total);

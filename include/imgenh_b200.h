@@ -174,6 +174,11 @@ int ie_invert_preproc_f32(const float* img, int pitch, int coff, int nch, const 
 int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
                         const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream);
 
+/* Tuning / A-B knob of ie_eval_metrics_f32 (tools/metric_sweep.py): rows per bulk-copy batch and warps per block of
+ * the row-streaming kernel (0 = default), legacy != 0 selects the 32x32-tile kernel that also serves pointers that
+ * are not 16-byte aligned.  Process-wide; not part of the reference-facing surface.                     */
+int ie_eval_metrics_tune(int rows_per_batch, int warps, int legacy);
+
 /* Per-image sums of ie_eval_metrics_f32 -> the additive totals one eval step contributes (fp64, T+6 values):
  *   [ sum_n psnr_deblur, sum_n psnr_frame_0..T-1, sum_n psnr_burst0, sum_n psnr_average,
  *     sum_n loss_deblur_n, sum_n loss_perlayer_n, n ],  psnr = -10 log10(mse) (data_utils.py:118-119),
@@ -211,6 +216,10 @@ int ie_preprocess_u8(const uint8_t* src, int n, int hs, int ws, int c, const int
 int ie_preprocess_u8_rng(const uint8_t* src, int n, int hs, int ws, int c, const int32_t* org, int up, float degamma,
                          const float* wl, const float* sig_read, const float* sig_shot, unsigned long long seed,
                          int layer_type, int h, int w, int T, float* x, float* truth, void* stream);
+
+/* A-B knob: legacy != 0 forces the one-pixel-per-thread kernel (any up / c / T / alignment); by default upscale 4,
+ * grey source, w % 4 == 0, T in {4, 8} run the 4-pixels-per-thread kernel.  Process-wide.                   */
+int ie_preprocess_tune(int legacy);
 
 #ifdef __cplusplus
 }

@@ -306,6 +306,46 @@ def test_fused_eval_metrics(cuda, n, h, w, T):
     assert rel(got["psnr_average"], ref["psnr_average"]) < 1e-5
 
 
+@pytest.mark.parametrize("n,h,w,T,pitch", [(2, 40, 56, 4, 5), (1, 33, 49, 2, 2), (2, 50, 300, 3, 4), (1, 48, 160, 6, 8)])
+def test_fused_eval_metrics_kernel_variants(cuda, n, h, w, T, pitch):
+    """Row-streaming kernel (16-byte aligned tensors, every rows-per-batch / block width) and the tile kernel that
+    serves misaligned views give the same per-image sums: even channel counts (bank conflicts, not errors), widths
+    beyond one block, burst pitch > T, pointers offset by one float."""
+    from imageenhancement_mp_b200 import _lib, data_utils as du
+    g = torch.Generator().manual_seed(n * h + w)
+    truth = torch.rand(n, h, w, 2, generator=g) * 0.5 + 0.25
+    truth[..., 1] = torch.rand(n, 1, 1, generator=g) * 0.5 + 0.5
+    recon = (truth[..., :1] + 0.03 * torch.randn(n, h, w, T + 1, generator=g)).contiguous()
+    burst = (truth[..., :1] + 0.05 * torch.randn(n, h, w, pitch, generator=g)).contiguous()
+    ref = oracle.eval_step(recon.double(), burst.double(), truth.double(), T)
+    lib = _lib.load()
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-12)
+
+    def check(got):
+        for key in ("loss1", "perlayer_loss", "psnr", "psnr_noise0", "psnr_average"):
+            assert rel(got[key], ref[key]) < 1e-5, key
+        for t in range(T):
+            assert rel(got["psnr_perlayer"][t], ref["psnr_perlayer"][t]) < 1e-5
+
+    rc, bc, tc = recon.to(cuda), burst.to(cuda), truth.to(cuda)
+    try:
+        for rb, warps in ((0, 0), (1, 2), (3, 3), (4, 4)):
+            lib.ie_eval_metrics_tune(rb, warps, 0)
+            check(du.eval_metrics(rc, bc, tc, T))
+        lib.ie_eval_metrics_tune(0, 0, 1)
+        check(du.eval_metrics(rc, bc, tc, T))
+    finally:
+        lib.ie_eval_metrics_tune(0, 0, 0)
+
+    def shifted(t):                                             # same values at a data pointer that is 4 (mod 16)
+        buf = torch.empty(t.numel() + 1, device=cuda)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 16 == 4 and v.is_contiguous()
+        return v
+    check(du.eval_metrics(shifted(rc), shifted(bc), shifted(tc), T))
+
+
 def test_psnr_known_answer(cuda):
     from imageenhancement_mp_b200 import data_utils as du
     a = torch.rand(4, 50, 60, device=cuda)
@@ -325,14 +365,16 @@ def test_ssim(cuda, n, h, w):
 
 
 # ------------------------------------------------------------------ preprocessing
-@pytest.mark.parametrize("layer_type,color", [("singlestd", False), ("dualparams", True), ("empty", False)])
-def test_preprocess(cuda, layer_type, color):
+@pytest.mark.parametrize("layer_type,color,T", [("singlestd", False, 3), ("dualparams", True, 3), ("empty", False, 3),
+                                                ("singlestd", False, 4), ("dualparams", False, 8), ("empty", False, 4)])
+def test_preprocess(cuda, layer_type, color, T):
+    """T = 3 / colour: one-pixel-per-thread kernel; grey T in {4, 8}: the 4-pixels-per-thread kernel."""
     from oracle import preprocess as opre
     from imageenhancement_mp_b200 import data_utils as du
-    params = dict(synth.DEFAULT_PARAMS, height=24, width=32, BURST_LENGTH=3, layer_type=layer_type)
+    params = dict(synth.DEFAULT_PARAMS, height=24, width=32, BURST_LENGTH=T, layer_type=layer_type)
     C = 3 if color else 1
     g = torch.Generator().manual_seed(51)
-    N, T, up, jit, sj = 2, 3, 4, 16, 2
+    N, up, jit, sj = 2, 4, 16, 2
     hs, ws = 24 * up + 2 * jit * up + 7, 32 * up + 2 * jit * up + 5
     xs, ts, orgs, wl, sr, ss, nr, ns = [], [], [], [], [], [], [], []
     src = torch.randint(0, 256, (N, hs, ws, C), generator=g, dtype=torch.uint8)
@@ -361,6 +403,40 @@ def test_preprocess(cuda, layer_type, color):
                                  f(wl), f(sr), f(ss), torch.stack(nr).to(cuda), torch.stack(ns).to(cuda))
     assert torch.allclose(gx.cpu().double(), torch.stack(xs), atol=2e-6, rtol=2e-5)
     assert torch.allclose(gt.cpu().double(), torch.stack(ts), atol=2e-6, rtol=2e-5)
+
+
+@pytest.mark.parametrize("T,layer_type,h,w", [(4, "singlestd", 20, 28), (8, "dualparams", 9, 12), (4, "empty", 33, 260)])
+def test_preprocess_quad_kernel_vs_general_kernel(cuda, T, layer_type, h, w):
+    """The 4-px-per-thread kernel against the one-pixel-per-thread kernel (itself checked against the oracle above)
+    on crops that LEAVE the source on every side (zero padding, data_utils.py:436-438) and on odd source pitches:
+    truth within the rounding of a re-ordered 16-term sum, noisy frames within the MUFU.SQRT rounding."""
+    from imageenhancement_mp_b200 import _lib, data_utils as du
+    params = dict(synth.DEFAULT_PARAMS, height=h, width=w, BURST_LENGTH=T, layer_type=layer_type)
+    N, up = 3, 4
+    g = torch.Generator().manual_seed(h * w + T)
+    hs, ws = h * up + 13, w * up + 7
+    src = torch.randint(0, 256, (N, hs, ws, 1), generator=g, dtype=torch.uint8).to(cuda)
+    org = torch.randint(-9, 21, (N, T, 2), generator=g, dtype=torch.int32)
+    org[0, 0] = torch.tensor([0, 0]); org[1, 1] = torch.tensor([13, 7]); org[2, 0] = torch.tensor([-3, 18])
+    org = org.to(cuda)
+    wl = torch.tensor([0.3, 0.7, 1.0], device=cuda)
+    sr = torch.tensor([0.01, 0.003, 0.02], device=cuda)
+    ss = torch.tensor([0.05, 0.02, 0.09], device=cuda)
+    nr = torch.randn(N, h, w, T, generator=g).to(cuda)
+    ns = torch.randn(N, h, w, T, generator=g).to(cuda)
+    lib = _lib.load()
+    try:
+        lib.ie_preprocess_tune(1)
+        x_ref, t_ref = du.preprocess_image(src, org, params, wl, sr, ss, nr, ns)
+        xr_ref, _ = du.preprocess_image(src, org, params, wl, sr, ss, seed=77)
+    finally:
+        lib.ie_preprocess_tune(0)
+    x_new, t_new = du.preprocess_image(src, org, params, wl, sr, ss, nr, ns)
+    xr_new, tr_new = du.preprocess_image(src, org, params, wl, sr, ss, seed=77)
+    assert torch.equal(t_new, tr_new)
+    assert torch.allclose(t_new, t_ref, atol=1e-7, rtol=2e-6)       # clipped windows are summed in a different order
+    assert torch.allclose(x_new, x_ref, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(xr_new, xr_ref, atol=1e-6, rtol=1e-5)
 
 
 def test_preprocess_device_noise_matches_numpy_philox(cuda):

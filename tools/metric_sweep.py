@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--h", type=int, default=2160); ap.add_argument("--w", type=int, default=3840)
 ap.add_argument("--batches", type=int, nargs="+", default=[1, 2, 4, 8, 16])
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--variants", action="store_true", help="also time the A-B variants (legacy kernels, rows per batch)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 _lib.load()
@@ -60,21 +61,34 @@ for n in a.batches:
         burst = torch.rand(n, h, w, T + 1, device=dev, generator=g)
         tr2 = torch.rand(n, h, w, 2, device=dev, generator=g)
         sums = torch.zeros(n, 2 * T + 4, dtype=torch.float64, device=dev)
-        rows.append(("eval_metrics_fused(ie_eval_metrics_f32,T=4)", 4 * (2 * T + 2) * px,
-                     timed(lambda: call("ie_eval_metrics_f32", ptr(recon), ptr(burst), T + 1, ptr(tr2), ptr(wl), n, h, w, T, 8,
-                                        ptr(sums), stream()))))
+        em = lambda: call("ie_eval_metrics_f32", ptr(recon), ptr(burst), T + 1, ptr(tr2), ptr(wl), n, h, w, T, 8,
+                          ptr(sums), stream())
+        rows.append(("eval_metrics_fused(ie_eval_metrics_f32,T=4)", 4 * (2 * T + 2) * px, timed(em)))
+        if a.variants:
+            lib = _lib.load()
+            for tag, knobs in (("legacy-tile", (0, 0, 1)), ("rb1", (1, 4, 0)), ("rb4", (4, 4, 0)), ("rb8", (8, 4, 0)),
+                               ("rb2-3warps", (2, 3, 0))):
+                lib.ie_eval_metrics_tune(*knobs)
+                rows.append((f"eval_metrics_fused[{tag}]", 4 * (2 * T + 2) * px, timed(em)))
+            lib.ie_eval_metrics_tune(0, 0, 0)
         del recon, burst, tr2
     if n <= 4:
         # preprocess: u8 [n, 4h, 4w, 1] -> x [n,h,w,5], truth [n,h,w,2]   (4x AREA down-sample, T=4 frames)
-        src = torch.randint(0, 256, (n, 4 * h, 4 * w, 1), dtype=torch.uint8, device=dev, generator=g)
+        src = torch.randint(0, 256, (n, 4 * h + 8, 4 * w + 16, 1), dtype=torch.uint8, device=dev, generator=g)
         params = dict(synth.DEFAULT_PARAMS, height=h, width=w)
         org = torch.zeros(n, T, 2, dtype=torch.int32, device=dev)
         one = torch.full((n,), 0.5, device=dev)
         nr = torch.randn(n, h, w, T, device=dev, generator=g)
         ns = torch.randn(n, h, w, T, device=dev, generator=g)
         nbytes = 16 * px + 4 * (T + 1 + 2) * px + 2 * 4 * T * px      # u8 in (read once) + outputs + noise inputs
-        rows.append(("preprocess(ie_preprocess_u8,up=4,T=4)", nbytes,
-                     timed(lambda: du.preprocess_image(src, org, params, one, one * 0.01, one * 0.05, nr, ns))))
+        org[:, 1:] = torch.randint(0, 9, (n, T - 1, 2), dtype=torch.int32, device=dev, generator=g)   # frame jitter
+        pre = lambda: du.preprocess_image(src, org, params, one, one * 0.01, one * 0.05, nr, ns)
+        rows.append(("preprocess(ie_preprocess_u8,up=4,T=4)", nbytes, timed(pre)))
+        if a.variants:
+            lib = _lib.load()
+            lib.ie_preprocess_tune(1)
+            rows.append(("preprocess[legacy-1px]", nbytes, timed(pre)))
+            lib.ie_preprocess_tune(0)
         del src, nr, ns
     for name, nbytes, ms in rows:
         gbs = nbytes / ms / 1e6
