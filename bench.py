@@ -207,8 +207,10 @@ def run_ours(args, cfg_name):
 
     def step(xb, tb):
         out = model(xb)[0]
-        sums = du.eval_metric_sums(out, xb, tb, T)
-        tot = du.reduce_metric_sums(sums, h, w, T)
+        wl = du.white_level_of(tb)
+        sums = du.eval_metric_sums(out, xb, tb, T, white_noise=wl)
+        # SSIM (BASELINE metric "fwd+PSNR/SSIM"; an extension - the reference's eval.py reports PSNR and losses only)
+        tot = du.reduce_metric_sums(sums, h, w, T, ssim_sums=du.ssim_deblur_sums(out, tb, white_noise=wl))
         idist.all_reduce_totals(tot)                       # the one collective of the step
         return tot
 
@@ -269,12 +271,14 @@ def run_ours(args, cfg_name):
         for i in range(k):
             yield host[i % NROT]
 
-    ieval.evaluate(model, host_batches(max(2, args.warmup // 2)), params, out=None, step_results=[], pre_sharded=True)
+    ieval.evaluate(model, host_batches(max(2, args.warmup // 2)), params, out=None, step_results=[], pre_sharded=True,
+                   ssim=True)
     sync_all()
     res = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_report = ieval.evaluate(model, host_batches(args.steps), params, out=None, step_results=res, pre_sharded=True)
+    e2e_report = ieval.evaluate(model, host_batches(args.steps), params, out=None, step_results=res, pre_sharded=True,
+                                ssim=True)
     e1.record()
     sync_all()
     e2e_ms = e0.elapsed_time(e1)
@@ -321,7 +325,8 @@ def run_ours(args, cfg_name):
                      if traffic_src else "no ncu capture for this config",
                      "peak_source": peaks["source"] + " sustained bf16", "frac_of_burst": achieved / peaks["bf16_burst"],
                      "conv_ms_per_step": conv_ms / args.steps, "conv_tflop_per_step": conv_flops_step / 1e12},
-        "quality": {"psnr": report["psnr"], "psnr_noise0": report["psnr_noise0"], "psnr_average": report["psnr_average"]},
+        "quality": {"psnr": report["psnr"], "psnr_noise0": report["psnr_noise0"], "psnr_average": report["psnr_average"],
+                    "ssim": report["ssim"]},
     }
     if world == 1 and not args.no_cpu_baseline:
         sample_n = 16 if h * w <= 128 * 128 else 1

@@ -55,6 +55,8 @@ SIGNATURES = {
     "ie_eval_metrics_f32": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "ie_eval_metrics_tune": [_I, _I, _I],
     "ie_preprocess_tune": [_I],
+    "ie_ssim_tune": [_I],
+    "ie_metric_totals_ssim_f64": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "ie_metric_totals_f64": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_sqdiff_sum_f32": [_P, _P, _I, _LL, _P, _P],
     "ie_img_loss_sums_f32": [_P, _P, _I, _I, _I, _P, _P],

@@ -159,14 +159,27 @@ def psnr_average_f(invert_gt, white_noise, x_batch_burst):
     return psnr_tf_batch(invert_preproc(x_batch_burst[..., 0], white_noise, _nch=T), invert_gt)
 
 
-def ssim(a, b):
-    """EXTENSION (not in the reference): per-image SSIM of [N,H,W] pairs, tf.image.ssim semantics."""
+def ssim_map_sums(a, b):
+    """EXTENSION: per-image SUM of the SSIM map of [N,H,W] pairs ((H-10)*(W-10) values each), fp64 on the device."""
     _lib.require_cuda(a, b)
     a, b = a.contiguous().float(), b.contiguous().float()
     n, h, w = a.shape
     sums = torch.zeros(n, dtype=torch.float64, device=a.device)
     call("ie_ssim_f32", ptr(a), ptr(b), n, h, w, ptr(sums), stream())
-    return (sums / ((h - 10) * (w - 10))).float()
+    return sums
+
+
+def ssim(a, b):
+    """EXTENSION (not in the reference): per-image SSIM of [N,H,W] pairs, tf.image.ssim semantics."""
+    n, h, w = a.shape
+    return (ssim_map_sums(a, b) / ((h - 10) * (w - 10))).float()
+
+
+def ssim_deblur_sums(reconstructed, x_batch_truth, white_noise=None):
+    """EXTENSION: SSIM-map sums of invert_preproc(deblurred) vs invert_preproc(ground truth) - the pair eval.py:146-149
+    feeds to psnr_deblur - per image (3 launches: two invert_preproc, one SSIM)."""
+    wl = white_level_of(x_batch_truth) if white_noise is None else white_noise
+    return ssim_map_sums(invert_preproc(reconstructed[..., 0], wl), invert_preproc(x_batch_truth[..., 0], wl))
 
 
 # ------------------------------------------------------------------ fused path
@@ -186,7 +199,7 @@ def eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, 
     return sums
 
 
-def reduce_metric_sums(sums, h, w, T):
+def reduce_metric_sums(sums, h, w, T, ssim_sums=None):
     """Per-image sums -> additive totals (fp64, on device, no sync):
 
     [ sum_n psnr_deblur, sum_n psnr_frame_0..T-1, sum_n psnr_burst0, sum_n psnr_average,
@@ -196,6 +209,11 @@ def reduce_metric_sums(sums, h, w, T):
     """
     _lib.require_cuda(sums)
     assert sums.dtype == torch.float64 and sums.shape[1] == 2 * T + 4 and sums.is_contiguous()
+    if ssim_sums is not None:                       # extension: [..., sum_n mean-SSIM_n, n]  (T + 7 values)
+        assert ssim_sums.dtype == torch.float64 and ssim_sums.shape == (sums.shape[0],) and ssim_sums.is_contiguous()
+        tot = torch.empty(T + 7, dtype=torch.float64, device=sums.device)
+        call("ie_metric_totals_ssim_f64", ptr(sums), ptr(ssim_sums), sums.shape[0], h, w, T, LBUFF, ptr(tot), stream())
+        return tot
     tot = torch.empty(T + 6, dtype=torch.float64, device=sums.device)
     call("ie_metric_totals_f64", ptr(sums), sums.shape[0], h, w, T, LBUFF, ptr(tot), stream())
     return tot
@@ -205,7 +223,10 @@ def totals_to_report(tot, T):
     """Host-side view of the additive totals (a list / 1-D tensor on CPU)."""
     tot = [float(v) for v in tot]
     n = tot[-1]
+    assert len(tot) in (T + 6, T + 7)
+    extra = {"ssim": tot[T + 5] / n} if len(tot) == T + 7 else {}
     return {
+        **extra,
         "psnr": tot[0] / n,
         "psnr_perlayer": [tot[1 + t] / n for t in range(T)],
         "psnr_noise0": tot[T + 1] / n,

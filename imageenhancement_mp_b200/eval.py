@@ -25,24 +25,28 @@ REPORT_KEYS = ("val_deblur_loss", "val_perlayer_loss", "val_total_loss", "val_ps
                "val_psnrburst0", "val_psnraverage")
 
 
-def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None):
+def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None, ssim=False):
     """Forward + fused metrics for one (local) batch -> additive fp64 totals on the device.
+
+    ``ssim`` (EXTENSION, not in the reference): also the SSIM of the deblurred vs ground-truth sRGB crops; the totals
+    then carry one more value (``ie_metric_totals_ssim_f64``).
 
     ``vis``: optional dict of lists receiving the reference's visualisation arrays for this batch (eval.py:164-169):
     invert_gt, invert_deblur, invert_perlayer, Basis, originbasis (numpy, one device->host copy each)."""
     res = model(x_batch_burst)                                                    # eval.py:143
     reconstructed = res[0]
     n, h, w, _ = reconstructed.shape
-    sums = du.eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length)   # :144-182
+    wl = du.white_level_of(x_batch_truth)                                         # :144-145
+    sums = du.eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=wl)   # :146-182
     if vis is not None:
-        wl = du.white_level_of(x_batch_truth)                                     # :144-145
         vis["invert_gt"].append(du.invert_preproc(x_batch_truth[..., 0], wl).cpu().numpy())         # :146-147
         vis["invert_deblur"].append(du.invert_preproc(reconstructed[..., 0], wl).cpu().numpy())     # :148-149
         vis["invert_perlayer"].append(du.invert_deblur_layer(reconstructed, wl).cpu().numpy())      # :158
         vis["Basis"].append(res[1].cpu().numpy())
         if len(res) > 2:
             vis["originbasis"].append(res[2].cpu().numpy())
-    return du.reduce_metric_sums(sums, h, w, burst_length)
+    ssim_sums = du.ssim_deblur_sums(reconstructed, x_batch_truth, white_noise=wl) if ssim else None
+    return du.reduce_metric_sums(sums, h, w, burst_length, ssim_sums=ssim_sums)
 
 
 def staged_batches(val_batches, device, depth=2, pre_sharded=False):
@@ -96,7 +100,9 @@ def make_report(totals, num_batches, burst_length):
     plain mean.
     """
     r = du.totals_to_report(totals, burst_length)
+    extra = {"val_ssim": r["ssim"]} if "ssim" in r else {}      # extension
     return {
+        **extra,
         "val_deblur_loss": r["loss1"],
         "val_perlayer_loss": r["perlayer_loss"],
         "val_total_loss": r["loss1"] + r["perlayer_loss"],
@@ -116,7 +122,7 @@ def format_report(report, step=1):
 
 
 def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, step_results=None, device=None,
-             pre_sharded=False, visualization=False, dump_path=None):
+             pre_sharded=False, visualization=False, dump_path=None, ssim=False):
     """Validation loop.  val_batches yields (x_batch_burst [N,H,W,T+add], x_batch_truth [N,H,W,2]), on the
     device or in (pinned) host memory.
 
@@ -129,6 +135,8 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
     ``visualization`` (eval.py:41 ``--visualization``): also collect invert_gt / invert_deblur / invert_perlayer /
     Basis / originbasis of every local batch and write them with ``np.savez`` like eval.py:201-207 (to ``dump_path``,
     default ``data<time>.npz``; with several ranks every rank writes ``<stem>.rank<r>.npz`` for its shard).
+    ``ssim`` (EXTENSION): also report ``val_ssim`` (deblurred vs ground truth, tf.image.ssim semantics); it travels
+    in the same all-reduced totals vector.
     Returns the report dict (identical on all ranks); rank 0 prints it through ``out``.
     """
     T = params["BURST_LENGTH"]
@@ -137,7 +145,7 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
     if step_totals is not None:
         fn = step_totals
     else:
-        fn = lambda m, xb, xt, T_: gpu_step_totals(m, xb, xt, T_, vis=vis)
+        fn = lambda m, xb, xt, T_: gpu_step_totals(m, xb, xt, T_, vis=vis, ssim=ssim)
     totals = None
     nb = 0
     if step_totals is None:

@@ -185,6 +185,12 @@ int ie_eval_metrics_tune(int rows_per_batch, int warps, int legacy);
  *   loss = mse + mean|grad diff| (:46-51).  This is the vector that is all-reduced across ranks.          */
 int ie_metric_totals_f64(const double* sums, int n, int h, int w, int T, int crop, double* totals, void* stream);
 
+/* Same with one more total for the SSIM EXTENSION (not in the reference): ssim_sums[n] = sum of image n's SSIM map
+ * (ie_ssim_f32 on the cropped sRGB'd deblurred / ground-truth images); totals (T+7 values) =
+ *   [ ...the T+5 values above..., sum_n mean-SSIM_n, n ].                                                  */
+int ie_metric_totals_ssim_f64(const double* sums, const double* ssim_sums, int n, int h, int w, int T, int crop,
+                              double* totals, void* stream);
+
 /* psnr_tf_batch's inner reduction (data_utils.py:118-119): sums[n] += sum (a-b)^2 over `count` px.    */
 int ie_sqdiff_sum_f32(const float* a, const float* b, int n, long long count, double* sums, void* stream);
 
@@ -195,6 +201,8 @@ int ie_img_loss_sums_f32(const float* a, const float* b, int n, int h, int w, do
 /* SSIM, tf.image.ssim semantics (11x11 Gaussian sigma 1.5, VALID, K1=.01, K2=.03, max_val 1).
  * EXTENSION: not in the reference.  sums[n] += sum of the SSIM map of image n ((h-10)*(w-10) values). */
 int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream);
+/* A-B knob: legacy != 0 forces the one-column-per-thread kernel (any w / alignment).  Process-wide.      */
+int ie_ssim_tune(int legacy);
 
 /* ---- preprocessing (data_utils.py:198-265 arithmetic with explicit random draws) ------------------ */
 

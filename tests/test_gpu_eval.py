@@ -51,6 +51,41 @@ def test_evaluate_matches_oracle_report(cuda, where, nb, n, h, w):
     assert abs(float(tot[0]) / float(tot[-1]) - rep["val_psnr"]) <= 1e-9
 
 
+def test_evaluate_with_ssim_extension(cuda):
+    """evaluate(ssim=True): val_ssim rides in the same totals vector (T+7 values) and equals the fp64 tf.image.ssim
+    restatement applied to the oracle's invert_preproc'd deblurred / ground-truth images, batch-mean of image means;
+    every other report number is unchanged by the flag."""
+    from imageenhancement_mp_b200 import eval as ieval, model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    T = params["BURST_LENGTH"]
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    batches = [synth.make_batch(3, 48, 56, params, seed=90 + i) for i in range(2)]
+    model = ml.Simplemodel(params, weights=W)
+    fed = [(x.to(cuda), t.to(cuda)) for x, t in batches]
+    per_step = []
+    rep = ieval.evaluate(model, fed, params, out=None, ssim=True, step_results=per_step)
+    base = ieval.evaluate(model, fed, params, out=None)
+    assert per_step[0].numel() == T + 7 and "val_ssim" not in base
+    for k in base:
+        assert rep[k] == base[k], k
+    vals = []
+    for x, t in batches:
+        out = oracle.simplemodel_forward(W, params, x)[0]
+        wl = t[..., 1:2].double().mean(dim=(1, 2), keepdim=True)
+        vals.append(oracle.ssim(oracle.invert_preproc(out[..., 0].double(), wl),
+                                oracle.invert_preproc(t[..., 0].double(), wl)).mean())
+    ref = float(torch.stack(vals).mean())
+    assert abs(rep["val_ssim"] - ref) <= 5e-3          # bf16 trunk; the SSIM kernel itself is checked to 2e-5 elsewhere
+    # on identical kernels' inputs the extension is exact: SSIM of the GPU's own deblurred image, fp64 oracle
+    from imageenhancement_mp_b200 import data_utils as du
+    x, t = fed[0]
+    o = model(x)[0]
+    wl = du.white_level_of(t)
+    a, b = du.invert_preproc(o[..., 0], wl), du.invert_preproc(t[..., 0], wl)
+    got = du.ssim_deblur_sums(o, t) / ((a.shape[1] - 10) * (a.shape[2] - 10))
+    assert torch.allclose(got.cpu(), oracle.ssim(a.cpu().double(), b.cpu().double()).double(), atol=2e-5, rtol=1e-4)
+
+
 def test_evaluate_visualization_dump(cuda, tmp_path):
     """--visualization (eval.py:41,164-169,201-207): the .npz holds the same five arrays, one entry per batch."""
     import numpy as np

@@ -352,16 +352,24 @@ def test_psnr_known_answer(cuda):
     assert abs(float(du.psnr_tf_batch(a + 0.1, a)) - 20.0) < 1e-4      # constant error 0.1 -> 20 dB
 
 
-@pytest.mark.parametrize("n,h,w", [(2, 11, 11), (2, 64, 80), (1, 100, 137), (1, 210, 330)])
+@pytest.mark.parametrize("n,h,w", [(2, 11, 11), (2, 64, 80), (1, 100, 137), (1, 210, 330), (3, 12, 12), (1, 150, 270)])
 def test_ssim(cuda, n, h, w):
     """SSIM extension vs the fp64 tf.image.ssim restatement."""
     from imageenhancement_mp_b200 import data_utils as du
     g = torch.Generator().manual_seed(41)
     a = torch.rand(n, h, w, generator=g)
     b = (a + 0.1 * torch.randn(n, h, w, generator=g)).clamp(0, 1)
-    got = du.ssim(a.to(cuda), b.to(cuda)).cpu().double()
-    assert torch.allclose(got, oracle.ssim(a, b), atol=2e-5, rtol=1e-4)
-    assert torch.allclose(du.ssim(a.to(cuda), a.to(cuda)).cpu(), torch.ones(n), atol=1e-5)
+    from imageenhancement_mp_b200 import _lib
+    lib = _lib.load()
+    ref = oracle.ssim(a, b)
+    try:
+        for legacy in (0, 1):          # two-column / four-moment kernel (even w) and the one-column kernel
+            lib.ie_ssim_tune(legacy)
+            got = du.ssim(a.to(cuda), b.to(cuda)).cpu().double()
+            assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), legacy
+            assert torch.allclose(du.ssim(a.to(cuda), a.to(cuda)).cpu(), torch.ones(n), atol=1e-5)
+    finally:
+        lib.ie_ssim_tune(0)
 
 
 # ------------------------------------------------------------------ preprocessing
