@@ -3,6 +3,7 @@
 // box mean -> channel mean -> white level -> read/shot noise -> noise-level channel -> NHWC.
 // The reference draws crops / levels / normals from TF's RNG; here every draw is an input.
 #include "ie_common.cuh"
+#include "ie_ptx.cuh"
 
 namespace ie {
 
@@ -170,84 +171,185 @@ __device__ __noinline__ float4 box16_clipped(const uint8_t* __restrict__ img, in
   return make_float4(s[0], s[1], s[2], s[3]);
 }
 
-template <int T, int ADD, bool RNG>
-__global__ void __launch_bounds__(256)
-preprocess_u8_quad_kernel(const uint8_t* __restrict__ src, int hs, int ws, const int32_t* __restrict__ org,
+// 1-D TMA bulk copies (global <-> shared, no LSU wavefronts, no registers)
+__device__ __forceinline__ void bulk_load(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(float* gdst, const float* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+// Every WARP walks its own tiles of 32 consecutive quads (128 pixels, contiguous in every tensor).  What limited the
+// first 4-px-per-thread version was the L1 data pipe (77 % busy): besides the 64 table lookups per pixel it carried the
+// noise loads and the output stores as 128-bit accesses with a 64 / 80 / 32-byte lane stride, i.e. 16-20 wavefronts
+// per instruction.  Here the tile's read / shot noise arrives by TMA bulk copy into the warp's slice of shared memory
+// (the next tile's copy is in flight during the lookups) and x / truth leave by TMA bulk store from a staging slice;
+// the threads touch them only with conflict-free 128-bit shared accesses (noise: lane-rotated order, un-rotated with
+// selects).  Warps never meet at a block barrier after the table is built (a block-wide version of this pipeline was
+// barrier- and latency-bound: one 512-thread block per SM, 0.9 stalled warps per issue at the barriers).
+template <int T, int ADD, bool RNG, int NT>
+__global__ void __launch_bounds__(NT)
+preprocess_u8_tile_kernel(const uint8_t* __restrict__ src, int hs, int ws, const int32_t* __restrict__ org,
                           float degamma, const float* __restrict__ wl, const float* __restrict__ sig_read,
                           const float* __restrict__ sig_shot, const float* __restrict__ n_read,
                           const float* __restrict__ n_shot, unsigned long long seed, int n_img, int h, int w,
                           float* __restrict__ x, float* __restrict__ truth) {
-  extern __shared__ float lutr[];                                // [256][64]: entry b, copy l at float b * 64 + l (l < 32)
-  {
+  constexpr int CH = T + ADD;
+  constexpr int ROTBITS = (T == 4) ? 2 : 3;
+  static_assert(T == 4 || T == 8, "tile kernel: T must be 4 or 8");
+  extern __shared__ float4 pre_dyn4[];
+  float* lutr = reinterpret_cast<float*>(pre_dyn4);              // [256][64]: entry b, copy l at float b * 64 + l (l < 32)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = NT / 32;
+  float* s_ns = lutr + 256 * 64 + warp * 32 * 4 * T;             // [NW][32][4 T] shot normals of the warp's tile
+  float* s_nr = lutr + 256 * 64 + NT * 4 * T + warp * 32 * 4 * T;   // read normals
+  float* s_x = lutr + 256 * 64 + 2 * NT * 4 * T + warp * 32 * 4 * CH;          // [NW][32][4 CH] staged x
+  float* s_t = lutr + 256 * 64 + 2 * NT * 4 * T + NT * 4 * CH + warp * 32 * 8;  // [NW][32][8]    staged truth
+  __shared__ uint64_t bars[NW];
+  if (threadIdx.x < 256) {
     const float v = powf((float)threadIdx.x / 255.f, degamma);
     const int l = threadIdx.x & 31;
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) lutr[threadIdx.x * 64 + ((l + j) & 31)] = v;
   }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
   __syncthreads();
+  uint64_t* bar = &bars[warp];
   const char* lut_b = reinterpret_cast<const char*>(lutr);
-  const uint32_t lane4 = (threadIdx.x & 31) * 4;
-  constexpr int CH = T + ADD;
+  const uint32_t lane4 = lane * 4;
   const int n = blockIdx.z;
   const float wln = wl[n], sr = sig_read[n], ss = sig_shot[n];
   const long long img_off = (long long)n * hs * ws;
   const long long src_total = (long long)n_img * hs * ws;
   const int qw = w >> 2;
   const int nquads = h * qw;
+  const long long img_px = (long long)n * h * w;
   const float inv_area = 1.f / 16.f;
+  const bool have_noise = !RNG && (n_read != nullptr) && (n_shot != nullptr);
   int oys[T], oxs[T];
 #pragma unroll
   for (int f = 0; f < T; ++f) {
     oys[f] = org[((long long)n * T + f) * 2];
     oxs[f] = org[((long long)n * T + f) * 2 + 1];
   }
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += gridDim.x * blockDim.x) {
-    const int py = q / qw, px = (q - py * qw) * 4;
-    const long long t0 = ((long long)n * h + py) * w + px;
-    float xv[4 * CH], tv[8];
-    float4 nsv[T], nrv[T];                                       // noise of the quad: element p * T + f
-    const bool have_noise = !RNG && (n_read != nullptr) && (n_shot != nullptr);
-    if (have_noise) {
+  auto load_noise = [&](int q0) {                                // lane 0 only
+    const uint32_t bytes = (uint32_t)min(32, nquads - q0) * 4u * T * 4u;
+    mbar_arrive_expect_tx(bar, 2 * bytes);
+    bulk_load(s_ns, n_shot + (img_px + 4ll * q0) * T, bytes, bar);
+    bulk_load(s_nr, n_read + (img_px + 4ll * q0) * T, bytes, bar);
+  };
+  const int q_first = (blockIdx.x * NW + warp) * 32, q_step = gridDim.x * NW * 32;
+  if (have_noise && lane == 0 && q_first < nquads) load_noise(q_first);
+  // reads the thread's 4T noise floats (element p * T + f) of one tensor: unit u = float4 number u; slot j reads unit
+  // (j + r) & (T-1) so that the 8 lanes of a shared-memory wavefront cover all 32 banks, then the rotation is undone
+  // with log2(T) select stages
+  auto read_noise = [&](const float* sbase, float (&out)[4 * T]) {
+    const int r = (T == 4) ? ((lane >> 1) & 3) : (lane & 7);
+    float4 a[T], a2[T];
 #pragma unroll
-      for (int j = 0; j < T; ++j) {
-        nsv[j] = __ldcs(reinterpret_cast<const float4*>(n_shot + t0 * T) + j);
-        nrv[j] = __ldcs(reinterpret_cast<const float4*>(n_read + t0 * T) + j);
+    for (int j = 0; j < T; ++j) a[j] = reinterpret_cast<const float4*>(sbase + lane * 4 * T)[(j + r) & (T - 1)];
+#pragma unroll
+    for (int bit = 0; bit < ROTBITS; ++bit) {
+      const bool on = (r >> bit) & 1;
+#pragma unroll
+      for (int u = 0; u < T; ++u) {
+        const float4 o = a[(u - (1 << bit)) & (T - 1)], k = a[u];
+        a2[u] = make_float4(on ? o.x : k.x, on ? o.y : k.y, on ? o.z : k.z, on ? o.w : k.w);
       }
-    }
-    const float* nsf = reinterpret_cast<const float*>(nsv);
-    const float* nrf = reinterpret_cast<const float*>(nrv);
 #pragma unroll
-    for (int f = 0; f < T; ++f) {
-      const int oy = oys[f] + py * 4, ox = oxs[f] + px * 4;
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
-      const long long off_last = img_off + (long long)(oy + 3) * ws + ox;
-      if (oy >= 0 && oy + 4 <= hs && ox >= 0 && ox + 16 <= ws && (off_last & ~15ll) + 32 <= src_total) {
+      for (int u = 0; u < T; ++u) a[u] = a2[u];
+    }
+#pragma unroll
+    for (int u = 0; u < T; ++u) { out[4 * u] = a[u].x; out[4 * u + 1] = a[u].y; out[4 * u + 2] = a[u].z; out[4 * u + 3] = a[u].w; }
+  };
+  int it = 0;
+  for (int q0 = q_first; q0 < nquads; q0 += q_step, ++it) {
+    const int q = q0 + lane;
+    const bool active = q < nquads;
+    const int py = q / qw, px = (q - py * qw) * 4;
+    const long long t0 = img_px + 4ll * q;
+    float xv[4 * CH], tv[8];
+
+    // ---- phase 1: clean frames.  The source rows of frame f + 1 are requested right after frame f's 64 lookups.
+    if (active) {
+      auto in_range = [&](int f) {
+        const int oy = oys[f] + py * 4, ox = oxs[f] + px * 4;
+        const long long off_last = img_off + (long long)(oy + 3) * ws + ox;
+        return oy >= 0 && oy + 4 <= hs && ox >= 0 && ox + 16 <= ws && (off_last & ~15ll) + 32 <= src_total;
+      };
+      auto fetch = [&](int f, uint4 (&buf)[8]) {
+        const int oy = oys[f] + py * 4, ox = oxs[f] + px * 4;
 #pragma unroll
         for (int dy = 0; dy < 4; ++dy) {
           const long long off = img_off + (long long)(oy + dy) * ws + ox;
           const uint4* p16 = reinterpret_cast<const uint4*>(src + (off & ~15ll));
-          const uint4 lo = __ldg(p16), hi = __ldg(p16 + 1);
-          row16(lo, hi, (int)(off & 15), lut_b, lane4, s);
+          buf[2 * dy] = __ldg(p16);
+          buf[2 * dy + 1] = __ldg(p16 + 1);
         }
-      } else {
-        const float4 b = box16_clipped(src + img_off, hs, ws, oy, ox, lut_b, lane4);
-        s[0] = b.x; s[1] = b.y; s[2] = b.z; s[3] = b.w;
+      };
+      uint4 cur[8];
+      bool fast_cur = in_range(0);
+      if (fast_cur) fetch(0, cur);
+#pragma unroll
+      for (int f = 0; f < T; ++f) {
+        const int oy = oys[f] + py * 4, ox = oxs[f] + px * 4;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        if (fast_cur) {
+#pragma unroll
+          for (int dy = 0; dy < 4; ++dy) {
+            const long long off = img_off + (long long)(oy + dy) * ws + ox;
+            row16(cur[2 * dy], cur[2 * dy + 1], (int)(off & 15), lut_b, lane4, s);
+          }
+        } else {
+          const float4 b = box16_clipped(src + img_off, hs, ws, oy, ox, lut_b, lane4);
+          s[0] = b.x; s[1] = b.y; s[2] = b.z; s[3] = b.w;
+        }
+        if (f + 1 < T) {                                         // (requesting them before the lookups needs 32 more
+          fast_cur = in_range(f + 1);                            //  registers: spills at 512 threads, slower at 384)
+          if (fast_cur) fetch(f + 1, cur);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float csum = s[p] * inv_area;
+          xv[p * CH + f] = wln * (csum / 1.f);                   // :230 (grey source: channel mean of one channel)
+        }
       }
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float csum = s[p] * inv_area;
-        const float tr = wln * (csum / 1.f);                     // :230 (grey source: channel mean of one channel)
-        float v = tr;
-        if (have_noise) {
-          v = tr + sqrt_approx(tr) * ss * nsf[p * T + f] + sr * nrf[p * T + f];   // :463-465
-        } else if (RNG) {
+      for (int p = 0; p < 4; ++p) { tv[2 * p] = xv[p * CH]; tv[2 * p + 1] = wln; }   // :248-252
+    }
+
+    // ---- phase 2: noise (data_utils.py:462-466).  The tile's normals were requested a whole tile ago.
+    if (have_noise) {
+      float nsf[4 * T], nrf[4 * T];
+      mbar_wait(bar, it & 1);
+      read_noise(s_ns, nsf);
+      read_noise(s_nr, nrf);
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int f = 0; f < T; ++f) {
+          const float tr = xv[p * CH + f];
+          xv[p * CH + f] = tr + sqrt_approx(tr) * ss * nsf[p * T + f] + sr * nrf[p * T + f];
+        }
+    } else if (RNG) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int f = 0; f < T; ++f) {
+          const float tr = xv[p * CH + f];
           float zs, zr;
           normal_pair(seed, (unsigned long long)((t0 + p) * T + f), zs, zr);
-          v = tr + sqrt_approx(tr) * ss * zs + sr * zr;
+          xv[p * CH + f] = tr + sqrt_approx(tr) * ss * zs + sr * zr;
         }
-        xv[p * CH + f] = v;
-        if (f == 0) { tv[2 * p] = tr; tv[2 * p + 1] = wln; }     // :248-252
-      }
     }
     if (ADD == 1) {
 #pragma unroll
@@ -256,13 +358,28 @@ preprocess_u8_quad_kernel(const uint8_t* __restrict__ src, int hs, int ws, const
 #pragma unroll
       for (int p = 0; p < 4; ++p) { xv[p * CH + T] = sr; xv[p * CH + T + 1] = ss; }                     // :257
     }
-    float4* xo = reinterpret_cast<float4*>(x + t0 * CH);
+    // the previous tile's bulk stores must have read the staging slice before it is overwritten
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();                                                // noise slice consumed, staging slice free
+    if (have_noise && lane == 0 && q0 + q_step < nquads) load_noise(q0 + q_step);
+    if (active) {
+      float4* xo = reinterpret_cast<float4*>(s_x + lane * 4 * CH);
 #pragma unroll
-    for (int j = 0; j < CH; ++j) __stcs(xo + j, make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]));
-    float4* to = reinterpret_cast<float4*>(truth + t0 * 2);
-    __stcs(to, make_float4(tv[0], tv[1], tv[2], tv[3]));
-    __stcs(to + 1, make_float4(tv[4], tv[5], tv[6], tv[7]));
+      for (int j = 0; j < CH; ++j) xo[j] = make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]);
+      float4* to = reinterpret_cast<float4*>(s_t + lane * 8);
+      to[0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+      to[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+    }
+    fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the bulk store
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t nq = (uint32_t)min(32, nquads - q0);
+      bulk_store(x + (img_px + 4ll * q0) * CH, s_x, nq * 4u * CH * 4u);
+      bulk_store(truth + (img_px + 4ll * q0) * 2, s_t, nq * 8u * 4u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int g_pre_legacy = 0;
@@ -270,16 +387,19 @@ template <int T, int ADD>
 static int launch_quad(const uint8_t* src, int n, int hs, int ws, const int32_t* org, float degamma, const float* wl,
                        const float* sig_read, const float* sig_shot, const float* n_read, const float* n_shot,
                        unsigned long long seed, int use_rng, int h, int w, float* x, float* truth, cudaStream_t st) {
-  const size_t smem = 256 * 64 * sizeof(float);
-  auto kern = use_rng ? preprocess_u8_quad_kernel<T, ADD, true> : preprocess_u8_quad_kernel<T, ADD, false>;
+  constexpr int NT = (T == 4) ? 512 : 256;                     // one block per SM (the table alone is 64 KB)
+  constexpr int CH = T + ADD;
+  const size_t smem = sizeof(float) * (256 * 64 + 2 * NT * 4 * T + NT * 4 * CH + NT * 8);
+  auto kern = use_rng ? preprocess_u8_tile_kernel<T, ADD, true, NT> : preprocess_u8_tile_kernel<T, ADD, false, NT>;
+  const int nt = NT;                                          // (576 / 640 threads measured the same)
   IE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nquads = (long long)h * (w / 4);
-  long long gx = (nquads + 255) / 256;
-  const long long cap = (12ll * sm_count() + n - 1) / n;       // the 32 KB table is built once per block: few, long blocks
+  long long gx = (nquads + NT - 1) / NT;
+  long long cap = sm_count() / n;                              // persistent: the grid fills the SMs once, warps stride
+  if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  kern<<<dim3((unsigned)gx, 1, n), 256, smem, st>>>(src, hs, ws, org, degamma, wl, sig_read, sig_shot, n_read, n_shot, seed,
-                                                    n, h, w, x, truth);
+  kern<<<dim3((unsigned)gx, 1, n), nt, smem, st>>>(src, hs, ws, org, degamma, wl, sig_read, sig_shot, n_read, n_shot, seed,
+                                                   n, h, w, x, truth);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -91,8 +91,9 @@ for n in a.batches:
         rows.append(("preprocess(ie_preprocess_u8,up=4,T=4)", nbytes, timed(pre)))
         if a.variants:
             lib = _lib.load()
-            lib.ie_preprocess_tune(1)
-            rows.append(("preprocess[legacy-1px]", nbytes, timed(pre)))
+            for tag, knob in (("legacy-1px", 1),):
+                lib.ie_preprocess_tune(knob)
+                rows.append((f"preprocess[{tag}]", nbytes, timed(pre)))
             lib.ie_preprocess_tune(0)
         del src, nr, ns
     for name, nbytes, ms in rows:
