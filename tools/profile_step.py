@@ -21,8 +21,10 @@ model = ml.Simplemodel(params, weights=weights.init_weights(weights.simplemodel_
 batches = [tuple(t.to(dev) for t in synth.make_batch(a.n, a.h, a.w, params, seed=1234 + i)) for i in range(2)]
 
 def step(xb, tb):
-    out = model(xb)[0]
-    return du.reduce_metric_sums(du.eval_metric_sums(out, xb, tb, T), a.h, a.w, T)
+    out = model(xb)[0]                                  # the bench step (bench.py::run_ours.step)
+    wl = du.white_level_of(tb)
+    sums = du.eval_metric_sums(out, xb, tb, T, white_noise=wl)
+    return du.reduce_metric_sums(sums, a.h, a.w, T, ssim_sums=du.ssim_deblur_sums(out, tb, white_noise=wl))
 
 step(*batches[0]); torch.cuda.synchronize()
 torch.cuda.profiler.start()
