@@ -773,6 +773,135 @@ ssim_stream2_kernel(const float* __restrict__ a, const float* __restrict__ b, in
   if (threadIdx.x == 0) atomicAdd(&sums[n], (double)red[0] + (double)red[1] + (double)red[2] + (double)red[3]);
 }
 
+// Same arithmetic, rows staged by TMA.  In the kernel above every input row is fresh data: 24 scalar loads per thread
+// and row, each stalling the warp on the long scoreboard (4.3 stalled warps per issued instruction at 16 warps per SM).
+// Here the block's row segments (256 + 10 columns of both images) arrive in shared memory by 1-D TMA bulk copies, 11
+// rows (one turn of the register window) per batch, the next batch in flight while this one is filtered - the
+// pipeline of eval_metrics_rows_kernel.  The filter reads shared memory only.
+__global__ void __launch_bounds__(128)
+ssim_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, int n_img, int h, int w, int rows_per_block,
+                 double* __restrict__ sums) {
+  extern __shared__ float4 ssim_dyn4[];
+  float* sm = reinterpret_cast<float*>(ssim_dyn4);
+  __shared__ uint64_t full[2];
+  constexpr int kCols = 2 * 128 + 2 * kSR;                        // input columns of a block
+  constexpr int kStride = ((kCols + 6) >> 2) << 2;                // floats per staged row (+ misalignment slack)
+  constexpr int kBuf = 2 * kSTaps * kStride;                      // one batch: 11 rows of a, 11 rows of b
+  const int n = blockIdx.z;
+  const int ho = h - 2 * kSR, wo = w - 2 * kSR;
+  const int x0 = 2 * blockIdx.x * 128;
+  const int x = x0 + 2 * threadIdx.x;                             // first output column of the pair
+  const int y0 = blockIdx.y * rows_per_block;
+  const int y1 = min(y0 + rows_per_block, ho);
+  const int yin_end = y1 + 2 * kSR;                               // input rows y0 .. yin_end - 1
+  const int ncols = min(kCols, w - x0);
+  const long long total = (long long)n_img * h * w;
+  float g[kSTaps];
+  {
+    float gs = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSTaps; ++k) {
+      const float c = (float)(k - kSR);
+      g[k] = expf(-0.5f * c * c / (1.5f * 1.5f));
+      gs += g[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kSTaps; ++k) g[k] /= gs;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], kSTaps);
+    mbar_init(&full[1], kSTaps);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int batch) {                                   // lane r of warp 0: row r of the batch
+    const int r = threadIdx.x;
+    if (r < kSTaps) {
+      uint64_t* bar = &full[batch & 1];
+      const int yi = y0 + batch * kSTaps + r;
+      if (yi < yin_end) {
+        float* da = sm + (batch & 1) * kBuf + r * kStride;
+        float* db = da + kSTaps * kStride;
+        const long long e = ((long long)n * h + yi) * w + x0;
+        RowCopy ca, cb;
+        ca.plan(da, a, total, e, ncols);
+        cb.plan(db, b, total, e, ncols);
+        mbar_arrive_expect_tx(bar, ca.bytes() + cb.bytes());
+        ca.go(da, a, bar);
+        cb.go(db, b, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+  };
+  float acc = 0.f;
+  const bool col_ok = x < wo;
+  float2 w_ab[2][kSTaps], w_sp[2][kSTaps];                         // [column][window slot]
+  const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+  const int nbatch = (yin_end - y0 + kSTaps - 1) / kSTaps;
+  issue(0);
+  for (int bi = 0; bi < nbatch; ++bi) {
+    if (bi + 1 < nbatch) issue(bi + 1);
+    mbar_wait(&full[bi & 1], (bi >> 1) & 1);
+    const float* buf = sm + (bi & 1) * kBuf;
+    const int yi0 = y0 + bi * kSTaps;
+    if (col_ok) {
+#pragma unroll
+      for (int slot = 0; slot < kSTaps; ++slot) {
+        const int yi = yi0 + slot;
+        if (yi < yin_end) {
+          const int mis = (int)((((long long)n * h + yi) * w + x0) & 3);
+          const float* ra = buf + slot * kStride + mis + 2 * threadIdx.x;
+          const float* rb = ra + kSTaps * kStride;
+          float2 h_ab[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          float2 h_sp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+          for (int i = 0; i < kSTaps + 1; ++i) {
+            const float va = ra[i], vb = rb[i];
+            const float2 ab = make_float2(va, vb);
+            const float2 sp = make_float2(fmaf(va, va, vb * vb), va * vb);
+            if (i < kSTaps) {
+              const float2 gg = make_float2(g[i], g[i]);
+              h_ab[0] = __ffma2_rn(gg, ab, h_ab[0]);
+              h_sp[0] = __ffma2_rn(gg, sp, h_sp[0]);
+            }
+            if (i >= 1) {
+              const float2 gg = make_float2(g[i - 1], g[i - 1]);
+              h_ab[1] = __ffma2_rn(gg, ab, h_ab[1]);
+              h_sp[1] = __ffma2_rn(gg, sp, h_sp[1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) { w_ab[j][slot] = h_ab[j]; w_sp[j][slot] = h_sp[j]; }
+          if (yi - 2 * kSR >= y0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              float2 v_ab = make_float2(0.f, 0.f), v_sp = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int r = 0; r < kSTaps; ++r) {
+                const int sl = (slot - r + kSTaps) % kSTaps;         // compile-time
+                const float2 gg = make_float2(g[kSTaps - 1 - r], g[kSTaps - 1 - r]);
+                v_ab = __ffma2_rn(gg, w_ab[j][sl], v_ab);
+                v_sp = __ffma2_rn(gg, w_sp[j][sl], v_sp);
+              }
+              const float num0 = 2.f * v_ab.x * v_ab.y, den0 = fmaf(v_ab.x, v_ab.x, v_ab.y * v_ab.y);
+              const float num = (num0 + c1) * (2.f * v_sp.y - num0 + c2);
+              const float den = (den0 + c1) * (v_sp.x - den0 + c2);
+              acc += __fdividef(num, den);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                              // the buffer is refilled by the next iteration's issue
+  }
+  __shared__ float red[4];
+  const float s = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&sums[n], (double)red[0] + (double)red[1] + (double)red[2] + (double)red[3]);
+}
+
 }  // namespace ie
 
 using namespace ie;
@@ -944,7 +1073,7 @@ extern "C" int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, 
   const int ho = h - 2 * kSR, wo = w - 2 * kSR;
   const int gy = (ho + kSsimRows - 1) / kSsimRows;
   IE_REQUIRE(n <= 65535 && gy <= 65535, "ssim: grid too large");
-  const bool pairs = g_ssim_legacy == 0 && (w % 2 == 0) &&
+  const bool pairs = g_ssim_legacy != 1 && (w % 2 == 0) &&
                      ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 7) == 0;
   if (pairs) {
     // rows per block: 128 (8 % vertical halo) for large images, down to 16 when small images would leave SMs idle
@@ -954,7 +1083,15 @@ extern "C" int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, 
     int rows = (int)((ho + want - 1) / want);
     if (rows < 16) rows = 16;
     if (rows > kSsimRows) rows = kSsimRows;
-    ssim_stream2_kernel<<<dim3(gx, (ho + rows - 1) / rows, n), 128, 0, S(stream)>>>(a, b, h, w, rows, sums);
+    const dim3 grid(gx, (ho + rows - 1) / rows, n);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+    if (g_ssim_legacy == 2 || !al16) {
+      ssim_stream2_kernel<<<grid, 128, 0, S(stream)>>>(a, b, h, w, rows, sums);
+    } else {
+      const size_t smem = sizeof(float) * 2 * 2 * kSTaps * ((((2 * 128 + 2 * kSR) + 6) >> 2) << 2);
+      IE_CUDA(cudaFuncSetAttribute(ssim_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ssim_rows_kernel<<<grid, 128, smem, S(stream)>>>(a, b, n, h, w, rows, sums);
+    }
     IE_LAUNCH_CHECK();
     return IE_OK;
   }

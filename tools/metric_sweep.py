@@ -55,9 +55,10 @@ for n in a.batches:
     rows.append(("ssim(ie_ssim_f32)", 8 * px,
                  timed(lambda: call("ie_ssim_f32", ptr(pred), ptr(truth), n, h, w, ptr(sums1), stream()))))
     if a.variants:
-        _lib.load().ie_ssim_tune(1)
-        rows.append(("ssim[legacy-1col]", 8 * px,
-                     timed(lambda: call("ie_ssim_f32", ptr(pred), ptr(truth), n, h, w, ptr(sums1), stream()))))
+        for tag, knob in (("legacy-1col", 1), ("2col-global-loads", 2)):
+            _lib.load().ie_ssim_tune(knob)
+            rows.append((f"ssim[{tag}]", 8 * px,
+                         timed(lambda: call("ie_ssim_f32", ptr(pred), ptr(truth), n, h, w, ptr(sums1), stream()))))
         _lib.load().ie_ssim_tune(0)
     rows.append(("invert_preproc(ie_invert_preproc_f32)", 4 * px + 4 * n * (h - 16) * (w - 16),
                  timed(lambda: call("ie_invert_preproc_f32", ptr(pred), 1, 0, 1, ptr(wl), n, h, w, 8, ptr(inv), stream()))))
