@@ -589,6 +589,9 @@ struct WideParams {
 __device__ __forceinline__ void epi_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }
 
 // Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
+// PAIR: the CTA is one half of a cta_group::2 pair; the pair walks the tile list two tiles at a time (rank r takes
+// tile 2u + r of unit u) and the "accumulator drained" arrivals go to the leader CTA, whose MMA warp feeds both.
+template <bool PAIR>
 __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const CUtensorMap* tm_y32,
                                                    const CUtensorMap* tm_y31, const SmemTail& t, uint32_t tmem_base,
                                                    int warp, int lane) {
@@ -599,8 +602,13 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
   const float* sbias = t.bias();
   const int set = (warp - 2) >> 2;
   float* xch = t.xch() + set * (kXchBytes / 4);
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int nprog = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int prog = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_units = PAIR ? (p.m_tiles + 1) >> 1 : p.m_tiles;
   int it = set;
-  for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
+  for (int u = prog + set * nprog; u < n_units; u += t.nsets * nprog, it += t.nsets) {
+    const int tile = PAIR ? 2 * u + rank : u;
     const int buf = it & 1;
     const uint32_t use = static_cast<uint32_t>(it >> 1);
     const int row0 = tile * wp_.tile_rows - 1;  // raster row of tile-local row 0
@@ -626,7 +634,10 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
       if (c == 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t.tempty()[buf]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&t.tempty()[buf]), 0));
+          else mbar_arrive(&t.tempty()[buf]);
+        }
       }
       // rows on warp boundaries travel through shared memory
       const uint32_t mine = smem_u32(xch + ((c * 4 + q) * 2) * 32);
@@ -905,7 +916,7 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp >= 2 + 4 * p.nsets) {
     // second epilogue set not in use
   } else if (p.e.epilogue == IE_EPI_BF16_RASTER) {
-    epilogue_wide_bf16(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
+    epilogue_wide_bf16<false>(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
   } else {
     epilogue_wide_f32(p, t, tmem_base, warp, lane);
   }
@@ -913,6 +924,140 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+
+// =================================================================================================
+// Wide-N kernel on CTA PAIRS (cta_group::2, cluster 2x1x1) for the 64 -> 64 layers (one channel block, resident
+// weights, a whole 3 x 64 filter row set per stage).  The single-CTA kernel above is bound by the shared-memory port:
+// per 126-pixel tile the tensor core reads 48 KB of A and 72 KB of weights.  In a pair every MMA is M = 256 (each CTA
+// supplies the 128 rows of ITS tile) x N = 192, and each CTA supplies only HALF of the weight columns (96 of 192):
+// 36 KB of weight reads per tile and CTA, 36 KB of resident weights instead of 72 (room for a third A stage).
+// Roles per CTA: warp 0 TMA producer (its own A boxes and weight half; bytes complete on the LEADER's barriers),
+// warp 1 TMEM allocation and - in the leader only - the MMA issuer for both CTAs (commits are multicast to the
+// barriers of both), warps 2-9 the two epilogue sets, each draining the accumulator of its own CTA.
+// =================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+conv_wide_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b64,
+                      const __grid_constant__ CUtensorMap tm_b32, const __grid_constant__ CUtensorMap tm_y32,
+                      const __grid_constant__ CUtensorMap tm_y31, const WideParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  constexpr int kBHalf = 96 * 128;                 // one filter row's weight half: [96 columns][64 k] bf16
+  constexpr int kBRes = 3 * kBHalf;
+  uint8_t* a_base_ptr = base + kBRes;
+  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes, p.nsets};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_units = (p.e.m_tiles + 1) >> 1;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b64);
+    tma_prefetch_desc(&tm_b32);
+    tma_prefetch_desc(&tm_y32);
+    tma_prefetch_desc(&tm_y31);
+  }
+  // ---- setup (cta_setup with pair-wide barrier counts and a cluster barrier)
+  for (int i = threadIdx.x; i < kMaxCout; i += blockDim.x) t.bias()[i] = (i < p.e.cout && p.e.bias) ? p.e.bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&t.full()[s], 2);                // one arrive.expect_tx per CTA of the pair (used in the leader)
+      mbar_init(&t.empty()[s], 1);               // multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t.tfull()[b], 1);               // multicast commit
+      mbar_init(&t.tempty()[b], 8);               // 4 epilogue warps x 2 CTAs (used in the leader)
+    }
+    mbar_init(t.bres(), 2);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(t.tmem_slot(), kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // the peer's barriers exist before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *t.tmem_slot();
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx_cluster(mapa_rank(smem_u32(t.bres()), 0), static_cast<uint32_t>(kBRes));
+      for (int dy = 0; dy < 3; ++dy) {
+        uint8_t* b = base + dy * kBHalf;
+        if (rank == 0) {      // columns 0-95: tap dx = 0 (64 output channels) + channels 0-31 of dx = 1
+          tma_load_2d_pair(b, &tm_b64, t.bres(), (dy * 3 + 0) * p.cin, 0);
+          tma_load_2d_pair(b + 64 * 128, &tm_b32, t.bres(), (dy * 3 + 1) * p.cin, 0);
+        } else {              // columns 96-191: channels 32-63 of dx = 1 + tap dx = 2
+          tma_load_2d_pair(b, &tm_b32, t.bres(), (dy * 3 + 1) * p.cin, 32);
+          tma_load_2d_pair(b + 32 * 128, &tm_b64, t.bres(), (dy * 3 + 2) * p.cin, 0);
+        }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = pair; u < n_units; u += npairs) {
+        const int row0 = (2 * u + rank) * p.tile_rows - 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx_cluster(mapa_rank(smem_u32(&full_bar[stage]), 0), 3u * kABytes);
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+          tma_load_2d_pair(a_base_ptr + stage * p.a_slot_bytes + g * kABytes, &tm_a, &full_bar[stage], p.x_coff,
+                           row0 + p.dy_shift[g]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ============================
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * kBlockM, 3 * p.gw);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base_ptr));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(base));
+      const uint32_t a_stride = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
+      mbar_wait(t.bres(), 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = pair; u < n_units; u += npairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = static_cast<uint32_t>(it >> 1);
+        mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_slot_lo = a_lo0 + stage * a_stride;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const uint32_t a = a_slot_lo + g * (kABytes >> 4);
+            const uint32_t b = b_lo0 + g * (kBHalf >> 4);
+            umma_bf16_ss_lo_pair(d_tmem, a, b, idesc, g == 0 ? 0u : 1u);
+            umma_bf16_ss_lo_pair(d_tmem, a + 2, b + 2, idesc, 1u);
+            umma_bf16_ss_lo_pair(d_tmem, a + 4, b + 4, idesc, 1u);
+            umma_bf16_ss_lo_pair(d_tmem, a + 6, b + 6, idesc, 1u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          umma_commit_pair(&t.tfull()[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    epilogue_wide_bf16<true>(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // the leader reads the peer's shared memory until its last MMA
+  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 
@@ -1078,6 +1223,7 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 // Tuning / test hooks (not part of the documented ABI surface): force a main-loop flavour.
 static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
+static int g_pair_mode = 0;          // 1: 64 -> 64 wide layers on CTA pairs (cta_group::2)
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
 // (measured on B200: the 128B swizzle is a function of the absolute smem address, so row-shifted descriptor starts
@@ -1089,6 +1235,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_force_mode = mode;
   ie::g_fuse_rows = (flags & 2) ? 0 : 1;
   ie::g_wide_flags = (flags >> 2) & 7;
+  ie::g_pair_mode = (flags >> 8) & 1;
   return IE_OK;
 }
 
@@ -1208,7 +1355,23 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
                                  (int)kMaxSmem));                                                                 \
     conv_wide_kernel<RES_, G_><<<grid, kThreads2, smem, st>>>(tm_a, tm_b, tm_y, tm_y31, p);                        \
   } while (0)
-    if (fuse) IE_LAUNCH_WIDE(true, 3);
+    const bool pairs = fuse && !wide_f32 && g_pair_mode == 1 && grid_cap >= 2;
+    if (pairs) {
+      // CTA pairs: half of the weights per CTA (36 KB), one more A stage
+      WideParams q = p;
+      q.nsets = 2;
+      const int tail2 = tail_bytes(q.nsets);
+      int st2 = ((int)kMaxSmem - 1024 - tail2 - 3 * 96 * 128) / q.a_slot_bytes;
+      q.stages = st2 > kMaxStages ? kMaxStages : st2;
+      CUtensorMap tm_b32;
+      rc = make_tmap_2d_bf16(&tm_b32, w_packed, (uint64_t)ktot, (uint64_t)p.gw, (uint64_t)ktot, 64, 32);
+      if (rc) return rc;
+      const size_t smem2 = 1024 + (size_t)3 * 96 * 128 + (size_t)q.stages * q.a_slot_bytes + tail2;
+      const int units = (q.e.m_tiles + 1) / 2;
+      const int npairs = units < grid_cap / 2 ? units : grid_cap / 2;
+      IE_CUDA(cudaFuncSetAttribute(conv_wide_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      conv_wide_pair_kernel<<<2 * npairs, kThreads2, smem2, st>>>(tm_a, tm_b, tm_b32, tm_y, tm_y31, q);
+    } else if (fuse) IE_LAUNCH_WIDE(true, 3);
     else if (res) IE_LAUNCH_WIDE(true, 1);
     else IE_LAUNCH_WIDE(false, 1);
 #undef IE_LAUNCH_WIDE
