@@ -95,6 +95,21 @@ def test_totals_layout_roundtrip():
     assert r["psnr_noise0"] == 3.0 and r["psnr_average"] == 3.5 and r["loss1"] == 4.0 and r["perlayer_loss"] == 4.5
 
 
+def test_totals_layout_with_ssim_extension():
+    """T+7 totals (ie_metric_totals_ssim_f64): the mean-SSIM sum sits before the image count; the reference's numbers
+    keep their places and `val_ssim` appears only then."""
+    tot = torch.arange(T + 7, dtype=torch.float64) + 1
+    tot[-1] = 2
+    r = du.totals_to_report(tot, T)
+    assert r["psnr"] == 0.5 and r["perlayer_loss"] == 4.5 and r["count"] == 2
+    assert r["ssim"] == (T + 6) / 2
+    rep = ieval.make_report(tot, 3, T)
+    assert rep["val_ssim"] == (T + 6) / 2 and rep["val_psnr"] == 0.5
+    assert "val_ssim" not in ieval.make_report(torch.cat([tot[:T + 5], tot[-1:]]), 3, T)
+    with pytest.raises(AssertionError):
+        du.totals_to_report(torch.ones(T + 8, dtype=torch.float64), T)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
