@@ -113,6 +113,31 @@ def test_ssim_identities():
     assert torch.all(s < 1) and torch.allclose(s, oracle.ssim(b, a))
 
 
+def test_ssim_against_scipy_separable_gaussian():
+    """Independent restatement of tf.image.ssim's published definition (Wang et al. 2004 with an 11-tap sigma-1.5
+    Gaussian window, VALID region, K1 = .01, K2 = .03, L = 1) on scipy.ndimage: separable correlate1d, the
+    variance / covariance form of the formula - against oracle.ssim's single 2-D convolution + moment form."""
+    import numpy as np
+    from scipy import ndimage
+    rng = np.random.default_rng(5)
+    a = rng.random((3, 37, 52))
+    b = np.clip(a + 0.15 * rng.standard_normal(a.shape), 0, 1)
+    x = np.arange(11) - 5.0
+    g = np.exp(-0.5 * (x / 1.5) ** 2)
+    g /= g.sum()
+
+    def blur(img):                                          # VALID part of the separable Gaussian correlation
+        t = ndimage.correlate1d(img, g, axis=1, mode="constant")
+        t = ndimage.correlate1d(t, g, axis=2, mode="constant")
+        return t[:, 5:-5, 5:-5]
+    mu_a, mu_b = blur(a), blur(b)
+    var_a, var_b, cov = blur(a * a) - mu_a ** 2, blur(b * b) - mu_b ** 2, blur(a * b) - mu_a * mu_b
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    ref = ((2 * mu_a * mu_b + c1) * (2 * cov + c2) / ((mu_a ** 2 + mu_b ** 2 + c1) * (var_a + var_b + c2))).mean(axis=(1, 2))
+    got = oracle.ssim(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+    assert np.allclose(got, ref, rtol=0, atol=1e-12)
+
+
 def test_preprocess_area_resize_matches_cv2():
     cv2 = pytest.importorskip("cv2")
     g = torch.Generator().manual_seed(5)
