@@ -691,91 +691,9 @@ ssim_stream_kernel(const float* __restrict__ a, const float* __restrict__ b, int
 // each).  Per pixel: 12 loads, 18 product ops, 22 + 22 packed FMAs, ~14 for the SSIM quotient (one MUFU.RCP) - about
 // 95 issue slots against ~170 of the one-column kernel above.  The kernel is bound by the FP32 pipe: 88 FMA-lane
 // operations per pixel for the two separable passes alone put the ceiling at ~37 % of the HBM roofline.
-// Requires even w and 8-byte aligned images (w - 10 outputs per row then pair up exactly).
-__global__ void __launch_bounds__(128)
-ssim_stream2_kernel(const float* __restrict__ a, const float* __restrict__ b, int h, int w, int rows_per_block,
-                    double* __restrict__ sums) {
-  const int n = blockIdx.z;
-  const int ho = h - 2 * kSR, wo = w - 2 * kSR;
-  const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);      // first output column of the pair
-  const int y0 = blockIdx.y * rows_per_block;
-  const int y1 = min(y0 + rows_per_block, ho);
-  float g[kSTaps];
-  {
-    float gs = 0.f;
-#pragma unroll
-    for (int k = 0; k < kSTaps; ++k) {
-      const float c = (float)(k - kSR);
-      g[k] = expf(-0.5f * c * c / (1.5f * 1.5f));
-      gs += g[k];
-    }
-#pragma unroll
-    for (int k = 0; k < kSTaps; ++k) g[k] /= gs;
-  }
-  float acc = 0.f;
-  if (x < wo) {
-    const float* pa = a + (long long)n * h * w + x;
-    const float* pb = b + (long long)n * h * w + x;
-    float2 w_ab[2][kSTaps], w_sp[2][kSTaps];                       // [column][window slot]
-    const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
-    for (int yi0 = y0; yi0 < y1 + 2 * kSR; yi0 += kSTaps) {
-#pragma unroll
-      for (int slot = 0; slot < kSTaps; ++slot) {
-        const int yi = yi0 + slot;
-        if (yi < y1 + 2 * kSR) {
-          const float* ra = pa + (long long)yi * w;
-          const float* rb = pb + (long long)yi * w;
-          float2 h_ab[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-          float2 h_sp[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-          for (int i = 0; i < kSTaps + 1; ++i) {
-            const float va = __ldg(ra + i), vb = __ldg(rb + i);
-            const float2 ab = make_float2(va, vb);
-            const float2 sp = make_float2(fmaf(va, va, vb * vb), va * vb);
-            if (i < kSTaps) {
-              const float2 gg = make_float2(g[i], g[i]);
-              h_ab[0] = __ffma2_rn(gg, ab, h_ab[0]);
-              h_sp[0] = __ffma2_rn(gg, sp, h_sp[0]);
-            }
-            if (i >= 1) {
-              const float2 gg = make_float2(g[i - 1], g[i - 1]);
-              h_ab[1] = __ffma2_rn(gg, ab, h_ab[1]);
-              h_sp[1] = __ffma2_rn(gg, sp, h_sp[1]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 2; ++j) { w_ab[j][slot] = h_ab[j]; w_sp[j][slot] = h_sp[j]; }
-          if (yi - 2 * kSR >= y0) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float2 v_ab = make_float2(0.f, 0.f), v_sp = make_float2(0.f, 0.f);
-#pragma unroll
-              for (int r = 0; r < kSTaps; ++r) {
-                const int sl = (slot - r + kSTaps) % kSTaps;         // compile-time
-                const float2 gg = make_float2(g[kSTaps - 1 - r], g[kSTaps - 1 - r]);
-                v_ab = __ffma2_rn(gg, w_ab[j][sl], v_ab);
-                v_sp = __ffma2_rn(gg, w_sp[j][sl], v_sp);
-              }
-              const float num0 = 2.f * v_ab.x * v_ab.y, den0 = fmaf(v_ab.x, v_ab.x, v_ab.y * v_ab.y);
-              const float num = (num0 + c1) * (2.f * v_sp.y - num0 + c2);
-              const float den = (den0 + c1) * (v_sp.x - den0 + c2);
-              acc += __fdividef(num, den);
-            }
-          }
-        }
-      }
-    }
-  }
-  __shared__ float red[4];
-  const float s = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(&sums[n], (double)red[0] + (double)red[1] + (double)red[2] + (double)red[3]);
-}
-
-// Same arithmetic, rows staged by TMA.  In the kernel above every input row is fresh data: 24 scalar loads per thread
-// and row, each stalling the warp on the long scoreboard (4.3 stalled warps per issued instruction at 16 warps per SM).
-// Here the block's row segments (256 + 10 columns of both images) arrive in shared memory by 1-D TMA bulk copies, 11
+// Rows staged by TMA.  With plain global loads (first version of this kernel, 17 % of the HBM roofline) every input
+// row is fresh data: 24 scalar loads per thread and row, each stalling the warp on the long scoreboard (4.3 stalled
+// warps per issued instruction at 16 warps per SM).  Here the block's row segments (256 + 10 columns of both images) arrive in shared memory by 1-D TMA bulk copies, 11
 // rows (one turn of the register window) per batch, the next batch in flight while this one is filtered - the
 // pipeline of eval_metrics_rows_kernel.  The filter reads shared memory only.
 __global__ void __launch_bounds__(128)
@@ -1073,9 +991,10 @@ extern "C" int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, 
   const int ho = h - 2 * kSR, wo = w - 2 * kSR;
   const int gy = (ho + kSsimRows - 1) / kSsimRows;
   IE_REQUIRE(n <= 65535 && gy <= 65535, "ssim: grid too large");
-  const bool pairs = g_ssim_legacy != 1 && (w % 2 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 7) == 0;
-  if (pairs) {
+  // even width + 16-byte aligned images: two columns per thread, rows staged by TMA; anything else: one column per thread
+  const bool rows_ok = g_ssim_legacy == 0 && (w % 2 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (rows_ok) {
     // rows per block: 128 (8 % vertical halo) for large images, down to 16 when small images would leave SMs idle
     const int gx = ie_ceil_div(wo / 2, 128);
     long long want = 4ll * sm_count() / ((long long)gx * n);
@@ -1083,15 +1002,9 @@ extern "C" int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, 
     int rows = (int)((ho + want - 1) / want);
     if (rows < 16) rows = 16;
     if (rows > kSsimRows) rows = kSsimRows;
-    const dim3 grid(gx, (ho + rows - 1) / rows, n);
-    const bool al16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
-    if (g_ssim_legacy == 2 || !al16) {
-      ssim_stream2_kernel<<<grid, 128, 0, S(stream)>>>(a, b, h, w, rows, sums);
-    } else {
-      const size_t smem = sizeof(float) * 2 * 2 * kSTaps * ((((2 * 128 + 2 * kSR) + 6) >> 2) << 2);
-      IE_CUDA(cudaFuncSetAttribute(ssim_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ssim_rows_kernel<<<grid, 128, smem, S(stream)>>>(a, b, n, h, w, rows, sums);
-    }
+    const size_t smem = sizeof(float) * 2 * 2 * kSTaps * ((((2 * 128 + 2 * kSR) + 6) >> 2) << 2);
+    IE_CUDA(cudaFuncSetAttribute(ssim_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ssim_rows_kernel<<<dim3(gx, (ho + rows - 1) / rows, n), 128, smem, S(stream)>>>(a, b, n, h, w, rows, sums);
     IE_LAUNCH_CHECK();
     return IE_OK;
   }

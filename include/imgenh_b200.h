@@ -201,7 +201,8 @@ int ie_img_loss_sums_f32(const float* a, const float* b, int n, int h, int w, do
 /* SSIM, tf.image.ssim semantics (11x11 Gaussian sigma 1.5, VALID, K1=.01, K2=.03, max_val 1).
  * EXTENSION: not in the reference.  sums[n] += sum of the SSIM map of image n ((h-10)*(w-10) values). */
 int ie_ssim_f32(const float* a, const float* b, int n, int h, int w, double* sums, void* stream);
-/* A-B knob: legacy != 0 forces the one-column-per-thread kernel (any w / alignment).  Process-wide.      */
+/* A-B knob: legacy != 0 forces the one-column-per-thread kernel that also serves odd widths and images that are
+ * not 16-byte aligned.  Process-wide.                                                                   */
 int ie_ssim_tune(int legacy);
 
 /* ---- preprocessing (data_utils.py:198-265 arithmetic with explicit random draws) ------------------ */

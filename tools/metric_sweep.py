@@ -55,7 +55,7 @@ for n in a.batches:
     rows.append(("ssim(ie_ssim_f32)", 8 * px,
                  timed(lambda: call("ie_ssim_f32", ptr(pred), ptr(truth), n, h, w, ptr(sums1), stream()))))
     if a.variants:
-        for tag, knob in (("legacy-1col", 1), ("2col-global-loads", 2)):
+        for tag, knob in (("legacy-1col", 1),):
             _lib.load().ie_ssim_tune(knob)
             rows.append((f"ssim[{tag}]", 8 * px,
                          timed(lambda: call("ie_ssim_f32", ptr(pred), ptr(truth), n, h, w, ptr(sums1), stream()))))
