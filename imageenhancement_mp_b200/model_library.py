@@ -38,13 +38,13 @@ class _KpnModel:
         if weights is None:
             weights = _weights.init_weights(type(self)._layers(params), seed=seed, scheme=init)
         elif isinstance(weights, str):
-            weights = _weights.load(weights)          # .npz, or a TensorFlow checkpoint directory / prefix
+            weights = _weights.load(weights, layers=type(self)._layers(params))   # .npz or a TensorFlow checkpoint
         self._engine = Engine(type(self)._arch, self.params, weights, device=device)
 
     # Keras-like conveniences
     def load_weights(self, weights):
         if isinstance(weights, str):
-            weights = _weights.load(weights)
+            weights = _weights.load(weights, layers=type(self)._layers(self.params))
         self._engine.load_weights(weights)
 
     @property

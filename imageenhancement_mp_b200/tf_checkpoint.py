@@ -212,11 +212,30 @@ def latest_checkpoint(directory):
     return None
 
 
-def load_tf_checkpoint(prefix, root="net", dtype=np.float32):
+def _resolve_path(path, layer_order):
+    """Attribute path of a variable.  Keras also reaches every layer through ``layer_with_weights-N`` edges (creation
+    order); a checkpoint saver that happened to name variables through them is mapped back: the top-level index into
+    ``layer_order`` (the model's weight-bearing attributes in creation order), a nested one into ``conv2d<N+1>`` (the
+    blocks of model_library.py:65-101 create conv2d1..3 in that order)."""
+    out = []
+    for depth, comp in enumerate(path):
+        if comp.startswith("layer_with_weights-"):
+            idx = int(comp.rsplit("-", 1)[1])
+            if depth == 0:
+                if layer_order is None or idx >= len(layer_order):
+                    raise CheckpointFormatError(f"variable path {'/'.join(path)} needs the model's layer order")
+                comp = layer_order[idx]
+            else:
+                comp = "conv2d%d" % (idx + 1)
+        out.append(comp)
+    return out
+
+
+def load_tf_checkpoint(prefix, root="net", dtype=np.float32, layer_order=None):
     """``{layer name: (kernel [kh,kw,cin,cout], bias [cout])}`` (torch tensors, the format of ``weights.load_npz``) from
     the variables under ``root`` - the keyword the model was given in ``tf.train.Checkpoint`` (``net`` at
     run_training.py:114; eval.py:112 uses the same object).  Layer names are the Keras attribute paths joined with
-    ``.`` (``down1.conv2d1``, ``layer0``, ...), as everywhere in this package."""
+    ``.`` (``down1.conv2d1``, ``layer0``, ...), as everywhere in this package.  ``layer_order``: see _resolve_path."""
     import torch
     want = root + "/"
     tensors = read_bundle(prefix, keys=lambda k: k.startswith(want) and k.endswith(VARIABLE_SUFFIX)
@@ -226,6 +245,7 @@ def load_tf_checkpoint(prefix, root="net", dtype=np.float32):
         path = key[len(want):-len(VARIABLE_SUFFIX)].split("/")
         if len(path) < 2 or path[-1] not in ("kernel", "bias"):
             continue
+        path = _resolve_path(path[:-1], layer_order) + path[-1:]
         (kernels if path[-1] == "kernel" else biases)[".".join(path[:-1])] = arr
     if not kernels:
         raise CheckpointFormatError(

@@ -125,23 +125,32 @@ def load_npz(path):
     return {n: (torch.from_numpy(z[n + "/kernel"]), torch.from_numpy(z[n + "/bias"])) for n in names}
 
 
-def load(path, root="net"):
+def load(path, root="net", layers=None):
     """Weights from a file: the flat ``.npz`` of this package, or a TensorFlow object-graph checkpoint of the reference
     (eval.py:112-118) - a checkpoint directory (its ``checkpoint`` state file names the latest prefix, like
     ``tf.train.latest_checkpoint``) or a prefix ``.../ckpt-12`` (``.index`` + ``.data-*`` files).  ``root`` is the
     keyword the model was stored under in ``tf.train.Checkpoint`` (``net`` in the reference).  The TF reader is a
-    restatement of the published file formats, not validated against TensorFlow here (tf_checkpoint.py)."""
+    restatement of the published file formats, not validated against TensorFlow here (tf_checkpoint.py).
+    ``layers``: the model's layer list (``simplemodel_layers(params)``), only needed for checkpoints whose variables
+    are named through Keras' ``layer_with_weights-N`` edges."""
     import os
     from . import tf_checkpoint as tfc
     if path.endswith(".npz"):
         return load_npz(path)
+    order = None
+    if layers is not None:
+        order = []
+        for entry in layers:
+            top = entry[0].split(".")[0]
+            if top not in order:
+                order.append(top)
     if os.path.isdir(path):
         prefix = tfc.latest_checkpoint(path)
         if prefix is None:
             raise FileNotFoundError(f"{path}: no 'checkpoint' state file (tf.train.CheckpointManager writes one)")
-        return tfc.load_tf_checkpoint(prefix, root=root)
+        return tfc.load_tf_checkpoint(prefix, root=root, layer_order=order)
     if path.endswith(".index"):
         path = path[:-len(".index")]
     if os.path.exists(path + ".index"):
-        return tfc.load_tf_checkpoint(path, root=root)
+        return tfc.load_tf_checkpoint(path, root=root, layer_order=order)
     raise FileNotFoundError(f"{path}: neither an .npz file nor a TensorFlow checkpoint prefix / directory")

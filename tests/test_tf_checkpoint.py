@@ -197,6 +197,25 @@ def test_weights_dict_is_the_npz_format(tmp_path):
         weights.load(str(tmp_path / "nothing-here"))
 
 
+def test_layer_with_weights_aliases(tmp_path):
+    """Variables named through Keras' creation-order edges map back to the attribute names."""
+    from imageenhancement_mp_b200 import synth, weights
+    layers = weights.simplemodel_layers(dict(synth.DEFAULT_PARAMS))
+    rng = np.random.default_rng(8)
+    t = {f"net/layer_with_weights-0/kernel{SUF}": rng.standard_normal((3, 3, 5, 4)).astype("<f4"),
+         f"net/layer_with_weights-0/bias{SUF}": rng.standard_normal(4).astype("<f4"),
+         f"net/layer_with_weights-1/layer_with_weights-1/kernel{SUF}": rng.standard_normal((3, 3, 4, 4)).astype("<f4"),
+         f"net/layer_with_weights-5/conv2d3/kernel{SUF}": rng.standard_normal((3, 3, 4, 2)).astype("<f4")}
+    prefix = str(tmp_path / "ckpt-2")
+    write_bundle(prefix, t)
+    W = weights.load(prefix, layers=layers)
+    assert sorted(W) == ["Coef_up1.conv2d3", "down1.conv2d2", "layer0"]
+    assert np.array_equal(W["down1.conv2d2"][0].numpy(), t[f"net/layer_with_weights-1/layer_with_weights-1/kernel{SUF}"])
+    assert float(W["down1.conv2d2"][1].abs().sum()) == 0.0            # no bias stored: zeros
+    with pytest.raises(tfc.CheckpointFormatError, match="layer order"):
+        tfc.load_tf_checkpoint(prefix)
+
+
 def test_latest_checkpoint_and_errors(tmp_path):
     d = str(tmp_path)
     assert tfc.latest_checkpoint(d) is None
