@@ -47,6 +47,7 @@ SIGNATURES = {
     "ie_broadcast_hw_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "ie_raster_to_nhwc_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "ie_softmax_taps_f32": [_P, _I, _I, _I, _P, _P],
+    "ie_cost_volume_f32": [_P, _I, _I, _I, _I, _P, _P, _P],
     "ie_kpn_apply_f32": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ie_kpn_apply_tf32": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ie_convolve_filts_f32": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P],

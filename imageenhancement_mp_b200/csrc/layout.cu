@@ -348,6 +348,63 @@ __global__ void softmax_taps_kernel(const float* __restrict__ in, int taps, int 
   for (int i = threadIdx.x; i < taps; i += blockDim.x) dst[(long long)i * b] = expf(src[(long long)i * b] - mx) * inv;
 }
 
+// ------------------------------------------------------------------------------- cost_volume (data_utils.py:97-113)
+// One block per image over Bas [taps][t][b]: the mean over the (tap, frame) rows of the variance across the b
+// bases, and the mean over the (frame, basis) columns of (max(sum over taps, 0.75) - 0.75)^2; fp64 accumulation,
+// fixed summation order.  per_image[img] = -variance + 0.1 * divergent.
+__global__ void cost_volume_kernel(const float* __restrict__ bas, int taps, int tb, int b,
+                                   double* __restrict__ per_image) {
+  const float* src = bas + (long long)blockIdx.x * taps * tb;
+  const int rows = taps * (tb / b);
+  __shared__ double red[2][32];
+  double var = 0.0, dvg = 0.0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* row = src + (long long)r * b;
+    double s = 0.0, s2 = 0.0;
+    for (int i = 0; i < b; ++i) {
+      const double v = row[i];
+      s += v;
+      s2 += v * v;
+    }
+    const double m = s / b;
+    var += s2 / b - m * m;
+  }
+  for (int c = threadIdx.x; c < tb; c += blockDim.x) {
+    double s = 0.0;
+    for (int i = 0; i < taps; ++i) s += src[(long long)i * tb + c];
+    const double d = fmax(s, 0.75) - 0.75;
+    dvg += d * d;
+  }
+  for (int o = 16; o; o >>= 1) {
+    var += __shfl_xor_sync(0xffffffffu, var, o);
+    dvg += __shfl_xor_sync(0xffffffffu, dvg, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = var;
+    red[1][threadIdx.x >> 5] = dvg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    var = dvg = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      var += red[0][i];
+      dvg += red[1][i];
+    }
+    per_image[blockIdx.x] = -var / rows + 0.1 * dvg / tb;
+  }
+}
+
+// mean of the per-image values (the batch-level reduce_mean of the reference), one warp, fixed order
+__global__ void cost_volume_mean_kernel(const double* __restrict__ per_image, int n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) s += per_image[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) {
+    out[0] = s / n;
+    out[1] = s;
+  }
+}
+
 }  // namespace ie
 
 using namespace ie;
@@ -489,6 +546,17 @@ extern "C" int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, 
 extern "C" int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float* bas, void* stream) {
   IE_REQUIRE(originbasis && bas && n > 0 && taps > 0 && b > 0, "softmax_taps: bad arguments");
   softmax_taps_kernel<<<n * b, 256, 0, S(stream)>>>(originbasis, taps, b, bas);
+  IE_LAUNCH_CHECK();
+  return IE_OK;
+}
+
+extern "C" int ie_cost_volume_f32(const float* bas, int n, int taps, int tb, int b, double* per_image, double* out,
+                                  void* stream) {
+  IE_REQUIRE(bas && per_image && out && n > 0 && taps > 0 && b > 0 && tb > 0 && tb % b == 0,
+             "cost_volume: bad arguments");
+  cost_volume_kernel<<<n, 256, 0, S(stream)>>>(bas, taps, tb, b, per_image);
+  IE_LAUNCH_CHECK();
+  cost_volume_mean_kernel<<<1, 32, 0, S(stream)>>>(per_image, n, out);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -117,6 +117,25 @@ def deblur_layer_loss(y_pred, invert_gt, white_noise):
     return loss
 
 
+def cost_volume_sums(Basis):
+    """fp64 [2] on the device: {cost_volume(Basis) (data_utils.py:97-113), the same summed over the images} - the
+    second value is additive over equal-size batches and ranks."""
+    _lib.require_cuda(Basis)
+    bas = Basis.contiguous().float()
+    assert bas.dim() == 5 and bas.shape[1] == bas.shape[2], "Basis must be [N,K,K,T,B]"
+    n, K, _, T, B = bas.shape
+    per_image = torch.empty(n, dtype=torch.float64, device=bas.device)
+    out = torch.empty(2, dtype=torch.float64, device=bas.device)
+    call("ie_cost_volume_f32", ptr(bas), n, K * K, T * B, B, ptr(per_image), ptr(out), stream())
+    return out
+
+
+def cost_volume(Basis):
+    """data_utils.py:97-113: -(mean variance across the bases) + 0.1 * (mean squared excess of the per-basis tap sums
+    over 0.75), a 0-dim fp32 tensor like the reference's."""
+    return cost_volume_sums(Basis)[0].float()
+
+
 def invert_deblur_layer(y_pred, white_noise):
     """data_utils.py:74-80: inverted frames concatenated along the last (width) axis."""
     burst_size = y_pred.shape[-1] - 1

@@ -11,8 +11,8 @@ Batches may live in (pinned) host memory: they are then staged to the device on 
 slots deep, so the host->device copy of batch i+1 overlaps the forward of batch i - the reference's
 tf.data ``prefetch`` (data_utils.py:393) moved to where it matters on a GPU.
 
-Out of scope here: argparse CLI, checkpoint restore, TensorBoard writer,
-the ``.npz`` visualisation dump.
+The ``--visualization`` ``.npz`` dump (eval.py:201-207) and the ``ps`` lines (``cost_volume`` of the basis,
+eval.py:159-162,189-191) are covered; out of scope: argparse CLI, TensorBoard writer.
 """
 from __future__ import annotations
 
@@ -25,8 +25,11 @@ REPORT_KEYS = ("val_deblur_loss", "val_perlayer_loss", "val_total_loss", "val_ps
                "val_psnrburst0", "val_psnraverage")
 
 
-def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None, ssim=False):
+def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None, ssim=False, ps=False):
     """Forward + fused metrics for one (local) batch -> additive fp64 totals on the device.
+
+    ``ps`` (params["ps"], eval.py:159-162): returns ``(totals, cv)`` with cv = fp64 [1], ``cost_volume(Bas)`` summed
+    over the images of the batch.
 
     ``ssim`` (EXTENSION, not in the reference): also the SSIM of the deblurred vs ground-truth sRGB crops; the totals
     then carry one more value (``ie_metric_totals_ssim_f64``).
@@ -46,7 +49,10 @@ def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None,
         if len(res) > 2:
             vis["originbasis"].append(res[2].cpu().numpy())
     ssim_sums = du.ssim_deblur_sums(reconstructed, x_batch_truth, white_noise=wl) if ssim else None
-    return du.reduce_metric_sums(sums, h, w, burst_length, ssim_sums=ssim_sums)
+    totals = du.reduce_metric_sums(sums, h, w, burst_length, ssim_sums=ssim_sums)
+    if ps:
+        return totals, du.cost_volume_sums(res[1])[1:2]                            # :160-162
+    return totals
 
 
 def staged_batches(val_batches, device, depth=2, pre_sharded=False):
@@ -92,8 +98,11 @@ def staged_batches(val_batches, device, depth=2, pre_sharded=False):
             released[cur_k].record(main)
 
 
-def make_report(totals, num_batches, burst_length):
+def make_report(totals, num_batches, burst_length, cost_volume_sum=None, beta_coef=100.0):
     """Totals (after the all-reduce) -> the numbers eval.py:186-195 prints.
+
+    ``cost_volume_sum`` (params["ps"]): adds ``variance`` (the mean of cost_volume(Bas), eval.py:162,191) and
+    ``variance loss`` = beta_coef * variance (:160,190).
 
     ``val_psnrnoshow0`` reproduces the reference's leading-zero bias (its per-layer lists start as
     ``[0]``, eval.py:136,193): mean over num_batches+1 entries.  ``val_psnrnoshow0_unbiased`` is the
@@ -101,6 +110,9 @@ def make_report(totals, num_batches, burst_length):
     """
     r = du.totals_to_report(totals, burst_length)
     extra = {"val_ssim": r["ssim"]} if "ssim" in r else {}      # extension
+    if cost_volume_sum is not None:
+        variance = float(cost_volume_sum) / r["count"]
+        extra.update({"variance loss": beta_coef * variance, "variance": variance})
     return {
         **extra,
         "val_deblur_loss": r["loss1"],
@@ -117,12 +129,15 @@ def make_report(totals, num_batches, burst_length):
 
 
 def format_report(report, step=1):
-    """The seven lines of eval.py:186-195, verbatim format."""
-    return ['epoch %s: %s = %s' % (int(step), k, report[k]) for k in REPORT_KEYS]
+    """The seven lines of eval.py:186-195 (nine with the two ``ps`` lines of :189-191), verbatim format and order."""
+    keys = list(REPORT_KEYS)
+    if "variance" in report:
+        keys[3:3] = ["variance loss", "variance"]
+    return ['epoch %s: %s = %s' % (int(step), k, report[k]) for k in keys]
 
 
 def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, step_results=None, device=None,
-             pre_sharded=False, visualization=False, dump_path=None, ssim=False):
+             pre_sharded=False, visualization=False, dump_path=None, ssim=False, beta_coef=100.0):
     """Validation loop.  val_batches yields (x_batch_burst [N,H,W,T+add], x_batch_truth [N,H,W,2]), on the
     device or in (pinned) host memory.
 
@@ -135,18 +150,23 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
     ``visualization`` (eval.py:41 ``--visualization``): also collect invert_gt / invert_deblur / invert_perlayer /
     Basis / originbasis of every local batch and write them with ``np.savez`` like eval.py:201-207 (to ``dump_path``,
     default ``data<time>.npz``; with several ranks every rank writes ``<stem>.rank<r>.npz`` for its shard).
+    ``params["ps"]`` (eval.py:103,159-162,189-191): also report ``variance`` = mean ``cost_volume(Bas)`` and
+    ``variance loss`` = ``beta_coef`` * variance.  The reference's eval.py never defines ``beta_coef`` (its ``ps`` branch
+    raises NameError at :160); the default here is run_training.py:178 at iterate 0 (anneal^0 * 10^2).  The step
+    function then returns ``(totals, cost_volume_sum[1])``; the sum rides in the same all-reduce as the totals.
     ``ssim`` (EXTENSION): also report ``val_ssim`` (deblurred vs ground truth, tf.image.ssim semantics); it travels
     in the same all-reduced totals vector.
     Returns the report dict (identical on all ranks); rank 0 prints it through ``out``.
     """
     T = params["BURST_LENGTH"]
+    ps = bool(params.get("ps", False))
     vis = {k: [] for k in ("invert_gt", "invert_deblur", "invert_perlayer", "Basis", "originbasis")} \
         if (visualization and step_totals is None) else None
     if step_totals is not None:
         fn = step_totals
     else:
-        fn = lambda m, xb, xt, T_: gpu_step_totals(m, xb, xt, T_, vis=vis, ssim=ssim)
-    totals = None
+        fn = lambda m, xb, xt, T_: gpu_step_totals(m, xb, xt, T_, vis=vis, ssim=ssim, ps=ps)
+    totals = cv_total = None
     nb = 0
     if step_totals is None:
         if device is None:
@@ -159,6 +179,9 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
         if xb.shape[0] == 0:
             continue
         t = fn(model, xb, xt, T)
+        if ps:
+            t, cv = t
+            cv_total = cv.clone() if cv_total is None else cv_total.add_(cv)
         if step_results is not None:
             host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
             host.copy_(t, non_blocking=True)
@@ -166,8 +189,14 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
         totals = t.clone() if totals is None else totals.add_(t)
     if totals is None:
         raise ValueError("evaluate: no validation data on this rank")
+    if ps:
+        totals = torch.cat([totals, cv_total.to(totals.dtype)])
     _dist.all_reduce_totals(totals)                                                # the one exchange step
-    report = make_report(totals.cpu(), nb, T)                                      # the one D2H copy
+    host = totals.cpu()                                                            # the one D2H copy
+    if ps:
+        report = make_report(host[:-1], nb, T, cost_volume_sum=host[-1], beta_coef=beta_coef)
+    else:
+        report = make_report(host, nb, T)
     if vis is not None:
         import datetime
         import numpy as np

@@ -131,6 +131,14 @@ int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, int x_pitch
 /* softmax over the taps axis of [n][taps][b] (model_library.py:436-437).                              */
 int ie_softmax_taps_f32(const float* originbasis, int n, int taps, int b, float* bas, void* stream);
 
+/* cost_volume(Basis) (data_utils.py:97-113; printed by eval.py:159-162,189-191 when params["ps"]): per image
+ *   -mean_{tap,t}( var_b bas[tap][t][b] ) + 0.1 * mean_{t,b}( (max(sum_tap bas[tap][t][b], 0.75) - 0.75)^2 ),
+ * then the mean over the batch.  bas [n][taps = K*K][tb = T*B] fp32 with b = B; per_image [n] fp64 (scratch, holds
+ * the per-image values afterwards); out [2] fp64 = {batch mean (the reference's scalar), sum over images (the
+ * additive form that is all-reduced)}.                                                                  */
+int ie_cost_volume_f32(const float* bas, int n, int taps, int tb, int b, double* per_image, double* out,
+                       void* stream);
+
 /* Filter synthesis + Convolve + Convolve_perlayer (model_library.py:439-451, 114-168), fused:
  *   out[n,y,x,1+t] = T * sum_b coef[n,y,x,b] * sum_{i,j} bas[n,i,j,t,b] * pad0(burst)[n,y+i-K/2,x+j-K/2,t]
  *   out[n,y,x,0]   = mean_t out[n,y,x,1+t]

@@ -34,6 +34,7 @@ from .metrics import (  # noqa: F401
     psnr_each_layer,
     psnr_burst0,
     psnr_average_f,
+    cost_volume,
     eval_step,
     eval_report,
 )

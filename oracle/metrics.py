@@ -73,6 +73,19 @@ def deblur_loss(invert_deblur, invert_gt):
     return basic_img_loss(invert_deblur, invert_gt)
 
 
+def cost_volume(Basis):
+    """data_utils.py:97-113: ``-variance + 0.1 * divergent`` of Basis [N,K,K,T,B] (the similarity regulariser that
+    eval.py:159-162 reports when params["ps"])."""
+    ish = Basis.shape
+    average = Basis.mean(dim=-1)                                               # :100
+    average_2 = Basis.square().mean(dim=-1)                                    # :102
+    cost = average_2 - average.square()                                        # :105
+    variance = cost.mean()                                                     # :107
+    sum_value = Basis.reshape(ish[0], ish[1] ** 2, -1).sum(dim=1).clamp_min(0.75)   # :110
+    divergent = (sum_value - 0.75).square().mean()                             # :111
+    return -variance + 0.1 * divergent                                         # :113
+
+
 def psnr_tf_batch(estimate, truth):
     """data_utils.py:118-119: per-image PSNR (peak 1), then batch mean."""
     n = estimate.shape[0]

@@ -117,3 +117,38 @@ def test_evaluate_rejects_cpu_model_inputs(cuda):
     x, _ = synth.make_batch(1, 32, 32, params)
     with pytest.raises(ImgEnhError):
         model(x)                       # CPU tensor straight into the model: no fallback
+
+
+def test_cost_volume_and_ps_report(cuda):
+    """data_utils.cost_volume (ie_cost_volume_f32) against the fp64 oracle on softmaxed bases (Simplemodel T=4/B=10 and
+    a Basis_kpn-sized T=8/B=90), and evaluate() with params["ps"]: `variance` = mean over batches of
+    cost_volume(Bas of the GPU forward), the other report numbers unchanged."""
+    from imageenhancement_mp_b200 import data_utils as du, eval as ieval, model_library as ml
+    g = torch.Generator().manual_seed(21)
+    for n, K, T, B, scale in [(3, 15, 4, 10, 6.0), (2, 15, 8, 90, 9.0), (1, 15, 1, 1, 1.0)]:
+        bas = torch.softmax(torch.randn(n, K * K * T, B, generator=g) * scale, dim=1).view(n, K, K, T, B)
+        got = du.cost_volume(bas.to(cuda))
+        ref = oracle.cost_volume(bas.double())
+        assert got.dtype == torch.float32 and got.dim() == 0
+        assert abs(float(got) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref))) + 1e-9, (n, K, T, B)
+        sums = du.cost_volume_sums(bas.to(cuda)).cpu()
+        per = torch.stack([oracle.cost_volume(bas[i:i + 1].double()) for i in range(n)])
+        assert torch.allclose(sums, torch.stack([per.mean(), per.sum()]), rtol=1e-6, atol=1e-10)
+    params = dict(synth.DEFAULT_PARAMS, ps=True)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    batches = [synth.make_batch(3, 32, 40, params, seed=60 + i) for i in range(2)]
+    fed = [(x.to(cuda), t.to(cuda)) for x, t in batches]
+    model = ml.Simplemodel(params, weights=W)
+    lines = []
+    rep = ieval.evaluate(model, fed, params, out=lines.append)
+    base = ieval.evaluate(model, fed, dict(params, ps=False), out=None)
+    for k in base:
+        assert rep[k] == base[k], k
+    ref = float(torch.stack([oracle.cost_volume(model(x)[1].cpu().double()) for x, _ in fed]).mean())
+    assert abs(rep["variance"] - ref) <= 1e-6 * max(1.0, abs(ref))
+    assert rep["variance loss"] == pytest.approx(100.0 * rep["variance"])
+    assert len(lines) == 10 and lines[4].startswith("epoch 1: variance loss = ")
+    # against the oracle's own forward (bf16 trunk on the GPU side)
+    ref2 = float(torch.stack([oracle.cost_volume(oracle.simplemodel_forward(W, params, x)[1].double())
+                              for x, _ in batches]).mean())
+    assert abs(rep["variance"] - ref2) <= 0.1 * abs(ref2) + 1e-5

@@ -238,3 +238,25 @@ def test_spatial_sharding_matches_the_unsharded_forward(cuda, H, W_, world):
         assert float((ob - ref_ob).abs().max()) <= 1e-2 * float(ref_ob.abs().max())      # bf16 ulps, see above
         assert float((bas - ref_bas).abs().max()) <= 1e-4
         assert float((out - ref_out[:, a:b]).abs().max()) <= 5e-4, (a, b)
+
+def test_model_loads_weights_from_files(cuda, tmp_path):
+    """Simplemodel(params, weights=<path>): the flat .npz and a TensorFlow-format checkpoint prefix (written by the
+    restated writer of tests/test_tf_checkpoint.py) give the same forward as the in-memory dict."""
+    from imageenhancement_mp_b200 import model_library as ml
+    from tests.test_tf_checkpoint import write_bundle, SUF
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress", seed=5)
+    npz = str(tmp_path / "w.npz")
+    weights.save_npz(npz, W)
+    t = {}
+    for name, (k, b) in W.items():
+        t["net/" + name.replace(".", "/") + "/kernel" + SUF] = k.numpy()
+        t["net/" + name.replace(".", "/") + "/bias" + SUF] = b.numpy()
+    prefix = str(tmp_path / "ckpt-1")
+    write_bundle(prefix, t, block_size=4096)
+    x, _ = synth.make_batch(1, 32, 32, params, seed=3)
+    xd = x.to(cuda)
+    ref = ml.Simplemodel(params, weights=W)(xd)[0]
+    for path in (npz, prefix):
+        out = ml.Simplemodel(params, weights=path)(xd)[0]
+        assert torch.equal(out, ref), path

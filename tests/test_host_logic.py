@@ -87,6 +87,33 @@ def test_single_process_report_matches_oracle_aggregation():
     assert [l.split(":")[1].split("=")[0].strip() for l in lines[1:]] == list(ieval.REPORT_KEYS)
 
 
+def test_ps_lines_of_the_report():
+    """params["ps"] (eval.py:103,159-162,189-191): the step returns (totals, sum over images of cost_volume); the report
+    gains `variance loss` / `variance` after val_total_loss, like the reference prints them."""
+    batches = make_batches(3, 4, 40, 48)
+    params = dict(synth.DEFAULT_PARAMS, ps=True)
+    g = torch.Generator().manual_seed(3)
+    bases = [torch.softmax(torch.randn(4, 15 * 15 * T, 10, generator=g, dtype=torch.float64) * 5, dim=1)
+             .view(4, 15, 15, T, 10) for _ in batches]
+    it = iter(bases)
+
+    def step(model, xb, xt, burst_length):
+        bas = next(it)
+        cv = sum(oracle.cost_volume(bas[i:i + 1]) for i in range(bas.shape[0]))
+        return oracle_step_totals(model, xb, xt, burst_length), cv.reshape(1)
+
+    lines = []
+    rep = ieval.evaluate(fake_model, batches, params, step=2, out=lines.append, step_totals=step, beta_coef=50.0)
+    ref = float(torch.stack([oracle.cost_volume(b) for b in bases]).mean())     # Keras Mean of the batch values
+    assert rep["variance"] == pytest.approx(ref, rel=1e-9)
+    assert rep["variance loss"] == pytest.approx(50.0 * ref, rel=1e-9)
+    names = [l.split(":")[1].split("=")[0].strip() for l in lines[1:]]
+    assert names == list(ieval.REPORT_KEYS[:3]) + ["variance loss", "variance"] + list(ieval.REPORT_KEYS[3:])
+    base = reference_report(batches)
+    for k in ieval.REPORT_KEYS:
+        assert rep[k] == pytest.approx(base[k], rel=1e-6, abs=1e-6), k
+
+
 def test_totals_layout_roundtrip():
     tot = torch.arange(T + 6, dtype=torch.float64) + 1
     tot[-1] = 2

@@ -219,3 +219,24 @@ def test_conv_pool_resize_against_independent_implementations():
     bas = omodel.basis_softmax(ob, 15, 4, 10)                                   # softmax over the 900 taps per basis
     ref = softmax(ob.numpy().reshape(2, 900, 10), axis=1).reshape(2, 15, 15, 4, 10)
     assert np.allclose(bas.numpy(), ref, atol=1e-14)
+
+
+def test_cost_volume_known_answers():
+    """cost_volume (data_utils.py:97-113): analytic cases + an independent numpy restatement.
+    Uniform taps: every basis is the same (variance 0) and every per-frame tap sum is 1/T <= 0.75 (divergent 0).
+    One-hot at (tap 0, frame 0) for every basis: variance 0 again, T*B columns of which B reach 1.0 -> 0.25^2 excess:
+    cost = 0.1 * 0.0625 / T."""
+    N, K, T, B = 2, 15, 4, 10
+    uni = torch.full((N, K, K, T, B), 1.0 / (K * K * T), dtype=torch.float64)
+    assert float(oracle.cost_volume(uni)) == pytest.approx(0.0, abs=1e-15)
+    hot = torch.zeros(N, K, K, T, B, dtype=torch.float64)
+    hot[:, 0, 0, 0, :] = 1.0
+    assert float(oracle.cost_volume(hot)) == pytest.approx(0.1 * 0.0625 / T, rel=1e-12)
+    g = torch.Generator().manual_seed(11)
+    bas = omodel.basis_softmax(torch.relu(torch.randn(N, K, K, T * B, generator=g, dtype=torch.float64) * 6), K, T, B)
+    a = bas.numpy()
+    var = a.var(axis=-1).mean()                                       # population variance across the bases
+    sums = a.reshape(N, K * K, T * B).sum(axis=1)
+    ref = -var + 0.1 * np.mean((np.maximum(sums, 0.75) - 0.75) ** 2)
+    assert float(oracle.cost_volume(bas)) == pytest.approx(ref, rel=1e-10)
+    assert ref < 0 and (sums > 0.75).any()                            # both terms exercised
