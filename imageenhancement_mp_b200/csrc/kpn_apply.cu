@@ -312,7 +312,7 @@ extern "C" int ie_convolve_filts_f32(const float* burst, int burst_pitch, const 
 }
 
 // =================================================================================================
-// Tensor-core variant of the fused filter (K = 15, B <= 16, T <= 4): G = Bas (*) burst as warp-level
+// Tensor-core variant of the fused filter (K = 15; one launch = 16 bases x 4 frames, more of either as further launches): G = Bas (*) burst as warp-level
 // mma.sync m16n8k8 with TF32 operands and fp32 accumulation.
 //
 // Why mma.sync and not tcgen05: the A operand of this GEMM is the 225-tap im2col of a ONE-channel image, i.e. a
@@ -337,7 +337,7 @@ namespace ie {
 
 // ring: the 4 rows of the group being filtered + halo; pitch 144 floats
 constexpr int kTfK = 15, kTfRing = 4 + kTfK - 1, kTfTileW = 128, kTfSw = kTfTileW + kTfK - 1 + 2;
-constexpr int kTfMaxT = 4;
+constexpr int kTfMaxT = 4, kTfMaxB = 128;
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -359,8 +359,9 @@ __device__ __forceinline__ void cp_async4_tf(float* smem_dst, const float* gsrc,
 }
 
 struct KpnTfParams {
-  int H, W, Hc, Wc, T, B, burst_pitch;   // T = frames handled by this launch
+  int H, W, Hc, Wc, T, B, burst_pitch;   // T = frames, B = bases (<= 16) handled by this launch
   int t0, Ttot, accumulate;              // first frame, frames of the burst, add the frame sum to out[...,0]
+  int b0, Btot, accumulate_frames;       // first basis, bases of the model, add to out[...,1+t] (basis chunks > 0)
   int col_tiles, row_splits, rows_per_block;
 };
 
@@ -380,7 +381,7 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int px = xpx + 16 * m + g + 8 * hrow;
-      const float* cp = coef + (((long long)img * P.Hc + y) * P.Wc + (px < W ? px : 0)) * B;
+      const float* cp = coef + (((long long)img * P.Hc + y) * P.Wc + (px < W ? px : 0)) * P.Btot + P.b0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int b = (q >> 1) * 8 + 2 * c + (q & 1);
@@ -434,7 +435,10 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
           for (int e = 0; e < 2; ++e) s = fmaf(cf[m][hrow][nt * 2 + e], acc[m][nt][2 * hrow + e], s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (c == 0 && px < W) out[(((long long)img * P.H + y) * W + px) * (P.Ttot + 1) + 1 + P.t0 + t] = s * fT;
+        if (c == 0 && px < W) {
+          float* of = out + (((long long)img * P.H + y) * W + px) * (P.Ttot + 1) + 1 + P.t0 + t;
+          *of = P.accumulate_frames ? fmaf(s, fT, *of) : s * fT;
+        }
         dsum[m][hrow] += s;
       }
     }
@@ -469,7 +473,7 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* burst_img = burst + (long long)img * H * W * P.burst_pitch;
-  const float* bas_img = bas + (long long)img * kTfK * kTfK * P.Ttot * B;
+  const float* bas_img = bas + (long long)img * kTfK * kTfK * P.Ttot * P.Btot;
 
   // ---- basis -> B fragments (once per block).  Fragment (t, i, ks, nt), lane (g, c):
   //      b0 = Bas[i][j = 8 ks + c][t][n = 8 nt + g],  b1 = Bas[i][j = 8 ks + c + 4][t][n]   (zero for j >= 15, n >= B)
@@ -478,7 +482,7 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
     float* bf = reinterpret_cast<float*>(s_bfrag);
     for (int idx = threadIdx.x; idx < T * kTfK * 2 * 2 * 32 * 2; idx += blockDim.x) bf[idx] = 0.f;
     __syncthreads();
-    const int tb = T * B;                      // this launch's frames [t0, t0+T) are contiguous within a tap
+    const int tb = T * B;                      // this launch's frames [t0, t0+T) x bases [b0, b0+B) of every tap
     const float inv_tb = 1.f / (float)tb, inv_b = 1.f / (float)B;
     for (int idx = threadIdx.x; idx < kTfK * kTfK * tb; idx += blockDim.x) {
       const int tap = (int)(((float)idx + 0.5f) * inv_tb), r = idx - tap * tb;
@@ -487,7 +491,7 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
       const int ks = j >> 3, cpos = j & 7, cc = cpos & 3, half = cpos >> 2;
       const int nt = n >> 3, gg = n & 7;
       bf[(((((t * kTfK + i) * 2 + ks) * 2 + nt) * 32) + gg * 4 + cc) * 2 + half] =
-          to_tf32(__ldg(bas_img + ((long long)tap * P.Ttot + P.t0) * B + r));
+          to_tf32(__ldg(bas_img + ((long long)tap * P.Ttot + P.t0 + t) * P.Btot + P.b0 + n));
     }
   }
 
@@ -557,11 +561,12 @@ extern "C" int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const floa
   using namespace ie;
   IE_REQUIRE(burst && coef && bas && out, "kpn_apply_tf32: null pointer");
   IE_REQUIRE(n > 0 && h > 0 && w > 0, "kpn_apply_tf32: bad sizes");
-  IE_REQUIRE(K == kTfK && B >= 1 && B <= 16 && T >= 1 && T <= 2 * kTfMaxT,
-             "kpn_apply_tf32: built for K = 15, B <= 16, T <= %d (got K=%d B=%d T=%d); use ie_kpn_apply_f32", 2 * kTfMaxT, K, B, T);
+  IE_REQUIRE(K == kTfK && B >= 1 && B <= kTfMaxB && T >= 1 && T <= 2 * kTfMaxT,
+             "kpn_apply_tf32: built for K = 15, B <= %d, T <= %d (got K=%d B=%d T=%d); use ie_kpn_apply_f32", kTfMaxB,
+             2 * kTfMaxT, K, B, T);
   IE_REQUIRE(burst_pitch >= T && hc >= h && wc >= w, "kpn_apply_tf32: bad pitch / coef extent");
   KpnTfParams P{};
-  P.H = h; P.W = w; P.Hc = hc; P.Wc = wc; P.B = B; P.burst_pitch = burst_pitch; P.Ttot = T;
+  P.H = h; P.W = w; P.Hc = hc; P.Wc = wc; P.Btot = B; P.burst_pitch = burst_pitch; P.Ttot = T;
   P.col_tiles = (w + kTfTileW - 1) / kTfTileW;
   // blocks: ~4 per SM so that the last wave is short, but at least 4 row groups each (the basis fragments and the
   // 14 halo rows are staged once per block)
@@ -574,15 +579,22 @@ extern "C" int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const floa
   P.row_splits = (h + P.rows_per_block - 1) / P.rows_per_block;
   const long long blocks = base * P.row_splits;
   IE_REQUIRE(blocks < (1ll << 31), "kpn_apply_tf32: too many blocks");
-  // the basis fragments of 4 frames fill the shared memory: longer bursts run as two passes over the frames, the
-  // second adding its frame sum to out[...,0]
-  for (int t0 = 0; t0 < T; t0 += kTfMaxT) {
-    P.t0 = t0;
-    P.T = (T - t0 < kTfMaxT) ? T - t0 : kTfMaxT;
-    P.accumulate = t0 > 0;
-    const size_t smem = sizeof(float) * ((size_t)P.T * kTfK * 2 * 2 * 32 * 2 + (size_t)P.T * kTfRing * kTfSw);
-    IE_CUDA(cudaFuncSetAttribute(kpn_apply_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpn_apply_tf32_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(burst, coef, bas, out, P);
+  // the basis fragments of 4 frames x 16 bases fill the shared memory: longer bursts run as two passes over the
+  // frames, the second adding its frame sum to out[...,0]; more bases (Basis_kpn of the remote/ configs: up to 90)
+  // run as chunks of 16 - the output is a sum over the bases - each later chunk adding to every output channel
+  for (int b0 = 0; b0 < B; b0 += 16) {
+    P.b0 = b0;
+    P.B = (B - b0 < 16) ? B - b0 : 16;
+    P.accumulate_frames = b0 > 0;
+    for (int t0 = 0; t0 < T; t0 += kTfMaxT) {
+      P.t0 = t0;
+      P.T = (T - t0 < kTfMaxT) ? T - t0 : kTfMaxT;
+      P.accumulate = t0 > 0 || b0 > 0;
+      const size_t smem = sizeof(float) * ((size_t)P.T * kTfK * 2 * 2 * 32 * 2 + (size_t)P.T * kTfRing * kTfSw);
+      IE_CUDA(cudaFuncSetAttribute(kpn_apply_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kpn_apply_tf32_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(burst, coef, bas, out, P);
+      IE_LAUNCH_CHECK();
+    }
   }
   IE_LAUNCH_CHECK();
   return IE_OK;

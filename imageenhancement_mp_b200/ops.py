@@ -208,14 +208,14 @@ def softmax_taps(originbasis, T, B):
 
 
 def kpn_tf32_supported(T, K, B):
-    return K == 15 and B <= 16 and T <= 8
+    return K == 15 and B <= 128 and T <= 8
 
 
 def kpn_apply(x, T, coef, bas, out=None, precision="fp32"):
     """Per-pixel filter (model_library.py:439-451).  x: fp32 NHWC whose first T channels are the burst.
 
     precision "fp32": CUDA-core kernel, 1e-5 of the fp64 oracle.  "tf32": tensor-core kernel (burst and basis rounded
-    to TF32, fp32 accumulation; K = 15, B <= 16, T <= 8), < 1e-3 absolute on [0,1] pixels, ~2.5x faster."""
+    to TF32, fp32 accumulation; K = 15, B <= 128 in chunks of 16, T <= 8), < 1e-3 absolute on [0,1] pixels, ~2.5x faster."""
     _lib.require_cuda(x, coef, bas)
     n, h, w, pitch = x.shape
     K, B = bas.shape[1], bas.shape[-1]

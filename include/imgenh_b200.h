@@ -148,9 +148,11 @@ int ie_cost_volume_f32(const float* bas, int n, int taps, int tb, int b, double*
 int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
                      float* out, int n, int h, int w, int T, int K, int B, void* stream);
 
-/* Same contract on the tensor cores (warp-level TF32 MMA, fp32 accumulate) for K = 15, B <= 16, T <= 8: burst and
+/* Same contract on the tensor cores (warp-level TF32 MMA, fp32 accumulate) for K = 15, B <= 128, T <= 8: burst and
  * basis are rounded to TF32 (10-bit mantissa), so the result differs from ie_kpn_apply_f32 by < 2^-10 of the
- * pixel range - inside the path's tolerance (max-abs 1e-2 on [0,1] pixels), ~2.5x faster.                 */
+ * pixel range - inside the path's tolerance (max-abs 1e-2 on [0,1] pixels), ~2.5x faster.  One launch handles 4
+ * frames x 16 bases; longer bursts / more bases (Basis_kpn, remote/record.txt: B up to 90) run as further launches
+ * that add into `out` (the output is a sum over the bases).                                               */
 int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
                       float* out, int n, int h, int w, int T, int K, int B, void* stream);
 

@@ -173,7 +173,9 @@ def test_kpn_apply_vs_literal(cuda, n, h, w, T, B):
 
 
 @pytest.mark.parametrize("n,h,w,T,B", [(2, 16, 24, 4, 10), (1, 40, 72, 2, 10), (3, 104, 104, 4, 10), (1, 21, 150, 3, 16),
-                                       (1, 200, 300, 1, 7), (2, 64, 64, 8, 10), (1, 33, 47, 6, 12)])
+                                       (1, 200, 300, 1, 7), (2, 64, 64, 8, 10), (1, 33, 47, 6, 12),
+                                       # more than 16 bases: chunks of 16 accumulated into the output (Basis_kpn, remote/)
+                                       (2, 24, 24, 4, 17), (1, 20, 30, 2, 32), (1, 33, 47, 3, 20), (1, 40, 72, 8, 90)])
 def test_kpn_apply_tf32_tensor_core_variant(cuda, n, h, w, T, B):
     """The mma.sync TF32 variant: same contract; operands rounded to a 10-bit mantissa, fp32 accumulation.  Stated
     bound: the output is a convex combination of burst pixels, so |err| <= 2^-10 * max|burst| (observed ~1e-4)."""
