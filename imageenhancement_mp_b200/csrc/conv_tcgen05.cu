@@ -63,8 +63,9 @@ struct EpiParams {
   int relu;
   int epilogue;
   const float* bias;
-  float* y_f32;
+  float* y_f32;       // already advanced by the output slice's first channel
   float* y_aux;
+  int f32_pitch;      // floats per pixel of y_f32 / y_aux (= cout unless the caller writes a channel slice)
 };
 
 // Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
@@ -256,8 +257,8 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
         }
         continue;
       }
-      float* dst = p.y_f32 + pix * p.cout;
-      float* aux = p.y_aux ? p.y_aux + pix * p.cout : nullptr;
+      float* dst = p.y_f32 + pix * p.f32_pitch;
+      float* aux = p.y_aux ? p.y_aux + pix * p.f32_pitch : nullptr;
       float mx = -INFINITY, inv = 1.f;
       uint32_t v[16];
       if (sm_mode) {
@@ -1213,7 +1214,12 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
                "conv: bad output slice (coff %d, cout %d, pitch %d)", d->y_coff, d->cout, d->y_pitch);
   } else if (d->epilogue == IE_EPI_F32_NHWC || d->epilogue == IE_EPI_F32_SOFTMAX) {
     IE_REQUIRE(y_f32, "conv: y_f32 is null");
-    IE_REQUIRE(d->cout <= 256, "conv: fp32 epilogues need cout <= 256 (got %d)", d->cout);
+    IE_REQUIRE(d->cout <= 256, "conv: fp32 epilogues need cout <= 256 per launch (got %d)", d->cout);
+    if (d->y_pitch > 0) {      // channel slice of a wider fp32 NHWC tensor (layers with more than 256 outputs run in chunks)
+      IE_REQUIRE(d->epilogue == IE_EPI_F32_NHWC && d->cout > 16 && d->y_coff >= 0 && d->y_coff + d->cout <= d->y_pitch,
+                 "conv: bad fp32 output slice (coff %d, cout %d, pitch %d; plain NHWC epilogue, cout > 16 only)",
+                 d->y_coff, d->cout, d->y_pitch);
+    }
   } else {
     IE_REQUIRE(false, "conv: unknown epilogue %d", d->epilogue);
   }
@@ -1267,7 +1273,12 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   e.relu = d->relu;
   e.epilogue = d->epilogue;
   e.bias = bias;
+  e.f32_pitch = d->cout;
   e.y_f32 = y_f32;
+  if (d->epilogue != IE_EPI_BF16_RASTER && d->y_pitch > 0) {
+    e.f32_pitch = d->y_pitch;
+    e.y_f32 = y_f32 + d->y_coff;
+  }
   e.y_aux = y_aux;
   const int ntaps = d->kh * d->kw;
   const int ktot = ntaps * d->cin;

@@ -81,7 +81,9 @@ __global__ void naive_conv_f32_kernel(const __nv_bfloat16* __restrict__ x, const
     }
     for (int co = 0; co < p.cout; ++co) y[pix * p.cout + co] = v[co] / s;
   } else {
-    for (int co = 0; co < p.cout; ++co) y[pix * p.cout + co] = v[co];
+    const int pitch = p.y_pitch > 0 ? p.y_pitch : p.cout;          // fp32 channel slice (chunked wide layers)
+    const int coff = p.y_pitch > 0 ? p.y_coff : 0;
+    for (int co = 0; co < p.cout; ++co) y[pix * pitch + coff + co] = v[co];
   }
 }
 

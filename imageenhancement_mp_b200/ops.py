@@ -104,6 +104,7 @@ def pack_input_im2col3x3(x, out=None):
 
 
 FIRST_LAYER_FUSED_CHANNELS = (3, 5)
+F32_HEAD_MAX_COUT = 256        # output channels one launch of an fp32-epilogue convolution handles (one N tile)
 
 
 def conv_first_layer(x, w_packed, bias, dst: Slice, relu=True):
@@ -149,8 +150,20 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
     r = src.r
     hv, wv = (r.h, r.w) if valid is None else valid
     epi = IE_EPI_F32_SOFTMAX if softmax else IE_EPI_F32_NHWC
-    d = _desc(src, k, k, cout, relu, epi, None, valid)
     y = torch.empty(r.n, hv, wv, cout, dtype=torch.float32, device=r.data.device)
+    if cout > F32_HEAD_MAX_COUT:
+        # Basis_kpn's layer3_3 with the remote/ settings (T*B = 8*50 .. 8*90 output channels): chunks of 256 output
+        # channels, each launch writing its channel slice of the same NHWC tensor
+        if softmax:
+            raise _lib.ImgEnhError(f"softmax heads support at most {F32_HEAD_MAX_COUT} channels (got {cout})")
+        for c0 in range(0, cout, F32_HEAD_MAX_COUT):
+            cc = min(F32_HEAD_MAX_COUT, cout - c0)
+            d = _desc(src, k, k, cc, relu, epi, None, valid)
+            d.y_pitch, d.y_coff = cout, c0
+            _timed_conv(fn, C.byref(d), ptr(r.data), w_packed[c0:].data_ptr(), bias[c0:].data_ptr(), None, ptr(y), None,
+                        stream())
+        return y
+    d = _desc(src, k, k, cout, relu, epi, None, valid)
     aux = torch.empty_like(y) if (softmax and want_logits) else None
     _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed), ptr(bias), None, ptr(y), ptr(aux), stream())
     return (y, aux) if softmax else y

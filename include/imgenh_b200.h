@@ -53,8 +53,9 @@ typedef struct ie_conv_desc {
   int32_t x_pitch;     /* channels per row of x                                                          */
   int32_t x_coff;      /* first channel of x to read, multiple of 64                                     */
   int32_t cout;        /* output channels                                                                */
-  int32_t y_pitch;     /* channels per row of y (IE_EPI_BF16_RASTER)                                     */
-  int32_t y_coff;      /* first channel of y to write, multiple of 64                                    */
+  int32_t y_pitch;     /* channels per row of y (IE_EPI_BF16_RASTER); IE_EPI_F32_NHWC: 0 = dense [..][cout], else the
+                          floats per pixel of a wider NHWC tensor of which this launch writes a channel slice    */
+  int32_t y_coff;      /* first channel of y to write (bf16 raster: multiple of 64)                      */
   int32_t relu;        /* 1: max(0, .) after the bias                                                    */
   int32_t epilogue;    /* IE_EPI_*                                                                       */
 } ie_conv_desc;

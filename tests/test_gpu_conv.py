@@ -201,7 +201,10 @@ def test_conv_deep_k_vs_naive(cuda):
 
 
 @pytest.mark.parametrize("cout,softmax", [(10, True), (40, False), (16, True), (64, False), (80, False), (90, True),
-                                          (12, False), (7, True)])
+                                          (12, False), (7, True),
+                                          # Basis_kpn's layer3_3 with the remote/ settings: T*B > 256 channels run as
+                                          # chunks of 256 writing channel slices of one NHWC tensor
+                                          (256, False), (360, False), (400, False), (720, False)])
 def test_conv_f32_heads(cuda, cout, softmax):
     """The two small fp32 epilogues: coef conv + softmax (model_library.py:405-406) and layer3_3."""
     from imageenhancement_mp_b200 import ops
@@ -220,6 +223,11 @@ def test_conv_f32_heads(cuda, cout, softmax):
         y = ops.conv2d_f32(src.slice(), wp, b.to(cuda), cout, valid=(15, 15))
         torch.cuda.synchronize()
         assert torch.allclose(y.cpu(), ref[:, :15, :15], atol=2e-4, rtol=1e-4)
+        if cout > 256:       # the naive validation kernel takes the same chunked route
+            y2 = ops.conv2d_f32(src.slice(), wp, b.to(cuda), cout, valid=(15, 15), fn="ie_debug_conv2d_naive")
+            assert torch.allclose(y2, y, atol=2e-4, rtol=1e-4)
+            with pytest.raises(Exception):
+                ops.conv2d_f32(src.slice(), wp, b.to(cuda), cout, softmax=True)
 
 
 def test_conv_rejects_bad_descriptors(cuda):

@@ -147,6 +147,19 @@ def test_basis_kpn_parity(cuda):
     assert rel_l2(bas_g.cpu(), res_o[1]) <= REL_L2_TOL
 
 
+def test_basis_kpn_remote_settings(cuda):
+    """Basis_kpn as remote/running_train_remote.py:29,34 runs it: T = 8, Basis_num = 50 (record.txt: up to 90) on 64x64
+    patches - the 400-channel layer3_3 (chunks of 256 output channels), the 50-way coef softmax and the per-pixel filter
+    over 50 bases (TF32 kernel in chunks of 16)."""
+    params = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=8, layer_type="dualparams", Basis_num=50)
+    res_g, taps_g, res_o, taps_o, x, truth = run_pair(cuda, "basis_kpn", params, 1, 64, 64, "stress")
+    out_g, bas_g = res_g
+    assert out_g.shape == (1, 64, 64, 9) and bas_g.shape == (1, 15, 15, 8, 50)
+    assert float((out_g.cpu() - res_o[0]).abs().max()) <= OUT_TOL
+    assert rel_l2(taps_g["coef_logits"].cpu(), taps_o["coef_logits"]) <= REL_L2_TOL
+    assert rel_l2(bas_g.cpu(), res_o[1]) <= REL_L2_TOL
+
+
 def test_zero_weights_known_answer(cuda):
     """All-zero weights: Coef = 1/B, Bas = 1/(K*K*T) => each frame output is the zero-padded 15x15 box mean."""
     from imageenhancement_mp_b200 import model_library as ml
