@@ -4,7 +4,10 @@ without TensorFlow:  ``<prefix>.index`` + ``<prefix>.data-00000-of-0000N``  ->  
 
 STATUS - PARITY UNPINNED: TensorFlow is not installable in the build environment and the reference ships no
 checkpoint, so this reader has never seen a TensorFlow-written file.  It restates the published on-disk formats
-(below); ``tests/test_tf_checkpoint.py`` round-trips it against a writer restated from the same definitions.
+(below); ``tests/test_tf_checkpoint.py`` round-trips it against a writer restated from the same definitions, and pins
+the pieces that TensorFlow-authored code in this image covers (tensorboard's copies of TensorShapeProto, the DataType
+enum, TrackableObjectGraph and its crc32c / mask) against that code.  BundleEntryProto and the table layout remain
+restated only.
 
 Formats restated:
 * ``.index`` is a LevelDB-format sorted string table (tensorflow/core/lib/io/table*, a fork of LevelDB's
@@ -85,6 +88,35 @@ def parse_proto(buf):
     return out
 
 
+# ------------------------------------------------------------------ crc32c (Castagnoli), masked as LevelDB / TensorFlow store it
+_CRC_TABLE = None
+CRC_MASK_DELTA = 0xA282EAD8
+
+
+def crc32c(data):
+    """CRC-32C of a bytes-like object (tensorflow/core/lib/hash/crc32c.h); table-driven, for index blocks and small
+    tensors - pure Python, about 5 MB/s."""
+    global _CRC_TABLE
+    if _CRC_TABLE is None:
+        table = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+            table.append(c)
+        _CRC_TABLE = table
+    table = _CRC_TABLE
+    c = 0xFFFFFFFF
+    for b in bytes(data):
+        c = table[(c ^ b) & 0xFF] ^ (c >> 8)
+    return c ^ 0xFFFFFFFF
+
+
+def mask_crc(crc):
+    """crc32c::Mask: rotate right by 15 bits and add a constant, so that a CRC of data that embeds CRCs stays useful."""
+    return (((crc >> 15) | (crc << 17)) + CRC_MASK_DELTA) & 0xFFFFFFFF
+
+
 def _signed64(v):
     return v - (1 << 64) if v >= (1 << 63) else v
 
@@ -101,7 +133,7 @@ def parse_shape(buf):
 
 
 # ------------------------------------------------------------------ LevelDB-format table
-def _read_block(buf, offset, size):
+def _read_block(buf, offset, size, verify=True):
     end = offset + size
     if end + BLOCK_TRAILER_LEN > len(buf):
         raise CheckpointFormatError("block handle points past the end of the index file")
@@ -111,6 +143,10 @@ def _read_block(buf, offset, size):
                                     "this file was produced by something else")
     if ctype != 0:
         raise CheckpointFormatError(f"unknown block compression type {ctype}")
+    if verify:         # trailer: masked crc32c over the block contents and the compression-type byte (table/format.cc)
+        stored = struct.unpack_from("<I", buf, end + 1)[0]
+        if stored != mask_crc(crc32c(buf[offset:end + 1])):
+            raise CheckpointFormatError(f"checksum mismatch in the table block at offset {offset}: the index file is corrupt")
     return buf[offset:end]
 
 
@@ -135,8 +171,9 @@ def _block_entries(block):
         pos += vlen
 
 
-def read_table(path):
-    """All (key, value) pairs of a LevelDB-format table file, in key order."""
+def read_table(path, verify=True):
+    """All (key, value) pairs of a LevelDB-format table file, in key order.  ``verify``: check every block's masked
+    crc32c trailer."""
     with open(path, "rb") as fh:
         buf = fh.read()
     if len(buf) < FOOTER_LEN:
@@ -150,18 +187,24 @@ def read_table(path):
     idx_off, pos = read_varint(footer, pos)
     idx_size, pos = read_varint(footer, pos)
     out = []
-    for _, handle in _block_entries(_read_block(buf, idx_off, idx_size)):
+    for _, handle in _block_entries(_read_block(buf, idx_off, idx_size, verify)):
         off, p = read_varint(handle, 0)
         size, _ = read_varint(handle, p)
-        out.extend(_block_entries(_read_block(buf, off, size)))
+        out.extend(_block_entries(_read_block(buf, off, size, verify)))
     return out
 
 
 # ------------------------------------------------------------------ TensorBundle
-def read_bundle(prefix, keys=None):
+def read_bundle(prefix, keys=None, verify="index"):
     """``{key: numpy array}`` of the numeric tensors of the bundle ``prefix`` (``keys``: optional filter callable).
-    String / variant tensors (the object graph itself) are skipped."""
-    entries = read_table(prefix + ".index")
+    String / variant tensors (the object graph itself) are skipped.
+
+    ``verify``: "index" (default) checks the masked crc32c trailer of every index block; "all" also checks every
+    tensor's bytes against ``BundleEntryProto.crc32c`` (pure Python, ~5 MB/s: minutes for the reference's 200 MB of
+    weights - meant for a one-off integrity check); "none" checks nothing."""
+    if verify not in ("index", "all", "none"):
+        raise ValueError("verify must be 'index', 'all' or 'none'")
+    entries = read_table(prefix + ".index", verify=verify != "none")
     if not entries or entries[0][0] != b"":
         raise CheckpointFormatError("bundle index has no header entry")
     header = parse_proto(entries[0][1])
@@ -194,7 +237,10 @@ def read_bundle(prefix, keys=None):
         data = shards[shard]
         if off + size > data.shape[0]:
             raise CheckpointFormatError(f"{key}: tensor bytes run past the end of the data shard")
-        out[key] = np.frombuffer(data[off:off + size].tobytes(), dtype=dtype).reshape(shape).copy()
+        raw = data[off:off + size].tobytes()
+        if verify == "all" and 6 in e and e[6][0] != mask_crc(crc32c(raw)):
+            raise CheckpointFormatError(f"{key}: checksum mismatch - the tensor bytes in the data shard are corrupt")
+        out[key] = np.frombuffer(raw, dtype=dtype).reshape(shape).copy()
     return out
 
 

@@ -119,7 +119,7 @@ def write_bundle(prefix, tensors, strings=(), num_shards=1, shard_of=lambda key:
             if shard:
                 e += field(3, 0, varint(shard))
             e += field(4, 0, varint(len(data[shard]))) + field(5, 0, varint(len(raw))) + \
-                field(6, 5, struct.pack("<I", masked(crc32c(raw[:64]))))
+                field(6, 5, struct.pack("<I", masked(crc32c(raw))))
             data[shard] += raw
         entries.append((key.encode(), e))
     write_table(prefix + ".index", entries, block_size)
@@ -233,4 +233,89 @@ def test_latest_checkpoint_and_errors(tmp_path):
     write_bundle(prefix, t)
     os.remove(prefix + ".data-00000-of-00001")
     with pytest.raises(tfc.CheckpointFormatError, match="missing"):
+        tfc.read_bundle(prefix)
+
+
+# ------------------------------------------------------------------ pins against TensorFlow-authored code in this image
+# tensorboard ships TensorFlow's own protobuf definitions (tensorboard.compat.proto) and its own crc32c / mask
+# (tensorboard.compat.tensorflow_stub.pywrap_tensorflow, used for event files): the parts of the checkpoint format
+# they cover are checked against them.  BundleEntryProto / the table format itself are not in tensorboard.
+def test_crc32c_and_mask_match_tensorflows_own():
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    assert tfc.crc32c(b"123456789") == 0xE3069283                      # the CRC-32C check value (RFC 3720 B.4)
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 64, 1000):
+        data = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        assert tfc.crc32c(data) == pw.crc32c(data) == crc32c(data)
+        assert tfc.mask_crc(tfc.crc32c(data)) == pw.masked_crc32c(data) == masked(crc32c(data))
+
+
+def test_shape_and_dtype_decoding_match_tensorflows_protos():
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    for dims in [(), (64,), (3, 3, 5, 64), (3, 3, 2048, 512), (0, 7), (1 << 40, 2)]:
+        msg = shape_pb2.TensorShapeProto(dim=[shape_pb2.TensorShapeProto.Dim(size=d) for d in dims])
+        assert tfc.parse_shape(msg.SerializeToString()) == dims
+    with pytest.raises(tfc.CheckpointFormatError):
+        tfc.parse_shape(shape_pb2.TensorShapeProto(unknown_rank=True).SerializeToString())
+    names = {1: "DT_FLOAT", 2: "DT_DOUBLE", 3: "DT_INT32", 4: "DT_UINT8", 5: "DT_INT16", 6: "DT_INT8", 9: "DT_INT64",
+             10: "DT_BOOL", 17: "DT_UINT16", 19: "DT_HALF", 22: "DT_UINT32", 23: "DT_UINT64"}
+    assert set(names) == set(tfc.DTYPES)
+    np_of = {"DT_FLOAT": "<f4", "DT_DOUBLE": "<f8", "DT_INT32": "<i4", "DT_UINT8": "u1", "DT_INT16": "<i2", "DT_INT8": "i1",
+             "DT_INT64": "<i8", "DT_BOOL": "bool", "DT_UINT16": "<u2", "DT_HALF": "<f2", "DT_UINT32": "<u4",
+             "DT_UINT64": "<u8"}
+    for num, name in names.items():
+        assert types_pb2.DataType.Value(name) == num and tfc.DTYPES[num] == np.dtype(np_of[name])
+    assert types_pb2.DataType.Value("DT_STRING") not in tfc.DTYPES            # the object graph entry is skipped
+
+
+def test_object_graph_entry_is_skipped_and_its_keys_are_the_ones_read(tmp_path):
+    """A tf.train.Checkpoint stores its TrackableObjectGraph (proto from tensorboard.compat.proto) as a DT_STRING entry
+    `_CHECKPOINTABLE_OBJECT_GRAPH`; each variable's SerializedTensor.checkpoint_key is the key of its bundle entry.
+    Build that graph for net.down1.conv2d1.{kernel,bias}, store it next to the tensors, and read the bundle back."""
+    tog = pytest.importorskip("tensorboard.compat.proto.trackable_object_graph_pb2")
+    g = tog.TrackableObjectGraph()
+    root, net, down1, conv, kernel, bias = (g.nodes.add() for _ in range(6))
+    root.children.add(node_id=1, local_name="net")
+    net.children.add(node_id=2, local_name="down1")
+    down1.children.add(node_id=3, local_name="conv2d1")
+    conv.children.add(node_id=4, local_name="kernel")
+    conv.children.add(node_id=5, local_name="bias")
+    keys = {}
+    for node, leaf in ((kernel, "kernel"), (bias, "bias")):
+        key = "net/down1/conv2d1/%s/.ATTRIBUTES/VARIABLE_VALUE" % leaf
+        node.attributes.add(name="VARIABLE_VALUE", full_name="down1/conv2d1/" + leaf, checkpoint_key=key)
+        keys[leaf] = key
+        assert key.endswith(tfc.VARIABLE_SUFFIX)
+    rng = np.random.default_rng(2)
+    tensors = {keys["kernel"]: rng.standard_normal((3, 3, 64, 64)).astype("<f4"),
+               keys["bias"]: rng.standard_normal(64).astype("<f4")}
+    prefix = str(tmp_path / "ckpt-3")
+    write_bundle(prefix, tensors, strings=("_CHECKPOINTABLE_OBJECT_GRAPH",))
+    got = tfc.read_bundle(prefix, verify="all")
+    assert sorted(got) == sorted(tensors)
+    for k in tensors:
+        assert np.array_equal(got[k], tensors[k])
+    W = tfc.load_tf_checkpoint(prefix)
+    assert list(W) == ["down1.conv2d1"] and tuple(W["down1.conv2d1"][0].shape) == (3, 3, 64, 64)
+
+
+def test_corruption_is_detected(tmp_path):
+    rng = np.random.default_rng(4)
+    t = {"net/layer0/kernel" + SUF: rng.standard_normal((3, 3, 5, 64)).astype("<f4"),
+         "net/layer0/bias" + SUF: rng.standard_normal(64).astype("<f4")}
+    prefix = str(tmp_path / "ckpt-1")
+    write_bundle(prefix, t)
+    assert len(tfc.read_bundle(prefix, verify="all")) == 2
+    data = prefix + ".data-00000-of-00001"
+    raw = bytearray(open(data, "rb").read())
+    raw[100] ^= 0x10
+    open(data, "wb").write(raw)
+    assert len(tfc.read_bundle(prefix)) == 2                        # default: the index only
+    with pytest.raises(tfc.CheckpointFormatError, match="checksum"):
+        tfc.read_bundle(prefix, verify="all")
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    idx[10] ^= 0x01
+    open(prefix + ".index", "wb").write(idx)
+    with pytest.raises(tfc.CheckpointFormatError):
         tfc.read_bundle(prefix)
