@@ -366,7 +366,8 @@ struct KpnTfParams {
 };
 
 // One output row segment of MT 16-px M tiles, all frames: the body of a warp's work in a row group.
-template <int MT>
+// NT = N tiles of 8 bases: 2 for up to 16 bases, 1 when the launch's bases fit one tile (B <= 8: half the MMAs).
+template <int MT, int NT>
 __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag, const float* __restrict__ s_ring,
                                              const float* __restrict__ coef, float* __restrict__ out,
                                              const KpnTfParams& P, int img, int y, int xpx, int s0, int xw, int lane) {
@@ -383,18 +384,18 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
       const int px = xpx + 16 * m + g + 8 * hrow;
       const float* cp = coef + (((long long)img * P.Hc + y) * P.Wc + (px < W ? px : 0)) * P.Btot + P.b0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2 * NT; ++q) {
         const int b = (q >> 1) * 8 + 2 * c + (q & 1);
         cf[m][hrow][q] = (px < W && b < B) ? __ldg(cp + b) : 0.f;
       }
     }
   }
   for (int t = 0; t < T; ++t) {
-    float acc[MT][2][4];
+    float acc[MT][NT][4];
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[m][nt][e] = 0.f;
     const float2* bf_t = s_bfrag + (t * kTfK) * 128 + lane;
@@ -406,19 +407,25 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
       uint32_t w[4 * MT + 2];
 #pragma unroll
       for (int q = 0; q < 4 * MT + 2; ++q) w[q] = __float_as_uint(rp[4 * q]);            // already rounded to TF32
-      const float2 b00 = bf_t[(i * 4 + 0) * 32], b01 = bf_t[(i * 4 + 1) * 32];   // ks 0: nt 0, 1
-      const float2 b10 = bf_t[(i * 4 + 2) * 32], b11 = bf_t[(i * 4 + 3) * 32];   // ks 1: nt 0, 1
+      const float2 b00 = bf_t[(i * 4 + 0) * 32], b10 = bf_t[(i * 4 + 2) * 32];   // nt 0: ks 0, 1
+      float2 b01 = b00, b11 = b10;                                                // nt 1: ks 0, 1
+      if (NT == 2) {
+        b01 = bf_t[(i * 4 + 1) * 32];
+        b11 = bf_t[(i * 4 + 3) * 32];
+      }
       // A[r][k] = row[16 m + r + 8 ks + k]:  a0 (g, c), a1 (g+8, c), a2 (g, c+4), a3 (g+8, c+4).
       // All 2*MT accumulators of K step 0 first, then K step 1: dependent MMAs are 2*MT issues apart.
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         mma_tf32(acc[m][0], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b00.x), __float_as_uint(b00.y));
-        mma_tf32(acc[m][1], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b01.x), __float_as_uint(b01.y));
+        if (NT == 2)
+          mma_tf32(acc[m][NT - 1], w[4 * m], w[4 * m + 2], w[4 * m + 1], w[4 * m + 3], __float_as_uint(b01.x), __float_as_uint(b01.y));
       }
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         mma_tf32(acc[m][0], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b10.x), __float_as_uint(b10.y));
-        mma_tf32(acc[m][1], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b11.x), __float_as_uint(b11.y));
+        if (NT == 2)
+          mma_tf32(acc[m][NT - 1], w[4 * m + 2], w[4 * m + 4], w[4 * m + 3], w[4 * m + 5], __float_as_uint(b11.x), __float_as_uint(b11.y));
       }
     }
     // mix with the per-pixel coefficients: thread holds G[px][2c, 2c+1] (nt 0) and G[px][8+2c, 9+2c] (nt 1)
@@ -430,7 +437,7 @@ __device__ __forceinline__ void kpn_tf32_row(const float2* __restrict__ s_bfrag,
         const int px = xpx + 16 * m + g + 8 * hrow;
         float s = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) s = fmaf(cf[m][hrow][nt * 2 + e], acc[m][nt][2 * hrow + e], s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -548,8 +555,14 @@ kpn_apply_tf32_kernel(const float* __restrict__ burst, const float* __restrict__
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       const int m_left = mt - 2 * half;                                   // warp-uniform
-      if (m_left >= 2) kpn_tf32_row<2>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xw + 32 * half, s0, xw + 32 * half, lane);
-      else if (m_left == 1) kpn_tf32_row<1>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xw + 32 * half, s0, xw + 32 * half, lane);
+      const int xs = xw + 32 * half;
+      if (B > 8) {                                                        // block-uniform
+        if (m_left >= 2) kpn_tf32_row<2, 2>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xs, s0, xs, lane);
+        else if (m_left == 1) kpn_tf32_row<1, 2>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xs, s0, xs, lane);
+      } else {
+        if (m_left >= 2) kpn_tf32_row<2, 1>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xs, s0, xs, lane);
+        else if (m_left == 1) kpn_tf32_row<1, 1>(s_bfrag, s_ring, coef, out, P, img, y, x0 + xs, s0, xs, lane);
+      }
     }
   }
 }

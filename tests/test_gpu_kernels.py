@@ -143,14 +143,17 @@ def test_channel_mean_and_broadcast(cuda):
     assert border_is_zero(dst)
 
 
-def test_softmax_taps(cuda):
+@pytest.mark.parametrize("n,T,B", [(3, 4, 10), (2, 8, 90), (1, 8, 50), (2, 1, 1), (1, 2, 256), (1, 1, 300), (5, 3, 7)])
+def test_softmax_taps(cuda, n, T, B):
+    """Row-tiled kernel (B <= 256; 1024 threads when the basis is large) and the strided one (B > 256)."""
     from imageenhancement_mp_b200 import ops
     g = torch.Generator().manual_seed(5)
-    ob = torch.relu(torch.randn(3, 15, 15, 40, generator=g) * 2)
-    got = ops.softmax_taps(ob.to(cuda), 4, 10).cpu()
-    ref = omodel.basis_softmax(ob, 15, 4, 10)
-    assert torch.allclose(got, ref, atol=1e-7, rtol=1e-5)
-    assert torch.allclose(got.sum(dim=(1, 2, 3)), torch.ones(3, 10), atol=1e-5)
+    ob = torch.relu(torch.randn(n, 15, 15, T * B, generator=g) * 2)
+    got = ops.softmax_taps(ob.to(cuda), T, B).cpu()
+    ref = omodel.basis_softmax(ob.double(), 15, T, B)
+    assert got.shape == (n, 15, 15, T, B)
+    assert torch.allclose(got.double(), ref, atol=1e-7, rtol=2e-5)
+    assert torch.allclose(got.sum(dim=(1, 2, 3)), torch.ones(n, B), atol=1e-5)
 
 
 # ------------------------------------------------------------------ per-pixel filter
