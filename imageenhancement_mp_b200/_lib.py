@@ -67,7 +67,7 @@ SIGNATURES = {
 }
 
 _lib = None
-LAUNCHES = collections.Counter()      # C-ABI calls made (each enqueues exactly one kernel of ours)
+LAUNCHES = collections.Counter()      # C-ABI calls made (each enqueues at least one kernel of ours; exactly one per call in bench.py's step)
 TRACE = None                          # set to a list to collect (name, start_event, end_event) per call (profiling)
 
 
