@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Latency of eval.py's default configuration (one 32x32 patch per step): eager launches vs CUDA-graph replay."""
+"""Latency of small batches (eval.py's default: one 32x32 patch per step; BASELINE configs[0]: 32 patches of 100x100):
+eager launches vs CUDA-graph replay, to place Engine.graph_max_pixels at the crossover."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,9 +8,9 @@ from imageenhancement_mp_b200 import synth, weights, model_library as ml
 dev = torch.device("cuda", 0)
 params = dict(synth.DEFAULT_PARAMS)
 W = weights.init_weights(weights.simplemodel_layers(params))
-for name, p in (("eager", dict(params, graph_max_pixels=0)), ("graph", params)):
+for name, p in (("eager", dict(params, graph_max_pixels=0)), ("graph", dict(params, graph_max_pixels=1 << 30))):
     model = ml.Simplemodel(p, weights=W, device=dev)
-    for n, h, w in ((1, 32, 32), (4, 64, 64)):
+    for n, h, w in ((1, 32, 32), (4, 64, 64), (8, 100, 100), (16, 100, 100), (32, 100, 100), (64, 100, 100), (128, 100, 100)):
         x = synth.make_batch(n, h, w, params)[0].to(dev)
         for _ in range(5):
             model(x)
