@@ -48,7 +48,14 @@ def make(name, arch, params, n, h, w, scheme):
 
 if __name__ == "__main__":
     P = dict(synth.DEFAULT_PARAMS)
+    only = sys.argv[1:]
+    if only:                                    # regenerate just the named fixtures
+        _make = make
+        make = lambda name, *a: _make(name, *a) if name in only else None
     make("simple_glorot_32", "simple", P, 2, 32, 32, "glorot")          # eval.py defaults (32x32, T=4)
     make("simple_stress_32", "simple", P, 2, 32, 32, "stress")
     make("simple_stress_100", "simple", P, 1, 100, 100, "stress")       # BASELINE config shape (padded to 104)
     make("simple_stress_T2", "simple", dict(P, BURST_LENGTH=2), 1, 40, 48, "stress")   # 3-channel reading
+    # the second entry point with the remote/ settings (running_train_remote.py:29,34: T = 8, Basis_num = 50, 64x64)
+    make("basis_kpn_stress_64", "basis_kpn", dict(P, BURST_LENGTH=8, layer_type="dualparams", Basis_num=50), 1, 64, 64,
+         "stress")

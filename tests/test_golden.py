@@ -15,6 +15,7 @@ CASES = {
     "simple_stress_32": (dict(synth.DEFAULT_PARAMS), "stress"),
     "simple_stress_100": (dict(synth.DEFAULT_PARAMS), "stress"),
     "simple_stress_T2": (dict(synth.DEFAULT_PARAMS, BURST_LENGTH=2), "stress"),
+    "basis_kpn_stress_64": (dict(synth.DEFAULT_PARAMS, BURST_LENGTH=8, layer_type="dualparams", Basis_num=50), "stress"),
 }
 
 
@@ -30,7 +31,9 @@ def test_fixtures_present():
 def test_oracle_matches_golden(name):
     params, scheme = CASES[name]
     z = load(name)
-    W = weights.init_weights(weights.simplemodel_layers(params), seed=1234, scheme=scheme)
+    kpn = name.startswith("basis_kpn")
+    layers = weights.basis_kpn_layers(params) if kpn else weights.simplemodel_layers(params)
+    W = weights.init_weights(layers, seed=1234, scheme=scheme)
     chk = sum(float(w.double().abs().sum()) + float(b.double().abs().sum()) for w, b in W.values())
     assert chk == pytest.approx(float(z["weight_checksum"]), rel=1e-9)      # same weights from the same seed
     x, truth = torch.from_numpy(z["x"]), torch.from_numpy(z["truth"])
@@ -38,8 +41,13 @@ def test_oracle_matches_golden(name):
     xs, ts = synth.make_batch(n, h, w, params, seed=1234)
     # synthetic inputs are reproducible (ulp slack: pow/interpolate may vectorise differently per host)
     assert torch.allclose(xs, x, rtol=1e-5, atol=1e-7) and torch.allclose(ts, truth, rtol=1e-5, atol=1e-7)
-    xp, _ = synth.pad_to_multiple(x, 8)
-    out, bas, ob = oracle.simplemodel_forward(W, params, xp)
+    xp, _ = synth.pad_to_multiple(x, 32 if kpn else 8)
+    if kpn:
+        taps = {}
+        out, bas = oracle.basis_kpn_forward(W, params, xp, taps=taps)
+        ob = taps["originbasis"]
+    else:
+        out, bas, ob = oracle.simplemodel_forward(W, params, xp)
     out = out[:, :h, :w]
     assert np.allclose(out.numpy(), z["output"], atol=2e-5)
     assert np.allclose(bas.numpy(), z["Bas"], atol=1e-7, rtol=1e-3)

@@ -127,6 +127,26 @@ def test_against_committed_golden_vectors(cuda, name):
     assert abs(got["psnr_noise0"] - rep[3 + T]) <= 1e-3 and abs(got["psnr_average"] - rep[4 + T]) <= 1e-3
 
 
+def test_basis_kpn_against_committed_golden_vectors(cuda):
+    """Basis_kpn with the remote/ settings (T = 8, dualparams, Basis_num = 50) vs tests/golden/basis_kpn_stress_64.npz."""
+    import os
+    import numpy as np
+    from imageenhancement_mp_b200 import model_library as ml, data_utils as du
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "basis_kpn_stress_64.npz"))
+    T = 8
+    params = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=T, layer_type="dualparams", Basis_num=50)
+    W = weights.init_weights(weights.basis_kpn_layers(params), seed=1234, scheme="stress")
+    x, truth = torch.from_numpy(z["x"]).to(cuda), torch.from_numpy(z["truth"]).to(cuda)
+    out, bas = ml.Basis_kpn(params, weights=W)(x)
+    assert bas.shape == (1, 15, 15, 8, 50)
+    assert float((out.cpu() - torch.from_numpy(z["output"])).abs().max()) <= OUT_TOL
+    assert rel_l2(bas.cpu(), torch.from_numpy(z["Bas"])) <= REL_L2_TOL
+    got = du.eval_metrics(out, x, truth, T)
+    rep = z["report"]           # loss1, perlayer_loss, psnr, psnr_perlayer[T], psnr_noise0, psnr_average
+    assert abs(got["psnr"] - rep[2]) <= PSNR_TOL
+    assert abs(got["psnr_noise0"] - rep[3 + T]) <= 1e-3 and abs(got["psnr_average"] - rep[4 + T]) <= 1e-3
+
+
 def test_simplemodel_three_channel_reading(cuda):
     """The literal 'x3' reading of BASELINE.json: T=2 + singlestd -> 3 input channels (run_training_val.py:28)."""
     params = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=2)
