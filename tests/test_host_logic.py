@@ -158,6 +158,55 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _ps_bases(nb, n):
+    g = torch.Generator().manual_seed(17)
+    return [torch.softmax(torch.randn(n, 15 * 15 * T, 10, generator=g, dtype=torch.float64) * 5, dim=1)
+            .view(n, 15, 15, T, 10) for _ in range(nb)]
+
+
+def _worker_ps(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    idist.init_from_env(backend="gloo")
+    batches = make_batches(2, 5, 40, 48)
+    bases = iter(_ps_bases(2, 5))
+
+    def step(model, xb, xt, burst_length):
+        lo, hi = idist.shard_range(5, rank, world)           # this rank's images of the batch, like shard_batch
+        bas = next(bases)[lo:hi]
+        cv = sum(oracle.cost_volume(bas[i:i + 1]) for i in range(bas.shape[0]))
+        return oracle_step_totals(model, xb, xt, burst_length), cv.reshape(1)
+
+    rep = ieval.evaluate(fake_model, batches, dict(synth.DEFAULT_PARAMS, ps=True), out=None, step_totals=step)
+    q.put((rank, {k: rep[k] for k in ("variance", "variance loss", "count", "val_psnr")}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_ps_variance_rides_in_the_all_reduce():
+    """params["ps"] under two ranks with an uneven 3/2 split: the per-rank cost_volume sums are appended to the totals
+    vector, all-reduced once, and `variance` equals the mean over ALL images on both ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ps, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    per_image = [oracle.cost_volume(b[i:i + 1]) for b in _ps_bases(2, 5) for i in range(5)]
+    ref = float(torch.stack(per_image).mean())
+    base = reference_report(make_batches(2, 5, 40, 48))
+    for rank in (0, 1):
+        assert got[rank]["count"] == 10
+        assert got[rank]["variance"] == pytest.approx(ref, rel=1e-9)
+        assert got[rank]["variance loss"] == pytest.approx(100.0 * ref, rel=1e-9)
+        assert got[rank]["val_psnr"] == pytest.approx(base["val_psnr"], rel=1e-6)
+
+
 def test_two_rank_gloo_evaluate_equals_single_process():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
