@@ -11,8 +11,11 @@ restatement of the reference's arithmetic, op for op, each function citing the
 reference ``file:line`` it follows.  It is pinned only by (a) the analytic
 known-answer tests derivable from the reference's own code (tests/test_oracle_kat.py),
 (b) two independent formulations of the per-pixel filter agreeing to 1e-6, and
-(c) fp32-vs-fp64 agreement.  TensorFlow semantics that are assumed rather than
-observed are listed in DESIGN.md ("Oracle").
+(c) fp32-vs-fp64 agreement, (d) cross-checks of the assumed op semantics against
+independent implementations present in this image (scipy correlate2d / ndimage / softmax,
+OpenCV half-pixel INTER_LINEAR and INTER_AREA, the Random123 Philox known answers) and
+(e) the self-generated regression fixtures of tests/golden/.  TensorFlow semantics that
+are assumed rather than observed are listed in DESIGN.md ("Oracle").
 """
 from .model import (  # noqa: F401
     simplemodel_forward,
