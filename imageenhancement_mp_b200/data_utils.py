@@ -297,3 +297,61 @@ def preprocess_image(src_u8, org, params, white_level, sig_read, sig_shot, n_rea
          float(params["degamma"]), ptr(f(white_level)), ptr(f(sig_read)), ptr(f(sig_shot)), ptr(nr), ptr(ns), lt,
          h, w, T, ptr(x), ptr(truth), stream())
     return x, truth
+
+
+# ------------------------------------------------------------------ validation batches from decoded uint8 images
+def draw_burst_params(n, src_hw, params, generator=None):
+    """The per-image random draws of DataLoader.preprocess_image for ``n`` source images of size ``src_hw``, on the host
+    (data_utils.py:222-236 and the crops of make_first_truth :432-439 / make_truth_hqjitter :442-457):
+
+    * ``crop0``  [n,2]: origin of the (h*up + 2*jitter*up)-sized random crop of the source, in SOURCE pixels - negative
+      when the source is smaller than the crop and the reference zero-pads it symmetrically (:435-438);
+    * ``use_big`` [n,T-1] / ``frame_off`` [n,T-1,2]: per later frame, whether it is cropped from the big-jitter patch
+      (probability min(Poisson(1.5)/T, 1), :451-454) and its random_crop offset inside that patch;
+    * ``org`` [n,T,2] int32: the resulting absolute crop origin of every frame (what the kernel consumes);
+    * ``white_level`` = 10^U(-1,0), ``sig_read`` = 10^U(-3,-1.5), ``sig_shot`` = 10^U(-2,-1)  [n] fp32.
+
+    The distributions are the reference's; the random streams are torch's (``generator``), not TensorFlow's."""
+    g = generator
+    T, up = params["BURST_LENGTH"], params["upscale"]
+    h, w, jitter, sj = params["height"], params["width"], params["jitter"], params["smalljitter"]
+    hs, ws = src_hw
+    j_up, delta_up = jitter * up, (jitter - sj) * up
+    h_up, w_up = h * up + 2 * j_up, w * up + 2 * j_up
+    v_err, h_err = max((h_up - hs + 1) // 2, 0), max((w_up - ws + 1) // 2, 0)            # :435-436
+    ri = lambda hi, shape: torch.randint(0, hi + 1, shape, generator=g)                  # inclusive upper bound
+    crop0 = torch.stack([ri(hs + 2 * v_err - h_up, (n,)) - v_err, ri(ws + 2 * h_err - w_up, (n,)) - h_err], dim=-1)
+    prob = torch.clamp(torch.poisson(torch.full((n,), 1.5), generator=g) / T, max=1.0)   # :451
+    use_big = torch.rand(n, T - 1, generator=g) < prob[:, None]                           # :453-454
+    off_big = torch.stack([ri(2 * j_up, (n, T - 1)), ri(2 * j_up, (n, T - 1))], dim=-1)
+    off_small = torch.stack([ri(2 * sj * up, (n, T - 1)), ri(2 * sj * up, (n, T - 1))], dim=-1)
+    frame_off = torch.where(use_big[..., None], off_big, off_small)
+    base = torch.where(use_big, 0, delta_up)[..., None]
+    org = torch.cat([(crop0 + j_up)[:, None, :], crop0[:, None, :] + base + frame_off], dim=1).to(torch.int32)
+    u = lambda lo, hi: 10.0 ** (torch.rand(n, generator=g) * (hi - lo) + lo)
+    return {"crop0": crop0, "use_big": use_big, "frame_off": frame_off, "org": org,
+            "white_level": u(-1.0, 0.0).float(), "sig_read": u(-3.0, -1.5).float(), "sig_shot": u(-2.0, -1.0).float()}
+
+
+def val_batches_from_u8(images_u8, params, batch_size=None, seed=1234, device=None, shuffle=True):
+    """``DataLoader.get_val_ds`` (data_utils.py:387-394) for images that are already decoded: ``images_u8`` is a uint8
+    tensor [N,Hs,Ws,C] (host - pinned or not - or device).  Shuffles the images, turns every ``batch_size`` of them
+    into a synthetic burst on the device (``preprocess_image``: jittered crops, 4x AREA down-sample, white level,
+    read/shot noise drawn on the device) and yields ``(x [B,h,w,T+add], truth [B,h,w,2])`` CUDA tensors -
+    ``drop_remainder=True`` like the reference - ready for ``eval.evaluate(..., pre_sharded=...)``.
+    File listing, decoding and the tf.data cache are out of scope."""
+    if images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+        raise _lib.ImgEnhError("images_u8 must be a uint8 tensor [N,Hs,Ws,C]")
+    if device is None:
+        device = images_u8.device if images_u8.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    bs = int(params.get("batch_size", 1) if batch_size is None else batch_size)
+    n = images_u8.shape[0]
+    g = torch.Generator().manual_seed(int(seed))
+    order = torch.randperm(n, generator=g) if shuffle else torch.arange(n)
+    for b0 in range(0, n - bs + 1, bs):                                    # drop_remainder=True (:392)
+        idx = order[b0:b0 + bs]
+        d = draw_burst_params(bs, images_u8.shape[1:3], params, generator=g)
+        src = images_u8[idx.to(images_u8.device)].to(device, non_blocking=True)
+        noise_seed = int(torch.randint(0, 2 ** 62, (1,), generator=g))
+        yield preprocess_image(src, d["org"].to(device), params, d["white_level"].to(device), d["sig_read"].to(device),
+                               d["sig_shot"].to(device), seed=noise_seed)

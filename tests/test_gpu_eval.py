@@ -152,3 +152,36 @@ def test_cost_volume_and_ps_report(cuda):
     ref2 = float(torch.stack([oracle.cost_volume(oracle.simplemodel_forward(W, params, x)[1].double())
                               for x, _ in batches]).mean())
     assert abs(rep["variance"] - ref2) <= 0.1 * abs(ref2) + 1e-5
+
+
+def test_val_batches_from_u8_feed_evaluate(cuda):
+    """get_val_ds for decoded uint8 images (data_utils.py:387-394): shuffled, preprocessed on the device, batched with
+    drop_remainder; the batches equal a direct preprocess_image call with the same draws, are reproducible from the
+    seed, carry the reference's layout (noisy ++ sig, truth ++ white level) and drive evaluate()."""
+    from imageenhancement_mp_b200 import data_utils as du, eval as ieval, model_library as ml
+    params = dict(synth.DEFAULT_PARAMS, height=32, width=40, batch_size=3)
+    g = torch.Generator().manual_seed(8)
+    imgs = torch.randint(0, 256, (8, 300, 340, 1), generator=g, dtype=torch.uint8)      # host, not pinned
+    batches = list(du.val_batches_from_u8(imgs, params, seed=5))
+    assert len(batches) == 2                                                            # 8 // 3, remainder dropped
+    again = list(du.val_batches_from_u8(imgs.to(cuda), params, seed=5))                 # device source: same batches
+    for (x, t), (x2, t2) in zip(batches, again):
+        assert x.is_cuda and x.shape == (3, 32, 40, 5) and t.shape == (3, 32, 40, 2)
+        assert torch.equal(x, x2) and torch.equal(t, t2)
+        wl = t[..., 1]
+        assert torch.equal(wl, wl[:, :1, :1].expand_as(wl)) and 0.1 <= float(wl.min()) and float(wl.max()) <= 1.0
+        assert float(t[..., 0].min()) >= 0 and float((t[..., 0] / wl).max()) <= 1.0 + 1e-6
+        assert float((x[..., :4] - t[..., :1]).abs().mean()) < 0.2                       # noisy frames around the truth
+    # the first batch against a direct call with the same draws (same generator sequence as the loader)
+    gg = torch.Generator().manual_seed(5)
+    order = torch.randperm(8, generator=gg)
+    d = du.draw_burst_params(3, (300, 340), params, generator=gg)
+    seed = int(torch.randint(0, 2 ** 62, (1,), generator=gg))
+    x_ref, t_ref = du.preprocess_image(imgs[order[:3]].to(cuda), d["org"].to(cuda), params, d["white_level"].to(cuda),
+                                       d["sig_read"].to(cuda), d["sig_shot"].to(cuda), seed=seed)
+    assert torch.equal(batches[0][0], x_ref) and torch.equal(batches[0][1], t_ref)
+    other = next(iter(du.val_batches_from_u8(imgs, params, seed=6)))
+    assert not torch.equal(other[0], batches[0][0])
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    rep = ieval.evaluate(ml.Simplemodel(params, weights=W), du.val_batches_from_u8(imgs, params, seed=5), params, out=None)
+    assert rep["count"] == 6 and 5.0 < rep["val_psnrburst0"] < 60.0 and rep["val_psnraverage"] == rep["val_psnraverage"]

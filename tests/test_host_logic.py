@@ -223,3 +223,36 @@ def test_two_rank_gloo_evaluate_equals_single_process():
         assert got[rank]["count"] == 15
         for k in ieval.REPORT_KEYS:
             assert got[rank][k] == pytest.approx(ref[k], rel=1e-6, abs=1e-6), (rank, k)
+
+
+def test_draw_burst_params_follows_the_reference_crops():
+    """draw_burst_params: ranges and structure of the reference's random crops (data_utils.py:432-457), the absolute
+    origins against the oracle's frame_origins for the same draws, determinism, and the symmetric zero padding of a
+    source smaller than the crop (negative origins)."""
+    from oracle import preprocess as opre
+    params = dict(synth.DEFAULT_PARAMS, height=24, width=32, BURST_LENGTH=4)
+    up, jit, sj = params["upscale"], params["jitter"], params["smalljitter"]
+    g = torch.Generator().manual_seed(3)
+    n, hs, ws = 64, 400, 500
+    d = du.draw_burst_params(n, (hs, ws), params, generator=g)
+    h_up, w_up = 24 * up + 2 * jit * up, 32 * up + 2 * jit * up
+    assert d["org"].dtype == torch.int32 and d["org"].shape == (n, 4, 2)
+    assert int(d["crop0"][:, 0].min()) >= 0 and int(d["crop0"][:, 0].max()) <= hs - h_up
+    assert int(d["crop0"][:, 1].min()) >= 0 and int(d["crop0"][:, 1].max()) <= ws - w_up
+    big, off = d["use_big"], d["frame_off"]
+    assert int(off[big].max()) <= 2 * jit * up and int(off[~big].max()) <= 2 * sj * up and int(off.min()) >= 0
+    assert bool(big.any()) and bool((~big).any())
+    for i in range(n):
+        draws = {"crop0": tuple(int(v) for v in d["crop0"][i]), "use_big": [bool(v) for v in big[i]],
+                 "frame_off": [tuple(int(v) for v in o) for o in off[i]]}
+        assert opre.frame_origins(params, draws) == [tuple(int(v) for v in o) for o in d["org"][i]]
+    # every frame's (h*up x w*up) window stays inside the first crop, hence inside the source
+    assert int(d["org"].min()) >= 0
+    assert int(d["org"][..., 0].max()) + 24 * up <= hs and int(d["org"][..., 1].max()) + 32 * up <= ws
+    for k, lo, hi in (("white_level", 0.1, 1.0), ("sig_read", 10 ** -3, 10 ** -1.5), ("sig_shot", 10 ** -2, 10 ** -1)):
+        assert d[k].shape == (n,) and float(d[k].min()) >= lo * (1 - 1e-6) and float(d[k].max()) <= hi * (1 + 1e-6)
+    d2 = du.draw_burst_params(n, (hs, ws), params, generator=torch.Generator().manual_seed(3))
+    assert all(torch.equal(d[k], d2[k]) for k in d)
+    # source smaller than the crop: the reference pads (h_up - Hs + 1)//2 on both sides (:435-438) -> fixed negative origin
+    small = du.draw_burst_params(4, (100, 120), params, generator=g)
+    assert torch.equal(small["crop0"], torch.tensor([[-((h_up - 100 + 1) // 2), -((w_up - 120 + 1) // 2)]] * 4))
