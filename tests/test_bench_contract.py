@@ -27,3 +27,32 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_committed_gpu_bench_lines_keep_the_contract():
+    """Every committed GPU bench line under profiles/ (written by bench.py on a B200) carries the keys of the contract:
+    the base line, `e2e` with its byte counts, `gpu_launches`, `clocks`, `roofline` (bound / achieved / peak / frac /
+    traffic) and - at one GPU - `cpu_baseline`; frac = achieved / peak and value = pixels / time are self-consistent."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_cfg*.json")))
+    assert len(paths) >= 6
+    for path in paths:
+        d = json.loads(open(path).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (path, k)
+        assert d["unit"] == "MP/s" and d["scaling"] == "weak" and d["data"] == "synthetic" and d["vs_baseline"] is None
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and "l2" in d["config"]
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert d["e2e"]["value"] != d["value"]                                    # measured separately, not copied
+        r = d["roofline"]
+        assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert 0.3 < r["frac"] < 1.0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        h, w = d["config"]["image"]
+        mp = d["config"]["images_per_step"] * h * w / 1e6
+        assert abs(d["value"] - mp / (d["ms_per_step"] / 1e3)) <= 1e-6 * d["value"]
+        if d["n_gpus"] == 1:
+            cb = d["cpu_baseline"]
+            assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
