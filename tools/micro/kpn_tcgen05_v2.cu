@@ -1,5 +1,5 @@
-// PROTOTYPE v2 (not part of libimgenh_b200.so; written after v1 was measured, NOT yet run on a GPU - the round's GPU
-// budget was spent): tools/micro/kpn_tcgen05.cu with the pipeline its measurement asked for.  v1 (correct, 2.15 ms at
+// PROTOTYPE v2 (not part of libimgenh_b200.so yet): tools/micro/kpn_tcgen05.cu with the pipeline its measurement asked
+// for.  Ran on a B200 at the very end of round 1: all cases PASS, 0.656 ms at cfg2 (shipped mma.sync kernel: 0.91 ms).  v1 (correct, 2.15 ms at
 // cfg2) spends ~20 000 cycles per 128-px tile staging the coefficients and the burst window with dependent scalar loads
 // on 5 warps, then computes, then synchronises.  Here:
 //   * warps 9-12 are PRODUCERS: they stage tile i+1 (coefficients -> TF32, hand-swizzled A operand; burst window by
