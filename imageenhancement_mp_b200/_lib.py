@@ -50,6 +50,7 @@ SIGNATURES = {
     "ie_cost_volume_f32": [_P, _I, _I, _I, _I, _P, _P, _P],
     "ie_kpn_apply_f32": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ie_kpn_apply_tf32": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ie_kpn_apply_tc": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ie_convolve_filts_f32": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "ie_mean_hw_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_invert_preproc_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P],

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libimgenh_b200.so")
 OBJ = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "conv_tcgen05.cu", "debug_conv.cu", "layout.cu", "kpn_apply.cu", "metrics.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "conv_tcgen05.cu", "debug_conv.cu", "layout.cu", "kpn_apply.cu", "kpn_tcgen05.cu", "metrics.cu", "preprocess.cu"]
 HEADERS = ["ie_common.cuh", "ie_ptx.cuh"]
 
 NVCC_FLAGS = [

@@ -62,10 +62,11 @@ class Engine:
             raise ImgEnhError("Kernel_size must be 15: the basis branch emits 15x15 kernels (model_library.py:364)")
         self.device = torch.device(device)
         # per-pixel filter: "tf32" = tensor-core kernel (operands rounded to a 10-bit mantissa, fp32 accumulation,
-        # |err| <= 2^-10 of the pixel range) where it applies (K=15, B<=16, T<=8), "fp32" = CUDA-core kernel (1e-5)
+        # |err| <= 2^-10 of the pixel range) where it applies (K=15, B<=128, T<=8), "fp32" = CUDA-core kernel (1e-5),
+        # "tcgen05" = opt-in tcgen05 filter-synthesis kernel (same TF32 rounding; falls back to "tf32" where it does not apply)
         self.filter_precision = params.get("filter_precision", "tf32")
-        if self.filter_precision not in ("tf32", "fp32"):
-            raise ImgEnhError("filter_precision must be 'tf32' or 'fp32'")
+        if self.filter_precision not in ("tf32", "fp32", "tcgen05"):
+            raise ImgEnhError("filter_precision must be 'tf32', 'fp32' or 'tcgen05'")
         self.stride = 2 ** len(self.arch["downs"])          # 8 for Simplemodel, 32 for Basis_kpn
         self.wp, self.bias = {}, {}
         self.load_weights(weights)
@@ -283,8 +284,13 @@ class Engine:
         originbasis = ops.conv2d_f32(cur, W[tail[-1]], Bv[tail[-1]], self.T * self.B, valid=(15, 15), fn=conv_fn)
         bas = ops.softmax_taps(originbasis, self.T, self.B)              # :436-438
         # ---- per-pixel filter (model_library.py:439-451)
-        tf32 = self.filter_precision == "tf32" and ops.kpn_tf32_supported(self.T, self.K, self.B)
-        out = ops.kpn_apply(x, self.T, coef, bas, precision="tf32" if tf32 else "fp32")
+        if self.filter_precision == "tcgen05" and ops.kpn_tcgen05_supported(self.T, self.K, self.B):
+            prec = "tcgen05"                     # opt-in this round: csrc/kpn_tcgen05.cu
+        elif self.filter_precision != "fp32" and ops.kpn_tf32_supported(self.T, self.K, self.B):
+            prec = "tf32"
+        else:
+            prec = "fp32"
+        out = ops.kpn_apply(x, self.T, coef, bas, precision=prec)
         if taps is not None:
             taps["Coef"], taps["coef_logits"] = coef, logits
         return out, bas, originbasis

@@ -224,21 +224,28 @@ def kpn_tf32_supported(T, K, B):
     return K == 15 and B <= 128 and T <= 8
 
 
+def kpn_tcgen05_supported(T, K, B):
+    """ie_kpn_apply_tc (csrc/kpn_tcgen05.cu): filter synthesis as a tcgen05 GEMM + apply in the epilogue.  Opt-in."""
+    return K == 15 and T % 4 == 0 and T >= 4 and B <= 32
+
+
 def kpn_apply(x, T, coef, bas, out=None, precision="fp32"):
     """Per-pixel filter (model_library.py:439-451).  x: fp32 NHWC whose first T channels are the burst.
 
     precision "fp32": CUDA-core kernel, 1e-5 of the fp64 oracle.  "tf32": tensor-core kernel (burst and basis rounded
-    to TF32, fp32 accumulation; K = 15, B <= 128 in chunks of 16, T <= 8), < 1e-3 absolute on [0,1] pixels, ~2.5x faster."""
+    to TF32, fp32 accumulation; K = 15, B <= 128 in chunks of 16, T <= 8), < 1e-3 absolute on [0,1] pixels, ~2.5x faster.
+    "tcgen05" (OPT-IN, see csrc/kpn_tcgen05.cu): the same TF32 rounding, the filter synthesised by a tcgen05 GEMM and
+    applied in its epilogue; K = 15, T % 4 == 0, B <= 32."""
     _lib.require_cuda(x, coef, bas)
     n, h, w, pitch = x.shape
     K, B = bas.shape[1], bas.shape[-1]
     hc, wc = coef.shape[1], coef.shape[2]          # >= (h, w): the network runs at the stride-padded size
     assert x.is_contiguous() and coef.is_contiguous() and bas.is_contiguous()
     assert coef.shape[0] == n and coef.shape[3] == B and hc >= h and wc >= w and bas.shape == (n, K, K, T, B)
-    assert precision in ("fp32", "tf32")
+    assert precision in ("fp32", "tf32", "tcgen05")
     if out is None:
         out = torch.empty(n, h, w, T + 1, dtype=torch.float32, device=x.device)
-    fn = "ie_kpn_apply_tf32" if precision == "tf32" else "ie_kpn_apply_f32"
+    fn = {"fp32": "ie_kpn_apply_f32", "tf32": "ie_kpn_apply_tf32", "tcgen05": "ie_kpn_apply_tc"}[precision]
     call(fn, ptr(x), pitch, ptr(coef), hc, wc, ptr(bas), ptr(out), n, h, w, T, K, B, stream())
     return out
 

@@ -157,6 +157,14 @@ int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int
 int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
                       float* out, int n, int h, int w, int T, int K, int B, void* stream);
 
+/* Same contract on tcgen05 (kind::tf32) in the reference's own order of operations: the per-pixel filter is synthesised
+ * as a GEMM coef x Bas into TMEM and applied to the burst window in the epilogue (csrc/kpn_tcgen05.cu); same TF32
+ * rounding of coef / basis as above.  K = 15, T a multiple of 4, B <= 32.  OPT-IN this round (filter_precision =
+ * "tcgen05"): the kernel passed its standalone self-check on a B200 (0.66 vs 0.91 ms at 256 x 104 x 104), the
+ * integration behind this entry point has not run on a GPU yet.                                              */
+int ie_kpn_apply_tc(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
+                    float* out, int n, int h, int w, int T, int K, int B, void* stream);
+
 /* Convolve / cus_convolve / Convolve_perlayer (model_library.py:114-168) with MATERIALISED filters, for callers
  * that build `filts` [n][h][w][K][K][T] themselves (the models never do - they use ie_kpn_apply_f32):
  *   out[n,y,x,0]   = sum_{i,j,t} pad0(burst)[n,y+i-K/2,x+j-K/2,t] * filts[n,y,x,i,j,t]        (Convolve.call)

@@ -1,5 +1,6 @@
 """GPU parity of the non-GEMM kernels against the CPU oracle (through the C ABI / ops wrappers)."""
 import math
+import os
 
 import pytest
 import torch
@@ -199,6 +200,32 @@ def test_kpn_apply_tf32_tensor_core_variant(cuda, n, h, w, T, B):
     got1 = ops.kpn_apply(ones, T, coef.to(cuda), bas.to(cuda), precision="tf32").cpu()
     if h > 14 and w > 14:
         assert float((got1[:, 7:-7, 7:-7, 0] - 1).abs().max()) <= 1e-3
+
+
+@pytest.mark.skipif(os.environ.get("IE_EXPERIMENTAL") != "1",
+                    reason="ie_kpn_apply_tc is opt-in this round: its kernel passed the standalone self-check on a B200 "
+                           "(tools/micro/kpn_tcgen05_v2.cu) but this integration has not run on a GPU yet; "
+                           "IE_EXPERIMENTAL=1 runs the test")
+@pytest.mark.parametrize("n,h,w,T,B,pad", [(2, 16, 24, 4, 10, 0), (1, 40, 72, 8, 10, 0), (3, 104, 104, 4, 10, 0),
+                                           (1, 21, 150, 4, 16, 0), (1, 33, 47, 4, 32, 0), (2, 20, 28, 4, 10, 4)])
+def test_kpn_apply_tcgen05_variant(cuda, n, h, w, T, B, pad):
+    """The tcgen05 filter-synthesis kernel: same contract and the same TF32 bound as the mma.sync variant, incl. a coef
+    tensor at the stride-padded extent and a burst pitch that is not T + 1."""
+    from imageenhancement_mp_b200 import ops
+    x, coef, bas = _kpn_inputs(n, h, w, T, B, 13)
+    x = torch.cat([x, torch.rand(n, h, w, 1)], -1) if T > 4 else x
+    ref = oracle.kpn_apply_algebraic(x[..., :T].double(), coef.double(), bas.double())
+    big = torch.rand(n, h + pad, w + pad, B)
+    big[:, :h, :w] = coef
+    got = ops.kpn_apply(x.to(cuda), T, big.to(cuda), bas.to(cuda), precision="tcgen05").cpu()
+    bound = 2.0 ** -10 * float(x.abs().max()) * 1.05
+    assert float((got[..., 0].double() - ref[..., 0]).abs().max()) <= bound
+    assert float((got[..., 1:].double() - ref[..., 1:]).abs().max()) <= T * bound
+    tf32 = ops.kpn_apply(x.to(cuda), T, big.to(cuda), bas.to(cuda), precision="tf32").cpu()
+    assert float((got - tf32).abs().max()) <= T * bound
+    with pytest.raises(Exception):
+        ops.kpn_apply(x[..., :3].contiguous().to(cuda), 3, coef.to(cuda), bas[:, :, :, :3].contiguous().to(cuda),
+                      precision="tcgen05")                      # T = 3 is outside its scope
 
 
 def test_kpn_apply_coef_at_padded_size(cuda):
