@@ -10,6 +10,8 @@
 //   * no __syncthreads in the tile loop: mbarriers in_full / in_empty (A + window slots), acc_full / acc_empty (TMEM
 //     buffers), part_full (partial sums).
 // Same scope and the same self-check as v1 (K = 15, frames in passes of 4, B <= 32).
+// The maintained copy of this kernel is imageenhancement_mp_b200/csrc/kpn_tcgen05.cu (ie_kpn_apply_tc, opt-in); this file
+// stays as the standalone artefact behind profiles/r01_kpn_tcgen05_v2_prototype.txt.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o kpn_tcgen05_v2 kpn_tcgen05_v2.cu && ./kpn_tcgen05_v2
 #include <cmath>
 #include <cstdio>
