@@ -160,8 +160,8 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
             cc = min(F32_HEAD_MAX_COUT, cout - c0)
             d = _desc(src, k, k, cc, relu, epi, None, valid)
             d.y_pitch, d.y_coff = cout, c0
-            _timed_conv(fn, C.byref(d), ptr(r.data), w_packed[c0:].data_ptr(), bias[c0:].data_ptr(), None, ptr(y), None,
-                        stream())
+            _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed[c0:]), ptr(bias[c0:]) if bias is not None else None, None,
+                        ptr(y), None, stream())
         return y
     d = _desc(src, k, k, cout, relu, epi, None, valid)
     aux = torch.empty_like(y) if (softmax and want_logits) else None
