@@ -15,11 +15,15 @@
 // buffer s = chunks s, s+2; set 1 hands its partial sums to set 0 through shared memory), 8 MMA issuer, 9-12 producers
 // staging the next tile (coefficients -> TF32 -> swizzled A slot; burst window by 4-byte cp.async with zero fill).
 //
-// STATUS: the kernel below is tools/micro/kpn_tcgen05_v2.cu, which ran on a B200 at the end of round 1 (all six cases
-// of its self-check PASS, <= 2.1e-4 of a naive fp32 kernel; 0.656 ms at 256 x 104 x 104, T = 4, B = 10 against 0.91 ms
-// for kpn_apply_tf32_kernel).  The integration behind the C ABI (coef at the padded extent, argument checks) has NOT
-// run on a GPU yet - no GPU time was left - so ie_kpn_apply_tc is opt-in (filter_precision = "tcgen05") and its parity
-// test is gated behind IE_EXPERIMENTAL=1.  Scope: K = 15, T a multiple of 4, B <= 32.
+// Persistent CTAs: the launch's (image, tile) list is cut into gridDim.x contiguous ranges; a CTA re-stages the basis
+// whenever its range crosses into the next image (a CTA-wide barrier; ~1.7 images per CTA at 256 images on 148 SMs -
+// one CTA per (image, strip) left 15 % of the time to the second, partial wave).
+// More than 32 bases (Basis_kpn of remote/: B = 50, 90): the filter is linear in the bases, so blocks of 32 bases run as
+// further launches that ADD into the output; T > 4 likewise in passes of four frames.
+//
+// Measured on B200 (round 2): parity test green through the C ABI (coef at the padded extent, pitch != T + 1); the
+// epilogue is bound by the TMEM read path - every pixel reads its 900 synthesised filter values (3.6 KB) with tcgen05.ld.
+// Scope: K = 15, T a multiple of 4, any B (blocks of 32).
 // =================================================================================================
 #include "ie_common.cuh"
 #include "ie_ptx.cuh"
@@ -78,8 +82,10 @@ struct Params {
   const float* coef;
   const float* bas;
   float* out;
-  int h, w, hc, wc, pitch, Ttot, B, t0, accumulate;   // coef is [n][hc][wc][B], hc >= h, wc >= w
-  int tiles_x, tiles_y, strips, ksteps;
+  int n, h, w, hc, wc, pitch, Ttot, B, t0;            // coef is [n][hc][wc][B], hc >= h, wc >= w
+  int b0, nb;                                          // this launch mixes bases [b0, b0 + nb), nb <= 32
+  int acc0, accf;                                      // add into out[..., 0] / into the per-frame channels
+  int tiles_x, tiles_y, ksteps;
 };
 
 // 4-byte asynchronous global->shared copy; src_bytes = 0 zero-fills (tf.pad, model_library.py:126)
@@ -142,7 +148,6 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x / p.strips, strip = blockIdx.x - img * p.strips;
   const int kused = p.ksteps * 8;
 
   if (threadIdx.x == 0) {
@@ -159,145 +164,164 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  // ---- the image's basis -> B operand (once per CTA): Bas[img][tap][t0 + t][b] -> row tap * 4 + t, slot b, TF32
-  {
-    const float* bas_img = p.bas + static_cast<long long>(img) * kTaps * p.Ttot * p.B;
-    for (int idx = threadIdx.x; idx < kBRows * kused; idx += kThreads) {
-      const int n = idx / kused, b = idx - n * kused;
-      float v = 0.f;
-      if (n < kTaps * kTP && b < p.B) {
-        const int tap = n >> 2, t = n & 3;
-        v = to_tf32(__ldg(bas_img + (static_cast<long long>(tap) * p.Ttot + p.t0 + t) * p.B + b));
-      }
-      *reinterpret_cast<float*>(s_b + sw128_off(n, b)) = v;
-    }
-  }
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.tiles_x * p.tiles_y;
+  // this CTA's contiguous range of the (image, tile) list
+  const long long total = static_cast<long long>(p.n) * tiles;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long g_begin = blockIdx.x * per;
+  const long long g_end = (g_begin + per < total) ? g_begin + per : total;
+  int it = 0;                                             // tiles this CTA has processed: slot / barrier phases
 
-  if (warp >= kFirstProducerWarp) {
-    // ================================ producers: stage tile `it` into slot it & 1 ==================
-    const int pid = threadIdx.x - kFirstProducerWarp * 32;                        // 0..127 = pixel of the tile
-    const float* burst_img = p.burst + static_cast<long long>(img) * p.h * p.w * p.pitch;
-    int it = 0;
-    for (int tile = strip; tile < tiles; tile += p.strips, ++it) {
-      const int slot = it & 1;
-      const uint32_t use = static_cast<uint32_t>(it >> 1);
-      const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-      const int y0 = ty * kTileH, x0 = tx * kTileW;
-      // this thread's pixel: its coefficients first into registers (all loads in flight), rounded to TF32
-      const int y = y0 + (pid >> 4), x = x0 + (pid & 15);
-      const bool inside = y < p.h && x < p.w;
-      const float* cp = p.coef + ((static_cast<long long>(img) * p.hc + (inside ? y : 0)) * p.wc + (inside ? x : 0)) * p.B;
-      float v[32];
-#pragma unroll
-      for (int b = 0; b < 32; ++b) v[b] = (b < kused && b < p.B && inside) ? __ldg(cp + b) : 0.f;
-      mbar_wait(&in_empty[slot], (use & 1u) ^ 1u);                                // both epilogue sets are done with the slot
-      // the burst window: 22 x 30 pixels x 4 frames, 4-byte asynchronous copies, zero outside the image
-      {
-        const uint32_t sb = smem_u32(s_burst + slot * kBurstBytes);
-        for (int idx = pid; idx < kSH * kSW * kTP; idx += 128) {
-          const int t = idx & 3, pix = idx >> 2;
-          const int r = pix / kSW, c = pix - r * kSW;
-          const int gy = y0 - kK / 2 + r, gx = x0 - kK / 2 + c;
-          const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-          const float* src = burst_img + (static_cast<long long>(ok ? gy : 0) * p.w + (ok ? gx : 0)) * p.pitch + p.t0 + t;
-          cp_async4_zfill(sb + idx * 4, src, ok ? 4 : 0);
+  for (long long g = g_begin; g < g_end;) {
+    const int img = static_cast<int>(g / tiles);
+    const int tile_lo = static_cast<int>(g - static_cast<long long>(img) * tiles);
+    const long long seg_end = (static_cast<long long>(img + 1) * tiles < g_end) ? static_cast<long long>(img + 1) * tiles : g_end;
+    const int tile_hi = tile_lo + static_cast<int>(seg_end - g);
+    // ---- the image's basis -> B operand: Bas[img][tap][t0 + t][b0 + b] -> row tap * 4 + t, slot b, TF32.  Every MMA
+    //      that read the previous image's rows has completed: the epilogue consumed its results before the barrier below.
+    {
+      const float* bas_img = p.bas + static_cast<long long>(img) * kTaps * p.Ttot * p.B;
+      for (int idx = threadIdx.x; idx < kBRows * kused; idx += kThreads) {
+        const int n = idx / kused, b = idx - n * kused;
+        float v = 0.f;
+        if (n < kTaps * kTP && b < p.nb) {
+          const int tap = n >> 2, t = n & 3;
+          v = to_tf32(__ldg(bas_img + (static_cast<long long>(tap) * p.Ttot + p.t0 + t) * p.B + p.b0 + b));
         }
-      }
-      const uint32_t rowa = smem_u32(s_a + slot * kABytes) + pid * 128;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        if (ch * 4 < kused)
-          sts128(rowa + ((ch ^ (pid & 7)) << 4), to_tf32(v[4 * ch]), to_tf32(v[4 * ch + 1]), to_tf32(v[4 * ch + 2]),
-                 to_tf32(v[4 * ch + 3]));
-      cp_async_wait_all();
-      fence_proxy_async_smem();                                                   // A is read by the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&in_full[slot]);
-    }
-  } else if (warp == kMmaWarp) {
-    // ================================ MMA issuer ==================================
-    const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_a));
-    const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_b));
-    int it = 0;
-    for (int tile = strip; tile < tiles; tile += p.strips, ++it) {
-      const int slot = it & 1;
-      mbar_wait(&in_full[slot], static_cast<uint32_t>(it >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t a_lo = a_lo0 + static_cast<uint32_t>((slot * kABytes) >> 4);
-      for (int c = 0; c < kNumChunks; ++c) {
-        const int buf = c & 1;                                                    // = the epilogue set that drains it
-        const uint32_t use = static_cast<uint32_t>(it * 2 + (c >> 1));            // uses of this buffer so far
-        mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 256);
-          const uint32_t idesc = idesc_tf32(128, c == kNumChunks - 1 ? kLastN : kChunkN);
-          const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((c * kChunkN * 128) >> 4);
-          for (int ks = 0; ks < p.ksteps; ++ks)                                    // 8 TF32 = 32 bytes per k-step
-            umma_tf32_ss_lo(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, ks > 0 ? 1u : 0u);
-          umma_commit(&acc_full[buf]);
-        }
-        __syncwarp();
+        *reinterpret_cast<float*>(s_b + sw128_off(n, b)) = v;
       }
     }
-  } else {
-    // ================================ epilogue sets: apply the filter ====================
-    const int set = warp >> 2;                                                     // 0: chunks 0, 2   1: chunks 1, 3
-    const int px = (warp & 3) * 32 + lane;                                         // TMEM lane = pixel of the tile
-    const int ry = px >> 4, cx = px & 15;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(set * 256);
-    int it = 0;
-    for (int tile = strip; tile < tiles; tile += p.strips, ++it) {
-      const int slot = it & 1;
-      const uint32_t slot_use = static_cast<uint32_t>(it >> 1);
-      const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-      const int y0 = ty * kTileH, x0 = tx * kTileW;
-      mbar_wait(&in_full[slot], slot_use & 1u);                                    // the burst window of the tile
-      const float4* burst_tile = reinterpret_cast<const float4*>(s_burst + slot * kBurstBytes);
-      float acc[kTP] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = set + 2 * cc;
-        const uint32_t use = static_cast<uint32_t>(it * 2 + cc);
-        mbar_wait(&acc_full[set], use & 1u);
-        tc_fence_after();
-        const float4* win = burst_tile + (ry + c * kRowsPerChunk) * kSW + cx;
-        if (c < kNumChunks - 1) apply_chunk<kChunkTaps>(taddr, win, acc);
-        else apply_chunk<kLastTaps>(taddr, win, acc);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[set]);
-      }
-      if (set == 1) {
-        s_part[slot * 128 + px] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&part_full[slot]);
-      } else {
-        mbar_wait(&part_full[slot], slot_use & 1u);
-        const float4 o1 = s_part[slot * 128 + px];
-        acc[0] += o1.x; acc[1] += o1.y; acc[2] += o1.z; acc[3] += o1.w;
-        const int y = y0 + ry, x = x0 + cx;
-        if (y < p.h && x < p.w) {
-          float* o = p.out + ((static_cast<long long>(img) * p.h + y) * p.w + x) * (p.Ttot + 1);
-          const float fT = static_cast<float>(p.Ttot);
-          float sum = 0.f;
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (warp >= kFirstProducerWarp) {
+      // ================================ producers: stage tile `it` into slot it & 1 ==================
+      const int pid = threadIdx.x - kFirstProducerWarp * 32;                        // 0..127 = pixel of the tile
+      const float* burst_img = p.burst + static_cast<long long>(img) * p.h * p.w * p.pitch;
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+        const int slot = it & 1;
+        const uint32_t use = static_cast<uint32_t>(it >> 1);
+        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int y0 = ty * kTileH, x0 = tx * kTileW;
+        // this thread's pixel: its coefficients first into registers (all loads in flight), rounded to TF32
+        const int y = y0 + (pid >> 4), x = x0 + (pid & 15);
+        const bool inside = y < p.h && x < p.w;
+        const float* cp = p.coef + ((static_cast<long long>(img) * p.hc + (inside ? y : 0)) * p.wc + (inside ? x : 0)) * p.B + p.b0;
+        float v[32];
 #pragma unroll
-          for (int t = 0; t < kTP; ++t) {
-            o[1 + p.t0 + t] = acc[t] * fT;                                         // Convolve_perlayer, :164
-            sum += acc[t];
+        for (int b = 0; b < 32; ++b) v[b] = (b < kused && b < p.nb && inside) ? __ldg(cp + b) : 0.f;
+        mbar_wait(&in_empty[slot], (use & 1u) ^ 1u);                                // both epilogue sets are done with the slot
+        // the burst window: 22 x 30 pixels x 4 frames, 4-byte asynchronous copies, zero outside the image
+        {
+          const uint32_t sb = smem_u32(s_burst + slot * kBurstBytes);
+          for (int idx = pid; idx < kSH * kSW * kTP; idx += 128) {
+            const int t = idx & 3, pix = idx >> 2;
+            const int r = pix / kSW, c = pix - r * kSW;
+            const int gy = y0 - kK / 2 + r, gx = x0 - kK / 2 + c;
+            const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+            const float* src = burst_img + (static_cast<long long>(ok ? gy : 0) * p.w + (ok ? gx : 0)) * p.pitch + p.t0 + t;
+            cp_async4_zfill(sb + idx * 4, src, ok ? 4 : 0);
           }
-          o[0] = p.accumulate ? o[0] + sum : sum;                                  // Convolve = mean of the frames
+        }
+        const uint32_t rowa = smem_u32(s_a + slot * kABytes) + pid * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          if (ch * 4 < kused)
+            sts128(rowa + ((ch ^ (pid & 7)) << 4), to_tf32(v[4 * ch]), to_tf32(v[4 * ch + 1]), to_tf32(v[4 * ch + 2]),
+                   to_tf32(v[4 * ch + 3]));
+        cp_async_wait_all();
+        fence_proxy_async_smem();                                                   // A is read by the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&in_full[slot]);
+      }
+    } else if (warp == kMmaWarp) {
+      // ================================ MMA issuer ==================================
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_a));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(s_b));
+      tc_fence_after();
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+        const int slot = it & 1;
+        mbar_wait(&in_full[slot], static_cast<uint32_t>(it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + static_cast<uint32_t>((slot * kABytes) >> 4);
+        for (int c = 0; c < kNumChunks; ++c) {
+          const int buf = c & 1;                                                    // = the epilogue set that drains it
+          const uint32_t use = static_cast<uint32_t>(it * 2 + (c >> 1));            // uses of this buffer so far
+          mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 256);
+            const uint32_t idesc = idesc_tf32(128, c == kNumChunks - 1 ? kLastN : kChunkN);
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((c * kChunkN * 128) >> 4);
+            for (int ks = 0; ks < p.ksteps; ++ks)                                    // 8 TF32 = 32 bytes per k-step
+              umma_tf32_ss_lo(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+            umma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&in_empty[slot]);                                 // window / A slot / partial slot free
+    } else {
+      // ================================ epilogue sets: apply the filter ====================
+      const int set = warp >> 2;                                                     // 0: chunks 0, 2   1: chunks 1, 3
+      const int px = (warp & 3) * 32 + lane;                                         // TMEM lane = pixel of the tile
+      const int ry = px >> 4, cx = px & 15;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(set * 256);
+      for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+        const int slot = it & 1;
+        const uint32_t slot_use = static_cast<uint32_t>(it >> 1);
+        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int y0 = ty * kTileH, x0 = tx * kTileW;
+        mbar_wait(&in_full[slot], slot_use & 1u);                                    // the burst window of the tile
+        const float4* burst_tile = reinterpret_cast<const float4*>(s_burst + slot * kBurstBytes);
+        float acc[kTP] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = set + 2 * cc;
+          const uint32_t use = static_cast<uint32_t>(it * 2 + cc);
+          mbar_wait(&acc_full[set], use & 1u);
+          tc_fence_after();
+          const float4* win = burst_tile + (ry + c * kRowsPerChunk) * kSW + cx;
+          if (c < kNumChunks - 1) apply_chunk<kChunkTaps>(taddr, win, acc);
+          else apply_chunk<kLastTaps>(taddr, win, acc);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[set]);
+        }
+        if (set == 1) {
+          s_part[slot * 128 + px] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&part_full[slot]);
+        } else {
+          mbar_wait(&part_full[slot], slot_use & 1u);
+          const float4 o1 = s_part[slot * 128 + px];
+          acc[0] += o1.x; acc[1] += o1.y; acc[2] += o1.z; acc[3] += o1.w;
+          const int y = y0 + ry, x = x0 + cx;
+          if (y < p.h && x < p.w) {
+            float* o = p.out + ((static_cast<long long>(img) * p.h + y) * p.w + x) * (p.Ttot + 1);
+            const float fT = static_cast<float>(p.Ttot);
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < kTP; ++t) {
+              const float v = acc[t] * fT;                                           // Convolve_perlayer, :164
+              o[1 + p.t0 + t] = p.accf ? o[1 + p.t0 + t] + v : v;
+              sum += acc[t];
+            }
+            o[0] = p.acc0 ? o[0] + sum : sum;                                        // Convolve = mean of the frames
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&in_empty[slot]);                                 // window / A slot / partial slot free
+      }
     }
+    // every role has finished the segment: the epilogue's last wait proves that no MMA still reads the basis
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    g = seg_end;
   }
   tc_fence_before();
   __syncthreads();
@@ -313,27 +337,29 @@ extern "C" int ie_kpn_apply_tc(const float* burst, int burst_pitch, const float*
   using namespace ie::tcf;
   IE_REQUIRE(burst && coef && bas && out, "kpn_apply_tc: null pointer");
   IE_REQUIRE(n > 0 && h > 0 && w > 0, "kpn_apply_tc: bad sizes");
-  IE_REQUIRE(K == kK && T >= kTP && T % kTP == 0 && B >= 1 && B <= 32,
-             "kpn_apply_tc: built for K = 15, T a multiple of 4, B <= 32 (got K=%d T=%d B=%d); use ie_kpn_apply_tf32", K, T, B);
+  IE_REQUIRE(K == kK && T >= kTP && T % kTP == 0 && B >= 1 && B <= 1024,
+             "kpn_apply_tc: built for K = 15, T a multiple of 4 (got K=%d T=%d B=%d); use ie_kpn_apply_tf32", K, T, B);
   IE_REQUIRE(burst_pitch >= T && hc >= h && wc >= w, "kpn_apply_tc: bad pitch / coef extent");
   Params p{};
   p.burst = burst; p.coef = coef; p.bas = bas; p.out = out;
-  p.h = h; p.w = w; p.hc = hc; p.wc = wc; p.pitch = burst_pitch; p.Ttot = T; p.B = B;
+  p.n = n; p.h = h; p.w = w; p.hc = hc; p.wc = wc; p.pitch = burst_pitch; p.Ttot = T; p.B = B;
   p.tiles_x = (w + kTileW - 1) / kTileW;
   p.tiles_y = (h + kTileH - 1) / kTileH;
-  p.ksteps = (B + 7) / 8;
-  const int tiles = p.tiles_x * p.tiles_y;
-  int strips = (sm_count() + n - 1) / n;                  // ~one CTA per SM; every CTA stages one image's basis once
-  if (strips > tiles) strips = tiles;
-  if (strips < 1) strips = 1;
-  p.strips = strips;
-  IE_REQUIRE((long long)n * strips < (1ll << 31), "kpn_apply_tc: too many blocks");
+  const long long total = (long long)n * p.tiles_x * p.tiles_y;
+  IE_REQUIRE(total < (1ll << 40), "kpn_apply_tc: too many tiles");
+  const int grid = total < sm_count() ? (int)total : sm_count();      // persistent: one CTA per SM
   IE_CUDA(cudaFuncSetAttribute(kpn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  for (int t0 = 0; t0 < T; t0 += kTP) {                   // frames in passes of four; later passes add to out[...,0]
-    p.t0 = t0;
-    p.accumulate = t0 > 0;
-    kpn_tcgen05_kernel<<<(unsigned)(n * strips), kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-    IE_LAUNCH_CHECK();
+  for (int b0 = 0; b0 < B; b0 += 32) {                    // bases in blocks of 32 (one 128-byte K row of TF32)
+    p.b0 = b0;
+    p.nb = B - b0 < 32 ? B - b0 : 32;
+    p.ksteps = (p.nb + 7) / 8;
+    for (int t0 = 0; t0 < T; t0 += kTP) {                 // frames in passes of four
+      p.t0 = t0;
+      p.accf = b0 > 0;                                    // later basis blocks add to everything,
+      p.acc0 = b0 > 0 || t0 > 0;                          // later frame passes to the frame mean out[..., 0]
+      kpn_tcgen05_kernel<<<(unsigned)grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+      IE_LAUNCH_CHECK();
+    }
   }
   return IE_OK;
 }

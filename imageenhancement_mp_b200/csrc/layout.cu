@@ -118,9 +118,9 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
         unpack8(__ldg(q + x_pitch_v), b);
         unpack8(__ldg(q + (long long)wpi * x_pitch_v), c);
         unpack8(__ldg(q + (long long)(wpi + 1) * x_pitch_v), d);
-#pragma unroll
         // statistics only over input rows [stat_y0, stat_y1) (both even): a spatial shard leaves its halo out
         const bool in_stats = (2 * (oy - 1) >= stat_y0) && (2 * (oy - 1) < stat_y1);
+#pragma unroll
         for (int e = 0; e < 8; ++e) {
           m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
           if (in_stats) acc[e] += (a[e] + b[e]) + (c[e] + d[e]);

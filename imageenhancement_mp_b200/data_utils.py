@@ -77,6 +77,8 @@ def invert_preproc(imgs, white_level, _nch=1):
     base, pitch, coff = _nhw_view(imgs)
     n, h, w = imgs.shape
     wl = _wl_vec(white_level, n)
+    if pitch < _nch:
+        raise _lib.ImgEnhError(f"invert_preproc: averaging {_nch} channels needs an NHWC view with pitch >= {_nch} (got {pitch})")
     out = torch.empty(n, h - 2 * LBUFF, w - 2 * LBUFF, dtype=torch.float32, device=imgs.device)
     call("ie_invert_preproc_f32", ptr(base), pitch, coff, _nch, ptr(wl), n, h, w, LBUFF, ptr(out), stream())
     return out
@@ -174,8 +176,9 @@ def psnr_burst0(invert_gt, white_noise, x_batch_burst):
 
 def psnr_average_f(invert_gt, white_noise, x_batch_burst):
     """data_utils.py:155-164: the burst mean is taken inside the invert kernel."""
-    T = x_batch_burst.shape[-1]
-    return psnr_tf_batch(invert_preproc(x_batch_burst[..., 0], white_noise, _nch=T), invert_gt)
+    xb = x_batch_burst.contiguous().float()      # dense NHWC fp32: the kernel reads the T channels of a pixel at pitch T
+    T = xb.shape[-1]
+    return psnr_tf_batch(invert_preproc(xb[..., 0], white_noise, _nch=T), invert_gt)
 
 
 def ssim_map_sums(a, b):

@@ -61,17 +61,24 @@ class Engine:
         if self.K != 15:
             raise ImgEnhError("Kernel_size must be 15: the basis branch emits 15x15 kernels (model_library.py:364)")
         self.device = torch.device(device)
-        # per-pixel filter: "tf32" = tensor-core kernel (operands rounded to a 10-bit mantissa, fp32 accumulation,
-        # |err| <= 2^-10 of the pixel range) where it applies (K=15, B<=128, T<=8), "fp32" = CUDA-core kernel (1e-5),
-        # "tcgen05" = opt-in tcgen05 filter-synthesis kernel (same TF32 rounding; falls back to "tf32" where it does not apply)
-        self.filter_precision = params.get("filter_precision", "tf32")
-        if self.filter_precision not in ("tf32", "fp32", "tcgen05"):
-            raise ImgEnhError("filter_precision must be 'tf32', 'fp32' or 'tcgen05'")
+        # per-pixel filter (model_library.py:439-451).  "auto" (default): the tcgen05 filter-synthesis kernel where it
+        # applies (K = 15, T % 4 == 0), else the mma.sync TF32 kernel (K = 15, B <= 128, T <= 8), else fp32.  Both
+        # tensor-core kernels round burst / basis / coefficients to TF32 (10-bit mantissa) and accumulate in fp32:
+        # |err| <= 2^-10 of the pixel range.  "fp32" = CUDA-core kernel (1e-5 of the fp64 oracle); "tf32" / "tcgen05"
+        # pin one tensor-core kernel (falling back down the same chain where it does not apply).
+        self.filter_precision = params.get("filter_precision", "auto")
+        if self.filter_precision not in ("auto", "tf32", "fp32", "tcgen05"):
+            raise ImgEnhError("filter_precision must be 'auto', 'tcgen05', 'tf32' or 'fp32'")
         self.stride = 2 ** len(self.arch["downs"])          # 8 for Simplemodel, 32 for Basis_kpn
+        if self.device.type != "cuda":
+            raise ImgEnhError("device must be a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.wp, self.bias = {}, {}
-        self.load_weights(weights)
         self._plans = {}
         self._graphs = {}
+        with torch.cuda.device(self.device):
+            self.load_weights(weights)
         # small batches are launch-bound (44 kernels through ctypes, ~1.5 ms of host time vs ~0.3 ms of GPU time for
         # eval.py's default batch of one 32x32 patch): replay a captured CUDA graph below this many pixels
         self.graph_max_pixels = int(params.get("graph_max_pixels", 1 << 17))
@@ -80,6 +87,9 @@ class Engine:
     def load_weights(self, weights):
         """weights: {name: (kernel HWIO, bias)} (CPU or CUDA).  Packs to bf16 [cout_pad, K] on the device."""
         f32_heads = {"coef": IE_EPI_F32_SOFTMAX, "layer3_3": IE_EPI_F32_NHWC}
+        # captured CUDA graphs bake in the packed-weight / bias pointers (and tensor maps built from them): a graph
+        # captured before this call would replay against freed memory
+        self._graphs = {}
         for name, k, cin, cout, _ in self.arch["layers"](self.params):
             w, b = weights[name]
             assert tuple(w.shape) == (k, k, cin, cout), (name, tuple(w.shape), (k, k, cin, cout))
@@ -137,8 +147,14 @@ class Engine:
     def forward_auto(self, x):
         """forward(), through a captured CUDA graph when the input is small enough to be launch-bound."""
         n, hs, ws, _ = x.shape
+        if x.is_cuda and x.device != self.device:
+            raise ImgEnhError(f"input is on {x.device}, the model on {self.device}")
         if n * hs * ws > self.graph_max_pixels or torch.cuda.is_current_stream_capturing():
             return self.forward(x)
+        with torch.cuda.device(self.device):
+            return self._forward_graph(x)
+
+    def _forward_graph(self, x):
         key = (tuple(x.shape), x.device.index)
         ent = self._graphs.get(key)
         if ent is None:
@@ -176,6 +192,12 @@ class Engine:
         """
         if not x.is_cuda:
             raise ImgEnhError("input must be a CUDA tensor (no CPU fallback)")
+        if x.device != self.device:
+            raise ImgEnhError(f"input is on {x.device}, the model on {self.device}")
+        with torch.cuda.device(self.device):      # kernels go to the current stream of the MODEL's device
+            return self._forward(x, taps, conv_fn, shard)
+
+    def _forward(self, x, taps, conv_fn, shard):
         n, hs, ws, c = x.shape
         if c != self.cin:
             raise ImgEnhError(f"expected {self.cin} input channels, got {c}")
@@ -284,9 +306,10 @@ class Engine:
         originbasis = ops.conv2d_f32(cur, W[tail[-1]], Bv[tail[-1]], self.T * self.B, valid=(15, 15), fn=conv_fn)
         bas = ops.softmax_taps(originbasis, self.T, self.B)              # :436-438
         # ---- per-pixel filter (model_library.py:439-451)
-        if self.filter_precision == "tcgen05" and ops.kpn_tcgen05_supported(self.T, self.K, self.B):
-            prec = "tcgen05"                     # opt-in this round: csrc/kpn_tcgen05.cu
-        elif self.filter_precision != "fp32" and ops.kpn_tf32_supported(self.T, self.K, self.B):
+        want = self.filter_precision
+        if want in ("auto", "tcgen05") and ops.kpn_tcgen05_supported(self.T, self.K, self.B):
+            prec = "tcgen05"
+        elif want != "fp32" and ops.kpn_tf32_supported(self.T, self.K, self.B):
             prec = "tf32"
         else:
             prec = "fp32"

@@ -188,11 +188,19 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
             step_results.append(host)
         totals = t.clone() if totals is None else totals.add_(t)
     if totals is None:
-        raise ValueError("evaluate: no validation data on this rank")
+        # this rank's shard of every batch was empty (batch_size < world size, e.g. the reference's default batch of
+        # one under torchrun): it still has to enter the collective - with zeros - or the other ranks block in the
+        # all-reduce until the NCCL timeout.  "No data anywhere" is decided AFTER the exchange, on every rank.
+        n_tot = T + (7 if (ssim and step_totals is None) else 6)
+        zdev = device if step_totals is None else "cpu"
+        totals = torch.zeros(n_tot, dtype=torch.float64, device=zdev)
+        cv_total = torch.zeros(1, dtype=torch.float64, device=zdev)
     if ps:
         totals = torch.cat([totals, cv_total.to(totals.dtype)])
     _dist.all_reduce_totals(totals)                                                # the one exchange step
     host = totals.cpu()                                                            # the one D2H copy
+    if float(host[-2 if ps else -1]) == 0.0:
+        raise ValueError("evaluate: no validation data on any rank")
     if ps:
         report = make_report(host[:-1], nb, T, cost_volume_sum=host[-1], beta_coef=beta_coef)
     else:

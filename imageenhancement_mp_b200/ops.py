@@ -156,8 +156,15 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
         # channels, each launch writing its channel slice of the same NHWC tensor
         if softmax:
             raise _lib.ImgEnhError(f"softmax heads support at most {F32_HEAD_MAX_COUT} channels (got {cout})")
-        for c0 in range(0, cout, F32_HEAD_MAX_COUT):
-            cc = min(F32_HEAD_MAX_COUT, cout - c0)
+        # equal-ish chunks that are multiples of 16: no remainder of <= 16 channels (the fp32 channel-slice epilogue
+        # is built for cout > 16; e.g. T*B = 264 runs as 144 + 120, not 256 + 8)
+        nchunks = -(-cout // F32_HEAD_MAX_COUT)
+        step = -(-(-(-cout // nchunks)) // 16) * 16
+        bounds = [min(i * step, cout) for i in range(nchunks + 1)]
+        if cout - bounds[-2] <= 16 and nchunks > 1:          # last chunk still tiny: borrow 16 channels from its neighbour
+            bounds[-2] -= 16
+        for c0, c1 in zip(bounds[:-1], bounds[1:]):
+            cc = c1 - c0
             d = _desc(src, k, k, cc, relu, epi, None, valid)
             d.y_pitch, d.y_coff = cout, c0
             _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed[c0:]), ptr(bias[c0:]) if bias is not None else None, None,
@@ -225,8 +232,9 @@ def kpn_tf32_supported(T, K, B):
 
 
 def kpn_tcgen05_supported(T, K, B):
-    """ie_kpn_apply_tc (csrc/kpn_tcgen05.cu): filter synthesis as a tcgen05 GEMM + apply in the epilogue.  Opt-in."""
-    return K == 15 and T % 4 == 0 and T >= 4 and B <= 32
+    """ie_kpn_apply_tc (csrc/kpn_tcgen05.cu): filter synthesis as a tcgen05 GEMM + apply in the epilogue; frames in
+    passes of four, bases in blocks of 32 (each further pass / block adds into the output)."""
+    return K == 15 and T % 4 == 0 and T >= 4 and B >= 1
 
 
 def kpn_apply(x, T, coef, bas, out=None, precision="fp32"):
@@ -234,8 +242,8 @@ def kpn_apply(x, T, coef, bas, out=None, precision="fp32"):
 
     precision "fp32": CUDA-core kernel, 1e-5 of the fp64 oracle.  "tf32": tensor-core kernel (burst and basis rounded
     to TF32, fp32 accumulation; K = 15, B <= 128 in chunks of 16, T <= 8), < 1e-3 absolute on [0,1] pixels, ~2.5x faster.
-    "tcgen05" (OPT-IN, see csrc/kpn_tcgen05.cu): the same TF32 rounding, the filter synthesised by a tcgen05 GEMM and
-    applied in its epilogue; K = 15, T % 4 == 0, B <= 32."""
+    "tcgen05" (the models' default where it applies, csrc/kpn_tcgen05.cu): the same TF32 rounding, the filter
+    synthesised by a tcgen05 GEMM and applied in its epilogue; K = 15, T % 4 == 0, any B (blocks of 32)."""
     _lib.require_cuda(x, coef, bas)
     n, h, w, pitch = x.shape
     K, B = bas.shape[1], bas.shape[-1]

@@ -202,12 +202,12 @@ def test_kpn_apply_tf32_tensor_core_variant(cuda, n, h, w, T, B):
         assert float((got1[:, 7:-7, 7:-7, 0] - 1).abs().max()) <= 1e-3
 
 
-@pytest.mark.skipif(os.environ.get("IE_EXPERIMENTAL") != "1",
-                    reason="ie_kpn_apply_tc is opt-in this round: its kernel passed the standalone self-check on a B200 "
-                           "(tools/micro/kpn_tcgen05_v2.cu) but this integration has not run on a GPU yet; "
-                           "IE_EXPERIMENTAL=1 runs the test")
 @pytest.mark.parametrize("n,h,w,T,B,pad", [(2, 16, 24, 4, 10, 0), (1, 40, 72, 8, 10, 0), (3, 104, 104, 4, 10, 0),
-                                           (1, 21, 150, 4, 16, 0), (1, 33, 47, 4, 32, 0), (2, 20, 28, 4, 10, 4)])
+                                           (1, 21, 150, 4, 16, 0), (1, 33, 47, 4, 32, 0), (2, 20, 28, 4, 10, 4),
+                                           # more than 32 bases: blocks of 32 added into the output (Basis_kpn, remote/)
+                                           (1, 24, 40, 4, 33, 0), (2, 40, 24, 8, 50, 0), (1, 64, 64, 8, 90, 0),
+                                           # more images than SMs x tiles per CTA: ranges cross image boundaries
+                                           (300, 8, 16, 4, 10, 0), (5, 50, 70, 4, 10, 0)])
 def test_kpn_apply_tcgen05_variant(cuda, n, h, w, T, B, pad):
     """The tcgen05 filter-synthesis kernel: same contract and the same TF32 bound as the mma.sync variant, incl. a coef
     tensor at the stride-padded extent and a burst pitch that is not T + 1."""
@@ -223,6 +223,10 @@ def test_kpn_apply_tcgen05_variant(cuda, n, h, w, T, B, pad):
     assert float((got[..., 1:].double() - ref[..., 1:]).abs().max()) <= T * bound
     tf32 = ops.kpn_apply(x.to(cuda), T, big.to(cuda), bas.to(cuda), precision="tf32").cpu()
     assert float((got - tf32).abs().max()) <= T * bound
+    # a second call into the same output buffer overwrites, never accumulates across calls
+    out = torch.full_like(got, 7.0).to(cuda)
+    again = ops.kpn_apply(x.to(cuda), T, big.to(cuda), bas.to(cuda), out=out, precision="tcgen05").cpu()
+    assert torch.equal(again, got)
     with pytest.raises(Exception):
         ops.kpn_apply(x[..., :3].contiguous().to(cuda), 3, coef.to(cuda), bas[:, :, :, :3].contiguous().to(cuda),
                       precision="tcgen05")                      # T = 3 is outside its scope

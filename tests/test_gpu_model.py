@@ -60,16 +60,48 @@ def test_small_batches_replay_a_cuda_graph(cuda):
 
 
 def test_filter_precision_switch(cuda):
-    """filter_precision='fp32' routes the per-pixel filter through the CUDA-core kernel; the default (tensor-core
-    TF32 kernel) differs from it by far less than the path's tolerance."""
-    from imageenhancement_mp_b200 import model_library as ml
+    """filter_precision='fp32' routes the per-pixel filter through the CUDA-core kernel; the default (the tcgen05
+    filter-synthesis kernel) and the mma.sync TF32 kernel differ from it by far less than the path's tolerance."""
+    from imageenhancement_mp_b200 import _lib, model_library as ml
     params = dict(synth.DEFAULT_PARAMS)
     W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
     x, _ = synth.make_batch(2, 40, 48, params)
-    out_tf32 = ml.Simplemodel(params, weights=W)(x.to(cuda))[0]
+    before = dict(_lib.LAUNCHES)
+    out_auto = ml.Simplemodel(params, weights=W)(x.to(cuda))[0]
+    assert _lib.LAUNCHES["ie_kpn_apply_tc"] > before.get("ie_kpn_apply_tc", 0)           # the default IS the tcgen05 kernel
+    assert _lib.LAUNCHES["ie_kpn_apply_tf32"] == before.get("ie_kpn_apply_tf32", 0)
+    out_tf32 = ml.Simplemodel(dict(params, filter_precision="tf32"), weights=W)(x.to(cuda))[0]
     out_fp32 = ml.Simplemodel(dict(params, filter_precision="fp32"), weights=W)(x.to(cuda))[0]
-    d = float((out_tf32 - out_fp32).abs().max())
-    assert 0 < d <= 1e-3, d
+    for o in (out_auto, out_tf32):
+        d = float((o - out_fp32).abs().max())
+        assert 0 < d <= 1e-3, d
+    # T = 2 (run_training_val.py:28) is outside the tcgen05 kernel's scope: "auto" falls back to the TF32 kernel
+    p2 = dict(params, BURST_LENGTH=2)
+    W2 = weights.init_weights(weights.simplemodel_layers(p2), scheme="stress")
+    x2, _ = synth.make_batch(1, 32, 32, p2)
+    before = _lib.LAUNCHES["ie_kpn_apply_tf32"]
+    ml.Simplemodel(p2, weights=W2)(x2.to(cuda))
+    assert _lib.LAUNCHES["ie_kpn_apply_tf32"] > before
+
+
+def test_load_weights_invalidates_captured_graphs(cuda):
+    """A small-batch forward replays a captured CUDA graph that bakes in the packed-weight pointers; load_weights()
+    must drop it: forward, load other weights, forward again == a fresh model with those weights."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    Wa = weights.init_weights(weights.simplemodel_layers(params), scheme="stress", seed=1)
+    Wb = weights.init_weights(weights.simplemodel_layers(params), scheme="stress", seed=2)
+    x, _ = synth.make_batch(1, 32, 32, params)
+    m = ml.Simplemodel(params, weights=Wa)
+    first = [t.clone() for t in m(x.to(cuda))]
+    assert len(m._engine._graphs) == 1
+    m.load_weights(Wb)
+    assert len(m._engine._graphs) == 0
+    second = m(x.to(cuda))
+    fresh = ml.Simplemodel(params, weights=Wb)(x.to(cuda))
+    for u, v in zip(second, fresh):
+        assert torch.equal(u, v)
+    assert not torch.equal(first[0], second[0])
 
 
 @pytest.mark.parametrize("scheme", ["glorot", "stress"])

@@ -207,6 +207,45 @@ def test_two_rank_gloo_ps_variance_rides_in_the_all_reduce():
         assert got[rank]["val_psnr"] == pytest.approx(base["val_psnr"], rel=1e-6)
 
 
+def _worker_batch1(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    idist.init_from_env(backend="gloo")
+    batches = make_batches(3, 1, 40, 48)          # the reference's default batch_size = 1 (eval.py:37): rank 1 gets nothing
+    rep = ieval.evaluate(fake_model, batches, dict(synth.DEFAULT_PARAMS), out=None, step_totals=oracle_step_totals)
+    q.put((rank, {k: rep[k] for k in ieval.REPORT_KEYS + ("count",)}))
+    # no data on ANY rank: every rank raises, after the collective
+    try:
+        ieval.evaluate(fake_model, [], dict(synth.DEFAULT_PARAMS), out=None, step_totals=oracle_step_totals)
+        q.put((rank + 10, "no error"))
+    except ValueError as e:
+        q.put((rank + 10, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_batch_of_one_does_not_hang():
+    """with batch_size 1 and two ranks, rank 1's shard of every batch is empty.  It must still enter the
+    all-reduce (with zeros) instead of raising before it, and both ranks report the single-process numbers."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_batch1, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(4))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = reference_report(make_batches(3, 1, 40, 48))
+    for rank in (0, 1):
+        assert got[rank]["count"] == 3
+        for k in ieval.REPORT_KEYS:
+            assert got[rank][k] == pytest.approx(ref[k], rel=1e-6, abs=1e-6), (rank, k)
+        assert "no validation data on any rank" in got[rank + 10]
+
+
 def test_two_rank_gloo_evaluate_equals_single_process():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
