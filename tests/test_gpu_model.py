@@ -219,11 +219,17 @@ def test_zero_weights_known_answer(cuda):
     params = dict(synth.DEFAULT_PARAMS)
     W = weights.init_weights(weights.simplemodel_layers(params), scheme="zeros")
     x, _ = synth.make_batch(2, 32, 40, params)
-    out, bas, ob = ml.Simplemodel(params, weights=W)(x.to(cuda))
     b = x[..., :4].permute(0, 3, 1, 2)
     box = F.avg_pool2d(F.pad(b, (7, 7, 7, 7)), 15, 1).permute(0, 2, 3, 1)
+    # exact with the fp32 filter; the default tensor-core filter rounds Coef = 0.1 and Bas = 1/900 to TF32
+    # (relative 2.4e-4 and 7e-5): within its stated bound of 2^-10 of the pixel range
+    out, bas, ob = ml.Simplemodel(dict(params, filter_precision="fp32"), weights=W)(x.to(cuda))
     assert torch.allclose(out.cpu()[..., 1:], box, atol=1e-5)
     assert torch.allclose(out.cpu()[..., 0], box.mean(-1), atol=1e-5)
+    out_tc = ml.Simplemodel(params, weights=W)(x.to(cuda))[0]
+    bound = 2.0 ** -10 * float(x[..., :4].abs().max())
+    assert float((out_tc.cpu()[..., 0] - box.mean(-1)).abs().max()) <= bound
+    assert float((out_tc.cpu()[..., 1:] - box).abs().max()) <= bound
     assert torch.allclose(bas.cpu(), torch.full_like(bas.cpu(), 1 / 900.0), rtol=1e-5)
     assert float(ob.abs().max()) == 0.0
 
@@ -275,6 +281,33 @@ def test_full_size_batch_is_image_independent(cuda):
     xc[..., :4] = 0.5
     oc = model(xc)[0]
     assert float((oc[:, 7:-7, 7:-7, 0] - 0.5).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("scheme", ["glorot", "stress"])
+def test_full_size_batch_against_the_oracle(cuda, scheme):
+    """BASELINE configs[1] at its real size: batch 256 of 100x100 through the CUDA path in ONE call; five images spread
+    over the batch (first, last, and three that sit in different CTAs' tile ranges) against the CPU oracle run on each
+    image alone, with the path's tolerances; plus the eval metrics of those five images."""
+    from imageenhancement_mp_b200 import data_utils as du, model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme=scheme)
+    model = ml.Simplemodel(params, weights=W)
+    x, truth = synth.make_batch(256, 100, 100, params, seed=4321)
+    out, bas, ob = model(x.to(cuda))
+    torch.cuda.synchronize()
+    pick = [0, 63, 128, 201, 255]
+    xs, ts = x[pick], truth[pick]
+    xp, _ = synth.pad_to_multiple(xs, 8)
+    out_o, bas_o, ob_o = oracle.simplemodel_forward(W, params, xp)
+    out_o = out_o[:, :100, :100]
+    og, bg, obg = out[pick].cpu(), bas[pick].cpu(), ob[pick].cpu()
+    assert float((og - out_o).abs().max()) <= OUT_TOL
+    assert rel_l2(bg, bas_o) <= REL_L2_TOL and rel_l2(obg, ob_o) <= REL_L2_TOL
+    ref = oracle.eval_step(out_o, xs, ts, 4)
+    got = du.eval_metrics(out[pick].contiguous(), xs.to(cuda), ts.to(cuda), 4)
+    assert abs(got["psnr"] - ref["psnr"]) <= PSNR_TOL
+    for t in range(4):
+        assert abs(got["psnr_perlayer"][t] - ref["psnr_perlayer"][t]) <= PSNR_TOL
 
 
 @pytest.mark.parametrize("H,W_,world", [(256, 96, 2), (320, 64, 3)])
