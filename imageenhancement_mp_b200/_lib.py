@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libimgenh_b200.so")
 
 IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX = 0, 1, 2
+IE_LAYOUT_X_DENSE, IE_LAYOUT_Y_DENSE = 1, 2
 
 
 class ImgEnhError(RuntimeError):
@@ -26,7 +27,7 @@ class ConvDesc(C.Structure):
     """struct ie_conv_desc (include/imgenh_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "n_img", "h", "w", "hv", "wv", "kh", "kw", "cin", "x_pitch", "x_coff",
-        "cout", "y_pitch", "y_coff", "relu", "epilogue")]
+        "cout", "y_pitch", "y_coff", "relu", "epilogue", "dense")]
 
 
 _P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -41,11 +42,11 @@ SIGNATURES = {
     "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
     "ie_conv_set_mode": [_I, _I],
     "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
-    "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _P],
-    "ie_upsample_bilinear_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
-    "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _LL, _P],
-    "ie_broadcast_hw_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
-    "ie_raster_to_nhwc_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _I, _P],
+    "ie_upsample_bilinear_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],
+    "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _LL, _I, _P],
+    "ie_broadcast_hw_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
+    "ie_raster_to_nhwc_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "ie_softmax_taps_f32": [_P, _I, _I, _I, _P, _P],
     "ie_cost_volume_f32": [_P, _I, _I, _I, _I, _P, _P, _P],
     "ie_kpn_apply_f32": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],

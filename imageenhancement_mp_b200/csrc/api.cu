@@ -63,6 +63,48 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_
   return IE_OK;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  });
+  return fn;
+}
+
+// Rank-4 bf16 NHWC tensor [n][h][w][pitch_elems] in TMA im2col mode for a (2*pad+1)^2 'same' convolution: the pixel
+// box runs from -pad to (size - 1 - pad) in W and H (lower corner -pad, upper corner -pad), so a load of
+// `pixels` consecutive output pixels starting at base coordinates (x0 - pad, y0 - pad, n0) with offsets (j, i) fetches
+// tap (i, j) of each of them, wrapping rows and images and zero-filling everything outside the image (measured on
+// B200: tools/micro/tma_im2col.cu).  64 channels per pixel (one 128-byte swizzle row).
+int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, uint64_t pitch_elems, int pad,
+                          uint32_t pixels) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col is not available from this driver");
+  IE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p is not 16-byte aligned", base);
+  IE_REQUIRE((pitch_elems * 2) % 16 == 0 && pitch_elems >= 64, "tensor map: bad pixel pitch %llu", (unsigned long long)pitch_elems);
+  IE_REQUIRE(pixels >= 1 && pixels <= 1024 && pad >= 0 && pad <= 64, "tensor map: bad im2col box (%u pixels, pad %d)", pixels, pad);
+  cuuint64_t gdim[4] = {pitch_elems, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstride[3] = {pitch_elems * 2, (cuuint64_t)w * pitch_elems * 2, (cuuint64_t)h * w * pitch_elems * 2};
+  int lo[2] = {-pad, -pad}, hi[2] = {-pad, -pad};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, lo, hi, 64, pixels, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed with CUresult %d (n %d h %d w %d pitch %llu pad %d)", (int)r, n,
+             h, w, (unsigned long long)pitch_elems, pad);
+  return IE_OK;
+}
+
 }  // namespace ie
 
 extern "C" int ie_version(void) { return IE_VERSION; }

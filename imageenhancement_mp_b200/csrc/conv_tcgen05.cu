@@ -66,6 +66,7 @@ struct EpiParams {
   float* y_f32;       // already advanced by the output slice's first channel
   float* y_aux;
   int f32_pitch;      // floats per pixel of y_f32 / y_aux (= cout unless the caller writes a channel slice)
+  int dense;          // x / y are dense NHWC (R = n*h*w rows, no border rows to mask)
 };
 
 // Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
@@ -143,7 +144,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
     const int pr = r - img * p.plane;
     const int y = pr / p.wp;
     const int x = pr - y * p.wp;
-    const bool valid = (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
+    const bool valid = p.dense ? (r < p.R) : ((r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv));
 
     mbar_wait(&tfull_bar[buf], use & 1u);
     tc_fence_after();
@@ -329,8 +330,12 @@ struct StreamParams {
   int cin;
   int stages;
   int b_stage_bytes;     // n_tile*128 rounded up to 1024
+  // dense NHWC input (IM2COL): image size, filter width and zero padding - tap t is offset (t % kw, t / kw) of the
+  // im2col tensor map, a tile is 128 consecutive pixels of the [n][h][w] index space
+  int img_h, img_w, kw, pad;
 };
 
+template <bool IM2COL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_y, const StreamParams p) {
@@ -362,13 +367,26 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int n_idx = tile - m_tile * p.e.n_tiles;
         const int r0 = m_tile * kBlockM;
         const int n0 = n_idx * p.e.n_tile;
+        int px0 = 0, py0 = 0, pn0 = 0;                    // IM2COL: first pixel of the tile in the pixel-box frame
+        if constexpr (IM2COL) {
+          const int plane = p.img_h * p.img_w;
+          pn0 = r0 / plane;
+          const int rem = r0 - pn0 * plane;
+          py0 = rem / p.img_w;
+          px0 = rem - py0 * p.img_w - p.pad;
+          py0 -= p.pad;
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int row = r0 + p.tap_shift[tap];
+          const int ti = tap / p.kw, tj = tap - ti * p.kw;
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             uint8_t* a_dst = base + stage * stage_bytes;
-            tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row);
+            if constexpr (IM2COL)
+              tma_load_im2col_4d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, px0, py0, pn0, tj, ti);
+            else
+              tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row);
             tma_load_2d(a_dst + kABytes, &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
@@ -1207,6 +1225,12 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
   IE_REQUIRE((long long)d->n_img * (d->h + 1) * (d->w + 1) < (1ll << 31) - 4096, "conv: raster too large for 32-bit rows");
   IE_REQUIRE((d->kh == 3 && d->kw == 3) || (d->kh == 2 && d->kw == 2) || (d->kh == 1 && d->kw == 1),
              "conv: unsupported kernel size %dx%d", d->kh, d->kw);
+  IE_REQUIRE(d->dense == 0 || d->dense == 1, "conv: dense must be 0 or 1 (got %d)", d->dense);
+  if (d->dense) {
+    IE_REQUIRE(d->kh != 2 && d->epilogue == IE_EPI_BF16_RASTER && d->hv == d->h && d->wv == d->w,
+               "conv: dense NHWC tensors support 3x3 'same' and 1x1 convolutions with the bf16 epilogue only");
+    IE_REQUIRE(d->h <= 32768 && d->w <= 32768, "conv: dense image too large for im2col coordinates");
+  }
   if (d->epilogue == IE_EPI_BF16_RASTER) {
     IE_REQUIRE(y_bf16, "conv: y_bf16 is null");
     IE_REQUIRE(d->cout % 64 == 0, "conv: bf16 raster epilogue needs cout %% 64 == 0 (got %d)", d->cout);
@@ -1250,9 +1274,10 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   using namespace ie;
   int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32);
   if (rc) return rc;
-  const long long R = (long long)d->n_img * (d->h + 1) * (d->w + 1);
+  const long long R = d->dense ? (long long)d->n_img * d->h * d->w : (long long)d->n_img * (d->h + 1) * (d->w + 1);
   const int wp = d->w + 1;
   EpiParams e{};
+  e.dense = d->dense;
   e.R = (int)R;
   e.plane = (d->h + 1) * wp;
   e.wp = wp;
@@ -1303,10 +1328,10 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   a_slot *= fuse_rows;
   const int res_stages = res_room > 0 ? res_room / a_slot : 0;
   bool resident = e.n_tiles == 1 && e.n_tile <= 64 && b_res_bytes <= 160 * 1024 && res_stages >= (fuse_rows == 3 ? 2 : 3);
-  if (g_force_mode == 0) resident = false;
+  if (g_force_mode == 0 || d->dense) resident = false;          // dense tensors: the streaming kernel with im2col loads
   if (g_force_mode == 1)
-    IE_REQUIRE(e.n_tiles == 1 && b_res_bytes <= 200 * 1024 && res_stages >= 2,
-               "conv: resident mode forced but the weights do not fit");
+    IE_REQUIRE(e.n_tiles == 1 && b_res_bytes <= 200 * 1024 && res_stages >= 2 && !d->dense,
+               "conv: resident mode forced but the weights do not fit (or the tensors are dense)");
   if (g_force_mode == 1) resident = true;
 
   const int grid_cap = sm_count();
@@ -1319,9 +1344,9 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   //   cin 640: streaming N = 64 870, wide-N 417 (weights streamed with the A tiles)
   // small fp32 heads (cout <= 16): three 16-column groups, N = 48 - a third of the A reads of the N = 16 resident path
   const bool wide_f32 = d->kh == 3 && d->kw == 3 && d->epilogue != IE_EPI_BF16_RASTER && d->cout <= 16 && d->cin <= 128;
-  bool wide = wide_ok || wide_f32;
+  bool wide = (wide_ok || wide_f32) && !d->dense;
   if (g_force_mode == 0 || g_force_mode == 1) wide = false;
-  if (g_force_mode == 2) wide = wide_ok || wide_f32;
+  if (g_force_mode == 2) wide = (wide_ok || wide_f32) && !d->dense;
   if (g_force_mode == 2) IE_REQUIRE(wide, "conv: wide-N mode forced on an unsupported layer");
   if (wide) {
     WideParams p{};
@@ -1436,14 +1461,25 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   p.b_stage_bytes = ((e.n_tile * 128 + 1023) / 1024) * 1024;
   int stages = (int)((kMaxSmem - 1024 - kTailBytes) / (kABytes + p.b_stage_bytes));
   p.stages = stages > kMaxStages ? kMaxStages : stages;
-  rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
-  if (rc) return rc;
-  if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
+  p.img_h = d->h;
+  p.img_w = d->w;
+  p.kw = d->kw;
+  p.pad = d->kh / 2;
   const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + kTailBytes;
-  IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   const int tiles = e.m_tiles * e.n_tiles;
   const int grid = tiles < grid_cap ? tiles : grid_cap;
-  conv_stream_kernel<<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
+  if (d->dense) {
+    rc = make_tmap_im2col_bf16(&tm_a, x, d->n_img, d->h, d->w, (uint64_t)d->x_pitch, p.pad, kBlockM);
+    if (rc) return rc;
+    IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    conv_stream_kernel<true><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
+  } else {
+    rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
+    if (rc) return rc;
+    if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
+    IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    conv_stream_kernel<false><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
+  }
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

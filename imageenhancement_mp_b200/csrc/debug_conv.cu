@@ -15,30 +15,40 @@ int choose_n_tile(int cout, int epilogue);
 
 struct NaiveParams {
   long long R;
-  int plane, wp, hv, wv, ntaps, cin, x_pitch, x_coff, cout, y_pitch, y_coff, relu, epilogue;
-  int tap_shift[9];
+  int h, w, b;          // image size and border (1 = shared-border raster, 0 = dense NHWC)
+  int hv, wv, kh, kw, pad, cin, x_pitch, x_coff, cout, y_pitch, y_coff, relu, epilogue;
 };
 
+// row of pixel (img, y, x) in either layout
+__device__ __forceinline__ long long naive_row(const NaiveParams& p, int img, int y, int x) {
+  return ((long long)img * (p.h + p.b) + y + p.b) * (p.w + p.b) + x;
+}
+
+// plain definition of the convolution: taps outside the image contribute nothing (zero padding)
 __device__ float naive_dot(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                           const NaiveParams& p, long long r, int co) {
+                           const NaiveParams& p, int img, int y, int xx, int co) {
   float acc = 0.f;
-  const int ktot = p.ntaps * p.cin;
-  for (int tap = 0; tap < p.ntaps; ++tap) {
-    const long long rr = r + p.tap_shift[tap];
-    if (rr < 0 || rr >= p.R) continue;
-    const __nv_bfloat16* xp = x + rr * p.x_pitch + p.x_coff;
-    const __nv_bfloat16* wp = w + (long long)co * ktot + tap * p.cin;
-    for (int c = 0; c < p.cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+  const int ktot = p.kh * p.kw * p.cin;
+  for (int i = 0; i < p.kh; ++i) {
+    for (int j = 0; j < p.kw; ++j) {
+      const int sy = y + i - p.pad, sx = xx + j - p.pad;
+      if (sy < 0 || sy >= p.h || sx < 0 || sx >= p.w) continue;
+      const __nv_bfloat16* xp = x + naive_row(p, img, sy, sx) * p.x_pitch + p.x_coff;
+      const __nv_bfloat16* wp = w + (long long)co * ktot + (i * p.kw + j) * p.cin;
+      for (int c = 0; c < p.cin; ++c) acc = fmaf(__bfloat162float(xp[c]), __bfloat162float(wp[c]), acc);
+    }
   }
   return acc;
 }
 
+// row r -> pixel; false for border rows (raster) and for pixels outside the valid output extent
 __device__ bool naive_valid(const NaiveParams& p, long long r, int& img, int& y, int& x) {
-  img = (int)(r / p.plane);
-  const int pr = (int)(r - (long long)img * p.plane);
-  y = pr / p.wp;
-  x = pr - y * p.wp;
-  return y >= 1 && y <= p.hv && x < p.wv;
+  const int wp = p.w + p.b, plane = (p.h + p.b) * wp;
+  img = (int)(r / plane);
+  const int pr = (int)(r - (long long)img * plane);
+  y = pr / wp - p.b;
+  x = pr - (y + p.b) * wp;
+  return y >= 0 && y < p.hv && x < p.wv;
 }
 
 __global__ void naive_conv_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
@@ -50,7 +60,7 @@ __global__ void naive_conv_bf16_kernel(const __nv_bfloat16* __restrict__ x, cons
   int img, yy, xx;
   float v = 0.f;
   if (naive_valid(p, r, img, yy, xx)) {
-    v = naive_dot(x, w, p, r, co) + (bias ? bias[co] : 0.f);
+    v = naive_dot(x, w, p, img, yy, xx, co) + (bias ? bias[co] : 0.f);
     if (p.relu) v = fmaxf(v, 0.f);
   }
   y[r * p.y_pitch + p.y_coff + co] = __float2bfloat16_rn(v);
@@ -63,11 +73,11 @@ __global__ void naive_conv_f32_kernel(const __nv_bfloat16* __restrict__ x, const
   if (r >= p.R) return;
   int img, yy, xx;
   if (!naive_valid(p, r, img, yy, xx)) return;
-  const long long pix = ((long long)img * p.hv + (yy - 1)) * p.wv + xx;
+  const long long pix = ((long long)img * p.hv + yy) * p.wv + xx;
   float v[256];
   float mx = -INFINITY;
   for (int co = 0; co < p.cout; ++co) {
-    float a = naive_dot(x, w, p, r, co) + (bias ? bias[co] : 0.f);
+    float a = naive_dot(x, w, p, img, yy, xx, co) + (bias ? bias[co] : 0.f);
     if (p.relu) a = fmaxf(a, 0.f);
     v[co] = a;
     mx = fmaxf(mx, a);
@@ -94,23 +104,12 @@ extern "C" int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const
   using namespace ie;
   if (int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32)) return rc;
   NaiveParams p{};
-  const int wp = d->w + 1;
-  if (d->kh == 3 && d->kw == 3) {
-    p.ntaps = 9;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) p.tap_shift[i * 3 + j] = (i - 1) * wp + (j - 1);
-  } else if (d->kh == 2 && d->kw == 2) {
-    p.ntaps = 4;
-    for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 2; ++j) p.tap_shift[i * 2 + j] = i * wp + j;
-  } else if (d->kh == 1 && d->kw == 1) {
-    p.ntaps = 1;
-  } else {
-    IE_REQUIRE(false, "debug conv: unsupported kernel size");
-  }
-  p.R = (long long)d->n_img * (d->h + 1) * wp;
-  p.plane = (d->h + 1) * wp;
-  p.wp = wp;
+  IE_REQUIRE((d->kh == 3 && d->kw == 3) || (d->kh == 2 && d->kw == 2) || (d->kh == 1 && d->kw == 1),
+             "debug conv: unsupported kernel size");
+  p.kh = d->kh; p.kw = d->kw;
+  p.pad = d->kh == 3 ? 1 : 0;                     // 3x3 'same' centred; 2x2 'valid' taps at +0/+1; 1x1
+  p.h = d->h; p.w = d->w; p.b = d->dense ? 0 : 1;
+  p.R = (long long)d->n_img * (d->h + p.b) * (d->w + p.b);
   p.hv = d->hv; p.wv = d->wv;
   p.cin = d->cin; p.x_pitch = d->x_pitch; p.x_coff = d->x_coff;
   p.cout = d->cout; p.y_pitch = d->y_pitch; p.y_coff = d->y_coff;

@@ -19,6 +19,10 @@ int sm_count();
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
                       uint32_t box_cols, uint32_t box_rows);
 
+// rank-4 bf16 NHWC tensor in TMA im2col mode ('same' convolution with `pad` zero pixels); see api.cu
+int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, uint64_t pitch_elems, int pad,
+                          uint32_t pixels);
+
 }  // namespace ie
 
 #define IE_REQUIRE(cond, ...)        \

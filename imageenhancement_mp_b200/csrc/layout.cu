@@ -95,23 +95,24 @@ constexpr int kPoolRows = 2;           // padded output rows per block
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, int x_pitch_v, int x_coff_v,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale,
-                int stat_y0, int stat_y1) {
-  const int ho = h >> 1, wo = w >> 1, wpo = wo + 1, wpi = w + 1;
+                int stat_y0, int stat_y1, int bi, int bo) {
+  // bi / bo: border of the input / output tensor (1 = shared-border raster, 0 = dense NHWC)
+  const int ho = h >> 1, wo = w >> 1, wpo = wo + bo, wpi = w + bi;
   const int cl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
   const int cv = blockIdx.x * cvb + cl;
   const int img = blockIdx.z;
   const int oy0 = blockIdx.y * kPoolRows;
-  const int rows = min(kPoolRows, ho + 1 - oy0);
+  const int rows = min(kPoolRows, ho + bo - oy0);
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (cv < cvec) {
     for (int p = pl; p < rows * wpo; p += npl) {
       const int ry = p / wpo, ox = p - ry * wpo;
-      const int oy = oy0 + ry;
+      const int oyp = oy0 + ry, oy = oyp - bo;              // row of the (padded) output / of the output image
       uint4 res = make_uint4(0, 0, 0, 0);
-      if (oy >= 1 && ox < wo) {
-        const long long rin = ((long long)img * (h + 1) + (2 * oy - 1)) * wpi + 2 * ox;
+      if (oy >= 0 && ox < wo) {
+        const long long rin = ((long long)img * (h + bi) + (2 * oy + bi)) * wpi + 2 * ox;
         const uint4* q = x + rin * x_pitch_v + x_coff_v + cv;
         float a[8], b[8], c[8], d[8], m[8];
         unpack8(__ldg(q), a);
@@ -119,7 +120,7 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
         unpack8(__ldg(q + (long long)wpi * x_pitch_v), c);
         unpack8(__ldg(q + (long long)(wpi + 1) * x_pitch_v), d);
         // statistics only over input rows [stat_y0, stat_y1) (both even): a spatial shard leaves its halo out
-        const bool in_stats = (2 * (oy - 1) >= stat_y0) && (2 * (oy - 1) < stat_y1);
+        const bool in_stats = (2 * oy >= stat_y0) && (2 * oy < stat_y1);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           m[e] = fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e]));
@@ -127,7 +128,7 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
         }
         res = pack8(m);
       }
-      const long long ro = ((long long)img * (ho + 1) + oy) * wpo + ox;
+      const long long ro = ((long long)img * (ho + bo) + oyp) * wpo + ox;
       y[ro * y_pitch_v + y_coff_v + cv] = res;
     }
   }
@@ -152,13 +153,13 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
 // grid = (ceil((wo+1)*cvec / 256), ho+1, n): the vertical taps / weights are block-uniform.
 __global__ void __launch_bounds__(256)
 upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v, int s,
-                uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const int ho = h * s, wo = w * s, wpo = wo + 1;
+                uint4* __restrict__ y, int y_pitch_v, int y_coff_v, int bi, int bo) {
+  const int ho = h * s, wo = w * s, wpo = wo + bo;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wpo * cvec) return;
   const int oxp = idx / cvec, cv = idx - oxp * cvec;
   const int oyp = blockIdx.y, img = blockIdx.z;
-  const int oy = oyp - 1, ox = oxp;
+  const int oy = oyp - bo, ox = oxp;
   uint4 res = make_uint4(0, 0, 0, 0);
   if (oy >= 0 && oy < ho && ox >= 0 && ox < wo) {
     const float inv = 1.f / (float)s;
@@ -168,14 +169,14 @@ upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
     const int y0 = max((int)fy, 0), y1 = min((int)ceilf(sy), h - 1);
     const int x0 = max((int)fx, 0), x1 = min((int)ceilf(sx), w - 1);
     const float ly = sy - fy, lx = sx - fx;
-    const int wpi = w + 1;
-    const long long base = (long long)img * (h + 1) * wpi;
+    const int wpi = w + bi;
+    const long long base = (long long)img * (h + bi) * wpi;
     const uint4* p = x + x_coff_v + cv;
     float a[8], b[8], c[8], d[8], o[8];
-    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x0) * x_pitch_v), a);
-    unpack8(__ldg(p + (base + (long long)(y0 + 1) * wpi + x1) * x_pitch_v), b);
-    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x0) * x_pitch_v), c);
-    unpack8(__ldg(p + (base + (long long)(y1 + 1) * wpi + x1) * x_pitch_v), d);
+    unpack8(__ldg(p + (base + (long long)(y0 + bi) * wpi + x0) * x_pitch_v), a);
+    unpack8(__ldg(p + (base + (long long)(y0 + bi) * wpi + x1) * x_pitch_v), b);
+    unpack8(__ldg(p + (base + (long long)(y1 + bi) * wpi + x0) * x_pitch_v), c);
+    unpack8(__ldg(p + (base + (long long)(y1 + bi) * wpi + x1) * x_pitch_v), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float top = a[e] + (b[e] - a[e]) * lx;
@@ -184,7 +185,7 @@ upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch
     }
     res = pack8(o);
   }
-  const long long ro = ((long long)img * (ho + 1) + oyp) * wpo + oxp;
+  const long long ro = ((long long)img * (ho + bo) + oyp) * wpo + oxp;
   y[ro * y_pitch_v + y_coff_v + cv] = res;
 }
 
@@ -206,29 +207,29 @@ __device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 l) {
 
 __global__ void __launch_bounds__(256)
 upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
-                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
+                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, int bi, int bo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (w + 1) * cvec) return;
   const int jb = idx / cvec, cv = idx - jb * cvec;
   const int j = jb - 1, i = (int)blockIdx.y - 1, img = blockIdx.z;
   const int y0 = max(i, 0), y1 = min(i + 1, h - 1), x0 = max(j, 0), x1 = min(j + 1, w - 1);
-  const int wpi = w + 1;
-  const long long base = (long long)img * (h + 1) * wpi;
+  const int wpi = w + bi;
+  const long long base = (long long)img * (h + bi) * wpi;
   const uint4* p = x + x_coff_v + cv;
   float2 a[4], b[4], c[4], d[4];
-  unpack8_pairs(__ldg(p + (base + (long long)(y0 + 1) * wpi + x0) * x_pitch_v), a);
-  unpack8_pairs(__ldg(p + (base + (long long)(y0 + 1) * wpi + x1) * x_pitch_v), b);
-  unpack8_pairs(__ldg(p + (base + (long long)(y1 + 1) * wpi + x0) * x_pitch_v), c);
-  unpack8_pairs(__ldg(p + (base + (long long)(y1 + 1) * wpi + x1) * x_pitch_v), d);
-  const int wo = 2 * w, ho = 2 * h, wpo = wo + 1;
-  // output pixel (oy, ox) = (2i+1+u, 2j+1+v), u, v in {0,1}; raster position (oy + 1, ox): oy = -1 is the
-  // shared zero row, ox = wo the shared zero column; oy = ho and ox = -1 have no slot
-  const long long ro = ((long long)img * (ho + 1) + (2 * i + 2)) * wpo + (2 * j + 1);
+  unpack8_pairs(__ldg(p + (base + (long long)(y0 + bi) * wpi + x0) * x_pitch_v), a);
+  unpack8_pairs(__ldg(p + (base + (long long)(y0 + bi) * wpi + x1) * x_pitch_v), b);
+  unpack8_pairs(__ldg(p + (base + (long long)(y1 + bi) * wpi + x0) * x_pitch_v), c);
+  unpack8_pairs(__ldg(p + (base + (long long)(y1 + bi) * wpi + x1) * x_pitch_v), d);
+  const int wo = 2 * w, ho = 2 * h, wpo = wo + bo;
+  // output pixel (oy, ox) = (2i+1+u, 2j+1+v), u, v in {0,1}.  Raster output (bo = 1): position (oy + 1, ox); oy = -1
+  // is the shared zero row, ox = wo the shared zero column (both written as zeros); oy = ho and ox = -1 have no
+  // slot.  Dense output (bo = 0): only the pixels inside the image exist.
   uint4* q = y + y_coff_v + cv;
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
     const int ox = 2 * j + 1 + v;
-    if (ox < 0) continue;                                   // left of the raster
+    if (ox < 0) continue;                                   // left of the tensor
     const float lxs = v ? 0.75f : 0.25f;
     const float2 lx = make_float2(lxs, lxs);
     float2 top[4], bot[4];
@@ -240,9 +241,11 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int oy = 2 * i + 1 + u;
-      if (oy >= ho) continue;                               // below the raster
+      if (oy >= ho) continue;                               // below the tensor
+      const bool inside = oy >= 0 && ox < wo;
+      if (!inside && bo == 0) continue;                     // a dense tensor has no border entries
       uint4 res = make_uint4(0, 0, 0, 0);
-      if (oy >= 0 && ox < wo) {
+      if (inside) {
         const float lys = u ? 0.75f : 0.25f;
         const float2 ly = make_float2(lys, lys);
         float2 o[4];
@@ -251,7 +254,7 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
         res = make_uint4(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y), pack_bf16x2(o[2].x, o[2].y),
                          pack_bf16x2(o[3].x, o[3].y));
       }
-      q[(ro + (long long)u * wpo + v) * y_pitch_v] = res;
+      q[(((long long)img * (ho + bo) + (oy + bo)) * wpo + ox) * y_pitch_v] = res;
     }
   }
 }
@@ -259,11 +262,11 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
 // ------------------------------------------------------------------------------- channel means
 // block = 256 threads = 32 pixel lanes x 8 vector lanes (64 channels); grid = (c/64, n, splits).
 __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, int x_pitch_v, int x_coff_v,
-                                    float* __restrict__ mean, int c, float scale, int y0, int y1) {
+                                    float* __restrict__ mean, int c, float scale, int y0, int y1, int bi) {
   const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int cb = blockIdx.x, img = blockIdx.y;
-  const int wp = w + 1;
-  const long long base = (long long)img * (h + 1) * wp;
+  const int wp = w + bi;
+  const long long base = (long long)img * (h + bi) * wp;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -271,7 +274,7 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
   for (int pix = blockIdx.z * 32 + pl; pix < npix; pix += gridDim.z * 32) {
     const int yr = pix / w, xx = pix - yr * w, yy = y0 + yr;
     float f[8];
-    unpack8(x[(base + (long long)(yy + 1) * wp + xx) * x_pitch_v + x_coff_v + cb * 8 + vl], f);
+    unpack8(x[(base + (long long)(yy + bi) * wp + xx) * x_pitch_v + x_coff_v + cb * 8 + vl], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += f[e];
   }
@@ -288,18 +291,18 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
 }
 
 __global__ void broadcast_kernel(const float* __restrict__ vec, int n, int kh, int kw, int cvec, int c,
-                                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v) {
-  const long long total = (long long)n * (kh + 1) * (kw + 1) * cvec;
+                                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, int bo) {
+  const long long total = (long long)n * (kh + bo) * (kw + bo) * cvec;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int cv = (int)(t % cvec);
   const long long ro = t / cvec;
-  const int wp = kw + 1, pl = (kh + 1) * wp;
+  const int wp = kw + bo, pl = (kh + bo) * wp;
   const int img = (int)(ro / pl);
   const int pr = (int)(ro - (long long)img * pl);
   const int oy = pr / wp, ox = pr % wp;
   uint4 res = make_uint4(0, 0, 0, 0);
-  if (oy >= 1 && oy <= kh && ox < kw) {
+  if (oy >= bo && oy < kh + bo && ox < kw) {
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = vec[(long long)img * c + cv * 8 + e];
@@ -309,7 +312,7 @@ __global__ void broadcast_kernel(const float* __restrict__ vec, int n, int kh, i
 }
 
 __global__ void raster_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int x_pitch,
-                                      int x_coff, float* __restrict__ y) {
+                                      int x_coff, float* __restrict__ y, int bi) {
   const long long total = (long long)n * h * w * c;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -318,7 +321,7 @@ __global__ void raster_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int n
   const int xx = (int)(pix % w);
   const int yy = (int)((pix / w) % h);
   const int img = (int)(pix / ((long long)w * h));
-  const long long r = ((long long)img * (h + 1) + yy + 1) * (w + 1) + xx;
+  const long long r = ((long long)img * (h + bi) + yy + bi) * (w + bi) + xx;
   y[t] = __bfloat162float(x[r * x_pitch + x_coff + ch]);
 }
 
@@ -488,13 +491,15 @@ static int check_slice(const char* who, int c, int pitch, int coff) {
 
 extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y,
                                      int y_pitch, int y_coff, float* chan_mean, int stat_y0, int stat_y1,
-                                     long long stat_count, void* stream) {
+                                     long long stat_count, int layout, void* stream) {
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "maxpool2: bad arguments (h %d, w %d)", h, w);
+  IE_REQUIRE(layout >= 0 && layout <= 3, "maxpool2: bad layout flags %d", layout);
+  const int bi = (layout & IE_LAYOUT_X_DENSE) ? 0 : 1, bo = (layout & IE_LAYOUT_Y_DENSE) ? 0 : 1;
   if (int rc = check_slice("maxpool2(x)", c, x_pitch, x_coff)) return rc;
   if (int rc = check_slice("maxpool2(y)", c, y_pitch, y_coff)) return rc;
   const int cvec = c / 8;
   const int cvb = cvec < 32 ? cvec : 32;
-  const int row_groups = (h / 2 + 1 + kPoolRows - 1) / kPoolRows;
+  const int row_groups = (h / 2 + bo + kPoolRows - 1) / kPoolRows;
   IE_REQUIRE(n <= 65535 && row_groups <= 65535, "maxpool2: grid too large");
   if (chan_mean) IE_CUDA(cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
   dim3 grid(ie_ceil_div(cvec, cvb), row_groups, n);
@@ -505,14 +510,16 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
              "maxpool2: bad statistics row range [%d, %d)", stat_y0, stat_y1);
   maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, cvec, cvb, x_pitch / 8, x_coff / 8,
                                                   static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, chan_mean,
-                                                  1.f / (float)stat_count, stat_y0, stat_y1);
+                                                  1.f / (float)stat_count, stat_y0, stat_y1, bi, bo);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
 
 extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff,
-                                              int scale, void* y, int y_pitch, int y_coff, void* stream) {
+                                              int scale, void* y, int y_pitch, int y_coff, int layout, void* stream) {
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && scale >= 1, "upsample: bad arguments");
+  IE_REQUIRE(layout >= 0 && layout <= 3, "upsample: bad layout flags %d", layout);
+  const int bi = (layout & IE_LAYOUT_X_DENSE) ? 0 : 1, bo = (layout & IE_LAYOUT_Y_DENSE) ? 0 : 1;
   if (int rc = check_slice("upsample(x)", c, x_pitch, x_coff)) return rc;
   if (int rc = check_slice("upsample(y)", c, y_pitch, y_coff)) return rc;
   IE_REQUIRE(n <= 65535 && h * scale + 2 <= 65535, "upsample: grid too large");
@@ -521,21 +528,23 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
     const int threads = row_block((long long)(w + 1) * (c / 8), &nb);
     dim3 grid(nb, h + 1, n);
     upsample2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8,
-                                                     static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
+                                                     static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bi, bo);
     IE_LAUNCH_CHECK();
     return IE_OK;
   }
-  const int threads = row_block((long long)(w * scale + 1) * (c / 8), &nb);
-  dim3 grid(nb, h * scale + 1, n);
+  const int threads = row_block((long long)(w * scale + bo) * (c / 8), &nb);
+  dim3 grid(nb, h * scale + bo, n);
   upsample_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8, scale,
-                                              static_cast<uint4*>(y), y_pitch / 8, y_coff / 8);
+                                              static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bi, bo);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
 
 extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff,
-                                         float* mean, int y0, int y1, long long count, void* stream) {
+                                         float* mean, int y0, int y1, long long count, int layout, void* stream) {
   IE_REQUIRE(x && mean && n > 0 && h > 0 && w > 0, "channel_mean: bad arguments");
+  IE_REQUIRE(layout == 0 || layout == IE_LAYOUT_X_DENSE, "channel_mean: bad layout flags %d", layout);
+  const int bi = (layout & IE_LAYOUT_X_DENSE) ? 0 : 1;
   IE_REQUIRE(c % 64 == 0, "channel_mean: c must be a multiple of 64 (got %d)", c);
   if (int rc = check_slice("channel_mean(x)", c, x_pitch, x_coff)) return rc;
   IE_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
@@ -551,28 +560,32 @@ extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int
   IE_REQUIRE(n <= 65535, "channel_mean: n too large");
   dim3 grid(c / 64, n, splits);
   channel_mean_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, x_pitch / 8, x_coff / 8, mean,
-                                                  c, 1.f / (float)count, y0, y1);
+                                                  c, 1.f / (float)count, y0, y1, bi);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
 
 extern "C" int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int c, void* y, int y_pitch, int y_coff,
-                                    void* stream) {
+                                    int layout, void* stream) {
   IE_REQUIRE(vec && y && n > 0 && kh > 0 && kw > 0, "broadcast: bad arguments");
+  IE_REQUIRE(layout == 0 || layout == IE_LAYOUT_Y_DENSE, "broadcast: bad layout flags %d", layout);
+  const int bo = (layout & IE_LAYOUT_Y_DENSE) ? 0 : 1;
   if (int rc = check_slice("broadcast(y)", c, y_pitch, y_coff)) return rc;
-  const long long total = (long long)n * (kh + 1) * (kw + 1) * (c / 8);
+  const long long total = (long long)n * (kh + bo) * (kw + bo) * (c / 8);
   broadcast_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(vec, n, kh, kw, c / 8, c, static_cast<uint4*>(y),
-                                                                  y_pitch / 8, y_coff / 8);
+                                                                  y_pitch / 8, y_coff / 8, bo);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
 
 extern "C" int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* y,
-                                     void* stream) {
+                                     int layout, void* stream) {
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && x_coff + c <= x_pitch, "raster_to_nhwc: bad arguments");
+  IE_REQUIRE(layout == 0 || layout == IE_LAYOUT_X_DENSE, "raster_to_nhwc: bad layout flags %d", layout);
+  const int bi = (layout & IE_LAYOUT_X_DENSE) ? 0 : 1;
   const long long total = (long long)n * h * w * c;
   raster_to_nhwc_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(x), n, h, w,
-                                                                       c, x_pitch, x_coff, y);
+                                                                       c, x_pitch, x_coff, y, bi);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }

@@ -70,6 +70,8 @@ class Engine:
         if self.filter_precision not in ("auto", "tf32", "fp32", "tcgen05"):
             raise ImgEnhError("filter_precision must be 'auto', 'tcgen05', 'tf32' or 'fp32'")
         self.stride = 2 ** len(self.arch["downs"])          # 8 for Simplemodel, 32 for Basis_kpn
+        # tensors at resolution 1/2^level and below are dense NHWC (TMA im2col); 99 = shared-border rasters everywhere
+        self.dense_from_level = int(params.get("dense_from_level", 2))
         if self.device.type != "cuda":
             raise ImgEnhError("device must be a CUDA device (no CPU fallback)")
         if self.device.index is None:
@@ -106,7 +108,14 @@ class Engine:
             return self._plans[key]
         A = self.arch
         dev = self.device
-        R = lambda hh, ww, c: ops.new_raster(n, hh, ww, c, dev)
+        # Layout per tensor: full and 1/2 resolution (the cout <= 64 wide-N kernels live there, and a border costs
+        # 2 - 4 % of the rows) are shared-border rasters; from 1/4 resolution down, and the small per-image tensors of
+        # the basis branch, are dense NHWC read through TMA im2col maps (a border would be 8 % of the GEMM rows at
+        # 26 x 26, 16 % at 13 x 13, 125 % at 2 x 2).  16 x 16 basis tensors stay rasters: the 2 x 2 'valid' conv and
+        # the fp32 head that follow them are raster kernels.
+        dense_levels = self.dense_from_level
+        lvl_dense = lambda l: l >= dense_levels
+        R = lambda hh, ww, c, dense=False: ops.new_raster(n, hh, ww, c, dev, dense=dense)
         p = {}
         chans = dict(A["downs"])
         # encoder rasters per level l (resolution h >> l)
@@ -118,26 +127,27 @@ class Engine:
             prev = cout
         for l, (dname, c) in enumerate(A["downs"]):
             hh, ww = h >> l, w >> l
-            p[dname + ".c1"] = R(hh, ww, c)
-            p["cat." + dname] = R(hh, ww, up_in[dname] + c)   # [0:up_in]=upsampled, [up_in:]=skip
-            p[dname + ".pool"] = R(hh >> 1, ww >> 1, c)
+            p[dname + ".c1"] = R(hh, ww, c, lvl_dense(l))
+            p["cat." + dname] = R(hh, ww, up_in[dname] + c, lvl_dense(l))   # [0:up_in]=upsampled, [up_in:]=skip
+            p[dname + ".pool"] = R(hh >> 1, ww >> 1, c, lvl_dense(l + 1))
         L = len(A["downs"])
         for i, bname in enumerate(A["bottleneck"]):
-            p[bname] = R(h >> L, w >> L, 1024)
+            p[bname] = R(h >> L, w >> L, 1024, lvl_dense(L))
         for name, cout, skip in A["coef_ups"]:
             l = [d for d, _ in A["downs"]].index(skip)
             for j in (1, 2, 3):
-                p[f"{name}.c{j}"] = R(h >> l, w >> l, cout)
+                p[f"{name}.c{j}"] = R(h >> l, w >> l, cout, lvl_dense(l))
         for hname in A["head"]:
             p[hname] = R(h, w, 64)
         # basis branch
+        small = lambda k: dense_levels < 99 and k <= 8
         prev = 1024
         for name, cout, skip, k, s in A["basis_ups"]:
-            p["bcat." + name] = R(k, k, prev + chans[skip])
+            p["bcat." + name] = R(k, k, prev + chans[skip], small(k))
             for j in (1, 2, 3):
-                p[f"{name}.c{j}"] = R(k, k, cout)
+                p[f"{name}.c{j}"] = R(k, k, cout, small(k))
             prev = cout
-        p["seed"] = R(1, 1, 1024)
+        p["seed"] = R(1, 1, 1024, small(1))
         for tname in A["tail"][:-1]:
             p[tname] = R(16, 16, 128)
         self._plans[key] = p

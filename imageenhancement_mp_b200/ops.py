@@ -1,8 +1,10 @@
 """Python-level wrappers of the C ABI, operating on torch CUDA tensors.
 
-A ``Raster`` is the library's activation container: bf16 ``[n*(h+1)*(w+1), pitch]``, every image
-preceded by one zero row and every image row followed by one zero pixel (a shared one-pixel
-border, see include/imgenh_b200.h).  ``Slice`` is a channel window
+A ``Raster`` is the library's activation container: bf16 ``[rows, pitch]`` in one of two layouts
+(include/imgenh_b200.h).  ``b = 1``: ``rows = n*(h+1)*(w+1)``, every image preceded by one zero row and every image
+row followed by one zero pixel (a shared one-pixel border: a k x k tap is a constant row shift).  ``b = 0``
+(dense NHWC): ``rows = n*h*w``; the convolution fetches its taps with TMA im2col tensor maps - the layout of the
+1/4-resolution and smaller tensors, where border rows would be 8 - 125 % of the GEMM.  ``Slice`` is a channel window
 of a raster - how the reference's ``layers.concatenate([up, skip])``
 (/root/reference/model_library.py:96) is expressed without a copy.
 """
@@ -14,7 +16,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX, call, ptr, stream
+from ._lib import (ConvDesc, IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX, IE_LAYOUT_X_DENSE, IE_LAYOUT_Y_DENSE,
+                   call, ptr, stream)
 
 
 # bench.py sets this to a list to collect (start, end) CUDA events around every convolution launch
@@ -38,6 +41,7 @@ class Raster:
     n: int
     h: int
     w: int
+    b: int = 1              # border: 1 = shared-border raster, 0 = dense NHWC
 
     @property
     def pitch(self):
@@ -45,7 +49,11 @@ class Raster:
 
     @property
     def rows(self):
-        return self.n * (self.h + 1) * (self.w + 1)
+        return self.n * (self.h + self.b) * (self.w + self.b)
+
+    @property
+    def dense(self):
+        return self.b == 0
 
     def slice(self, coff=0, c=None):
         return Slice(self, coff, self.pitch - coff if c is None else c)
@@ -58,9 +66,15 @@ class Slice:
     c: int
 
 
-def new_raster(n, h, w, c, device):
+def new_raster(n, h, w, c, device, dense=False):
     # torch.empty: every row (borders included) is written by the producing kernel
-    return Raster(torch.empty(n * (h + 1) * (w + 1), c, dtype=torch.bfloat16, device=device), n, h, w)
+    b = 0 if dense else 1
+    return Raster(torch.empty(n * (h + b) * (w + b), c, dtype=torch.bfloat16, device=device), n, h, w, b)
+
+
+def _layout(src=None, dst=None):
+    return (IE_LAYOUT_X_DENSE if (src is not None and src.r.dense) else 0) | \
+           (IE_LAYOUT_Y_DENSE if (dst is not None and dst.r.dense) else 0)
 
 
 def conv_n_tile(cout, epilogue):
@@ -134,11 +148,16 @@ def _desc(src: Slice, kh, kw, cout, relu, epilogue, dst: Slice | None, valid=Non
     d.cout = cout
     d.y_pitch, d.y_coff = (dst.r.pitch, dst.coff) if dst is not None else (0, 0)
     d.relu, d.epilogue = int(relu), epilogue
+    d.dense = int(r.dense)
+    if dst is not None and dst.r.dense != r.dense:
+        raise _lib.ImgEnhError("conv: input and output must use the same layout (both dense or both shared-border rasters)")
     return d
 
 
 def conv2d(src: Slice, w_packed, bias, dst: Slice, k=3, relu=True, valid=None, fn="ie_conv2d_nhwc_bf16"):
     """Conv2D(k, relu) from a raster slice into a raster slice (bf16 epilogue)."""
+    if dst.r.dense != src.r.dense:
+        raise _lib.ImgEnhError("conv: input and output must use the same layout (both dense or both shared-border rasters)")
     assert dst.r.rows == src.r.rows, "conv output must share the input raster geometry"
     d = _desc(src, k, k, dst.c, relu, IE_EPI_BF16_RASTER, dst, valid)
     _timed_conv(fn, C.byref(d), ptr(src.r.data), ptr(w_packed), ptr(bias), ptr(dst.r.data), None, None, stream())
@@ -184,7 +203,7 @@ def maxpool2(src: Slice, dst: Slice, want_mean=False, rows=None, count=0):
     mean = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device) if want_mean else None
     y0, y1 = rows if rows is not None else (0, 0)
     call("ie_maxpool2_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff,
-         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), y0, y1, int(count), stream())
+         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), y0, y1, int(count), _layout(src, dst), stream())
     return mean
 
 
@@ -192,7 +211,7 @@ def upsample_bilinear(src: Slice, dst: Slice, scale):
     r = src.r
     assert (dst.r.n, dst.r.h, dst.r.w) == (r.n, r.h * scale, r.w * scale) and dst.c == src.c
     call("ie_upsample_bilinear_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, scale,
-         ptr(dst.r.data), dst.r.pitch, dst.coff, stream())
+         ptr(dst.r.data), dst.r.pitch, dst.coff, _layout(src, dst), stream())
 
 
 def channel_mean(src: Slice, out=None, rows=None, count=0):
@@ -201,20 +220,20 @@ def channel_mean(src: Slice, out=None, rows=None, count=0):
         out = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device)
     y0, y1 = rows if rows is not None else (0, 0)
     call("ie_channel_mean_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(out), y0, y1, int(count),
-         stream())
+         _layout(src), stream())
     return out
 
 
 def broadcast_hw(vec, dst: Slice):
     assert vec.shape == (dst.r.n, dst.c) and vec.dtype == torch.float32
     call("ie_broadcast_hw_bf16", ptr(vec), dst.r.n, dst.r.h, dst.r.w, dst.c, ptr(dst.r.data), dst.r.pitch,
-         dst.coff, stream())
+         dst.coff, _layout(None, dst), stream())
 
 
 def raster_to_nhwc(src: Slice):
     r = src.r
     y = torch.empty(r.n, r.h, r.w, src.c, dtype=torch.float32, device=r.data.device)
-    call("ie_raster_to_nhwc_f32", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(y), stream())
+    call("ie_raster_to_nhwc_f32", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(y), _layout(src), stream())
     return y
 
 

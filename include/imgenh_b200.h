@@ -44,8 +44,17 @@ extern "C" {
 #define IE_EPI_F32_NHWC 1    /* bias(+ReLU) -> fp32 [n][hv][wv][cout] (interior only), cout <= 256         */
 #define IE_EPI_F32_SOFTMAX 2 /* as 1, then softmax over cout; y_aux (nullable) receives the logits        */
 
+/* Activation layouts.  RASTER (default): bf16 NHWC with a shared one-pixel zero border - rows = n*(h+1)*(w+1),
+ * pixel (n,y,x) at row (n*(h+1)+y+1)*(w+1)+x; a k x k tap is a constant row shift, fetched with plain 2-D TMA boxes.
+ * DENSE: plain bf16 NHWC, rows = n*h*w, pixel (n,y,x) at row (n*h+y)*w+x; the convolution fetches its taps with TMA
+ * im2col-mode tensor maps (the zero padding comes from the tensor map's pixel box), so no border row is ever
+ * multiplied - the layout of the 1/4-resolution and smaller tensors (a border costs 7.8 % of the rows at 26 x 26,
+ * 16 % at 13 x 13, 125 % at 2 x 2).  `layout` arguments of the glue kernels are a bit set of these flags.          */
+#define IE_LAYOUT_X_DENSE 1 /* the input tensor is dense NHWC  */
+#define IE_LAYOUT_Y_DENSE 2 /* the output tensor is dense NHWC */
+
 typedef struct ie_conv_desc {
-  int32_t n_img, h, w; /* interior size of the INPUT raster (rows = n_img*(h+1)*(w+1))                   */
+  int32_t n_img, h, w; /* interior size of the INPUT raster (rows = n_img*(h+1)*(w+1); dense: n_img*h*w)  */
   int32_t hv, wv;      /* valid OUTPUT extent inside the same raster geometry: (h,w) for 'same',
                           (h-1,w-1) for the 2x2 'valid' conv; everything outside is written as zero      */
   int32_t kh, kw;      /* 3x3 ('same', centred), 2x2 ('valid', taps at +0/+1) or 1x1                     */
@@ -58,6 +67,8 @@ typedef struct ie_conv_desc {
   int32_t y_coff;      /* first channel of y to write (bf16 raster: multiple of 64)                      */
   int32_t relu;        /* 1: max(0, .) after the bias                                                    */
   int32_t epilogue;    /* IE_EPI_*                                                                       */
+  int32_t dense;       /* 0: x and y are shared-border rasters; 1: both are dense NHWC (3x3 'same' / 1x1,
+                          IE_EPI_BF16_RASTER only; taps fetched by TMA im2col)                            */
 } ie_conv_desc;
 
 int ie_version(void);
@@ -107,24 +118,25 @@ int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const void* w_pa
  * shard of a larger image the statistics cover input rows [stat_y0, stat_y1) only (even numbers; stat_y1 <= 0: all
  * rows) and are divided by stat_count pixels (<= 0: h*w), so that a SUM over the shards is the global mean.      */
 int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y, int y_pitch,
-                          int y_coff, float* chan_mean, int stat_y0, int stat_y1, long long stat_count, void* stream);
+                          int y_coff, float* chan_mean, int stat_y0, int stat_y1, long long stat_count, int layout,
+                          void* stream);
 
 /* UpSampling2D(scale, 'bilinear') half-pixel centres (model_library.py:92) written straight into a
  * channel slice of the consumer's concat raster (model_library.py:96); border zeroed.               */
 int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, int scale,
-                                   void* y, int y_pitch, int y_coff, void* stream);
+                                   void* y, int y_pitch, int y_coff, int layout, void* stream);
 
 /* Per-image channel means over the interior (reduce_mean x2 :409-410, GlobalAveragePooling2D :110):
  * mean[n][c] fp32.  Rows [y0, y1) only when y1 > 0, divided by `count` pixels when count > 0 (spatial shards). */
 int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* mean, int y0,
-                              int y1, long long count, void* stream);
+                              int y1, long long count, int layout, void* stream);
 
 /* tf.tile of a [n][c] vector to a k_h x k_w raster slice (Poolskip :111-112), border zeroed.          */
-int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int c, void* y, int y_pitch, int y_coff,
+int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int c, void* y, int y_pitch, int y_coff, int layout,
                          void* stream);
 
 /* bf16 raster slice -> fp32 NHWC [n][h][w][c] (interior).  Debug / parity taps.                       */
-int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* y,
+int ie_raster_to_nhwc_f32(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* y, int layout,
                           void* stream);
 
 /* ---- basis softmax + per-pixel filter -------------------------------------------------------------- */

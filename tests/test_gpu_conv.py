@@ -20,6 +20,13 @@ def to_raster(x):
     return ops.Raster(data, n, h, w)
 
 
+def to_dense(x):
+    """fp32 NHWC (cuda) -> ops.Raster in the dense NHWC layout (no border)."""
+    from imageenhancement_mp_b200 import ops
+    n, h, w, c = x.shape
+    return ops.Raster(x.reshape(-1, c).to(torch.bfloat16).contiguous(), n, h, w, 0)
+
+
 def ref_conv(x, w, b, k, relu=True):
     """x NHWC fp32 (already bf16-representable), w HWIO; 3x3 same / 2x2 valid / 1x1."""
     pad = 1 if k == 3 else 0
@@ -83,6 +90,60 @@ def test_conv_bf16_vs_cpu(cuda, n, h, w, cin, cout, k):
     mask = torch.ones(h + 1, w + 1, dtype=torch.bool, device=cuda)
     mask[1:hv + 1, 0:wv] = False
     assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
+
+
+DENSE_CASES = [
+    # n, h, w, cin, cout, k      dense NHWC tensors, taps fetched by TMA im2col (csrc/conv_tcgen05.cu, IM2COL)
+    (3, 26, 26, 1024, 1024, 3),    # the dominant quarter-resolution layer: 2028 pixels = 15.8 tiles (ragged last tile)
+    (2, 13, 13, 128, 256, 3),      # 338 pixels: tiles cross image rows AND images
+    (5, 2, 2, 2048, 512, 3),       # basis branch: 20 pixels, every tap of every pixel touches the padding
+    (7, 1, 1, 1024, 512, 3),       # 1x1 images: only the centre tap is inside
+    (2, 4, 8, 64, 64, 3),          # narrow layer through the streaming kernel
+    (1, 24, 40, 192, 128, 1),      # 1x1 convolution (pad 0)
+    (2, 9, 31, 64, 128, 3),        # odd sizes, 558 pixels
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", DENSE_CASES)
+def test_conv_dense_im2col_vs_cpu(cuda, n, h, w, cin, cout, k):
+    """Dense NHWC in / out: the zero padding comes from the im2col tensor map's pixel box, tiles are 128 consecutive
+    pixels of the [n][h][w] index space, no border row is computed.  Also read from / written to channel slices."""
+    from imageenhancement_mp_b200 import ops
+    x, wt, b = make_case(n, h, w, cin, cout, k)
+    ref = bf16_round(ref_conv(x, wt, b, k))
+    # the input is channels [64 : 64 + cin] of a wider tensor, the output channels [64 : 64 + cout] of another
+    wide = torch.cat([torch.full((n, h, w, 64), 9.0), x, torch.full((n, h, w, 64), -9.0)], dim=-1)
+    src = to_dense(wide.to(cuda))
+    dst = ops.new_raster(n, h, w, cout + 128, cuda, dense=True)
+    assert dst.rows == n * h * w and dst.dense
+    dst.data.fill_(7.0)
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    ops.conv2d(src.slice(64, cin), wp, b.to(cuda), dst.slice(64, cout), k=k)
+    torch.cuda.synchronize()
+    got = ops.raster_to_nhwc(dst.slice(64, cout)).cpu()
+    assert_close_bf16(got, ref, f"dense conv {k}x{k} {cin}->{cout}")
+    assert torch.all(dst.data[:, :64] == 7.0) and torch.all(dst.data[:, 64 + cout:] == 7.0)
+    # same answer as the naive validation kernel on the same dense tensors, and as the raster path
+    d2 = ops.new_raster(n, h, w, cout, cuda, dense=True)
+    ops.conv2d(src.slice(64, cin), wp, b.to(cuda), d2.slice(), k=k, fn="ie_debug_conv2d_naive")
+    assert_close_bf16(got, ops.raster_to_nhwc(d2.slice()).cpu(), "dense conv vs naive")
+    d3 = ops.new_raster(n, h, w, cout, cuda)
+    ops.conv2d(to_raster(x.to(cuda)).slice(), wp, b.to(cuda), d3.slice(), k=k)
+    # (bit-identical when the raster path also takes the streaming kernel; the wide-N / resident kernels add the taps
+    # in a different order)
+    assert_close_bf16(ops.raster_to_nhwc(d3.slice()).cpu(), got, "dense vs raster layout")
+
+
+def test_conv_dense_rejects_what_it_does_not_support(cuda):
+    from imageenhancement_mp_b200 import ops, ImgEnhError
+    x, wt, b = make_case(1, 8, 8, 64, 64, 3)
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    with pytest.raises(ImgEnhError):                       # mixed layouts
+        ops.conv2d(to_dense(x.to(cuda)).slice(), wp, b.to(cuda), ops.new_raster(1, 8, 8, 64, cuda).slice())
+    x2, wt2, b2 = make_case(1, 8, 8, 64, 64, 2)
+    with pytest.raises(ImgEnhError):                       # 2x2 'valid' is a raster kernel
+        ops.conv2d(to_dense(x2.to(cuda)).slice(), ops.pack_conv_weights(wt2.to(cuda)), b2.to(cuda),
+                   ops.new_raster(1, 8, 8, 64, cuda, dense=True).slice(), k=2, valid=(7, 7))
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2], ids=["stream", "resident", "wideN"])

@@ -112,6 +112,54 @@ def test_maxpool(cuda):
         assert torch.allclose(mean.cpu(), x[..., coff:coff + c].mean(dim=(1, 2)), atol=1e-5, rtol=1e-5)
 
 
+def to_dense(x):
+    from imageenhancement_mp_b200 import ops
+    n, h, w, c = x.shape
+    return ops.Raster(x.reshape(-1, c).to(torch.bfloat16).contiguous(), n, h, w, 0)
+
+
+@pytest.mark.parametrize("din,dout", [(False, True), (True, True), (True, False)])
+def test_layout_glue_between_rasters_and_dense_tensors(cuda, din, dout):
+    """max-pool, bilinear up-sample (x2 and general), channel mean, broadcast with dense NHWC tensors on either side:
+    same numbers as the raster-to-raster kernels, nothing written outside the channel slice, borders (where the output
+    has one) zeroed."""
+    from imageenhancement_mp_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = bf16_round(torch.randn(3, 12, 20, 192, generator=g))
+    src = (to_dense if din else to_raster)(x.to(cuda))
+    # max-pool (+ fused channel means)
+    dst = ops.new_raster(3, 6, 10, 192, cuda, dense=dout)
+    dst.data.fill_(5.0)
+    mean = ops.maxpool2(src.slice(64, 128), dst.slice(64, 128), want_mean=True)
+    assert torch.equal(ops.raster_to_nhwc(dst.slice(64, 128)).cpu(), omodel.maxpool2(x[..., 64:192]))
+    assert torch.allclose(mean.cpu(), x[..., 64:192].mean(dim=(1, 2)), atol=1e-5, rtol=1e-5)
+    assert torch.all(dst.data[:, :64] == 5.0)
+    if not dout:
+        dst.data[:, :64] = 0
+        assert border_is_zero(dst)
+    # channel mean of a dense tensor
+    m = ops.channel_mean(src.slice(128, 64))
+    assert torch.allclose(m.cpu(), x[..., 128:].mean(dim=(1, 2)), atol=1e-5, rtol=1e-5)
+    # up-sampling
+    for scale in (2, 4):
+        up = ops.new_raster(3, 12 * scale, 20 * scale, 128, cuda, dense=dout)
+        up.data.fill_(float("nan"))
+        ops.upsample_bilinear(src.slice(0, 64), up.slice(64, 64), scale)
+        got = ops.raster_to_nhwc(up.slice(64, 64)).cpu()
+        assert torch.allclose(got, omodel.upsample_bilinear(x[..., :64], scale), atol=2e-2, rtol=2 ** -7)
+        assert bool(torch.isnan(up.data[:, :64]).all())
+        if not dout:
+            assert border_is_zero(ops.Raster(up.data[:, 64:].contiguous(), up.n, up.h, up.w))
+        else:
+            assert bool(torch.isfinite(up.data[:, 64:]).all())
+    # broadcast into a dense / raster slice
+    bc = ops.new_raster(3, 2, 2, 128, cuda, dense=dout)
+    bc.data.zero_()
+    ops.broadcast_hw(m, bc.slice(64, 64))
+    assert torch.equal(ops.raster_to_nhwc(bc.slice(64, 64)).cpu(), bf16_round(m.cpu())[:, None, None, :].expand(3, 2, 2, 64))
+    assert torch.all(bc.data[:, :64] == 0)
+
+
 @pytest.mark.parametrize("scale,h,w", [(2, 5, 7), (8, 2, 2), (2, 1, 1), (2, 13, 13)])
 def test_upsample_bilinear(cuda, scale, h, w):
     from imageenhancement_mp_b200 import ops
