@@ -39,9 +39,9 @@ SIGNATURES = {
     "ie_pack_conv_weights": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_pack_input_im2col3x3": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "ie_conv_first_layer_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P],
-    "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
+    "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P],
     "ie_conv_set_mode": [_I, _I],
-    "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P],
+    "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P],
     "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _I, _P],
     "ie_upsample_bilinear_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _LL, _I, _P],

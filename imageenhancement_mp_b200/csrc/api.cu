@@ -1,6 +1,8 @@
 // Library-wide pieces of the C ABI: version, error string, device info, tensor-map encoding.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "ie_common.cuh"
 
@@ -14,6 +16,17 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static int g_pdl_env = -1;          // IE_PDL=0 in the environment disables the attribute
+static int g_pdl_off = 0;           // ie_conv_set_mode flag bit 10 (tests / A-B timing)
+bool pdl_enabled() {
+  if (g_pdl_env < 0) {
+    const char* e = getenv("IE_PDL");
+    g_pdl_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl_env != 0 && !g_pdl_off;
+}
+void pdl_set(bool on) { g_pdl_off = on ? 0 : 1; }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -44,8 +57,39 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached by (kind, base pointer, shape, box): the descriptor depends on nothing else, an eager
+// forward re-creates the same ~100 maps on every call (3 - 5 driver calls per convolution), and activation buffers
+// are cached per input shape by the caller - so after the first forward every lookup hits.
+struct TmapKey {
+  uint64_t v[7];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 0xBF58476D1CE4E5B9ull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  auto it = g_tmap_cache.find(k);
+  if (it == g_tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache[k] = m;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_elems,
                       uint32_t box_cols, uint32_t box_rows) {
+  const TmapKey key{{1, reinterpret_cast<uint64_t>(base), cols, rows, pitch_elems, box_cols, box_rows}};
+  if (tmap_lookup(key, out)) return IE_OK;
   EncodeTiledFn fn = encode_fn();
   IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   IE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p is not 16-byte aligned", base);
@@ -60,6 +104,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (cols %llu rows %llu pitch %llu box %ux%u)",
              (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems, box_cols, box_rows);
+  tmap_store(key, *out);
   return IE_OK;
 }
 
@@ -88,6 +133,9 @@ static EncodeIm2colFn encode_im2col_fn() {
 // B200: tools/micro/tma_im2col.cu).  64 channels per pixel (one 128-byte swizzle row).
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, uint64_t pitch_elems, int pad,
                           uint32_t pixels) {
+  const TmapKey key{{2, reinterpret_cast<uint64_t>(base), (uint64_t)n, ((uint64_t)h << 32) | (uint32_t)w, pitch_elems,
+                     (uint64_t)pad, pixels}};
+  if (tmap_lookup(key, out)) return IE_OK;
   EncodeIm2colFn fn = encode_im2col_fn();
   IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col is not available from this driver");
   IE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p is not 16-byte aligned", base);
@@ -102,6 +150,7 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed with CUresult %d (n %d h %d w %d pitch %llu pad %d)", (int)r, n,
              h, w, (unsigned long long)pitch_elems, pad);
+  tmap_store(key, *out);
   return IE_OK;
 }
 

@@ -25,6 +25,8 @@
 //                         L2->smem traffic per tile 4.4x and issues 12 MMAs per barrier round trip - the
 //                         narrow layers are bound by single-thread issue overhead and operand traffic,
 //                         not by the tensor pipe.
+#include <cstdlib>
+
 #include "ie_common.cuh"
 #include "ie_ptx.cuh"
 
@@ -67,6 +69,11 @@ struct EpiParams {
   float* y_aux;
   int f32_pitch;      // floats per pixel of y_f32 / y_aux (= cout unless the caller writes a channel slice)
   int dense;          // x / y are dense NHWC (R = n*h*w rows, no border rows to mask)
+  // split-K (tiny M: the K loop of a tile is cut into `ksplit` work items so that more SMs stream the weights):
+  // work item = (tile, ks); its accumulator is written as raw fp32 to part[ks][row][col] and a second kernel sums
+  // the parts in a fixed order and applies bias / ReLU / mask (deterministic: no atomics)
+  int ksplit;
+  float* part;        // [ksplit][m_tiles*128][n_tiles*n_tile] fp32
 };
 
 // Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
@@ -93,6 +100,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // One-time CTA setup common to both kernels; returns the TMEM base address.
 __device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams& e, int stages, int warp, int lane,
                                               uint32_t full_count = 1) {
+  pdl_trigger();                      // the next kernel's CTAs may be scheduled (they wait in their own pdl_wait)
   for (int i = threadIdx.x; i < kMaxCout; i += blockDim.x) t.bias()[i] = (i < e.cout && e.bias) ? e.bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -113,6 +121,7 @@ __device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                         // everything above overlapped the previous kernel's tail; its outputs are visible now
   return *t.tmem_slot();
 }
 
@@ -129,9 +138,11 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
   const float* sbias = t.bias();
   uint64_t* tfull_bar = t.tfull();
   uint64_t* tempty_bar = t.tempty();
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   int it = set;
-  for (int tile = blockIdx.x + set * gridDim.x; tile < num_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
+  for (int item = blockIdx.x + set * gridDim.x; item < num_tiles; item += t.nsets * gridDim.x, it += t.nsets) {
+    const int tile = item / p.ksplit;
+    const int ks = item - tile * p.ksplit;
     const int m_tile = tile / p.n_tiles;
     const int n_idx = tile - m_tile * p.n_tiles;
     const int r0 = m_tile * kBlockM;
@@ -150,7 +161,25 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
     tc_fence_after();
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
 
-    if (p.epilogue == IE_EPI_BF16_RASTER) {
+    if (p.ksplit > 1) {
+      // raw fp32 partial sums of this K range: row r, columns n0.. of part[ks]
+      const int ncols = p.n_tiles * p.n_tile;
+      float* dst = p.part + (static_cast<long long>(ks) * p.m_tiles * kBlockM + r) * ncols + n0;
+      const int chunks = p.n_tile >> 5;
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_base + c * 32, v);
+        tmem_ld_wait();
+        if (c == chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(dst + c * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    } else if (p.epilogue == IE_EPI_BF16_RASTER) {
       const int chunks = p.n_tile >> 6;
       for (int c = 0; c < chunks; ++c) {
         uint32_t v0[32], v1[32];
@@ -356,13 +385,18 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint64_t* full_bar = t.full();
   uint64_t* empty_bar = t.empty();
 
+  // work item = (tile, ks): K blocks [ks * kb_per, ...) of tile (m_tile, n_idx); ksplit = 1 -> the whole K loop
+  const int num_items = num_tiles * p.e.ksplit;
+  const int kb_per = (kblocks + p.e.ksplit - 1) / p.e.ksplit;
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.e.n_tile) * 128u;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item / p.e.ksplit;
+        const int ks = item - tile * p.e.ksplit;
         const int m_tile = tile / p.e.n_tiles;
         const int n_idx = tile - m_tile * p.e.n_tiles;
         const int r0 = m_tile * kBlockM;
@@ -376,20 +410,23 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           px0 = rem - py0 * p.img_w - p.pad;
           py0 -= p.pad;
         }
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int row = r0 + p.tap_shift[tap];
-          const int ti = tap / p.kw, tj = tap - ti * p.kw;
-          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            uint8_t* a_dst = base + stage * stage_bytes;
-            if constexpr (IM2COL)
-              tma_load_im2col_4d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, px0, py0, pn0, tj, ti);
-            else
-              tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row);
-            tma_load_2d(a_dst + kABytes, &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        const int kb_begin = ks * kb_per;
+        const int kb_end = (kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
+        int tap = kb_begin / p.kblocks_per_tap;
+        int kb = kb_begin - tap * p.kblocks_per_tap;
+        for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          uint8_t* a_dst = base + stage * stage_bytes;
+          if constexpr (IM2COL) {
+            const int ti = tap / p.kw, tj = tap - ti * p.kw;
+            tma_load_im2col_4d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, px0, py0, pn0, tj, ti);
+          } else {
+            tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, r0 + p.tap_shift[tap]);
           }
+          tma_load_2d(a_dst + kABytes, &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
         }
       }
     }
@@ -403,25 +440,28 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int ks = item % p.e.ksplit;
+      const int kb_begin = ks * kb_per;
+      const int kb_end = (kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
       const int buf = it & 1;
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
-      for (int kbi = 0; kbi < kblocks; ++kbi) {
+      for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_lo = a_lo0 + stage * stage_stride;
           const uint32_t b_lo = b_lo0 + stage * stage_stride;
           // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-          umma_bf16_ss_lo(d_tmem, a_lo, b_lo, idesc, kbi != 0 ? 1u : 0u);
+          umma_bf16_ss_lo(d_tmem, a_lo, b_lo, idesc, kbi != kb_begin ? 1u : 0u);
           umma_bf16_ss_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
           umma_bf16_ss_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
           umma_bf16_ss_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1u);
           umma_commit(&empty_bar[stage]);                            // frees the smem slot when these retire
-          if (kbi == kblocks - 1) umma_commit(&t.tfull()[buf]);      // accumulator complete
+          if (kbi == kb_end - 1) umma_commit(&t.tfull()[buf]);       // accumulator complete
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -1205,6 +1245,47 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// Second half of a split-K convolution: sums the `ksplit` fp32 partial tiles of every output row in a fixed order,
+// adds the bias, applies ReLU and the border / valid-extent mask, and writes the bf16 row (8 channels per thread).
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ part, int ksplit, long long part_stride, int ncols, EpiParams p,
+                     uint4* __restrict__ y, int y_pitch_v) {
+  pdl_trigger();
+  pdl_wait();
+  const int cvec = p.cout >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(p.R) * cvec) return;
+  const int r = static_cast<int>(idx / cvec);
+  const int cv = static_cast<int>(idx - static_cast<long long>(r) * cvec);
+  bool valid = true;
+  if (!p.dense) {
+    const int img = r / p.plane;
+    const int pr = r - img * p.plane;
+    const int yy = pr / p.wp;
+    const int xx = pr - yy * p.wp;
+    valid = (yy >= 1) && (yy <= p.hv) && (xx < p.wv);
+  }
+  uint4 res = make_uint4(0, 0, 0, 0);
+  if (valid) {
+    const float* src = part + static_cast<long long>(r) * ncols + cv * 8;
+    float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 c = *reinterpret_cast<const float4*>(src + k * part_stride);
+      const float4 d = *reinterpret_cast<const float4*>(src + k * part_stride + 4);
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] += p.bias ? p.bias[cv * 8 + e] : 0.f;
+      if (p.relu) v[e] = fmaxf(v[e], 0.f);
+    }
+    res = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  y[static_cast<long long>(r) * y_pitch_v + (p.y_coff >> 3) + cv] = res;
+}
+
 // -------------------------------------------------------------------------------------------------
 int choose_n_tile(int cout, int epilogue) {
   if (epilogue != IE_EPI_BF16_RASTER) return ((cout + 15) / 16) * 16;
@@ -1254,6 +1335,7 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_pair_mode = 0;          // 1: 64 -> 64 wide layers on CTA pairs (cta_group::2)
+static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
 // (measured on B200: the 128B swizzle is a function of the absolute smem address, so row-shifted descriptor starts
@@ -1266,11 +1348,14 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_fuse_rows = (flags & 2) ? 0 : 1;
   ie::g_wide_flags = (flags >> 2) & 7;
   ie::g_pair_mode = (flags >> 8) & 1;
+  ie::g_splitk = ((flags >> 9) & 1) ? 0 : 1;
+  ie::pdl_set(((flags >> 10) & 1) == 0);
   return IE_OK;
 }
 
 extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                                   void* y_bf16, float* y_f32, float* y_aux, void* stream) {
+                                   void* y_bf16, float* y_f32, float* y_aux, void* workspace, long long workspace_bytes,
+                                   void* stream) {
   using namespace ie;
   int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32);
   if (rc) return rc;
@@ -1278,6 +1363,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   const int wp = d->w + 1;
   EpiParams e{};
   e.dense = d->dense;
+  e.ksplit = 1;
   e.R = (int)R;
   e.plane = (d->h + 1) * wp;
   e.wp = wp;
@@ -1389,7 +1475,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   do {                                                                                                            \
     IE_CUDA(cudaFuncSetAttribute(conv_wide_kernel<RES_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                  (int)kMaxSmem));                                                                 \
-    conv_wide_kernel<RES_, G_><<<grid, kThreads2, smem, st>>>(tm_a, tm_b, tm_y, tm_y31, p);                        \
+    IE_CUDA(launch_pdl(conv_wide_kernel<RES_, G_>, dim3(grid), dim3(kThreads2), smem, st, tm_a, tm_b, tm_y, tm_y31, p)); \
   } while (0)
     const bool pairs = fuse && !wide_f32 && g_pair_mode == 1 && grid_cap >= 2;
     if (pairs) {
@@ -1438,7 +1524,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   do {                                                                                                            \
     IE_CUDA(cudaFuncSetAttribute(conv_resident_kernel<NDX_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                  (int)kMaxSmem));                                                                 \
-    conv_resident_kernel<NDX_, G_><<<grid, kThreads2, smem, st>>>(tm_a, tm_b, tm_y, p);                            \
+    IE_CUDA(launch_pdl(conv_resident_kernel<NDX_, G_>, dim3(grid), dim3(kThreads2), smem, st, tm_a, tm_b, tm_y, p)); \
   } while (0)
     if (d->kw == 3 && fuse_rows == 3) IE_LAUNCH_RES(3, 3);
     else if (d->kw == 3) IE_LAUNCH_RES(3, 1);
@@ -1467,20 +1553,42 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   p.pad = d->kh / 2;
   const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + kTailBytes;
   const int tiles = e.m_tiles * e.n_tiles;
-  const int grid = tiles < grid_cap ? tiles : grid_cap;
+  // split-K for tiny M (eval.py's default call is ONE 32 x 32 patch: the 1024-channel layers are then 1 M tile x 16 N
+  // tiles with K = 9216 - 18432, i.e. 16 CTAs streaming 19 - 38 MB of weights while 132 SMs idle)
+  const int kblocks = ntaps * p.kblocks_per_tap;
+  int ksplit = 1;
+  const size_t per_split = (size_t)e.m_tiles * kBlockM * e.n_tiles * e.n_tile * sizeof(float);
+  static const bool splitk_env = !(getenv("IE_SPLITK") && getenv("IE_SPLITK")[0] == '0');      // A-B timing
+  if (g_splitk && splitk_env && workspace && d->epilogue == IE_EPI_BF16_RASTER && tiles * 2 <= grid_cap && kblocks >= 8) {
+    ksplit = grid_cap / tiles;
+    if (ksplit > kblocks / 4) ksplit = kblocks / 4;
+    while (ksplit > 1 && per_split * ksplit > (size_t)workspace_bytes) --ksplit;
+    const int kb_per = (kblocks + ksplit - 1) / ksplit;
+    ksplit = (kblocks + kb_per - 1) / kb_per;            // no empty split
+  }
+  p.e.ksplit = ksplit;
+  p.e.part = static_cast<float*>(workspace);
+  const int items = tiles * ksplit;
+  const int grid = items < grid_cap ? items : grid_cap;
   if (d->dense) {
     rc = make_tmap_im2col_bf16(&tm_a, x, d->n_img, d->h, d->w, (uint64_t)d->x_pitch, p.pad, kBlockM);
     if (rc) return rc;
     IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    conv_stream_kernel<true><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
+    IE_CUDA(launch_pdl(conv_stream_kernel<true>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
   } else {
     rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
     if (rc) return rc;
     if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
     IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    conv_stream_kernel<false><<<grid, kThreads, smem, st>>>(tm_a, tm_b, tm_y, p);
+    IE_CUDA(launch_pdl(conv_stream_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
   }
   IE_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    const long long total = R * (d->cout / 8);
+    const int ncols = e.n_tiles * e.n_tile;
+    IE_CUDA(launch_pdl(splitk_finish_kernel, dim3(ie_ceil_div(total, 256)), dim3(256), 0, st, (const float*)p.e.part, ksplit,
+                       (long long)e.m_tiles * kBlockM * ncols, ncols, p.e, static_cast<uint4*>(y_bf16), d->y_pitch / 8));
+  }
   return IE_OK;
 }
 
@@ -1509,6 +1617,7 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   p.e.y_coff = y_coff;
   p.e.relu = relu;
   p.e.epilogue = IE_EPI_BF16_RASTER;
+  p.e.ksplit = 1;
   p.e.bias = bias;
   p.x = x;
   p.hs = hs;
@@ -1524,10 +1633,10 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c == 5) {
     IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    conv_first_kernel<5><<<grid, kFirstThreads, smem, st>>>(tm_b, tm_y, p);
+    IE_CUDA(launch_pdl(conv_first_kernel<5>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));
   } else {
     IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    conv_first_kernel<3><<<grid, kFirstThreads, smem, st>>>(tm_b, tm_y, p);
+    IE_CUDA(launch_pdl(conv_first_kernel<3>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));
   }
   IE_LAUNCH_CHECK();
   return IE_OK;

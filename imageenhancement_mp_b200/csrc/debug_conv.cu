@@ -100,7 +100,8 @@ __global__ void naive_conv_f32_kernel(const __nv_bfloat16* __restrict__ x, const
 }  // namespace ie
 
 extern "C" int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                                     void* y_bf16, float* y_f32, float* y_aux, void* stream) {
+                                     void* y_bf16, float* y_f32, float* y_aux, void* /*workspace*/,
+                                     long long /*workspace_bytes*/, void* stream) {
   using namespace ie;
   if (int rc = validate_conv_desc(d, x, w_packed, y_bf16, y_f32)) return rc;
   NaiveParams p{};

@@ -23,6 +23,26 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n, int h, int w, uint64_t pitch_elems, int pad,
                           uint32_t pixels);
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in ie_ptx.cuh).  The kernel MUST call
+// pdl_wait() before touching anything an earlier kernel of the stream produced.  IE_PDL=0 in the environment (or
+// ie_conv_set_mode flag bit 10) turns the attribute off: plain stream-ordered launches.
+bool pdl_enabled();
+void pdl_set(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace ie
 
 #define IE_REQUIRE(cond, ...)        \

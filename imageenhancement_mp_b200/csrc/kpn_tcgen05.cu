@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kused = p.ksteps * 8;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                             // the basis, the coefficients and (later passes) out are ready
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.tiles_x * p.tiles_y;
   // this CTA's contiguous range of the (image, tile) list
@@ -357,8 +359,8 @@ extern "C" int ie_kpn_apply_tc(const float* burst, int burst_pitch, const float*
       p.t0 = t0;
       p.accf = b0 > 0;                                    // later basis blocks add to everything,
       p.acc0 = b0 > 0 || t0 > 0;                          // later frame passes to the frame mean out[..., 0]
-      kpn_tcgen05_kernel<<<(unsigned)grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-      IE_LAUNCH_CHECK();
+      IE_CUDA(launch_pdl(kpn_tcgen05_kernel, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmemBytes,
+                         static_cast<cudaStream_t>(stream), p));
     }
   }
   return IE_OK;

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(256)
 maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, int x_pitch_v, int x_coff_v,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale,
                 int stat_y0, int stat_y1, int bi, int bo) {
+  pdl_trigger();
+  pdl_wait();
   // bi / bo: border of the input / output tensor (1 = shared-border raster, 0 = dense NHWC)
   const int ho = h >> 1, wo = w >> 1, wpo = wo + bo, wpi = w + bi;
   const int cl = threadIdx.x % cvb, pl = threadIdx.x / cvb, npl = blockDim.x / cvb;
@@ -154,6 +156,8 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
 __global__ void __launch_bounds__(256)
 upsample_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v, int s,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, int bi, int bo) {
+  pdl_trigger();
+  pdl_wait();
   const int ho = h * s, wo = w * s, wpo = wo + bo;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= wpo * cvec) return;
@@ -208,6 +212,8 @@ __device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 l) {
 __global__ void __launch_bounds__(256)
 upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitch_v, int x_coff_v,
                  uint4* __restrict__ y, int y_pitch_v, int y_coff_v, int bi, int bo) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (w + 1) * cvec) return;
   const int jb = idx / cvec, cv = idx - jb * cvec;
@@ -263,6 +269,8 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
 // block = 256 threads = 32 pixel lanes x 8 vector lanes (64 channels); grid = (c/64, n, splits).
 __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, int x_pitch_v, int x_coff_v,
                                     float* __restrict__ mean, int c, float scale, int y0, int y1, int bi) {
+  pdl_trigger();
+  pdl_wait();
   const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int cb = blockIdx.x, img = blockIdx.y;
   const int wp = w + bi;
@@ -292,6 +300,8 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
 
 __global__ void broadcast_kernel(const float* __restrict__ vec, int n, int kh, int kw, int cvec, int c,
                                  uint4* __restrict__ y, int y_pitch_v, int y_coff_v, int bo) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)n * (kh + bo) * (kw + bo) * cvec;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -331,6 +341,8 @@ __global__ void raster_to_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int n
 // the row groups meet in shared memory (fixed order).  The per-(image, basis) kernel below reads with a stride of
 // b floats - one 32-byte sector per value - which was 0.6 ms at Basis_kpn's T = 8, B = 90 (166 MB of basis).
 __global__ void softmax_taps_rows_kernel(const float* __restrict__ in, int taps, int b, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];                         // [groups][b]
   const float* src = in + (long long)blockIdx.x * taps * b;
   float* dst = out + (long long)blockIdx.x * taps * b;
@@ -508,10 +520,9 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
   if (stat_count <= 0) stat_count = (long long)h * w;
   IE_REQUIRE(stat_y0 >= 0 && stat_y1 <= h && stat_y0 % 2 == 0 && stat_y1 % 2 == 0 && stat_y0 < stat_y1,
              "maxpool2: bad statistics row range [%d, %d)", stat_y0, stat_y1);
-  maxpool2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, cvec, cvb, x_pitch / 8, x_coff / 8,
-                                                  static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, chan_mean,
-                                                  1.f / (float)stat_count, stat_y0, stat_y1, bi, bo);
-  IE_LAUNCH_CHECK();
+  IE_CUDA(launch_pdl(maxpool2_kernel, grid, dim3(threads), 0, S(stream), static_cast<const uint4*>(x), h, w, cvec, cvb,
+                     x_pitch / 8, x_coff / 8, static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, chan_mean,
+                     1.f / (float)stat_count, stat_y0, stat_y1, bi, bo));
   return IE_OK;
 }
 
@@ -527,16 +538,14 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
   if (scale == 2) {
     const int threads = row_block((long long)(w + 1) * (c / 8), &nb);
     dim3 grid(nb, h + 1, n);
-    upsample2_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8,
-                                                     static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bi, bo);
-    IE_LAUNCH_CHECK();
+    IE_CUDA(launch_pdl(upsample2_kernel, grid, dim3(threads), 0, S(stream), static_cast<const uint4*>(x), h, w, c / 8,
+                       x_pitch / 8, x_coff / 8, static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bi, bo));
     return IE_OK;
   }
   const int threads = row_block((long long)(w * scale + bo) * (c / 8), &nb);
   dim3 grid(nb, h * scale + bo, n);
-  upsample_kernel<<<grid, threads, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, c / 8, x_pitch / 8, x_coff / 8, scale,
-                                              static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bi, bo);
-  IE_LAUNCH_CHECK();
+  IE_CUDA(launch_pdl(upsample_kernel, grid, dim3(threads), 0, S(stream), static_cast<const uint4*>(x), h, w, c / 8,
+                     x_pitch / 8, x_coff / 8, scale, static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bi, bo));
   return IE_OK;
 }
 
@@ -559,9 +568,8 @@ extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int
   if (splits > 65535) splits = 65535;
   IE_REQUIRE(n <= 65535, "channel_mean: n too large");
   dim3 grid(c / 64, n, splits);
-  channel_mean_kernel<<<grid, 256, 0, S(stream)>>>(static_cast<const uint4*>(x), h, w, x_pitch / 8, x_coff / 8, mean,
-                                                  c, 1.f / (float)count, y0, y1, bi);
-  IE_LAUNCH_CHECK();
+  IE_CUDA(launch_pdl(channel_mean_kernel, grid, dim3(256), 0, S(stream), static_cast<const uint4*>(x), h, w, x_pitch / 8,
+                     x_coff / 8, mean, c, 1.f / (float)count, y0, y1, bi));
   return IE_OK;
 }
 
@@ -572,9 +580,8 @@ extern "C" int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int
   const int bo = (layout & IE_LAYOUT_Y_DENSE) ? 0 : 1;
   if (int rc = check_slice("broadcast(y)", c, y_pitch, y_coff)) return rc;
   const long long total = (long long)n * (kh + bo) * (kw + bo) * (c / 8);
-  broadcast_kernel<<<ie_ceil_div(total, 256), 256, 0, S(stream)>>>(vec, n, kh, kw, c / 8, c, static_cast<uint4*>(y),
-                                                                  y_pitch / 8, y_coff / 8, bo);
-  IE_LAUNCH_CHECK();
+  IE_CUDA(launch_pdl(broadcast_kernel, dim3(ie_ceil_div(total, 256)), dim3(256), 0, S(stream), vec, n, kh, kw, c / 8, c,
+                     static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, bo));
   return IE_OK;
 }
 
@@ -595,7 +602,7 @@ extern "C" int ie_softmax_taps_f32(const float* originbasis, int n, int taps, in
   if (b <= 256) {
     const int threads = ((long long)taps * b > 16384) ? 1024 : 256;
     const size_t smem = sizeof(float) * (size_t)(threads / b) * b;
-    softmax_taps_rows_kernel<<<n, threads, smem, S(stream)>>>(originbasis, taps, b, bas);
+    IE_CUDA(launch_pdl(softmax_taps_rows_kernel, dim3(n), dim3(threads), smem, S(stream), originbasis, taps, b, bas));
   } else {
     softmax_taps_kernel<<<n * b, 256, 0, S(stream)>>>(originbasis, taps, b, bas);
   }

@@ -79,6 +79,7 @@ class Engine:
         self.wp, self.bias = {}, {}
         self._plans = {}
         self._graphs = {}
+        self._ws = None
         with torch.cuda.device(self.device):
             self.load_weights(weights)
         # small batches are launch-bound (44 kernels through ctypes, ~1.5 ms of host time vs ~0.3 ms of GPU time for
@@ -102,6 +103,13 @@ class Engine:
             self.bias[name] = b.to(self.device, torch.float32).contiguous()
 
     # ------------------------------------------------------------------ buffers
+    def _workspace(self):
+        """Split-K scratch of this engine (one per engine: its kernels are stream-ordered; a captured graph keeps using
+        the buffer it was captured with)."""
+        if self._ws is None:
+            self._ws = torch.empty(ops.SPLITK_WORKSPACE_BYTES, dtype=torch.uint8, device=self.device)
+        return self._ws
+
     def _plan(self, n, h, w):
         key = (n, h, w)
         if key in self._plans:
@@ -230,8 +238,12 @@ class Engine:
         chans = dict(A["downs"])
         dnames = [d for d, _ in A["downs"]]
 
+        # split-K scratch: the library only uses it for layers with too few output tiles to fill the SMs (small inputs,
+        # and the per-image basis branch of small batches)
+        ws = self._workspace()
+
         def conv(name, src, dst, k=3, valid=None):
-            ops.conv2d(src, W[name], Bv[name], dst, k=k, relu=True, valid=valid, fn=conv_fn)
+            ops.conv2d(src, W[name], Bv[name], dst, k=k, relu=True, valid=valid, fn=conv_fn, workspace=ws)
             if taps is not None:
                 hv, wv = (dst.r.h, dst.r.w) if valid is None else valid
                 taps[name] = ops.raster_to_nhwc(dst)[:, :hv, :wv]

@@ -154,13 +154,29 @@ def _desc(src: Slice, kh, kw, cout, relu, epilogue, dst: Slice | None, valid=Non
     return d
 
 
-def conv2d(src: Slice, w_packed, bias, dst: Slice, k=3, relu=True, valid=None, fn="ie_conv2d_nhwc_bf16"):
-    """Conv2D(k, relu) from a raster slice into a raster slice (bf16 epilogue)."""
+_WORKSPACES = {}
+SPLITK_WORKSPACE_BYTES = 32 << 20
+
+
+def conv_workspace(device):
+    """Per-(device, stream) split-K scratch for convolutions with very few output tiles (see ie_conv2d_nhwc_bf16).  One
+    buffer per stream: the two kernels that use it run back to back on that stream."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = _WORKSPACES[key] = torch.empty(SPLITK_WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+    return ws
+
+
+def conv2d(src: Slice, w_packed, bias, dst: Slice, k=3, relu=True, valid=None, fn="ie_conv2d_nhwc_bf16", workspace=None):
+    """Conv2D(k, relu) from a raster slice into a raster slice (bf16 epilogue).  ``workspace``: uint8 CUDA tensor for
+    split-K (tiny inputs); None = never split."""
     if dst.r.dense != src.r.dense:
         raise _lib.ImgEnhError("conv: input and output must use the same layout (both dense or both shared-border rasters)")
     assert dst.r.rows == src.r.rows, "conv output must share the input raster geometry"
     d = _desc(src, k, k, dst.c, relu, IE_EPI_BF16_RASTER, dst, valid)
-    _timed_conv(fn, C.byref(d), ptr(src.r.data), ptr(w_packed), ptr(bias), ptr(dst.r.data), None, None, stream())
+    _timed_conv(fn, C.byref(d), ptr(src.r.data), ptr(w_packed), ptr(bias), ptr(dst.r.data), None, None,
+                ptr(workspace), workspace.numel() if workspace is not None else 0, stream())
 
 
 def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, softmax=False, want_logits=False,
@@ -187,11 +203,11 @@ def conv2d_f32(src: Slice, w_packed, bias, cout, k=3, relu=True, valid=None, sof
             d = _desc(src, k, k, cc, relu, epi, None, valid)
             d.y_pitch, d.y_coff = cout, c0
             _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed[c0:]), ptr(bias[c0:]) if bias is not None else None, None,
-                        ptr(y), None, stream())
+                        ptr(y), None, None, 0, stream())
         return y
     d = _desc(src, k, k, cout, relu, epi, None, valid)
     aux = torch.empty_like(y) if (softmax and want_logits) else None
-    _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed), ptr(bias), None, ptr(y), ptr(aux), stream())
+    _timed_conv(fn, C.byref(d), ptr(r.data), ptr(w_packed), ptr(bias), None, ptr(y), ptr(aux), None, 0, stream())
     return (y, aux) if softmax else y
 
 

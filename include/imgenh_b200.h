@@ -96,19 +96,27 @@ int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, int c, int h,
                             const float* bias, int cout, int relu, void* y_bf16, int y_pitch, int y_coff, void* stream);
 
 /* y = epilogue(conv(x, w) + bias).  w_packed from ie_pack_conv_weights with ktot_pad = kh*kw*cin.
- * y_bf16 is used by IE_EPI_BF16_RASTER; y_f32 (and optional y_aux) by the fp32 epilogues.            */
+ * y_bf16 is used by IE_EPI_BF16_RASTER; y_f32 (and optional y_aux) by the fp32 epilogues.
+ * workspace (nullable, 16-byte aligned device memory of workspace_bytes, caller-owned like every other buffer): scratch
+ * for split-K.  When a layer has so few output tiles that most SMs would idle (eval.py's default call is ONE 32 x 32
+ * patch: 1024-channel layers with K up to 18432 on a single M tile), its K loop is cut into up to
+ * workspace_bytes / (128*ceil(rows/128) * cout_pad * 4) parts computed by different CTAs; the fp32 partial sums go
+ * through the workspace and a second kernel reduces them in a fixed order (deterministic).  NULL: never split.
+ * The workspace is only used between this call's two kernels; calls on the same stream may share it.            */
 int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_bf16,
-                        float* y_f32, float* y_aux, void* stream);
+                        float* y_f32, float* y_aux, void* workspace, long long workspace_bytes, void* stream);
 
 /* Tuning / test hook: force the main-loop flavour of ie_conv2d_nhwc_bf16 (-1 auto, 0 streaming, 1 resident
  * weights, 2 wide-N).  flags: bit 1 one filter row per stage in the resident kernel, bit 2 wide-N streams its
- * weights, bit 3 flip the number of epilogue warp sets, bit 4 one filter row per stage in wide-N.  Process-wide. */
+ * weights, bit 3 flip the number of epilogue warp sets, bit 4 one filter row per stage in wide-N, bit 8 CTA pairs for
+ * the 64 -> 64 wide-N layers, bit 9 never split the K loop (tiny-M layers otherwise run split-K).  Process-wide.  */
 int ie_conv_set_mode(int mode, int flags);
 
 /* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at
  * sizes the CPU oracle cannot reach).  Never called by the product path.                             */
 int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                          void* y_bf16, float* y_f32, float* y_aux, void* stream);
+                          void* y_bf16, float* y_f32, float* y_aux, void* workspace, long long workspace_bytes,
+                          void* stream);
 
 /* ---- layout glue of the U-Net (bandwidth kernels) ------------------------------------------------- */
 

@@ -134,6 +134,39 @@ def test_conv_dense_im2col_vs_cpu(cuda, n, h, w, cin, cout, k):
     assert_close_bf16(ops.raster_to_nhwc(d3.slice()).cpu(), got, "dense vs raster layout")
 
 
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 1024, 1024), (1, 4, 4, 2048, 512), (3, 2, 2, 2048, 512),
+                                            (1, 16, 16, 128, 128), (2, 8, 8, 512, 64)])
+def test_conv_split_k_for_tiny_m(cuda, dense, n, h, w, cin, cout):
+    """Tiny M (eval.py's default call: one 32 x 32 patch): the K loop of a tile is split over many CTAs, the fp32
+    partial sums are reduced in a fixed order by a second kernel.  Same numbers as the unsplit kernel (to fp32
+    summation order), deterministic from run to run, channel slices and borders intact."""
+    from imageenhancement_mp_b200 import _lib, ops
+    lib = _lib.load()
+    x, wt, b = make_case(n, h, w, cin, cout, 3)
+    ref = bf16_round(ref_conv(x, wt, b, 3))
+    src = (to_dense if dense else to_raster)(x.to(cuda))
+    wp = ops.pack_conv_weights(wt.to(cuda))
+    outs = []
+    try:
+        for flags in (0, 0, 1 << 9):                          # split-K (auto) twice, then forced off
+            lib.ie_conv_set_mode(0, flags)                    # mode 0: the streaming kernel
+            dst = ops.new_raster(n, h, w, cout + 64, cuda, dense=dense)
+            dst.data.fill_(3.0)
+            ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice(64, cout), workspace=ops.conv_workspace(cuda))
+            outs.append((ops.raster_to_nhwc(dst.slice(64, cout)).cpu(), dst))
+    finally:
+        lib.ie_conv_set_mode(-1, 0)
+    assert torch.equal(outs[0][0], outs[1][0]), "split-K must be deterministic"
+    assert_close_bf16(outs[0][0], ref, "split-K conv vs CPU")
+    assert_close_bf16(outs[0][0], outs[2][0], "split-K vs unsplit")
+    for _, dst in outs:
+        assert torch.all(dst.data[:, :64] == 3.0)
+        if not dense:
+            full = dst.data[:, 64:].float().view(n, h + 1, w + 1, cout)
+            assert torch.all(full[:, 0] == 0) and torch.all(full[:, :, -1] == 0)
+
+
 def test_conv_dense_rejects_what_it_does_not_support(cuda):
     from imageenhancement_mp_b200 import ops, ImgEnhError
     x, wt, b = make_case(1, 8, 8, 64, 64, 3)
