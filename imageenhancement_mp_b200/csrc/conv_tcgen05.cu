@@ -42,7 +42,7 @@ constexpr int kStgBytesPerWarp = 32 * 128;       // 32 rows x 64 bf16
 constexpr int kMaxCout = 1024;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;      // TMEM columns per accumulator buffer
-constexpr int kXchBytes = 2 * 4 * 2 * 32 * 4;     // wide-N epilogue: [half][warp][up/down][32] fp32 edge rows
+constexpr int kXchBytes = 2 * 4 * 2 * 32 * 4;     // wide-N exchange epilogue: [half][warp][up/down][32] fp32 edge rows
 // tail of the dynamic smem for `nsets` epilogue sets (4 warps each): staging + bias + barriers + exchange rows
 constexpr int tail_bytes(int nsets) {
   return nsets * 4 * kStgBytesPerWarp + kMaxCout * 4 + (2 * kMaxStages + 6) * 8 + 16 + nsets * kXchBytes;
@@ -627,10 +627,22 @@ conv_resident_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 // so each A row block is read once per filter row (12 MMAs of 10 KB per 128 pixels instead of 36 of 6 KB,
 // tensor-bound at 96 cycles each), and the epilogue applies the horizontal shift on the OUTPUT side:
 //     Y[r][co] = Z[r-1][co] + Z[r][64 + co] + Z[r+1][128 + co]
-// with warp shuffles (row r lives in TMEM lane r, i.e. in thread r of the epilogue) plus a 2 KB shared-memory
-// exchange for the rows on warp boundaries.  Tiles therefore overlap by two rows (126 outputs per 128-row tile).
+// Row r lives in TMEM lane r = thread r of the epilogue, so the shift is one __shfl_up and one __shfl_down per
+// channel.  The 128 accumulator rows of a tile are FOUR SLABS of 32 raster rows, one per epilogue warp, that start 30
+// rows apart: every warp owns the neighbours of its 30 inner rows itself (lanes 0 and 31 only feed the shuffles), so
+// the warps never exchange rows - no shared-memory hand-off, no barrier between them, no per-lane edge selects (the
+// round-1 kernel tiled 126 rows per 128 with a 2 KB exchange + bar.sync per 32 channels: 1 395 LSU wavefronts and
+// ~1 000 dependent instructions per tile, which is what bounded the 64 -> 64 layers; 120 rows per tile cost 5 % more
+// MMA work and four 32-row TMA boxes per filter row instead of one 128-row box).
 // Weights: resident in smem when they fit (cin <= 128), else streamed with the A tiles.
 // =================================================================================================
+constexpr int kSlabRows = 32;          // accumulator rows (TMEM lanes) per epilogue warp
+constexpr int kSlabOut = 30;           // of which are outputs
+constexpr int kWideTileRows = 4 * kSlabOut;
+constexpr int kXchTileRows = kBlockM - 2;          // exchange variant: one 128-row box, 126 outputs
+
+__device__ __forceinline__ void epi_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }
+
 struct WideParams {
   EpiParams e;
   int dy_shift[3];       // raster-row shift of filter row dy: (dy-1)*wp
@@ -641,17 +653,181 @@ struct WideParams {
   int gw;                // accumulator columns per horizontal tap (64; 16..32 for the fp32 heads)
   int b_tile_bytes;      // 3*gw*128: weights of one (filter row, channel block): [3*gw rows][64 k]
   int a_slot_bytes;      // bytes per pipeline stage
-  int tile_rows;         // output rows per tile = 126
   int nsets;             // epilogue sets in use (1: warps 6-9 idle, 16 KB more smem for the pipeline)
 };
 
-__device__ __forceinline__ void epi_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }
+// Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
+__device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const CUtensorMap* tm_y30, const SmemTail& t,
+                                                   uint32_t tmem_base, int warp, int lane) {
+  const EpiParams& p = wp_.e;
+  const int q = warp & 3;
+  uint8_t* stg = t.stg(warp - 2);
+  const float* sbias = t.bias();
+  const int set = (warp - 2) >> 2;
+  const bool inner = (lane >= 1) && (lane <= kSlabOut);
+  int it = set;
+  for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
+    const int buf = it & 1;
+    const uint32_t use = static_cast<uint32_t>(it >> 1);
+    const int srow0 = tile * kWideTileRows - 1 + q * kSlabOut;   // raster row of this warp's lane 0
+    const int r = srow0 + lane;
+    const int rr = r < 0 ? 0 : r;
+    const int img = rr / p.plane;
+    const int pr = rr - img * p.plane;
+    const int y = pr / p.wp;
+    const int x = pr - y * p.wp;
+    const bool valid = inner && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
+    mbar_wait(&t.tfull()[buf], use & 1u);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+    uint32_t pk[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t z0[32], z1[32], z2[32];
+      tmem_ld_x32(t_base + c * 32, z0);
+      tmem_ld_x32(t_base + 64 + c * 32, z1);
+      tmem_ld_x32(t_base + 128 + c * 32, z2);
+      tmem_ld_wait();
+      if (c == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t.tempty()[buf]);
+      }
+      const uint32_t bs = smem_u32(sbias + c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = lds128(bs + j * 4);
+        const float bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);      // Z[r-1][co]
+          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);    // Z[r+1][128 + co]
+          float a = up + __uint_as_float(z1[j + e]) + dn + bbv[e];
+          if (p.relu) a = fmaxf(a, 0.f);
+          v[e] = a;
+        }
+        pk[c * 16 + (j >> 1)] = valid ? pack_bf16x2(v[0], v[1]) : 0u;
+        pk[c * 16 + (j >> 1) + 1] = valid ? pack_bf16x2(v[2], v[3]) : 0u;
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+    // lanes 1..30 hold the warp's 30 output rows: staged one row up so that the TMA source starts on a 1024-byte
+    // boundary; 16-byte chunk j of a row goes to j ^ (row & 7)  (SWIZZLE_128B)
+    if (inner) {
+      const int srow = lane - 1;
+      const uint32_t rowa = smem_u32(stg) + srow * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128u(rowa + ((j ^ (srow & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm_y30, stg, p.y_coff, srow0 + 1);       // rows beyond the raster are clipped by TMA
+      tma_store_commit();
+    }
+  }
+  if (lane == 0) tma_store_wait<0>();
+}
+
+
+// Epilogue of the wide-N kernel for the small fp32 heads (cout <= 16, gw = 16: the `coef` conv + softmax,
+// model_library.py:405-406).  Same horizontal combine as above on 16-column groups, then the single-chunk
+// fp32 path of epilogue_loop: softmax in registers, rows compacted through the staging buffer, coalesced stores.
+__device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const SmemTail& t, uint32_t tmem_base,
+                                                  int warp, int lane) {
+  const EpiParams& p = wp_.e;
+  const int q = warp & 3;
+  float* sf = reinterpret_cast<float*>(t.stg(warp - 2));
+  const float* sbias = t.bias();
+  const int set = (warp - 2) >> 2;
+  const bool sm_mode = (p.epilogue == IE_EPI_F32_SOFTMAX);
+  const bool inner = (lane >= 1) && (lane <= kSlabOut);
+  int it = set;
+  for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
+    const int buf = it & 1;
+    const uint32_t use = static_cast<uint32_t>(it >> 1);
+    const int srow0 = tile * kWideTileRows - 1 + q * kSlabOut;
+    const int r = srow0 + lane;
+    const int rr = r < 0 ? 0 : r;
+    const int img = rr / p.plane;
+    const int pr = rr - img * p.plane;
+    const int y = pr / p.wp;
+    const int x = pr - y * p.wp;
+    const bool valid = inner && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
+    const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + x;
+    mbar_wait(&t.tfull()[buf], use & 1u);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+    uint32_t z0[16], z1[16], z2[16];
+    tmem_ld_x16(t_base, z0);
+    tmem_ld_x16(t_base + 16, z1);
+    tmem_ld_x16(t_base + 32, z2);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t.tempty()[buf]);
+    const uint32_t bs = smem_u32(sbias);
+    float a[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 bb = lds128(bs + j * 4);
+      const float bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);
+        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);
+        float v = up + __uint_as_float(z1[j + e]) + dn + bbv[e];
+        if (p.relu) v = fmaxf(v, 0.f);
+        a[j + e] = v;
+        if (j + e < p.cout) mx = fmaxf(mx, v);
+      }
+    }
+    float e_[16];
+    if (sm_mode) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        e_[j] = (j < p.cout) ? __expf(a[j] - mx) : 0.f;
+        sum += e_[j];
+      }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) e_[j] *= inv;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) e_[j] = a[j];
+    }
+    // valid pixels of the warp's rows are consecutive in the NHWC output (border pixels have no slot): compact them
+    // through the staging buffer and store fully coalesced
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (bal) {
+      const int rank = __popc(bal & ((1u << lane) - 1u));
+      const int nvalid = __popc(bal);
+      const long long pix_first = __shfl_sync(0xffffffffu, pix, __ffs(bal) - 1);
+      const int total = nvalid * p.cout;
+      for (int pass = 0; pass < ((sm_mode && p.y_aux) ? 2 : 1); ++pass) {
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < p.cout) sf[rank * p.cout + j] = pass ? a[j] : e_[j];
+        }
+        __syncwarp();
+        float* dst = (pass ? p.y_aux : p.y_f32) + pix_first * p.cout;
+        for (int i = lane; i < total; i += 32) dst[i] = sf[i];
+      }
+    }
+  }
+}
 
 // Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
-// PAIR: the CTA is one half of a cta_group::2 pair; the pair walks the tile list two tiles at a time (rank r takes
-// tile 2u + r of unit u) and the "accumulator drained" arrivals go to the leader CTA, whose MMA warp feeds both.
-template <bool PAIR>
-__device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const CUtensorMap* tm_y32,
+// EXCHANGE variant (layers with more than one channel block, whose long main loop hides it): ONE 128-row box per filter
+// row, 126 outputs per tile; the rows on warp boundaries travel through a 2 KB shared-memory exchange.
+__device__ __forceinline__ void epilogue_wide_bf16_xch(const WideParams& wp_, const CUtensorMap* tm_y32,
                                                    const CUtensorMap* tm_y31, const SmemTail& t, uint32_t tmem_base,
                                                    int warp, int lane) {
   const EpiParams& p = wp_.e;
@@ -661,23 +837,18 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
   const float* sbias = t.bias();
   const int set = (warp - 2) >> 2;
   float* xch = t.xch() + set * (kXchBytes / 4);
-  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
-  const int nprog = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int prog = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int n_units = PAIR ? (p.m_tiles + 1) >> 1 : p.m_tiles;
   int it = set;
-  for (int u = prog + set * nprog; u < n_units; u += t.nsets * nprog, it += t.nsets) {
-    const int tile = PAIR ? 2 * u + rank : u;
+  for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets) {
     const int buf = it & 1;
     const uint32_t use = static_cast<uint32_t>(it >> 1);
-    const int row0 = tile * wp_.tile_rows - 1;  // raster row of tile-local row 0
+    const int row0 = tile * kXchTileRows - 1;  // raster row of tile-local row 0
     const int r = row0 + m;
     const int rr = r < 0 ? 0 : r;
     const int img = rr / p.plane;
     const int pr = rr - img * p.plane;
     const int y = pr / p.wp;
     const int x = pr - y * p.wp;
-    const bool valid = (m >= 1) && (m <= wp_.tile_rows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) &&
+    const bool valid = (m >= 1) && (m <= kXchTileRows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) &&
                        (x < p.wv);
     mbar_wait(&t.tfull()[buf], use & 1u);
     tc_fence_after();
@@ -694,8 +865,7 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&t.tempty()[buf]), 0));
-          else mbar_arrive(&t.tempty()[buf]);
+          mbar_arrive(&t.tempty()[buf]);
         }
       }
       // rows on warp boundaries travel through shared memory
@@ -757,10 +927,9 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
 }
 
 
-// Epilogue of the wide-N kernel for the small fp32 heads (cout <= 16, gw = 16: the `coef` conv + softmax,
-// model_library.py:405-406).  Same horizontal combine as above on 16-column groups, then the single-chunk
+// EXCHANGE variant of the fp32-head epilogue (cout <= 16, more than one channel block).  Same horizontal combine as above on 16-column groups, then the single-chunk
 // fp32 path of epilogue_loop: softmax in registers, rows compacted through the staging buffer, coalesced stores.
-__device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const SmemTail& t, uint32_t tmem_base,
+__device__ __forceinline__ void epilogue_wide_f32_xch(const WideParams& wp_, const SmemTail& t, uint32_t tmem_base,
                                                   int warp, int lane) {
   const EpiParams& p = wp_.e;
   const int q = warp & 3;
@@ -774,14 +943,14 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
   for (int tile = blockIdx.x + set * gridDim.x; tile < p.m_tiles; tile += t.nsets * gridDim.x, it += t.nsets, ++local) {
     const int buf = it & 1;
     const uint32_t use = static_cast<uint32_t>(it >> 1);
-    const int row0 = tile * wp_.tile_rows - 1;
+    const int row0 = tile * kXchTileRows - 1;
     const int r = row0 + m;
     const int rr = r < 0 ? 0 : r;
     const int img = rr / p.plane;
     const int pr = rr - img * p.plane;
     const int y = pr / p.wp;
     const int x = pr - y * p.wp;
-    const bool valid = (m >= 1) && (m <= wp_.tile_rows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
+    const bool valid = (m >= 1) && (m <= kXchTileRows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
     const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + x;
     mbar_wait(&t.tfull()[buf], use & 1u);
     tc_fence_after();
@@ -864,11 +1033,12 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
 }
 
 // RES: weights resident in smem.  G: filter rows per pipeline stage (3 needs RES and kb == 1).
-template <bool RES, int G>
+// SLAB: tm_a is a box of kSlabRows rows (one slab of one filter row), 120 outputs per tile, tm_y1 = 30-row store box
+// (tm_y2 unused); else tm_a is ONE 128-row box, 126 outputs per tile, tm_y1 / tm_y2 = 32- / 31-row store boxes.
+template <bool RES, int G, bool SLAB>
 __global__ void __launch_bounds__(kThreads2, 1)
 conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_y32, const __grid_constant__ CUtensorMap tm_y31,
-                 const WideParams p) {
+                 const __grid_constant__ CUtensorMap tm_y1, const __grid_constant__ CUtensorMap tm_y2, const WideParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024(smem_raw);
   const int b_res_bytes = RES ? 3 * p.kb * p.b_tile_bytes : 0;
@@ -881,13 +1051,17 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    tma_prefetch_desc(&tm_y32);
-    tma_prefetch_desc(&tm_y31);
+    tma_prefetch_desc(&tm_y1);
+    tma_prefetch_desc(&tm_y2);
   }
   const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane);
   uint64_t* full_bar = t.full();
   uint64_t* empty_bar = t.empty();
   const int piece = p.gw * 128;                    // one horizontal tap's weights: [gw rows][64 k]
+  constexpr int kSlabBytes = kSlabRows * 128;
+  constexpr int kBoxes = SLAB ? 4 : 1;             // TMA boxes per filter row and channel block
+  constexpr int kBoxStep = SLAB ? kSlabOut : 0;
+  constexpr int kTileRows = SLAB ? kWideTileRows : kXchTileRows;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -903,14 +1077,16 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * p.tile_rows - 1;
+        const int row0 = tile * kTileRows - 1;                // raster row of accumulator row 0
         if constexpr (G == 3) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], 3u * kABytes);
 #pragma unroll
           for (int g = 0; g < 3; ++g)
-            tma_load_2d(a_base_ptr + stage * p.a_slot_bytes + g * kABytes, &tm_a, &full_bar[stage], p.x_coff,
-                        row0 + p.dy_shift[g]);
+#pragma unroll
+            for (int sl = 0; sl < kBoxes; ++sl)
+              tma_load_2d(a_base_ptr + stage * p.a_slot_bytes + g * kABytes + sl * kSlabBytes, &tm_a, &full_bar[stage],
+                          p.x_coff, row0 + sl * kBoxStep + p.dy_shift[g]);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         } else {
           for (int dy = 0; dy < 3; ++dy) {
@@ -918,7 +1094,10 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&full_bar[stage], kABytes + (RES ? 0u : static_cast<uint32_t>(p.b_tile_bytes)));
               uint8_t* a_dst = a_base_ptr + stage * p.a_slot_bytes;
-              tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, row0 + p.dy_shift[dy]);
+#pragma unroll
+              for (int sl = 0; sl < kBoxes; ++sl)
+                tma_load_2d(a_dst + sl * kSlabBytes, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK,
+                            row0 + sl * kBoxStep + p.dy_shift[dy]);
               if constexpr (!RES) {
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx)
@@ -975,148 +1154,16 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp >= 2 + 4 * p.nsets) {
     // second epilogue set not in use
   } else if (p.e.epilogue == IE_EPI_BF16_RASTER) {
-    epilogue_wide_bf16<false>(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
+    if constexpr (SLAB) epilogue_wide_bf16(p, &tm_y1, t, tmem_base, warp, lane);
+    else epilogue_wide_bf16_xch(p, &tm_y1, &tm_y2, t, tmem_base, warp, lane);
   } else {
-    epilogue_wide_f32(p, t, tmem_base, warp, lane);
+    if constexpr (SLAB) epilogue_wide_f32(p, t, tmem_base, warp, lane);
+    else epilogue_wide_f32_xch(p, t, tmem_base, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-
-// =================================================================================================
-// Wide-N kernel on CTA PAIRS (cta_group::2, cluster 2x1x1) for the 64 -> 64 layers (one channel block, resident
-// weights, a whole 3 x 64 filter row set per stage).  The single-CTA kernel above is bound by the shared-memory port:
-// per 126-pixel tile the tensor core reads 48 KB of A and 72 KB of weights.  In a pair every MMA is M = 256 (each CTA
-// supplies the 128 rows of ITS tile) x N = 192, and each CTA supplies only HALF of the weight columns (96 of 192):
-// 36 KB of weight reads per tile and CTA, 36 KB of resident weights instead of 72 (room for a third A stage).
-// Roles per CTA: warp 0 TMA producer (its own A boxes and weight half; bytes complete on the LEADER's barriers),
-// warp 1 TMEM allocation and - in the leader only - the MMA issuer for both CTAs (commits are multicast to the
-// barriers of both), warps 2-9 the two epilogue sets, each draining the accumulator of its own CTA.
-// =================================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
-conv_wide_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b64,
-                      const __grid_constant__ CUtensorMap tm_b32, const __grid_constant__ CUtensorMap tm_y32,
-                      const __grid_constant__ CUtensorMap tm_y31, const WideParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = align1024(smem_raw);
-  constexpr int kBHalf = 96 * 128;                 // one filter row's weight half: [96 columns][64 k] bf16
-  constexpr int kBRes = 3 * kBHalf;
-  uint8_t* a_base_ptr = base + kBRes;
-  SmemTail t{a_base_ptr + p.stages * p.a_slot_bytes, p.nsets};
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int rank = static_cast<int>(cluster_ctarank());
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int n_units = (p.e.m_tiles + 1) >> 1;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b64);
-    tma_prefetch_desc(&tm_b32);
-    tma_prefetch_desc(&tm_y32);
-    tma_prefetch_desc(&tm_y31);
-  }
-  // ---- setup (cta_setup with pair-wide barrier counts and a cluster barrier)
-  for (int i = threadIdx.x; i < kMaxCout; i += blockDim.x) t.bias()[i] = (i < p.e.cout && p.e.bias) ? p.e.bias[i] : 0.f;
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&t.full()[s], 2);                // one arrive.expect_tx per CTA of the pair (used in the leader)
-      mbar_init(&t.empty()[s], 1);               // multicast commit
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&t.tfull()[b], 1);               // multicast commit
-      mbar_init(&t.tempty()[b], 8);               // 4 epilogue warps x 2 CTAs (used in the leader)
-    }
-    mbar_init(t.bres(), 2);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc_pair(t.tmem_slot(), kTmemCols);
-    tmem_relinquish_pair();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                            // the peer's barriers exist before anything arrives on them
-  tc_fence_after();
-  const uint32_t tmem_base = *t.tmem_slot();
-  uint64_t* full_bar = t.full();
-  uint64_t* empty_bar = t.empty();
-
-  if (warp == 0) {
-    // ================================ TMA producer (both CTAs) ================================
-    if (lane == 0) {
-      mbar_arrive_expect_tx_cluster(mapa_rank(smem_u32(t.bres()), 0), static_cast<uint32_t>(kBRes));
-      for (int dy = 0; dy < 3; ++dy) {
-        uint8_t* b = base + dy * kBHalf;
-        if (rank == 0) {      // columns 0-95: tap dx = 0 (64 output channels) + channels 0-31 of dx = 1
-          tma_load_2d_pair(b, &tm_b64, t.bres(), (dy * 3 + 0) * p.cin, 0);
-          tma_load_2d_pair(b + 64 * 128, &tm_b32, t.bres(), (dy * 3 + 1) * p.cin, 0);
-        } else {              // columns 96-191: channels 32-63 of dx = 1 + tap dx = 2
-          tma_load_2d_pair(b, &tm_b32, t.bres(), (dy * 3 + 1) * p.cin, 32);
-          tma_load_2d_pair(b + 32 * 128, &tm_b64, t.bres(), (dy * 3 + 2) * p.cin, 0);
-        }
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = pair; u < n_units; u += npairs) {
-        const int row0 = (2 * u + rank) * p.tile_rows - 1;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx_cluster(mapa_rank(smem_u32(&full_bar[stage]), 0), 3u * kABytes);
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-          tma_load_2d_pair(a_base_ptr + stage * p.a_slot_bytes + g * kABytes, &tm_a, &full_bar[stage], p.x_coff,
-                           row0 + p.dy_shift[g]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (leader CTA only) ============================
-    if (rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(2 * kBlockM, 3 * p.gw);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base_ptr));
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(base));
-      const uint32_t a_stride = static_cast<uint32_t>(p.a_slot_bytes) >> 4;
-      mbar_wait(t.bres(), 0);
-      tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int u = pair; u < n_units; u += npairs, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = static_cast<uint32_t>(it >> 1);
-        mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_slot_lo = a_lo0 + stage * a_stride;
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const uint32_t a = a_slot_lo + g * (kABytes >> 4);
-            const uint32_t b = b_lo0 + g * (kBHalf >> 4);
-            umma_bf16_ss_lo_pair(d_tmem, a, b, idesc, g == 0 ? 0u : 1u);
-            umma_bf16_ss_lo_pair(d_tmem, a + 2, b + 2, idesc, 1u);
-            umma_bf16_ss_lo_pair(d_tmem, a + 4, b + 4, idesc, 1u);
-            umma_bf16_ss_lo_pair(d_tmem, a + 6, b + 6, idesc, 1u);
-          }
-          umma_commit_pair(&empty_bar[stage]);
-          umma_commit_pair(&t.tfull()[buf]);
-        }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else {
-    epilogue_wide_bf16<true>(p, &tm_y32, &tm_y31, t, tmem_base, warp, lane);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                            // the leader reads the peer's shared memory until its last MMA
-  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
 
@@ -1334,7 +1381,6 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 // Tuning / test hooks (not part of the documented ABI surface): force a main-loop flavour.
 static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
-static int g_pair_mode = 0;          // 1: 64 -> 64 wide layers on CTA pairs (cta_group::2)
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
@@ -1346,8 +1392,7 @@ static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if
 extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_force_mode = mode;
   ie::g_fuse_rows = (flags & 2) ? 0 : 1;
-  ie::g_wide_flags = (flags >> 2) & 7;
-  ie::g_pair_mode = (flags >> 8) & 1;
+  ie::g_wide_flags = ((flags >> 2) & 7) | (((flags >> 11) & 1) << 3);      // bit 11: exchange epilogue for one-block layers
   ie::g_splitk = ((flags >> 9) & 1) ? 0 : 1;
   ie::pdl_set(((flags >> 10) & 1) == 0);
   return IE_OK;
@@ -1437,8 +1482,6 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   if (wide) {
     WideParams p{};
     p.e = e;
-    p.tile_rows = kBlockM - 2;
-    p.e.m_tiles = (int)((R + p.tile_rows - 1) / p.tile_rows);
     for (int i = 0; i < 3; ++i) p.dy_shift[i] = (i - 1) * wp;
     p.kb = d->cin / 64;
     p.x_coff = d->x_coff;
@@ -1448,6 +1491,14 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     const int w_bytes = 3 * p.kb * p.b_tile_bytes;
     const bool res = w_bytes <= 150 * 1024 && !(g_wide_flags & 1);
     const bool fuse = res && p.kb == 1 && !(g_wide_flags & 4);
+    // one channel block (the 64 -> 64 layers, the coef head): the tile's main loop is 12 MMAs and the epilogue is the
+    // critical path -> per-warp slabs (no cross-warp exchange, 120 outputs per tile, four 32-row boxes per filter row).
+    // Deeper layers hide the epilogue behind their main loop and are bound by TMA latency / issue instead -> one
+    // 128-row box per stage, 126 outputs per tile, rows on warp boundaries exchanged through shared memory
+    // (measured on B200 with slabs everywhere: 640 -> 64 417 -> 601 us, 128 -> 64 370 -> 479 us).
+    const bool slab = fuse && !(g_wide_flags & 8);
+    const int tile_rows = slab ? kWideTileRows : kXchTileRows;
+    p.e.m_tiles = (int)((R + tile_rows - 1) / tile_rows);
     p.a_slot_bytes = fuse ? 3 * kABytes : kABytes + (res ? 0 : p.b_tile_bytes);
     // two epilogue sets when the main loop of a tile is short (one channel block); deeper layers hide the epilogue
     // anyway and need the 16 KB for pipeline stages (measured: 128->64 resident 378 us with one set, 487 with two)
@@ -1457,47 +1508,34 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     int stages = ((int)kMaxSmem - 1024 - tail - (res ? w_bytes : 0)) / p.a_slot_bytes;
     p.stages = stages > kMaxStages ? kMaxStages : stages;
     IE_REQUIRE(p.stages >= 2, "conv: wide-N pipeline does not fit in shared memory");
-    CUtensorMap tm_y31;
-    rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
+    CUtensorMap tm_y1, tm_y2;
+    rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, slab ? kSlabRows : kBlockM);
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&tm_b, w_packed, (uint64_t)ktot, (uint64_t)p.gw, (uint64_t)ktot, 64, (uint32_t)p.gw);
     if (rc) return rc;
     if (wide_f32) {
-      tm_y = tm_a;                      // unused by the fp32 epilogue
-      tm_y31 = tm_a;
+      tm_y1 = tm_a;                     // unused by the fp32 epilogues
+      tm_y2 = tm_a;
     } else {
-      rc = make_tmap_2d_bf16(&tm_y31, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 31);
+      rc = make_tmap_2d_bf16(&tm_y1, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, slab ? kSlabOut : 32);
+      if (rc) return rc;
+      rc = make_tmap_2d_bf16(&tm_y2, y_bf16, (uint64_t)d->y_pitch, (uint64_t)R, (uint64_t)d->y_pitch, 64, 31);
       if (rc) return rc;
     }
     const size_t smem = 1024 + (size_t)(res ? w_bytes : 0) + (size_t)p.stages * p.a_slot_bytes + tail;
     const int grid = p.e.m_tiles < grid_cap ? p.e.m_tiles : grid_cap;
-#define IE_LAUNCH_WIDE(RES_, G_)                                                                                  \
+#define IE_LAUNCH_WIDE(RES_, G_, SLAB_)                                                                           \
   do {                                                                                                            \
-    IE_CUDA(cudaFuncSetAttribute(conv_wide_kernel<RES_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+    IE_CUDA(cudaFuncSetAttribute(conv_wide_kernel<RES_, G_, SLAB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                  (int)kMaxSmem));                                                                 \
-    IE_CUDA(launch_pdl(conv_wide_kernel<RES_, G_>, dim3(grid), dim3(kThreads2), smem, st, tm_a, tm_b, tm_y, tm_y31, p)); \
+    IE_CUDA(launch_pdl(conv_wide_kernel<RES_, G_, SLAB_>, dim3(grid), dim3(kThreads2), smem, st, tm_a, tm_b, tm_y1, \
+                       tm_y2, p));                                                                                \
   } while (0)
-    const bool pairs = fuse && !wide_f32 && g_pair_mode == 1 && grid_cap >= 2;
-    if (pairs) {
-      // CTA pairs: half of the weights per CTA (36 KB), one more A stage
-      WideParams q = p;
-      q.nsets = 2;
-      const int tail2 = tail_bytes(q.nsets);
-      int st2 = ((int)kMaxSmem - 1024 - tail2 - 3 * 96 * 128) / q.a_slot_bytes;
-      q.stages = st2 > kMaxStages ? kMaxStages : st2;
-      CUtensorMap tm_b32;
-      rc = make_tmap_2d_bf16(&tm_b32, w_packed, (uint64_t)ktot, (uint64_t)p.gw, (uint64_t)ktot, 64, 32);
-      if (rc) return rc;
-      const size_t smem2 = 1024 + (size_t)3 * 96 * 128 + (size_t)q.stages * q.a_slot_bytes + tail2;
-      const int units = (q.e.m_tiles + 1) / 2;
-      const int npairs = units < grid_cap / 2 ? units : grid_cap / 2;
-      IE_CUDA(cudaFuncSetAttribute(conv_wide_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      conv_wide_pair_kernel<<<2 * npairs, kThreads2, smem2, st>>>(tm_a, tm_b, tm_b32, tm_y, tm_y31, q);
-    } else if (fuse) IE_LAUNCH_WIDE(true, 3);
-    else if (res) IE_LAUNCH_WIDE(true, 1);
-    else IE_LAUNCH_WIDE(false, 1);
+    if (fuse && slab) IE_LAUNCH_WIDE(true, 3, true);
+    else if (fuse) IE_LAUNCH_WIDE(true, 3, false);
+    else if (res) IE_LAUNCH_WIDE(true, 1, false);
+    else IE_LAUNCH_WIDE(false, 1, false);
 #undef IE_LAUNCH_WIDE
-    IE_LAUNCH_CHECK();
     return IE_OK;
   }
 

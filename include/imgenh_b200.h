@@ -108,8 +108,9 @@ int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_pack
 
 /* Tuning / test hook: force the main-loop flavour of ie_conv2d_nhwc_bf16 (-1 auto, 0 streaming, 1 resident
  * weights, 2 wide-N).  flags: bit 1 one filter row per stage in the resident kernel, bit 2 wide-N streams its
- * weights, bit 3 flip the number of epilogue warp sets, bit 4 one filter row per stage in wide-N, bit 8 CTA pairs for
- * the 64 -> 64 wide-N layers, bit 9 never split the K loop (tiny-M layers otherwise run split-K).  Process-wide.  */
+ * weights, bit 3 flip the number of epilogue warp sets, bit 4 one filter row per stage in wide-N, bit 9 never split
+ * the K loop (tiny-M layers otherwise run split-K), bit 10 plain stream-ordered launches instead of programmatic
+ * dependent launch.  Process-wide.                                                                              */
 int ie_conv_set_mode(int mode, int flags);
 
 /* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at

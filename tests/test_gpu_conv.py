@@ -212,36 +212,6 @@ def test_conv_narrow_flavours(cuda, mode, n, h, w, cin):
     assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
 
 
-@pytest.mark.parametrize("n,h,w", [(1, 8, 8), (2, 16, 24), (3, 40, 56), (7, 24, 104)])
-def test_conv_cta_pair_kernel(cuda, n, h, w):
-    """The cta_group::2 (M = 256, cluster of two CTAs) flavour of the 64 -> 64 wide-N kernel (`ie_conv_set_mode` flag
-    256; slower than the single-CTA kernel on B200 and therefore not the default): CPU parity,
-    zeroed borders, bit-identical to the default kernel - even and odd tile counts, fewer tiles than SMs."""
-    from imageenhancement_mp_b200 import ops, _lib
-    lib = _lib.load()
-    x, wt, b = make_case(n, h, w, 64, 64, 3, seed=77)
-    ref = bf16_round(ref_conv(x, wt, b, 3))
-    src = to_raster(x.to(cuda))
-    wp = ops.pack_conv_weights(wt.to(cuda))
-    outs = []
-    try:
-        for flags in (0, 256):
-            lib.ie_conv_set_mode(-1, flags)
-            dst = ops.new_raster(n, h, w, 64, cuda)
-            dst.data.fill_(float("nan"))
-            ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice())
-            torch.cuda.synchronize()
-            outs.append(dst)
-    finally:
-        lib.ie_conv_set_mode(-1, 0)
-    assert torch.equal(outs[0].data, outs[1].data)
-    assert_close_bf16(ops.raster_to_nhwc(outs[1].slice()).cpu(), ref, "cta pair 64->64")
-    full = outs[1].data.float().view(n, h + 1, w + 1, 64)
-    mask = torch.ones(h + 1, w + 1, dtype=torch.bool, device=cuda)
-    mask[1:h + 1, 0:w] = False
-    assert torch.all(full[:, mask] == 0), "border rows were not zeroed"
-
-
 def test_conv_slices_and_concat(cuda):
     """Input read from a channel window, output written into a channel window (concat by slices)."""
     from imageenhancement_mp_b200 import ops
