@@ -654,6 +654,7 @@ struct WideParams {
   int b_tile_bytes;      // 3*gw*128: weights of one (filter row, channel block): [3*gw rows][64 k]
   int a_slot_bytes;      // bytes per pipeline stage
   int nsets;             // epilogue sets in use (1: warps 6-9 idle, 16 KB more smem for the pipeline)
+  int prefetch;          // L2-prefetch the next tile's A boxes (G == 1 variants)
 };
 
 // Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
@@ -1089,8 +1090,19 @@ conv_wide_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                           p.x_coff, row0 + sl * kBoxStep + p.dy_shift[g]);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         } else {
+          // layers with several channel blocks keep only 3 - 5 A stages next to their weights and are bound by the
+          // latency of the A boxes (HBM under load: ~2 us for 48 - 80 KB in flight per SM): pull the NEXT tile's
+          // boxes into L2 while this tile's are consumed, so that the loads that fill the stages hit L2
+          const int next_tile = tile + gridDim.x;
+          const bool pf = p.prefetch && next_tile < num_tiles;
+          const int next_row0 = next_tile * kTileRows - 1;
           for (int dy = 0; dy < 3; ++dy) {
             for (int kb = 0; kb < p.kb; ++kb) {
+              if (pf) {
+#pragma unroll
+                for (int sl = 0; sl < kBoxes; ++sl)
+                  tma_prefetch_2d(&tm_a, p.x_coff + kb * kBlockK, next_row0 + sl * kBoxStep + p.dy_shift[dy]);
+              }
               mbar_wait(&empty_bar[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&full_bar[stage], kABytes + (RES ? 0u : static_cast<uint32_t>(p.b_tile_bytes)));
               uint8_t* a_dst = a_base_ptr + stage * p.a_slot_bytes;
@@ -1382,6 +1394,7 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
+static int g_wide_prefetch = 1;      // wide-N layers with several channel blocks: L2 prefetch of the next tile's A boxes
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
 // (measured on B200: the 128B swizzle is a function of the absolute smem address, so row-shifted descriptor starts
@@ -1395,6 +1408,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_wide_flags = ((flags >> 2) & 7) | (((flags >> 11) & 1) << 3);      // bit 11: exchange epilogue for one-block layers
   ie::g_splitk = ((flags >> 9) & 1) ? 0 : 1;
   ie::pdl_set(((flags >> 10) & 1) == 0);
+  ie::g_wide_prefetch = ((flags >> 12) & 1) ? 0 : 1;
   return IE_OK;
 }
 
@@ -1504,6 +1518,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
     // anyway and need the 16 KB for pipeline stages (measured: 128->64 resident 378 us with one set, 487 with two)
     p.nsets = (p.kb == 1) ? 2 : 1;
     if (g_wide_flags & 2) p.nsets = 3 - p.nsets;
+    p.prefetch = g_wide_prefetch && res;      // measured (B200): 128 -> 64 resident 379.6 -> 370.5 us; 640 -> 64 streamed 451 -> 454
     const int tail = tail_bytes(p.nsets);
     int stages = ((int)kMaxSmem - 1024 - tail - (res ? w_bytes : 0)) / p.a_slot_bytes;
     p.stages = stages > kMaxStages ? kMaxStages : stages;

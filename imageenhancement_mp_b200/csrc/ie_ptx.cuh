@@ -91,6 +91,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a 2-D box (no shared-memory destination, no barrier): the later tma_load_2d of the same box then hits L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 // im2col-mode load of a rank-4 NHWC tensor: `pixelsPerColumn` consecutive positions of the pixel box starting at
 // (w, h, n), each shifted by the filter offsets (off_w, off_h), 64 channels from channel c; out-of-image pixels are zeros
 __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
