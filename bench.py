@@ -62,7 +62,7 @@ CONFIGS = {
 }
 NETWORK = "Simplemodel T=4 K=15 B=10 singlestd, glorot init"
 PRECISION = ("bf16 operands / fp32 accumulation in the convolutions, fp32 softmaxes and metrics, "
-             "TF32 operands / fp32 accumulation in the per-pixel filter (tcgen05)")
+             "fp16 coefficient / basis operands, fp32 burst and accumulation in the per-pixel filter (tcgen05)")
 
 
 def build_config(cfg_name, world):

@@ -1,7 +1,7 @@
 // =================================================================================================
 // Per-pixel filter on tcgen05 in the reference's own order of operations (model_library.py:439-451):
 //
-//   1. filter synthesis as a GEMM:  F[128 px][(tap, t)] = coef[128 px][B] * Bas[B][(tap, t)]   (kind::tf32)
+//   1. filter synthesis as a GEMM:  F[128 px][(tap, t)] = coef[128 px][B] * Bas[B][(tap, t)]   (kind::f16, fp16 operands)
 //      A = the tile's coefficients (hand-swizzled K-major SWIZZLE_128B rows, one per pixel), B operand = the image's
 //      basis, resident in shared memory for the CTA's lifetime as rows n = tap * 4 + t (the basis' memory order),
 //      accumulators in TMEM: 240 columns = 4 filter rows x 15 x 4 frames per buffer, two buffers;
@@ -13,17 +13,21 @@
 // and mixes with coef afterwards), but here K = B is tiny and N = the taps, so the GEMM runs at tcgen05 rates and the
 // CUDA cores are left with K*K*T = 900 FMAs per pixel.  Warp roles: 0-3 / 4-7 two epilogue sets (set s drains TMEM
 // buffer s = chunks s, s+2; set 1 hands its partial sums to set 0 through shared memory), 8 MMA issuer, 9-12 producers
-// staging the next tile (coefficients -> TF32 -> swizzled A slot; burst window by 4-byte cp.async with zero fill).
+// staging the next tile (coefficients -> fp16 -> swizzled A slot; burst window by 4-byte cp.async with zero fill).
 //
 // Persistent CTAs: the launch's (image, tile) list is cut into gridDim.x contiguous ranges; a CTA re-stages the basis
 // whenever its range crosses into the next image (a CTA-wide barrier; ~1.7 images per CTA at 256 images on 148 SMs -
 // one CTA per (image, strip) left 15 % of the time to the second, partial wave).
-// More than 32 bases (Basis_kpn of remote/: B = 50, 90): the filter is linear in the bases, so blocks of 32 bases run as
+// Operand precision: coefficients and basis are softmax outputs in [0, 1]; fp16 (10-bit mantissa, round to nearest)
+// carries them exactly as well as TF32 does (values below 6e-5 fall into fp16's subnormals: absolute error <= 3e-8 per
+// tap), accumulation is fp32, the burst is never rounded.  fp16 rows hold 64 bases per 128-byte swizzle row instead of
+// 32: Basis_kpn's B = 50 is ONE block, B = 90 two.
+// More than 64 bases (Basis_kpn of remote/: B = 90): the filter is linear in the bases, so blocks of 64 bases run as
 // further launches that ADD into the output; T > 4 likewise in passes of four frames.
 //
 // Measured on B200 (round 2): parity test green through the C ABI (coef at the padded extent, pitch != T + 1); the
 // epilogue is bound by the TMEM read path - every pixel reads its 900 synthesised filter values (3.6 KB) with tcgen05.ld.
-// Scope: K = 15, T a multiple of 4, any B (blocks of 32).
+// Scope: K = 15, T a multiple of 4, any B (blocks of 64).
 // =================================================================================================
 #include "ie_common.cuh"
 #include "ie_ptx.cuh"
@@ -50,31 +54,27 @@ constexpr int kThreads = 416;        // warps 0-3 / 4-7: epilogue sets 0 / 1, wa
 constexpr int kMmaWarp = 8, kFirstProducerWarp = 9;
 constexpr int kTmemCols = 512;
 
-__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
-  // c_format f32 (1 << 4), a_format / b_format TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at 24
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+constexpr int kBlockBases = 64;                           // bases per launch: one 128-byte row of fp16
+
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
+  // c_format f32 (1 << 4), a_format / b_format F16 (0), both K-major, N >> 3 at bit 17, M >> 4 at 24
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi)
-      : "memory");
-}
-__device__ __forceinline__ float to_tf32(float x) {
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
-// byte offset of element k (fp32 slot) of row r inside a K-major SWIZZLE_128B operand: 128-byte rows, the 16-byte
-// chunk index XOR-ed with the row's position in its 8-row group (what TMA writes; csrc/conv_tcgen05.cu builds its
+__device__ __forceinline__ uint16_t to_h(float x) {
+  uint16_t r;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+// byte offset of element k (fp16) of row r inside a K-major SWIZZLE_128B operand: 128-byte rows, the 16-byte chunk
+// index XOR-ed with the row's position in its 8-row group (what TMA writes; csrc/conv_tcgen05.cu builds its
 // first-layer A tile the same way)
-__device__ __forceinline__ uint32_t sw128_off(int r, int k) {
-  return static_cast<uint32_t>(r * 128 + ((((k >> 2) ^ (r & 7)) << 4) | ((k & 3) << 2)));
+__device__ __forceinline__ uint32_t sw128_off_h(int r, int k) {
+  return static_cast<uint32_t>(r * 128 + ((((k >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1)));
 }
 
 struct Params {
@@ -83,7 +83,7 @@ struct Params {
   const float* bas;
   float* out;
   int n, h, w, hc, wc, pitch, Ttot, B, t0;            // coef is [n][hc][wc][B], hc >= h, wc >= w
-  int b0, nb;                                          // this launch mixes bases [b0, b0 + nb), nb <= 32
+  int b0, nb;                                          // this launch mixes bases [b0, b0 + nb), nb <= 64
   int acc0, accf;                                      // add into out[..., 0] / into the per-frame channels
   int tiles_x, tiles_y, ksteps;
 };
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kused = p.ksteps * 8;
+  const int kused = p.ksteps * 16;                       // fp16 elements of K in use (k-steps of 16)
   pdl_trigger();
 
   if (threadIdx.x == 0) {
@@ -183,18 +183,33 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
     const int tile_lo = static_cast<int>(g - static_cast<long long>(img) * tiles);
     const long long seg_end = (static_cast<long long>(img + 1) * tiles < g_end) ? static_cast<long long>(img + 1) * tiles : g_end;
     const int tile_hi = tile_lo + static_cast<int>(seg_end - g);
-    // ---- the image's basis -> B operand: Bas[img][tap][t0 + t][b0 + b] -> row tap * 4 + t, slot b, TF32.  Every MMA
+    // ---- the image's basis -> B operand: Bas[img][tap][t0 + t][b0 + b] -> row tap * 4 + t, slot b, fp16.  Every MMA
     //      that read the previous image's rows has completed: the epilogue consumed its results before the barrier below.
     {
       const float* bas_img = p.bas + static_cast<long long>(img) * kTaps * p.Ttot * p.B;
-      for (int idx = threadIdx.x; idx < kBRows * kused; idx += kThreads) {
-        const int n = idx / kused, b = idx - n * kused;
-        float v = 0.f;
-        if (n < kTaps * kTP && b < p.nb) {
-          const int tap = n >> 2, t = n & 3;
-          v = to_tf32(__ldg(bas_img + (static_cast<long long>(tap) * p.Ttot + p.t0 + t) * p.B + p.b0 + b));
+      // eight independent loads in flight per thread (the loop is latency-bound: up to 58 368 scattered 4-byte loads
+      // per image at 64 bases)
+      constexpr int kU = 8;
+      for (int idx0 = threadIdx.x; idx0 < kBRows * kused; idx0 += kThreads * kU) {
+        float v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int idx = idx0 + u * kThreads;
+          const int n = idx / kused, b = idx - n * kused;
+          v[u] = 0.f;
+          if (idx < kBRows * kused && n < kTaps * kTP && b < p.nb) {
+            const int tap = n >> 2, t = n & 3;
+            v[u] = __ldg(bas_img + (static_cast<long long>(tap) * p.Ttot + p.t0 + t) * p.B + p.b0 + b);
+          }
         }
-        *reinterpret_cast<float*>(s_b + sw128_off(n, b)) = v;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int idx = idx0 + u * kThreads;
+          if (idx < kBRows * kused) {
+            const int n = idx / kused, b = idx - n * kused;
+            *reinterpret_cast<uint16_t*>(s_b + sw128_off_h(n, b)) = to_h(v[u]);
+          }
+        }
       }
     }
     fence_proxy_async_smem();
@@ -209,13 +224,19 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
         const uint32_t use = static_cast<uint32_t>(it >> 1);
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int y0 = ty * kTileH, x0 = tx * kTileW;
-        // this thread's pixel: its coefficients first into registers (all loads in flight), rounded to TF32
+        // this thread's pixel: its coefficients first into registers (all loads in flight), rounded to fp16 below
         const int y = y0 + (pid >> 4), x = x0 + (pid & 15);
         const bool inside = y < p.h && x < p.w;
         const float* cp = p.coef + ((static_cast<long long>(img) * p.hc + (inside ? y : 0)) * p.wc + (inside ? x : 0)) * p.B + p.b0;
-        float v[32];
+        uint32_t pk[kBlockBases / 2];                                              // fp16 pairs
 #pragma unroll
-        for (int b = 0; b < 32; ++b) v[b] = (b < kused && b < p.nb && inside) ? __ldg(cp + b) : 0.f;
+        for (int hb = 0; hb < kBlockBases; hb += 32) {                             // 32 loads in flight at a time
+          float v[32];
+#pragma unroll
+          for (int b = 0; b < 32; ++b) v[b] = (hb + b < kused && hb + b < p.nb && inside) ? __ldg(cp + hb + b) : 0.f;
+#pragma unroll
+          for (int b = 0; b < 32; b += 2) pk[(hb + b) >> 1] = pack_h2(v[b], v[b + 1]);
+        }
         mbar_wait(&in_empty[slot], (use & 1u) ^ 1u);                                // both epilogue sets are done with the slot
         // the burst window: 22 x 30 pixels x 4 frames, 4-byte asynchronous copies, zero outside the image
         {
@@ -231,10 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
         }
         const uint32_t rowa = smem_u32(s_a + slot * kABytes) + pid * 128;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          if (ch * 4 < kused)
-            sts128(rowa + ((ch ^ (pid & 7)) << 4), to_tf32(v[4 * ch]), to_tf32(v[4 * ch + 1]), to_tf32(v[4 * ch + 2]),
-                   to_tf32(v[4 * ch + 3]));
+        for (int ch = 0; ch < 8; ++ch)                                              // 8 fp16 coefficients per 16-byte chunk
+          if (ch * 8 < kused)
+            sts128u(rowa + ((ch ^ (pid & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         cp_async_wait_all();
         fence_proxy_async_smem();                                                   // A is read by the tensor core (async proxy)
         __syncwarp();
@@ -257,10 +277,10 @@ __global__ void __launch_bounds__(kThreads, 1) kpn_tcgen05_kernel(const Params p
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 256);
-            const uint32_t idesc = idesc_tf32(128, c == kNumChunks - 1 ? kLastN : kChunkN);
+            const uint32_t idesc = idesc_f16(128, c == kNumChunks - 1 ? kLastN : kChunkN);
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((c * kChunkN * 128) >> 4);
-            for (int ks = 0; ks < p.ksteps; ++ks)                                    // 8 TF32 = 32 bytes per k-step
-              umma_tf32_ss_lo(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+            for (int ks = 0; ks < p.ksteps; ++ks)                                    // 16 fp16 = 32 bytes per k-step
+              umma_bf16_ss_lo(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, ks > 0 ? 1u : 0u);   // kind::f16, formats in idesc
             umma_commit(&acc_full[buf]);
           }
           __syncwarp();
@@ -351,10 +371,10 @@ extern "C" int ie_kpn_apply_tc(const float* burst, int burst_pitch, const float*
   IE_REQUIRE(total < (1ll << 40), "kpn_apply_tc: too many tiles");
   const int grid = total < sm_count() ? (int)total : sm_count();      // persistent: one CTA per SM
   IE_CUDA(cudaFuncSetAttribute(kpn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  for (int b0 = 0; b0 < B; b0 += 32) {                    // bases in blocks of 32 (one 128-byte K row of TF32)
+  for (int b0 = 0; b0 < B; b0 += kBlockBases) {           // bases in blocks of 64 (one 128-byte K row of fp16)
     p.b0 = b0;
-    p.nb = B - b0 < 32 ? B - b0 : 32;
-    p.ksteps = (p.nb + 7) / 8;
+    p.nb = B - b0 < kBlockBases ? B - b0 : kBlockBases;
+    p.ksteps = (p.nb + 15) / 16;
     for (int t0 = 0; t0 < T; t0 += kTP) {                 // frames in passes of four
       p.t0 = t0;
       p.accf = b0 > 0;                                    // later basis blocks add to everything,

@@ -63,8 +63,9 @@ class Engine:
         self.device = torch.device(device)
         # per-pixel filter (model_library.py:439-451).  "auto" (default): the tcgen05 filter-synthesis kernel where it
         # applies (K = 15, T % 4 == 0), else the mma.sync TF32 kernel (K = 15, B <= 128, T <= 8), else fp32.  Both
-        # tensor-core kernels round burst / basis / coefficients to TF32 (10-bit mantissa) and accumulate in fp32:
-        # |err| <= 2^-10 of the pixel range.  "fp32" = CUDA-core kernel (1e-5 of the fp64 oracle); "tf32" / "tcgen05"
+        # tensor-core kernels round their MMA operands to a 10-bit mantissa (tcgen05: coefficients and basis as fp16,
+        # the burst stays fp32; mma.sync: burst and basis as TF32) and accumulate in fp32: |err| <= 2^-10 of the pixel
+        # range.  "fp32" = CUDA-core kernel (1e-5 of the fp64 oracle); "tf32" / "tcgen05"
         # pin one tensor-core kernel (falling back down the same chain where it does not apply).
         self.filter_precision = params.get("filter_precision", "auto")
         if self.filter_precision not in ("auto", "tf32", "fp32", "tcgen05"):

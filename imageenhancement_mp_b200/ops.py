@@ -268,7 +268,7 @@ def kpn_tf32_supported(T, K, B):
 
 def kpn_tcgen05_supported(T, K, B):
     """ie_kpn_apply_tc (csrc/kpn_tcgen05.cu): filter synthesis as a tcgen05 GEMM + apply in the epilogue; frames in
-    passes of four, bases in blocks of 32 (each further pass / block adds into the output)."""
+    passes of four, bases in blocks of 64 (each further pass / block adds into the output)."""
     return K == 15 and T % 4 == 0 and T >= 4 and B >= 1
 
 
@@ -277,8 +277,9 @@ def kpn_apply(x, T, coef, bas, out=None, precision="fp32"):
 
     precision "fp32": CUDA-core kernel, 1e-5 of the fp64 oracle.  "tf32": tensor-core kernel (burst and basis rounded
     to TF32, fp32 accumulation; K = 15, B <= 128 in chunks of 16, T <= 8), < 1e-3 absolute on [0,1] pixels, ~2.5x faster.
-    "tcgen05" (the models' default where it applies, csrc/kpn_tcgen05.cu): the same TF32 rounding, the filter
-    synthesised by a tcgen05 GEMM and applied in its epilogue; K = 15, T % 4 == 0, any B (blocks of 32)."""
+    "tcgen05" (the models' default where it applies, csrc/kpn_tcgen05.cu): the filter synthesised by a tcgen05 GEMM
+    (coefficients and basis - softmax outputs in [0, 1] - as fp16: the same 10-bit mantissa as TF32; fp32 accumulation,
+    the burst is not rounded) and applied in its epilogue; K = 15, T % 4 == 0, any B (blocks of 64)."""
     _lib.require_cuda(x, coef, bas)
     n, h, w, pitch = x.shape
     K, B = bas.shape[1], bas.shape[-1]

@@ -144,13 +144,20 @@ def load(path, root="net", layers=None):
             top = entry[0].split(".")[0]
             if top not in order:
                 order.append(top)
+    def _tf(prefix):
+        import sys
+        print("imageenhancement_mp_b200.weights.load: TensorFlow checkpoint reader: UNPINNED against a TensorFlow-written "
+              "file (restated from the published formats; no TensorFlow in the build image) - check the report numbers "
+              f"against the reference before trusting them [{prefix}]", file=sys.stderr)
+        return tfc.load_tf_checkpoint(prefix, root=root, layer_order=order)
+
     if os.path.isdir(path):
         prefix = tfc.latest_checkpoint(path)
         if prefix is None:
             raise FileNotFoundError(f"{path}: no 'checkpoint' state file (tf.train.CheckpointManager writes one)")
-        return tfc.load_tf_checkpoint(prefix, root=root, layer_order=order)
+        return _tf(prefix)
     if path.endswith(".index"):
         path = path[:-len(".index")]
     if os.path.exists(path + ".index"):
-        return tfc.load_tf_checkpoint(path, root=root, layer_order=order)
+        return _tf(path)
     raise FileNotFoundError(f"{path}: neither an .npz file nor a TensorFlow checkpoint prefix / directory")

@@ -178,10 +178,11 @@ int ie_kpn_apply_f32(const float* burst, int burst_pitch, const float* coef, int
 int ie_kpn_apply_tf32(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
                       float* out, int n, int h, int w, int T, int K, int B, void* stream);
 
-/* Same contract on tcgen05 (kind::tf32) in the reference's own order of operations (model_library.py:439-451): the
- * per-pixel filter is synthesised as a GEMM coef x Bas into TMEM and applied to the burst window in the epilogue
- * (csrc/kpn_tcgen05.cu); the MMA operands (coef, basis) are rounded to TF32, the burst stays fp32.
- * K = 15, T a multiple of 4 (passes of four frames), any B (blocks of 32 bases; later passes / blocks add into `out`,
+/* Same contract on tcgen05 in the reference's own order of operations (model_library.py:439-451): the per-pixel
+ * filter is synthesised as a GEMM coef x Bas into TMEM and applied to the burst window in the epilogue
+ * (csrc/kpn_tcgen05.cu).  MMA operands: coef and basis (softmax outputs in [0, 1]) as fp16 - the 10-bit mantissa of
+ * TF32, 64 bases per 128-byte row; fp32 accumulation; the burst is not rounded: |err| <= 2^-10 of the pixel range.
+ * K = 15, T a multiple of 4 (passes of four frames), any B (blocks of 64 bases; later passes / blocks add into `out`,
  * the first overwrites it).  The models' default filter where it applies (validated on B200 through this entry
  * point: tests/test_gpu_kernels.py::test_kpn_apply_tcgen05_variant).                                              */
 int ie_kpn_apply_tc(const float* burst, int burst_pitch, const float* coef, int hc, int wc, const float* bas,
