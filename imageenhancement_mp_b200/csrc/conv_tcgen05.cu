@@ -1201,9 +1201,12 @@ __global__ void __launch_bounds__(kFirstThreads, 1)
 conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_y, const FirstParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024(smem_raw);
-  constexpr int kWBytes = 64 * 128;                       // [64 cout][64 k] bf16
+  constexpr int KB = (9 * C + 63) / 64;                   // 64-wide K blocks: 1 for C <= 7, 2 for C = 10 (Basis_kpn, T = 8)
+  constexpr int kWTile = 64 * 128;                        // [64 cout][64 k] bf16 per K block
+  constexpr int kWBytes = KB * kWTile;
+  constexpr int kStageBytes = KB * kABytes;
   uint8_t* a_base_ptr = base + kWBytes;
-  SmemTail t{a_base_ptr + p.stages * kABytes};
+  SmemTail t{a_base_ptr + p.stages * kStageBytes};
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.e.m_tiles;
@@ -1218,7 +1221,8 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(t.bres(), kWBytes);
-      tma_load_2d(base, &tm_b, t.bres(), 0, 0);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(base + kb * kWTile, &tm_b, t.bres(), kb * kBlockK, 0);
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
@@ -1238,11 +1242,15 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
-        const uint32_t a = a_lo0 + stage * (kABytes >> 4);
-        umma_bf16_ss_lo(d_tmem, a, b_lo, idesc, 0u);
-        umma_bf16_ss_lo(d_tmem, a + 2, b_lo + 2, idesc, 1u);
-        umma_bf16_ss_lo(d_tmem, a + 4, b_lo + 4, idesc, 1u);
-        umma_bf16_ss_lo(d_tmem, a + 6, b_lo + 6, idesc, 1u);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t a = a_lo0 + stage * (kStageBytes >> 4) + kb * (kABytes >> 4);
+          const uint32_t b = b_lo + kb * (kWTile >> 4);
+          umma_bf16_ss_lo(d_tmem, a, b, idesc, kb == 0 ? 0u : 1u);
+          umma_bf16_ss_lo(d_tmem, a + 2, b + 2, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, a + 4, b + 4, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, a + 6, b + 6, idesc, 1u);
+        }
         umma_commit(&empty_bar[stage]);
         umma_commit(&t.tfull()[buf]);
       }
@@ -1254,7 +1262,7 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
   } else {
     // ================================ A-tile builders ==============================
     // two sets of four warps; set s builds the CTA's tiles it = s, s+2, ... into stage it % stages (a single warp
-    // per scheduler cannot hide the latency of its 45 gathers, exactly like the epilogue)
+    // per scheduler cannot hide the latency of its gathers, exactly like the epilogue)
     const int bset = (warp - 6) >> 2;
     const int row_local = ((warp - 6) & 3) * 32 + lane;
     constexpr int C3 = 3 * C;
@@ -1275,24 +1283,30 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
         rowok[d] = interior && (y + d - 1 >= 0) && (y + d - 1 < p.hs);
         colok[d] = (x + d - 1 >= 0) && (x + d - 1 < p.ws);
       }
-      float v[64];
+      uint32_t pk[KB][32];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        v[k] = 0.f;
-        if (k < 9 * C) {
-          constexpr int dummy = 0; (void)dummy;
-          const int dy = k / C3, i = k % C3, g = i / C;
-          if (rowok[dy] && colok[g]) v[k] = __ldg(centre + (dy - 1) * p.ws * C + i);
+      for (int kb = 0; kb < KB; ++kb) {
+        float v[64];
+#pragma unroll
+        for (int kk = 0; kk < 64; ++kk) {
+          const int k = kb * 64 + kk;
+          v[kk] = 0.f;
+          if (k < 9 * C) {
+            const int dy = k / C3, i = k % C3, g = i / C;
+            if (rowok[dy] && colok[g]) v[kk] = __ldg(centre + (dy - 1) * p.ws * C + i);
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[kb][j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
       }
-      uint32_t pk[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      const uint32_t rowa = smem_u32(a_base_ptr + stage * kABytes) + row_local * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        sts128u(rowa + ((j ^ (row_local & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t rowa = smem_u32(a_base_ptr + stage * kStageBytes + kb * kABytes) + row_local * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128u(rowa + ((j ^ (row_local & 7)) << 4), pk[kb][4 * j], pk[kb][4 * j + 1], pk[kb][4 * j + 2], pk[kb][4 * j + 3]);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
@@ -1651,8 +1665,8 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   using namespace ie;
   IE_REQUIRE(x && w_packed && y_bf16, "conv_first: null pointer");
   IE_REQUIRE(n > 0 && hs > 0 && ws > 0 && hs <= h && ws <= w, "conv_first: source %dx%d must fit the %dx%d raster", hs, ws, h, w);
-  IE_REQUIRE(c == 3 || c == 5, "conv_first: fused first layer is built for 3 or 5 input channels (got %d); use "
-                               "ie_pack_input_im2col3x3 + ie_conv2d_nhwc_bf16", c);
+  IE_REQUIRE(c == 3 || c == 5 || c == 10, "conv_first: fused first layer is built for 3, 5 or 10 input channels (got %d); "
+                                         "use ie_pack_input_im2col3x3 + ie_conv2d_nhwc_bf16", c);
   IE_REQUIRE(cout == 64, "conv_first: cout must be 64 (got %d)", cout);
   IE_REQUIRE(y_coff % 64 == 0 && y_coff + cout <= y_pitch && y_pitch % 8 == 0, "conv_first: bad output slice");
   const long long R = (long long)n * (h + 1) * (w + 1);
@@ -1675,22 +1689,24 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   p.x = x;
   p.hs = hs;
   p.ws = ws;
-  p.stages = 6;
+  const int kb = (9 * c + 63) / 64;                       // K blocks of 64: w_packed is [64][64 * kb]
+  p.stages = kb == 1 ? 6 : 4;
   CUtensorMap tm_b, tm_y;
-  int rc = make_tmap_2d_bf16(&tm_b, w_packed, 64, 64, 64, 64, 64);
+  int rc = make_tmap_2d_bf16(&tm_b, w_packed, 64 * kb, 64, 64 * kb, 64, 64);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tm_y, y_bf16, (uint64_t)y_pitch, (uint64_t)R, (uint64_t)y_pitch, 64, 32);
   if (rc) return rc;
-  const size_t smem = 1024 + 64 * 128 + (size_t)p.stages * kABytes + kTailBytes;
+  const size_t smem = 1024 + (size_t)kb * 64 * 128 + (size_t)p.stages * kb * kABytes + kTailBytes;
   const int grid = p.e.m_tiles < sm_count() ? p.e.m_tiles : sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c == 5) {
-    IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    IE_CUDA(launch_pdl(conv_first_kernel<5>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));
-  } else {
-    IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    IE_CUDA(launch_pdl(conv_first_kernel<3>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));
-  }
-  IE_LAUNCH_CHECK();
+#define IE_LAUNCH_FIRST(C_)                                                                                        \
+  do {                                                                                                             \
+    IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
+    IE_CUDA(launch_pdl(conv_first_kernel<C_>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));          \
+  } while (0)
+  if (c == 5) IE_LAUNCH_FIRST(5);
+  else if (c == 3) IE_LAUNCH_FIRST(3);
+  else IE_LAUNCH_FIRST(10);
+#undef IE_LAUNCH_FIRST
   return IE_OK;
 }

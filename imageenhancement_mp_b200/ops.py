@@ -117,16 +117,16 @@ def pack_input_im2col3x3(x, out=None):
     return out
 
 
-FIRST_LAYER_FUSED_CHANNELS = (3, 5)
+FIRST_LAYER_FUSED_CHANNELS = (3, 5, 10)
 F32_HEAD_MAX_COUT = 256        # output channels one launch of an fp32-epilogue convolution handles (one N tile)
 
 
 def conv_first_layer(x, w_packed, bias, dst: Slice, relu=True):
-    """Conv2D(64, 3, 'same') on the raw fp32 NHWC input with the im2col fused into the kernel (c in 3, 5)."""
+    """Conv2D(64, 3, 'same') on the raw fp32 NHWC input with the im2col fused into the kernel (c in 3, 5, 10)."""
     _lib.require_cuda(x)
     n, hs, ws, c = x.shape
     r = dst.r
-    assert x.is_contiguous() and r.n == n and r.h >= hs and r.w >= ws and w_packed.shape == (64, 64)
+    assert x.is_contiguous() and r.n == n and r.h >= hs and r.w >= ws and w_packed.shape == (64, im2col_width(c))
     e0 = e1 = None
     if CONV_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -89,9 +89,10 @@ int ie_pack_conv_weights(const float* hwio, int kh, int kw, int cin, int cout, i
 int ie_pack_input_im2col3x3(const float* x, int n, int hs, int ws, int c, int h, int w, void* raster_bf16,
                             void* stream);
 
-/* The first layer with the im2col fused into the kernel (c = 3 or 5, cout = 64): x fp32 NHWC [n][hs][ws][c]
+/* The first layer with the im2col fused into the kernel (c = 3, 5 or 10, cout = 64): x fp32 NHWC [n][hs][ws][c]
  * (implicitly zero-padded to h x w) -> bias(+ReLU) -> bf16 raster slice.  w_packed = ie_pack_conv_weights of the
- * 3x3xcx64 kernel with ktot_pad = 64.  Same result as ie_pack_input_im2col3x3 + a 1x1 ie_conv2d_nhwc_bf16.    */
+ * 3x3xcx64 kernel with ktot_pad = 9*c rounded up to a multiple of 64 (64; 128 for c = 10: Basis_kpn with T = 8 +
+ * dualparams).  Same result as ie_pack_input_im2col3x3 + a 1x1 ie_conv2d_nhwc_bf16.                             */
 int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, int c, int h, int w, const void* w_packed,
                             const float* bias, int cout, int relu, void* y_bf16, int y_pitch, int y_coff, void* stream);
 

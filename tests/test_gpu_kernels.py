@@ -47,7 +47,9 @@ def test_im2col_first_layer(cuda):
     assert border_is_zero(dst)
 
 
-@pytest.mark.parametrize("c,n,hs,ws,h,w", [(5, 2, 16, 24, 16, 24), (3, 3, 13, 21, 16, 24), (5, 7, 100, 100, 104, 104)])
+@pytest.mark.parametrize("c,n,hs,ws,h,w", [(5, 2, 16, 24, 16, 24), (3, 3, 13, 21, 16, 24), (5, 7, 100, 100, 104, 104),
+                                           # Basis_kpn with T = 8 + dualparams: 10 channels, K = 90 -> two K blocks
+                                           (10, 2, 16, 24, 16, 24), (10, 5, 61, 64, 64, 64)])
 def test_first_layer_fused_im2col(cuda, c, n, hs, ws, h, w):
     """conv_first_kernel (im2col built in-kernel by the builder warps) == im2col raster + 1x1 GEMM, bit for bit,
     and == Conv2D(64, 3, 'same', relu) of the (zero-padded) input (model_library.py:323, 376)."""
@@ -56,11 +58,12 @@ def test_first_layer_fused_im2col(cuda, c, n, hs, ws, h, w):
     x = bf16_round(torch.rand(n, hs, ws, c, generator=g))
     wt = bf16_round(torch.randn(3, 3, c, 64, generator=g) * 0.2)
     b = torch.randn(64, generator=g) * 0.1
-    wp = ops.pack_conv_weights(wt.to(cuda), ktot_pad=64)
+    kw = ops.im2col_width(c)
+    wp = ops.pack_conv_weights(wt.to(cuda), ktot_pad=kw)
     fused = ops.new_raster(n, h, w, 128, cuda)
     fused.data.fill_(float("nan"))
     ops.conv_first_layer(x.to(cuda), wp, b.to(cuda), fused.slice(64, 64))
-    src = ops.pack_input_im2col3x3(x.to(cuda), ops.new_raster(n, h, w, 64, cuda))
+    src = ops.pack_input_im2col3x3(x.to(cuda), ops.new_raster(n, h, w, kw, cuda))
     two = ops.new_raster(n, h, w, 64, cuda)
     ops.conv2d(src.slice(), wp, b.to(cuda), two.slice(), k=1)
     torch.cuda.synchronize()

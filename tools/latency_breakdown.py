@@ -5,10 +5,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from imageenhancement_mp_b200 import _lib, synth, weights, model_library as ml
 n, h, w = (int(v) for v in (sys.argv[1:4] or (1, 32, 32)))
+arch = sys.argv[4] if len(sys.argv) > 4 else "simple"          # or "basis_kpn" (remote/ settings: T = 8, dualparams)
 dev = torch.device("cuda", 0)
-params = dict(synth.DEFAULT_PARAMS, graph_max_pixels=0)
-W = weights.init_weights(weights.simplemodel_layers(params))
-model = ml.Simplemodel(params, weights=W, device=dev)
+if arch == "simple":
+    params = dict(synth.DEFAULT_PARAMS, graph_max_pixels=0)
+    W = weights.init_weights(weights.simplemodel_layers(params))
+    model = ml.Simplemodel(params, weights=W, device=dev)
+else:
+    params = dict(synth.DEFAULT_PARAMS, graph_max_pixels=0, BURST_LENGTH=8, layer_type="dualparams",
+                  Basis_num=int(sys.argv[5]) if len(sys.argv) > 5 else 10)
+    W = weights.init_weights(weights.basis_kpn_layers(params))
+    model = ml.Basis_kpn(params, weights=W, device=dev)
 x = synth.make_batch(n, h, w, params)[0].to(dev)
 for _ in range(5):
     model(x)
