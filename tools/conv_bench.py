@@ -22,7 +22,10 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default="")
     ap.add_argument("--mode", type=int, default=-1, help="-1 auto, 0 stream, 1 resident, 2 wide-N (forced)")
-    ap.add_argument("--flags", type=int, default=0, help="ie_conv_set_mode flags (4: wide streams weights, 8: one epilogue set)")
+    ap.add_argument("--flags", type=int, default=0, help="ie_conv_set_mode flags (4: wide streams weights, 8: one epilogue set, "
+                    "2048: exchange epilogue for one-block wide layers, 8192: streaming layers on CTA pairs)")
+    ap.add_argument("--raster", action="store_true", help="shared-border rasters at every resolution (default: dense NHWC "
+                    "from 1/4 resolution down, like the engine)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     _lib.load().ie_conv_set_mode(a.mode, a.flags)
@@ -31,11 +34,12 @@ def main():
         if a.only and a.only not in name:
             continue
         h, w = a.h // div, a.w // div
-        src = ops.new_raster(a.n, h, w, cin, dev); src.data.normal_()
+        dense = (not a.raster) and div >= 4
+        src = ops.new_raster(a.n, h, w, cin, dev, dense=dense); src.data.normal_()
         wt = torch.randn(k, k, cin, cout, device=dev) * 0.05
         wp = ops.pack_conv_weights(wt, epi)
         b = torch.zeros(cout, device=dev)
-        dst = ops.new_raster(a.n, h, w, max(cout, 64), dev) if epi == 0 else None
+        dst = ops.new_raster(a.n, h, w, max(cout, 64), dev, dense=dense) if epi == 0 else None
         def run():
             if epi == 0:
                 ops.conv2d(src.slice(), wp, b, dst.slice(), k=k)
