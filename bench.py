@@ -454,6 +454,8 @@ def run_ours(args, cfg_name):
     per_px, per_img = weights.conv_flops(layers, params, hp, wp)
     conv_flops_step = wl_.n_local * (per_px * hp * wp + per_img)     # rank 0's share, at the computed (padded) size
     achieved = conv_flops_step / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    px_user, _ = weights.conv_flops(layers, params, h, w)
+    achieved_user = wl_.n_local * (px_user * h * w + per_img) / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = read_conv_traffic(cfg_name)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -471,7 +473,9 @@ def run_ours(args, cfg_name):
                      "peak_source": peaks["source"] + " sustained bf16", "frac_of_burst": achieved / peaks["bf16_burst"],
                      "conv_ms_per_step": conv_ms, "conv_tflop_per_step": conv_flops_step / 1e12,
                      "timing": f"CUDA events around each conv launch in a separate pass of {n_rf} steps after the timed loop",
-                     "step_tflops": conv_flops_step / (ms / args.steps / 1e3) / 1e12},
+                     "step_tflops": conv_flops_step / (ms / args.steps / 1e3) / 1e12,
+                     "flops_counted_at": [hp, wp],
+                     "frac_at_user_pixels": achieved_user / peaks["bf16_sustained"]},
         "quality": {"psnr": report["psnr"], "psnr_noise0": report["psnr_noise0"], "psnr_average": report["psnr_average"],
                     "ssim": report["ssim"]},
     }

@@ -8,23 +8,25 @@
 // Both operands are K-major with SWIZZLE_128B (rows of 64 bf16 = 128 B), so one shared-memory
 // descriptor + a 32-byte advance per UMMA_K=16 step addresses every MMA.  D lives in TMEM
 // (128 lanes x n_tile fp32 columns), double-buffered (2 x 256 columns) so the epilogue of tile i
-// overlaps the main loop of tile i+1.  Persistent CTAs, one per SM, 192 threads:
+// overlaps the main loop of tile i+1.  Persistent CTAs, one per SM, 192 threads (320 with a second epilogue set):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + tcgen05.mma issuer (warp-uniform loop, one elected lane issues)
 //   warps 2..5  epilogue: tcgen05.ld -> bias/ReLU/border mask -> bf16 -> swizzled smem -> TMA store
 //               (or fp32 global stores / per-pixel softmax for the two small heads)
 //
-// Two main-loop flavours share the epilogue:
-//   conv_stream_kernel    wide layers (n_tile 128/256): every (tap, 64-channel block) is one pipeline
-//                         stage = A box [128 rows x 64 ch] + B box [n_tile x 64]; MMA-bound (>90 %
-//                         tensor-pipe active in ncu).
-//   conv_resident_kernel  narrow layers (n_tile <= 64, 9*cin*n_tile*2 B of weights fit in smem): the
-//                         whole weight matrix is loaded once per CTA and stays resident; a stage is one
-//                         A box of 128+2 rows per (filter row, channel block), and the three horizontal
-//                         taps read it at +0/+1/+2 rows through the descriptor start address.  That cuts
-//                         L2->smem traffic per tile 4.4x and issues 12 MMAs per barrier round trip - the
-//                         narrow layers are bound by single-thread issue overhead and operand traffic,
-//                         not by the tensor pipe.
+// Main-loop flavours (the first three share epilogue_loop):
+//   conv_stream_kernel<IM2COL>  wide layers (n_tile 128/256): every (tap, 64-channel block) is one pipeline stage =
+//                         A box [128 rows x 64 ch] + B box [n_tile x 64]; MMA-bound (88-94 % tensor-pipe active in
+//                         ncu).  IM2COL: dense NHWC activations, the A box is a TMA im2col-mode load (no border rows).
+//                         Split-K over CTAs for layers with very few tiles (+ splitk_finish_kernel).
+//   conv_resident_kernel  1x1 / 2x2 / narrow 3x3 layers whose whole weight matrix fits in smem: loaded once per CTA;
+//                         a stage is one A box of 128+2 rows per (filter row, channel block), and the horizontal
+//                         taps read it at +0/+1/+2 rows through the descriptor start address.
+//   conv_first_kernel     first layer on the raw fp32 input: builder warps gather the 3x3xC neighbourhood and write the
+//                         swizzled A tile themselves (C = 3, 5, 10).
+//   conv_wide_kernel      3x3 layers with cout <= 64 and the fp32 coef head: the three horizontal taps are three column
+//                         groups of ONE N = 192 accumulator, combined in the epilogue (own epilogues; see below).
+// Every kernel is launched with programmatic stream serialization: cta_setup() ends with griddepcontrol.wait.
 #include <cstdlib>
 
 #include "ie_common.cuh"
