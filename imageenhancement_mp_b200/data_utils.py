@@ -342,19 +342,70 @@ def val_batches_from_u8(images_u8, params, batch_size=None, seed=1234, device=No
     into a synthetic burst on the device (``preprocess_image``: jittered crops, 4x AREA down-sample, white level,
     read/shot noise drawn on the device) and yields ``(x [B,h,w,T+add], truth [B,h,w,2])`` CUDA tensors -
     ``drop_remainder=True`` like the reference - ready for ``eval.evaluate(..., pre_sharded=...)``.
+    Host images are staged like tf.data's ``prefetch`` (:393): the source frames of batch i+1 cross PCIe on a side
+    stream (through a pinned gather buffer when the batch is not a contiguous slice of pinned memory) while batch i
+    is preprocessed and consumed; two device slots rotate.
     File listing, decoding and the tf.data cache are out of scope."""
     if images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
         raise _lib.ImgEnhError("images_u8 must be a uint8 tensor [N,Hs,Ws,C]")
     if device is None:
         device = images_u8.device if images_u8.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
     bs = int(params.get("batch_size", 1) if batch_size is None else batch_size)
     n = images_u8.shape[0]
     g = torch.Generator().manual_seed(int(seed))
     order = torch.randperm(n, generator=g) if shuffle else torch.arange(n)
-    for b0 in range(0, n - bs + 1, bs):                                    # drop_remainder=True (:392)
-        idx = order[b0:b0 + bs]
+    starts = list(range(0, n - bs + 1, bs))                                # drop_remainder=True (:392)
+    on_host = not images_u8.is_cuda
+    if on_host:
+        main = torch.cuda.current_stream(device)
+        copy = torch.cuda.Stream(device)
+        shape = (bs,) + tuple(images_u8.shape[1:])
+        dev_slots = [torch.empty(shape, dtype=torch.uint8, device=device) for _ in range(2)]
+        pin_slots = [None, None]
+        ready = [None, None]
+        released = [None, None]
+        copied = [None, None]                                              # the pinned gather buffer may be refilled
+
+    def stage(i):
+        """Start the host->device copy of batch i into slot i % 2 on the side stream."""
+        k = i % 2
+        idx = order[starts[i]:starts[i] + bs]
+        contiguous = bool((idx[1:] - idx[:-1] == 1).all()) if bs > 1 else True
+        if contiguous and images_u8.is_pinned():
+            src = images_u8[int(idx[0]):int(idx[0]) + bs]
+        else:
+            if pin_slots[k] is None:
+                pin_slots[k] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+            if copied[k] is not None:
+                copied[k].synchronize()                                    # the previous DMA out of this buffer is done
+            torch.index_select(images_u8, 0, idx, out=pin_slots[k])
+            src = pin_slots[k]
+        if released[k] is not None:
+            copy.wait_event(released[k])                                   # the consumer is done with the device slot
+        with torch.cuda.stream(copy):
+            dev_slots[k].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        ready[k] = copied[k] = ev
+
+    if on_host and starts:
+        stage(0)
+    for i, b0 in enumerate(starts):
         d = draw_burst_params(bs, images_u8.shape[1:3], params, generator=g)
-        src = images_u8[idx.to(images_u8.device)].to(device, non_blocking=True)
         noise_seed = int(torch.randint(0, 2 ** 62, (1,), generator=g))
-        yield preprocess_image(src, d["org"].to(device), params, d["white_level"].to(device), d["sig_read"].to(device),
+        if on_host:
+            k = i % 2
+            if i + 1 < len(starts):
+                stage(i + 1)                                               # overlaps this batch's kernels
+            main.wait_event(ready[k])
+            src = dev_slots[k]
+        else:
+            idx = order[b0:b0 + bs]
+            src = images_u8[idx.to(images_u8.device)].to(device, non_blocking=True)
+        out = preprocess_image(src, d["org"].to(device), params, d["white_level"].to(device), d["sig_read"].to(device),
                                d["sig_shot"].to(device), seed=noise_seed)
+        if on_host:
+            released[k] = torch.cuda.Event()
+            released[k].record(main)
+        yield out
