@@ -71,11 +71,14 @@ struct EpiParams {
   float* y_aux;
   int f32_pitch;      // floats per pixel of y_f32 / y_aux (= cout unless the caller writes a channel slice)
   int dense;          // x / y are dense NHWC (R = n*h*w rows, no border rows to mask)
-  // split-K (tiny M: the K loop of a tile is cut into `ksplit` work items so that more SMs stream the weights):
-  // work item = (tile, ks); its accumulator is written as raw fp32 to part[ks][row][col] and a second kernel sums
-  // the parts in a fixed order and applies bias / ReLU / mask (deterministic: no atomics)
+  // split-K: tiles [split_first, num_tiles) have their K loop cut into `ksplit` work items computed by different CTAs
+  // (split_first = 0: every tile - tiny M, more SMs stream the weights; split_first > 0: only the tiles of the last,
+  // partial wave of a persistent grid - the other SMs would idle while a few finish whole tiles).  A split item writes
+  // its raw fp32 accumulator to its own slab part[item - split_first][128][n_tile]; splitk_finish_kernel sums the
+  // slabs of a tile in a fixed order and applies bias / ReLU / mask (deterministic: no atomics).  ksplit = 1: off.
   int ksplit;
-  float* part;        // [ksplit][m_tiles*128][n_tiles*n_tile] fp32
+  int split_first;
+  float* part;
 };
 
 // Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
@@ -97,6 +100,28 @@ struct SmemTail {
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+// Work item -> (tile, K-range index): items [0, split_first) are whole tiles, the rest are (tile, ks) pairs.
+struct WorkItem {
+  int tile, ks;
+  bool split;
+};
+__device__ __forceinline__ int num_work_items(const EpiParams& e) {
+  const int tiles = e.m_tiles * e.n_tiles;
+  return e.split_first + (tiles - e.split_first) * e.ksplit;
+}
+__device__ __forceinline__ WorkItem decode_item(const EpiParams& e, int item) {
+  WorkItem w;
+  if (item < e.split_first) {
+    w.tile = item; w.ks = 0; w.split = false;
+  } else {
+    const int j = item - e.split_first;
+    w.tile = e.split_first + j / e.ksplit;
+    w.ks = j - (w.tile - e.split_first) * e.ksplit;
+    w.split = e.ksplit > 1;
+  }
+  return w;
 }
 
 // One-time CTA setup common to both kernels; returns the TMEM base address.
@@ -140,11 +165,11 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
   const float* sbias = t.bias();
   uint64_t* tfull_bar = t.tfull();
   uint64_t* tempty_bar = t.tempty();
-  const int num_tiles = p.m_tiles * p.n_tiles * p.ksplit;
+  const int num_items = num_work_items(p);
   int it = set;
-  for (int item = blockIdx.x + set * gridDim.x; item < num_tiles; item += t.nsets * gridDim.x, it += t.nsets) {
-    const int tile = item / p.ksplit;
-    const int ks = item - tile * p.ksplit;
+  for (int item = blockIdx.x + set * gridDim.x; item < num_items; item += t.nsets * gridDim.x, it += t.nsets) {
+    const WorkItem wi = decode_item(p, item);
+    const int tile = wi.tile;
     const int m_tile = tile / p.n_tiles;
     const int n_idx = tile - m_tile * p.n_tiles;
     const int r0 = m_tile * kBlockM;
@@ -163,10 +188,9 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
     tc_fence_after();
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
 
-    if (p.ksplit > 1) {
-      // raw fp32 partial sums of this K range: row r, columns n0.. of part[ks]
-      const int ncols = p.n_tiles * p.n_tile;
-      float* dst = p.part + (static_cast<long long>(ks) * p.m_tiles * kBlockM + r) * ncols + n0;
+    if (wi.split) {
+      // raw fp32 partial sums of this K range: row row_in_tile of the item's own slab [128][n_tile]
+      float* dst = p.part + (static_cast<long long>(item - p.split_first) * kBlockM + row_in_tile) * p.n_tile;
       const int chunks = p.n_tile >> 5;
       for (int c = 0; c < chunks; ++c) {
         uint32_t v[32];
@@ -387,8 +411,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint64_t* full_bar = t.full();
   uint64_t* empty_bar = t.empty();
 
-  // work item = (tile, ks): K blocks [ks * kb_per, ...) of tile (m_tile, n_idx); ksplit = 1 -> the whole K loop
-  const int num_items = num_tiles * p.e.ksplit;
+  // work item = whole tile, or (tile, ks) = K blocks [ks * kb_per, ...) of a split tile
+  const int num_items = num_work_items(p.e);
   const int kb_per = (kblocks + p.e.ksplit - 1) / p.e.ksplit;
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -397,8 +421,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t phase = 0;
       const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.e.n_tile) * 128u;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item / p.e.ksplit;
-        const int ks = item - tile * p.e.ksplit;
+        const WorkItem wi = decode_item(p.e, item);
+        const int tile = wi.tile;
         const int m_tile = tile / p.e.n_tiles;
         const int n_idx = tile - m_tile * p.e.n_tiles;
         const int r0 = m_tile * kBlockM;
@@ -412,8 +436,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           px0 = rem - py0 * p.img_w - p.pad;
           py0 -= p.pad;
         }
-        const int kb_begin = ks * kb_per;
-        const int kb_end = (kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
+        const int kb_begin = wi.split ? wi.ks * kb_per : 0;
+        const int kb_end = (wi.split && kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
         int tap = kb_begin / p.kblocks_per_tap;
         int kb = kb_begin - tap * p.kblocks_per_tap;
         for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
@@ -443,9 +467,9 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     uint32_t phase = 0;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int ks = item % p.e.ksplit;
-      const int kb_begin = ks * kb_per;
-      const int kb_end = (kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
+      const WorkItem wi = decode_item(p.e, item);
+      const int kb_begin = wi.split ? wi.ks * kb_per : 0;
+      const int kb_end = (wi.split && kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
       const int buf = it & 1;
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -1320,18 +1344,25 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// Second half of a split-K convolution: sums the `ksplit` fp32 partial tiles of every output row in a fixed order,
-// adds the bias, applies ReLU and the border / valid-extent mask, and writes the bf16 row (8 channels per thread).
+// Second half of a split-K convolution: for every split tile, sums the `ksplit` fp32 slabs in a fixed order, adds the
+// bias, applies ReLU and the border / valid-extent mask, and writes the bf16 rows (8 channels per thread).
 __global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float* __restrict__ part, int ksplit, long long part_stride, int ncols, EpiParams p,
-                     uint4* __restrict__ y, int y_pitch_v) {
+splitk_finish_kernel(EpiParams p, uint4* __restrict__ y, int y_pitch_v) {
   pdl_trigger();
   pdl_wait();
-  const int cvec = p.cout >> 3;
+  const int vec_per_row = p.n_tile >> 3;
+  const int per_tile = kBlockM * vec_per_row;
+  const int tiles = p.m_tiles * p.n_tiles - p.split_first;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= static_cast<long long>(p.R) * cvec) return;
-  const int r = static_cast<int>(idx / cvec);
-  const int cv = static_cast<int>(idx - static_cast<long long>(r) * cvec);
+  if (idx >= static_cast<long long>(tiles) * per_tile) return;
+  const int lt = static_cast<int>(idx / per_tile);                 // split tile number
+  const int rem = static_cast<int>(idx - static_cast<long long>(lt) * per_tile);
+  const int row = rem / vec_per_row, cv = rem - row * vec_per_row;
+  const int tile = p.split_first + lt;
+  const int m_tile = tile / p.n_tiles, n_idx = tile - m_tile * p.n_tiles;
+  const int r = m_tile * kBlockM + row;
+  const int col = n_idx * p.n_tile + cv * 8;
+  if (r >= p.R || col >= p.cout) return;
   bool valid = true;
   if (!p.dense) {
     const int img = r / p.plane;
@@ -1342,23 +1373,24 @@ splitk_finish_kernel(const float* __restrict__ part, int ksplit, long long part_
   }
   uint4 res = make_uint4(0, 0, 0, 0);
   if (valid) {
-    const float* src = part + static_cast<long long>(r) * ncols + cv * 8;
+    const long long slab = static_cast<long long>(kBlockM) * p.n_tile;
+    const float* src = p.part + static_cast<long long>(lt) * p.ksplit * slab + static_cast<long long>(row) * p.n_tile + cv * 8;
     float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-    for (int k = 1; k < ksplit; ++k) {
-      const float4 c = *reinterpret_cast<const float4*>(src + k * part_stride);
-      const float4 d = *reinterpret_cast<const float4*>(src + k * part_stride + 4);
+    for (int k = 1; k < p.ksplit; ++k) {
+      const float4 c = *reinterpret_cast<const float4*>(src + k * slab);
+      const float4 d = *reinterpret_cast<const float4*>(src + k * slab + 4);
       a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
       b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
     }
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      v[e] += p.bias ? p.bias[cv * 8 + e] : 0.f;
+      v[e] += p.bias ? p.bias[col + e] : 0.f;
       if (p.relu) v[e] = fmaxf(v[e], 0.f);
     }
     res = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
-  y[static_cast<long long>(r) * y_pitch_v + (p.y_coff >> 3) + cv] = res;
+  y[static_cast<long long>(r) * y_pitch_v + ((p.y_coff + col) >> 3)] = res;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1410,6 +1442,7 @@ int validate_conv_desc(const ie_conv_desc* d, const void* x, const void* w, void
 static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
+static int g_splitk_tail = 1;        // 0: split-K only for tiny M, not for the last partial wave of larger grids
 static int g_wide_prefetch = 1;      // wide-N layers with several channel blocks: L2 prefetch of the next tile's A boxes
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
@@ -1425,6 +1458,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_splitk = ((flags >> 9) & 1) ? 0 : 1;
   ie::pdl_set(((flags >> 10) & 1) == 0);
   ie::g_wide_prefetch = ((flags >> 12) & 1) ? 0 : 1;
+  ie::g_splitk_tail = ((flags >> 13) & 1) ? 0 : 1;
   return IE_OK;
 }
 
@@ -1439,6 +1473,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   EpiParams e{};
   e.dense = d->dense;
   e.ksplit = 1;
+  e.split_first = 0;                   // irrelevant while ksplit == 1 (every item is a whole tile)
   e.R = (int)R;
   e.plane = (d->h + 1) * wp;
   e.wp = wp;
@@ -1622,22 +1657,31 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   p.pad = d->kh / 2;
   const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + kTailBytes;
   const int tiles = e.m_tiles * e.n_tiles;
-  // split-K for tiny M (eval.py's default call is ONE 32 x 32 patch: the 1024-channel layers are then 1 M tile x 16 N
-  // tiles with K = 9216 - 18432, i.e. 16 CTAs streaming 19 - 38 MB of weights while 132 SMs idle)
+  // split-K (see EpiParams): (a) tiny M - eval.py's default call is ONE 32 x 32 patch: the 1024-channel layers are
+  // then 1 M tile x 16 N tiles with K = 9216 - 18432, i.e. 16 CTAs streaming 19 - 38 MB of weights while 132 SMs idle -
+  // every tile is split; (b) a persistent grid whose last wave is less than half full (2048 -> 512 at 256 x 26 x 26:
+  // 2704 tiles = 18.27 waves on 148 SMs): only the tiles of that wave are split, so all SMs finish together
   const int kblocks = ntaps * p.kblocks_per_tap;
-  int ksplit = 1;
-  const size_t per_split = (size_t)e.m_tiles * kBlockM * e.n_tiles * e.n_tile * sizeof(float);
+  int ksplit = 1, split_first = tiles;
+  const size_t slab_bytes = (size_t)kBlockM * e.n_tile * sizeof(float);
   static const bool splitk_env = !(getenv("IE_SPLITK") && getenv("IE_SPLITK")[0] == '0');      // A-B timing
-  if (g_splitk && splitk_env && workspace && d->epilogue == IE_EPI_BF16_RASTER && tiles * 2 <= grid_cap && kblocks >= 8) {
-    ksplit = grid_cap / tiles;
-    if (ksplit > kblocks / 4) ksplit = kblocks / 4;
-    while (ksplit > 1 && per_split * ksplit > (size_t)workspace_bytes) --ksplit;
-    const int kb_per = (kblocks + ksplit - 1) / ksplit;
-    ksplit = (kblocks + kb_per - 1) / kb_per;            // no empty split
+  if (g_splitk && splitk_env && workspace && d->epilogue == IE_EPI_BF16_RASTER && kblocks >= 8) {
+    int tail = tiles * 2 <= grid_cap ? tiles : tiles % grid_cap;            // (a) all tiles, (b) the last wave
+    if (tiles * 2 > grid_cap && (g_splitk_tail == 0 || tiles < grid_cap)) tail = 0;
+    if (tail > 0 && tail * 2 <= grid_cap) {
+      ksplit = grid_cap / tail;
+      if (ksplit > kblocks / 4) ksplit = kblocks / 4;
+      while (ksplit > 1 && slab_bytes * tail * ksplit > (size_t)workspace_bytes) --ksplit;
+      const int kb_per = (kblocks + ksplit - 1) / ksplit;
+      ksplit = (kblocks + kb_per - 1) / kb_per;            // no empty split
+      if (ksplit > 1) split_first = tiles - tail;
+    }
   }
+  if (ksplit == 1) split_first = tiles;
   p.e.ksplit = ksplit;
+  p.e.split_first = split_first;
   p.e.part = static_cast<float*>(workspace);
-  const int items = tiles * ksplit;
+  const int items = split_first + (tiles - split_first) * ksplit;
   const int grid = items < grid_cap ? items : grid_cap;
   if (d->dense) {
     rc = make_tmap_im2col_bf16(&tm_a, x, d->n_img, d->h, d->w, (uint64_t)d->x_pitch, p.pad, kBlockM);
@@ -1653,10 +1697,9 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   }
   IE_LAUNCH_CHECK();
   if (ksplit > 1) {
-    const long long total = R * (d->cout / 8);
-    const int ncols = e.n_tiles * e.n_tile;
-    IE_CUDA(launch_pdl(splitk_finish_kernel, dim3(ie_ceil_div(total, 256)), dim3(256), 0, st, (const float*)p.e.part, ksplit,
-                       (long long)e.m_tiles * kBlockM * ncols, ncols, p.e, static_cast<uint4*>(y_bf16), d->y_pitch / 8));
+    const long long total = (long long)(tiles - split_first) * kBlockM * (e.n_tile / 8);
+    IE_CUDA(launch_pdl(splitk_finish_kernel, dim3(ie_ceil_div(total, 256)), dim3(256), 0, st, p.e, static_cast<uint4*>(y_bf16),
+                       d->y_pitch / 8));
   }
   return IE_OK;
 }
@@ -1687,6 +1730,7 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   p.e.relu = relu;
   p.e.epilogue = IE_EPI_BF16_RASTER;
   p.e.ksplit = 1;
+  p.e.split_first = 0;
   p.e.bias = bias;
   p.x = x;
   p.hs = hs;

@@ -100,9 +100,10 @@ int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, int c, int h,
  * y_bf16 is used by IE_EPI_BF16_RASTER; y_f32 (and optional y_aux) by the fp32 epilogues.
  * workspace (nullable, 16-byte aligned device memory of workspace_bytes, caller-owned like every other buffer): scratch
  * for split-K.  When a layer has so few output tiles that most SMs would idle (eval.py's default call is ONE 32 x 32
- * patch: 1024-channel layers with K up to 18432 on a single M tile), its K loop is cut into up to
- * workspace_bytes / (128*ceil(rows/128) * cout_pad * 4) parts computed by different CTAs; the fp32 partial sums go
- * through the workspace and a second kernel reduces them in a fixed order (deterministic).  NULL: never split.
+ * patch: 1024-channel layers with K up to 18432 on a single M tile), or when the last wave of its persistent grid is
+ * less than half full, the K loop of those tiles is cut into parts computed by different CTAs (128 * n_tile * 4 bytes
+ * of workspace per part); the fp32 partial sums go through the workspace and a second kernel reduces them in a fixed
+ * order (deterministic).  NULL: never split.
  * The workspace is only used between this call's two kernels; calls on the same stream may share it.            */
 int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_bf16,
                         float* y_f32, float* y_aux, void* workspace, long long workspace_bytes, void* stream);
@@ -110,8 +111,9 @@ int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_pack
 /* Tuning / test hook: force the main-loop flavour of ie_conv2d_nhwc_bf16 (-1 auto, 0 streaming, 1 resident
  * weights, 2 wide-N).  flags: bit 1 one filter row per stage in the resident kernel, bit 2 wide-N streams its
  * weights, bit 3 flip the number of epilogue warp sets, bit 4 one filter row per stage in wide-N, bit 9 never split
- * the K loop (tiny-M layers otherwise run split-K), bit 10 plain stream-ordered launches instead of programmatic
- * dependent launch.  Process-wide.                                                                              */
+ * the K loop (tiny-M layers and the last partial wave of larger grids otherwise run split-K), bit 10 plain
+ * stream-ordered launches instead of programmatic dependent launch, bit 11 exchange epilogue for the one-block wide-N
+ * layers, bit 12 no L2 prefetch in wide-N, bit 13 split-K only for tiny M.  Process-wide.                        */
 int ie_conv_set_mode(int mode, int flags);
 
 /* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at

@@ -136,7 +136,10 @@ def test_conv_dense_im2col_vs_cpu(cuda, n, h, w, cin, cout, k):
 
 @pytest.mark.parametrize("dense", [False, True])
 @pytest.mark.parametrize("n,h,w,cin,cout", [(1, 8, 8, 1024, 1024), (1, 4, 4, 2048, 512), (3, 2, 2, 2048, 512),
-                                            (1, 16, 16, 128, 128), (2, 8, 8, 512, 64)])
+                                            (1, 16, 16, 128, 128), (2, 8, 8, 512, 64),
+                                            # a persistent grid with a partial last wave: only its tiles are split
+                                            (30, 26, 26, 256, 512),      # 159 M tiles x 2 N tiles = 318 = 2 waves + 22
+                                            (64, 13, 13, 128, 256)])     # 85 (dense) / 98 (raster) M tiles
 def test_conv_split_k_for_tiny_m(cuda, dense, n, h, w, cin, cout):
     """Tiny M (eval.py's default call: one 32 x 32 patch): the K loop of a tile is split over many CTAs, the fp32
     partial sums are reduced in a fixed order by a second kernel.  Same numbers as the unsplit kernel (to fp32

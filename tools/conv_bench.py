@@ -42,7 +42,7 @@ def main():
         dst = ops.new_raster(a.n, h, w, max(cout, 64), dev, dense=dense) if epi == 0 else None
         def run():
             if epi == 0:
-                ops.conv2d(src.slice(), wp, b, dst.slice(), k=k)
+                ops.conv2d(src.slice(), wp, b, dst.slice(), k=k, workspace=ops.conv_workspace(dev))
             else:
                 ops.conv2d_f32(src.slice(), wp, b, cout, k=k, softmax=True)
         try:
