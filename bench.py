@@ -320,9 +320,9 @@ def run_ours(args, cfg_name):
         for xb, tb in work.batches(buf, seed):
             out = model(xb)[0]
             wl = du.white_level_of(tb)
-            sums = du.eval_metric_sums(out, xb, tb, T, white_noise=wl)
             # SSIM (BASELINE metric "fwd+PSNR/SSIM"; an extension - the reference's eval.py reports PSNR and losses only)
-            t = du.reduce_metric_sums(sums, work.h, work.w, T, ssim_sums=du.ssim_deblur_sums(out, tb, white_noise=wl))
+            sums, ssim_sums = du.eval_metric_sums_with_ssim(out, xb, tb, T, white_noise=wl)
+            t = du.reduce_metric_sums(sums, work.h, work.w, T, ssim_sums=ssim_sums)
             tot = t if tot is None else tot.add_(t)
         if tot is None:                                    # strong scaling with fewer images than ranks
             tot = torch.zeros(T + 7, dtype=torch.float64, device=dev)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ie_mean_hw_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ie_invert_preproc_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P],
     "ie_eval_metrics_f32": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "ie_eval_metrics_crops_f32": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ie_eval_metrics_tune": [_I, _I, _I],
     "ie_preprocess_tune": [_I],
     "ie_ssim_tune": [_I],

@@ -300,7 +300,8 @@ template <int TT>
 __global__ void __launch_bounds__(128)
 eval_metrics_rows_kernel(const float* __restrict__ recon, const float* __restrict__ burst, int burst_pitch,
                          const float* __restrict__ truth, const float* __restrict__ wl, int n_img, int h, int w,
-                         int T_rt, int crop, int rows_per_block, int rb, double* __restrict__ sums) {
+                         int T_rt, int crop, int rows_per_block, int rb, double* __restrict__ sums,
+                         float* __restrict__ crop_deblur, float* __restrict__ crop_gt) {
   extern __shared__ float4 s_dyn4[];
   float* sm = reinterpret_cast<float*>(s_dyn4);
   __shared__ uint64_t full[2];
@@ -394,6 +395,13 @@ eval_metrics_rows_kernel(const float* __restrict__ recon, const float* __restric
       const bool hval = col_grad && row_own && (y < hc - 1);
       const bool vval = col_grad && (y > ys);
       const float g = curve(tr[0], wl_n);
+      if (crop_gt != nullptr && own) {
+        // by-product for the SSIM extension: invert_preproc(truth) and invert_preproc(deblurred) of this pixel
+        // (eval.py:146-149) - the values this kernel forms anyway - as dense [n][hc][wc] crops
+        const long long o = ((long long)n * hc + y) * wc + x;
+        crop_gt[o] = g;
+        crop_deblur[o] = curve(rc[0], wl_n);
+      }
 #pragma unroll
       for (int k = 0; k <= kMaxT; ++k) {
         if (k <= T) {
@@ -866,7 +874,8 @@ extern "C" int ie_eval_metrics_tune(int rows_per_batch, int warps, int legacy) {
 
 template <int TT>
 static int launch_eval_metrics_rows(const float* recon, const float* burst, int burst_pitch, const float* truth,
-                                    const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream) {
+                                    const float* wl, int n, int h, int w, int T, int crop, double* sums,
+                                    float* crop_deblur, float* crop_gt, void* stream) {
   const int hc = h - 2 * crop, wc = w - 2 * crop;
   int nwarps = g_em_warps;
   if (nwarps < 1 || nwarps > 4) {                              // narrowest block that wastes the fewest thread columns
@@ -892,13 +901,30 @@ static int launch_eval_metrics_rows(const float* recon, const float* burst, int 
   IE_REQUIRE(smem <= 200 * 1024, "eval_metrics: burst_pitch %d needs %zu bytes of shared memory", burst_pitch, smem);
   IE_CUDA(cudaFuncSetAttribute(eval_metrics_rows_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   eval_metrics_rows_kernel<TT><<<dim3(tiles_x, gy, n), nwarps * 32, smem, S(stream)>>>(
-      recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, rows_per_block, rb, sums);
+      recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, rows_per_block, rb, sums, crop_deblur, crop_gt);
   IE_LAUNCH_CHECK();
   return IE_OK;
 }
 
+static int eval_metrics_impl(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                             const float* wl, int n, int h, int w, int T, int crop, double* sums, float* crop_deblur,
+                             float* crop_gt, void* stream);
+
 extern "C" int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
                                    const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream) {
+  return eval_metrics_impl(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, nullptr, nullptr, stream);
+}
+
+extern "C" int ie_eval_metrics_crops_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                                         const float* wl, int n, int h, int w, int T, int crop, double* sums,
+                                         float* crop_deblur, float* crop_gt, void* stream) {
+  IE_REQUIRE(crop_deblur && crop_gt, "eval_metrics_crops: null crop pointer");
+  return eval_metrics_impl(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, crop_deblur, crop_gt, stream);
+}
+
+static int eval_metrics_impl(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                             const float* wl, int n, int h, int w, int T, int crop, double* sums, float* crop_deblur,
+                             float* crop_gt, void* stream) {
   IE_REQUIRE(recon && burst && truth && wl && sums, "eval_metrics: null pointer");
   IE_REQUIRE(n > 0 && T >= 1 && T <= kMaxT && burst_pitch >= T, "eval_metrics: bad T=%d (max %d)", T, kMaxT);
   IE_REQUIRE(crop >= 0 && h > 2 * crop + 1 && w > 2 * crop + 1, "eval_metrics: image %dx%d too small for crop %d", h, w, crop);
@@ -906,10 +932,12 @@ extern "C" int ie_eval_metrics_f32(const float* recon, const float* burst, int b
   const bool aligned = ((reinterpret_cast<uintptr_t>(recon) | reinterpret_cast<uintptr_t>(burst) |
                          reinterpret_cast<uintptr_t>(truth)) & 15) == 0;
   if (aligned && !g_em_legacy && burst_pitch <= 2 * kMaxT + 2) {
-    if (T == 4) return launch_eval_metrics_rows<4>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, stream);
-    if (T == 8) return launch_eval_metrics_rows<8>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, stream);
-    return launch_eval_metrics_rows<0>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, stream);
+    if (T == 4) return launch_eval_metrics_rows<4>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, crop_deblur, crop_gt, stream);
+    if (T == 8) return launch_eval_metrics_rows<8>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, crop_deblur, crop_gt, stream);
+    return launch_eval_metrics_rows<0>(recon, burst, burst_pitch, truth, wl, n, h, w, T, crop, sums, crop_deblur, crop_gt, stream);
   }
+  // the tile kernel (unaligned views) has no crop by-product: the caller falls back to ie_invert_preproc_f32
+  IE_REQUIRE(crop_deblur == nullptr, "eval_metrics_crops: needs 16-byte aligned recon / burst / truth (the row-streaming kernel)");
   const int tiles_x = (wc + kMT_W - 1) / kMT_W;
   // rows per block: a multiple of the 8-row sub-tile, as tall as still leaves ~4 blocks per SM in flight
   const int sub = (hc + kMT_H - 1) / kMT_H;

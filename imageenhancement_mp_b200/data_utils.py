@@ -205,20 +205,36 @@ def ssim_deblur_sums(reconstructed, x_batch_truth, white_noise=None):
 
 
 # ------------------------------------------------------------------ fused path
-def eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=None):
-    """ONE pass over (recon, burst, truth): per-image fp64 sums [N, (T+3)+(T+1)] (see imgenh_b200.h)."""
+def eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=None, want_crops=False):
+    """ONE pass over (recon, burst, truth): per-image fp64 sums [N, (T+3)+(T+1)] (see imgenh_b200.h).
+
+    ``want_crops``: also return ``(invert_preproc(deblurred), invert_preproc(gt))`` [N,h-16,w-16] - the two images
+    eval.py:146-149 forms and the SSIM extension consumes - as a by-product of the same pass."""
     _lib.require_cuda(reconstructed, x_batch_burst, x_batch_truth)
     T = burst_length
     rec = reconstructed.contiguous().float()
     xb = x_batch_burst.contiguous().float()
     tr = x_batch_truth.contiguous().float()
     n, h, w, _ = rec.shape
-    assert rec.shape[-1] == T + 1 and tr.shape == (n, h, w, 2) and xb.shape[:3] == (n, h, w)
-    wl = (white_level_of(tr) if white_noise is None else white_noise).reshape(-1).float().contiguous()
+    wl = _wl_vec(white_level_of(tr) if white_noise is None else white_noise, n)
     sums = torch.zeros(n, 2 * T + 4, dtype=torch.float64, device=rec.device)
+    if want_crops:
+        db = torch.empty(n, h - 2 * LBUFF, w - 2 * LBUFF, dtype=torch.float32, device=rec.device)
+        gt = torch.empty_like(db)
+        call("ie_eval_metrics_crops_f32", ptr(rec), ptr(xb), xb.shape[-1], ptr(tr), ptr(wl), n, h, w, T, LBUFF, ptr(sums),
+             ptr(db), ptr(gt), stream())
+        return sums, db, gt
     call("ie_eval_metrics_f32", ptr(rec), ptr(xb), xb.shape[-1], ptr(tr), ptr(wl), n, h, w, T, LBUFF, ptr(sums),
          stream())
     return sums
+
+
+def eval_metric_sums_with_ssim(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=None):
+    """``eval_metric_sums`` plus the per-image SSIM-map sums of the deblurred image (EXTENSION): the sRGB'd crops come out
+    of the fused metrics pass itself (no separate invert_preproc launches); two launches in total."""
+    sums, db, gt = eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=white_noise,
+                                    want_crops=True)
+    return sums, ssim_map_sums(db, gt)
 
 
 def reduce_metric_sums(sums, h, w, T, ssim_sums=None):

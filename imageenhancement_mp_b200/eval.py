@@ -40,7 +40,12 @@ def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None,
     reconstructed = res[0]
     n, h, w, _ = reconstructed.shape
     wl = du.white_level_of(x_batch_truth)                                         # :144-145
-    sums = du.eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length, white_noise=wl)   # :146-182
+    if ssim:        # the SSIM extension takes its two sRGB'd crops from the same pass
+        sums, ssim_sums = du.eval_metric_sums_with_ssim(reconstructed, x_batch_burst, x_batch_truth, burst_length,
+                                                        white_noise=wl)
+    else:
+        sums, ssim_sums = du.eval_metric_sums(reconstructed, x_batch_burst, x_batch_truth, burst_length,
+                                              white_noise=wl), None                                  # :146-182
     if vis is not None:
         vis["invert_gt"].append(du.invert_preproc(x_batch_truth[..., 0], wl).cpu().numpy())         # :146-147
         vis["invert_deblur"].append(du.invert_preproc(reconstructed[..., 0], wl).cpu().numpy())     # :148-149
@@ -48,7 +53,6 @@ def gpu_step_totals(model, x_batch_burst, x_batch_truth, burst_length, vis=None,
         vis["Basis"].append(res[1].cpu().numpy())
         if len(res) > 2:
             vis["originbasis"].append(res[2].cpu().numpy())
-    ssim_sums = du.ssim_deblur_sums(reconstructed, x_batch_truth, white_noise=wl) if ssim else None
     totals = du.reduce_metric_sums(sums, h, w, burst_length, ssim_sums=ssim_sums)
     if ps:
         return totals, du.cost_volume_sums(res[1])[1:2]                            # :160-162

@@ -219,6 +219,14 @@ int ie_invert_preproc_f32(const float* img, int pitch, int coff, int nch, const 
 int ie_eval_metrics_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
                         const float* wl, int n, int h, int w, int T, int crop, double* sums, void* stream);
 
+/* Same, and as a by-product the two images the SSIM extension needs - invert_preproc(recon[...,0]) and
+ * invert_preproc(truth[...,0]) (eval.py:146-149), which this kernel forms anyway - written as dense fp32
+ * [n][h-2*crop][w-2*crop] crops: saves the two ie_invert_preproc_f32 passes in front of ie_ssim_f32.  Needs 16-byte
+ * aligned recon / burst / truth (the row-streaming kernel); returns an error otherwise.                           */
+int ie_eval_metrics_crops_f32(const float* recon, const float* burst, int burst_pitch, const float* truth,
+                              const float* wl, int n, int h, int w, int T, int crop, double* sums, float* crop_deblur,
+                              float* crop_gt, void* stream);
+
 /* Tuning / A-B knob of ie_eval_metrics_f32 (tools/metric_sweep.py): rows per bulk-copy batch and warps per block of
  * the row-streaming kernel (0 = default), legacy != 0 selects the 32x32-tile kernel that also serves pointers that
  * are not 16-byte aligned.  Process-wide; not part of the reference-facing surface.                     */

@@ -558,3 +558,24 @@ def test_preprocess_device_noise_matches_numpy_philox(cuda):
     assert torch.allclose(x_rng, x_exp, atol=2e-6, rtol=1e-5)
     clean, _ = du.preprocess_image(src, org, params, wl, sr, ss)
     assert float((x_rng[..., :T] - clean[..., :T]).abs().max()) > 1e-3          # noise really was added
+
+
+@pytest.mark.parametrize("n,h,w,T", [(3, 40, 56, 4), (2, 100, 100, 4), (1, 33, 47, 8), (2, 32, 32, 2)])
+def test_fused_metrics_emit_the_ssim_crops(cuda, n, h, w, T):
+    """ie_eval_metrics_crops_f32: same sums as ie_eval_metrics_f32, and the two by-product crops equal
+    invert_preproc(deblurred) / invert_preproc(gt) (eval.py:146-149) - so the SSIM extension needs no extra passes."""
+    from imageenhancement_mp_b200 import data_utils as du
+    g = torch.Generator().manual_seed(21)
+    recon = torch.rand(n, h, w, T + 1, generator=g).to(cuda)
+    burst = torch.rand(n, h, w, T + 1, generator=g).to(cuda)
+    truth = torch.rand(n, h, w, 2, generator=g)
+    truth[..., 1] = torch.rand(n, 1, 1, generator=g) * 0.9 + 0.1
+    truth = truth.to(cuda)
+    wl = du.white_level_of(truth)
+    plain = du.eval_metric_sums(recon, burst, truth, T, white_noise=wl)
+    sums, db, gt = du.eval_metric_sums(recon, burst, truth, T, white_noise=wl, want_crops=True)
+    assert torch.allclose(sums, plain, rtol=1e-12, atol=0)
+    ref_db, ref_gt = du.invert_preproc(recon[..., 0], wl), du.invert_preproc(truth[..., 0], wl)
+    assert torch.allclose(db, ref_db, atol=2e-6) and torch.allclose(gt, ref_gt, atol=2e-6)
+    s2, ss = du.eval_metric_sums_with_ssim(recon, burst, truth, T, white_noise=wl)
+    assert torch.allclose(ss, du.ssim_deblur_sums(recon, truth, white_noise=wl), rtol=1e-5)

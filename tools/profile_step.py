@@ -23,8 +23,8 @@ batches = [tuple(t.to(dev) for t in synth.make_batch(a.n, a.h, a.w, params, seed
 def step(xb, tb):
     out = model(xb)[0]                                  # the bench step (bench.py::run_ours.step)
     wl = du.white_level_of(tb)
-    sums = du.eval_metric_sums(out, xb, tb, T, white_noise=wl)
-    return du.reduce_metric_sums(sums, a.h, a.w, T, ssim_sums=du.ssim_deblur_sums(out, tb, white_noise=wl))
+    sums, ssim_sums = du.eval_metric_sums_with_ssim(out, xb, tb, T, white_noise=wl)
+    return du.reduce_metric_sums(sums, a.h, a.w, T, ssim_sums=ssim_sums)
 
 step(*batches[0]); torch.cuda.synchronize()
 torch.cuda.profiler.start()
