@@ -1443,6 +1443,19 @@ static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
 static int g_splitk_tail = 1;        // 0: split-K only for tiny M, not for the last partial wave of larger grids
+static int g_splitk_wide = 1;        // 0: small grids always trade N-tile width for CTAs (the round-1 rule)
+static bool splitk_env() {           // IE_SPLITK=0: A-B timing without a rebuild
+  static const bool on = !(getenv("IE_SPLITK") && getenv("IE_SPLITK")[0] == '0');
+  return on;
+}
+static bool splitk_wide_env() {      // IE_SPLITK_WIDE=0: the round-1 rule
+  static const bool on = !(getenv("IE_SPLITK_WIDE") && getenv("IE_SPLITK_WIDE")[0] == '0');
+  return on;
+}
+static int splitk_max() {            // most K slices per tile (the finisher reads one fp32 slab per slice)
+  static const int v = getenv("IE_SPLITK_MAX") ? atoi(getenv("IE_SPLITK_MAX")) : 8;    // measured 8 / 16 / 36: 1x32x32 0.297 / 0.300 / 0.325 ms
+  return v < 1 ? 1 : v;
+}
 static int g_wide_prefetch = 1;      // wide-N layers with several channel blocks: L2 prefetch of the next tile's A boxes
 static int g_wide_flags = 0;         // tuning: bit 0 stream the weights even if they fit, bit 1 flip the number of
                                      // epilogue sets, bit 2 one filter row per stage even when cin = 64
@@ -1459,6 +1472,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::pdl_set(((flags >> 10) & 1) == 0);
   ie::g_wide_prefetch = ((flags >> 12) & 1) ? 0 : 1;
   ie::g_splitk_tail = ((flags >> 13) & 1) ? 0 : 1;
+  ie::g_splitk_wide = ((flags >> 14) & 1) ? 0 : 1;
   return IE_OK;
 }
 
@@ -1482,12 +1496,23 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   e.cout = d->cout;
   e.n_tile = choose_n_tile(d->cout, d->epilogue);
   e.m_tiles = (int)((R + kBlockM - 1) / kBlockM);
-  // small rasters (the per-image basis branch: 256 images x 2x2 px = 18 M tiles): trade N-tile width for CTAs
-  // until the grid covers the SMs - a 2048->512 layer on 36 CTAs ran 102 us with 112 SMs idle
+  // small rasters (the per-image basis branch: 256 images x 2x2 px = 8 M tiles): the grid must cover the SMs - a
+  // 2048->512 layer on 36 CTAs ran 102 us with 112 SMs idle. Two ways: narrower N tiles (every CTA re-reads the whole
+  // 128-row A tile for fewer output columns) or split-K over wide tiles (each A and weight byte is read once per
+  // N tile). With a workspace and a deep K loop split-K provides the CTAs and the tile stays wide.
+  const int kblocks_all = d->kh * d->kw * (d->cin / 64);
+  const bool can_split = g_splitk && splitk_env() && workspace && d->epilogue == IE_EPI_BF16_RASTER && kblocks_all >= 8;
   if (d->epilogue == IE_EPI_BF16_RASTER) {
     while (e.n_tile > 64 && d->cout % (e.n_tile / 2) == 0 &&
-           (long long)e.m_tiles * ((d->cout + e.n_tile - 1) / e.n_tile) * 2 <= sm_count())
+           (long long)e.m_tiles * ((d->cout + e.n_tile - 1) / e.n_tile) * 2 <= sm_count()) {
+      if (can_split && g_splitk_wide && splitk_wide_env()) {
+        const long long tiles_now = (long long)e.m_tiles * ((d->cout + e.n_tile - 1) / e.n_tile);
+        int max_split = kblocks_all / 4;
+        if (max_split > splitk_max()) max_split = splitk_max();
+        if (tiles_now * max_split * 2 > sm_count()) break;
+      }
       e.n_tile /= 2;
+    }
   }
   e.n_tiles = (d->cout + e.n_tile - 1) / e.n_tile;
   e.y_coff = d->y_coff;
@@ -1664,13 +1689,13 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   const int kblocks = ntaps * p.kblocks_per_tap;
   int ksplit = 1, split_first = tiles;
   const size_t slab_bytes = (size_t)kBlockM * e.n_tile * sizeof(float);
-  static const bool splitk_env = !(getenv("IE_SPLITK") && getenv("IE_SPLITK")[0] == '0');      // A-B timing
-  if (g_splitk && splitk_env && workspace && d->epilogue == IE_EPI_BF16_RASTER && kblocks >= 8) {
+  if (can_split) {
     int tail = tiles * 2 <= grid_cap ? tiles : tiles % grid_cap;            // (a) all tiles, (b) the last wave
     if (tiles * 2 > grid_cap && (g_splitk_tail == 0 || tiles < grid_cap)) tail = 0;
     if (tail > 0 && tail * 2 <= grid_cap) {
       ksplit = grid_cap / tail;
       if (ksplit > kblocks / 4) ksplit = kblocks / 4;
+      if (ksplit > splitk_max()) ksplit = splitk_max();
       while (ksplit > 1 && slab_bytes * tail * ksplit > (size_t)workspace_bytes) --ksplit;
       const int kb_per = (kblocks + ksplit - 1) / ksplit;
       ksplit = (kblocks + kb_per - 1) / kb_per;            // no empty split

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--mode", type=int, default=-1, help="-1 auto, 0 stream, 1 resident, 2 wide-N (forced)")
     ap.add_argument("--flags", type=int, default=0, help="ie_conv_set_mode flags (4: wide streams weights, 8: one epilogue set, "
-                    "2048: exchange epilogue for one-block wide layers, 8192: streaming layers on CTA pairs)")
+                    "2048: exchange epilogue for one-block wide layers, 8192: no tail split-K, 16384: narrow N tiles instead of split-K on small grids)")
     ap.add_argument("--raster", action="store_true", help="shared-border rasters at every resolution (default: dense NHWC "
                     "from 1/4 resolution down, like the engine)")
     a = ap.parse_args()
