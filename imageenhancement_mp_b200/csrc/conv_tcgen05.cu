@@ -27,6 +27,8 @@
 //   conv_wide_kernel      3x3 layers with cout <= 64 and the fp32 coef head: the three horizontal taps are three column
 //                         groups of ONE N = 192 accumulator, combined in the epilogue (own epilogues; see below).
 // Every kernel is launched with programmatic stream serialization: cta_setup() ends with griddepcontrol.wait.
+#include <climits>
+#include <utility>
 #include <cstdlib>
 
 #include "ie_common.cuh"
@@ -79,7 +81,33 @@ struct EpiParams {
   int ksplit;
   int split_first;
   float* part;
+  // r / plane and pr / wp by multiply-high (FastDiv below): every epilogue warp decodes its raster row once per tile
+  uint32_t plane_m, plane_s, wp_m, wp_s;
 };
+
+// floor(n / d) for 0 <= n < 2^31, d >= 2: with l = ceil(log2 d), m = floor(2^(31+l) / d) + 1, q = umulhi(n, m) >> (l - 1)
+// (a runtime integer division is ~20 dependent instructions; the epilogue / builder / stager warps each run one long
+//  dependent instruction stream per tile, which is what bounds the short-K kernels)
+struct FastDiv {
+  uint32_t m, s;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  FastDiv f;
+  f.m = static_cast<uint32_t>((1ull << (31 + l)) / d + 1);
+  f.s = l - 1;
+  return f;
+}
+static void set_raster_dims(EpiParams& e, int plane, int wp) {
+  e.plane = plane;
+  e.wp = wp;
+  const FastDiv fp = make_fastdiv((uint32_t)plane), fw = make_fastdiv((uint32_t)wp);
+  e.plane_m = fp.m; e.plane_s = fp.s; e.wp_m = fw.m; e.wp_s = fw.s;
+}
+__device__ __forceinline__ int fastdiv(int n, uint32_t m, uint32_t s) {
+  return static_cast<int>(__umulhi(static_cast<uint32_t>(n), m) >> s);
+}
 
 // Tail of the dynamic smem (after the operand buffers): staging, bias, barriers.
 struct SmemTail {
@@ -178,9 +206,9 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
     const uint32_t use = static_cast<uint32_t>(it >> 1);
     const int r = r0 + row_in_tile;
     // position inside the image raster -> is this an interior (kept) output?
-    const int img = r / p.plane;
+    const int img = fastdiv(r, p.plane_m, p.plane_s);
     const int pr = r - img * p.plane;
-    const int y = pr / p.wp;
+    const int y = fastdiv(pr, p.wp_m, p.wp_s);
     const int x = pr - y * p.wp;
     const bool valid = p.dense ? (r < p.R) : ((r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv));
 
@@ -699,9 +727,9 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
     const int srow0 = tile * kWideTileRows - 1 + q * kSlabOut;   // raster row of this warp's lane 0
     const int r = srow0 + lane;
     const int rr = r < 0 ? 0 : r;
-    const int img = rr / p.plane;
+    const int img = fastdiv(rr, p.plane_m, p.plane_s);
     const int pr = rr - img * p.plane;
-    const int y = pr / p.wp;
+    const int y = fastdiv(pr, p.wp_m, p.wp_s);
     const int x = pr - y * p.wp;
     const bool valid = inner && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
     mbar_wait(&t.tfull()[buf], use & 1u);
@@ -779,9 +807,9 @@ __device__ __forceinline__ void epilogue_wide_f32(const WideParams& wp_, const S
     const int srow0 = tile * kWideTileRows - 1 + q * kSlabOut;
     const int r = srow0 + lane;
     const int rr = r < 0 ? 0 : r;
-    const int img = rr / p.plane;
+    const int img = fastdiv(rr, p.plane_m, p.plane_s);
     const int pr = rr - img * p.plane;
-    const int y = pr / p.wp;
+    const int y = fastdiv(pr, p.wp_m, p.wp_s);
     const int x = pr - y * p.wp;
     const bool valid = inner && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
     const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + x;
@@ -871,9 +899,9 @@ __device__ __forceinline__ void epilogue_wide_bf16_xch(const WideParams& wp_, co
     const int row0 = tile * kXchTileRows - 1;  // raster row of tile-local row 0
     const int r = row0 + m;
     const int rr = r < 0 ? 0 : r;
-    const int img = rr / p.plane;
+    const int img = fastdiv(rr, p.plane_m, p.plane_s);
     const int pr = rr - img * p.plane;
-    const int y = pr / p.wp;
+    const int y = fastdiv(pr, p.wp_m, p.wp_s);
     const int x = pr - y * p.wp;
     const bool valid = (m >= 1) && (m <= kXchTileRows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) &&
                        (x < p.wv);
@@ -973,9 +1001,9 @@ __device__ __forceinline__ void epilogue_wide_f32_xch(const WideParams& wp_, con
     const int row0 = tile * kXchTileRows - 1;
     const int r = row0 + m;
     const int rr = r < 0 ? 0 : r;
-    const int img = rr / p.plane;
+    const int img = fastdiv(rr, p.plane_m, p.plane_s);
     const int pr = rr - img * p.plane;
-    const int y = pr / p.wp;
+    const int y = fastdiv(pr, p.wp_m, p.wp_s);
     const int x = pr - y * p.wp;
     const bool valid = (m >= 1) && (m <= kXchTileRows) && (r >= 0) && (r < p.R) && (y >= 1) && (y <= p.hv) && (x < p.wv);
     const long long pix = (static_cast<long long>(img) * p.hv + (y - 1)) * p.wv + x;
@@ -1219,8 +1247,10 @@ struct FirstParams {
   const float* x;
   int hs, ws;            // source size
   int stages;
+  long long total_floats;      // n * hs * ws * C (staged flavour: copy ranges are clamped to the tensor)
 };
-constexpr int kFirstThreads = 448;   // warp 0: weights, warp 1: MMA, warps 2-5: epilogue, warps 6-13: two builder sets
+
+constexpr int kFirstThreads = 448;   // gather flavour: warp 0 weights, 1 MMA, 2-5 epilogue, 6-13 two builder sets
 
 template <int C>
 __global__ void __launch_bounds__(kFirstThreads, 1)
@@ -1297,9 +1327,9 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
       const int stage = it % p.stages;
       const uint32_t phase = static_cast<uint32_t>(it / p.stages) & 1u;
       const int r = tile * kBlockM + row_local;
-      const int img = r / p.e.plane;
+      const int img = fastdiv(r, p.e.plane_m, p.e.plane_s);
       const int pr = r - img * p.e.plane;
-      const int yp = pr / p.e.wp;
+      const int yp = fastdiv(pr, p.e.wp_m, p.e.wp_s);
       const int y = yp - 1, x = pr - yp * p.e.wp;
       const bool interior = (r < p.e.R) && (y >= 0) && (y < p.e.hv) && (x >= 0) && (x < p.e.wv);
       const float* centre = p.x + ((static_cast<long long>(img) * p.hs + y) * p.ws + (x - 1)) * C;   // (y, x-1, 0)
@@ -1344,6 +1374,254 @@ conv_first_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// Staged flavour of the first layer (the default): the gathers of the kernel above are 45 scalar global loads per
+// pixel whose latency eight builder warps cannot hide (ncu: 183 us at 256 x 104^2, DRAM 24 %, no pipe above 33 %).
+// Here warp 0 copies, per tile and filter row, the contiguous run of source pixels the tile's 128 raster positions
+// touch (<= 130 pixels: in raster order the clamped source index (img, clamp(y + dy - 1), min(x, ws - 1)) moves by at
+// most one per position) with ONE cp.async.bulk each, several tiles ahead, into a small ring; the builders read
+// their 3 x 3C floats from shared memory (lane stride C floats: conflict-free for odd C) and write the swizzled A row
+// as before.  The copies start on the enclosing 16-byte boundary; the float index of each slot's first element is
+// passed through the ring's metadata words.  Requires a 16-byte aligned source whose float count is a multiple of 4.
+template <int C>
+struct FirstStaged {
+  // ring depth = tiles whose source rows are in flight: the copies come from DRAM (1 - 2 us under the kernel's own
+  // write traffic) and a tile takes ~0.5 us, so four stages left the builders waiting (measured: 148 us at 256 x 104^2)
+  static constexpr int kInStages = C <= 5 ? 12 : 6;
+  static constexpr int kAStages = C <= 7 ? 3 : 2;                            // built A tiles waiting for the MMA warp
+  static constexpr int kSlot = ((130 * C * 4 + 32 + 127) / 128) * 128;     // one filter row of one tile
+  static constexpr int kStage = 3 * kSlot + 128;                             // + metadata (3 ints), 128-byte aligned
+  // + 2 * kInStages barriers + a 128-byte zero page (what masked taps read); a multiple of 1024 because the
+  // epilogue's staging buffers behind it are 128B-swizzled
+  static constexpr int kBarBytes = ((2 * kInStages * 8 + 127) / 128) * 128;
+  static constexpr int kRing = ((kInStages * kStage + kBarBytes + 128 + 1023) / 1024) * 1024;
+};
+
+// im2col element k = tap * C + ch of a pixel: one ld.shared with the channel offset as an immediate
+template <int C, int K>
+__device__ __forceinline__ float load_tap(const uint32_t (&tapaddr)[9]) {
+  if constexpr (K < 9 * C) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(tapaddr[K / C]), "n"((K % C) * 4));
+    return v;
+  } else {
+    return 0.f;
+  }
+}
+template <int C, int KBASE, int... KK>
+__device__ __forceinline__ void load_taps(float (&v)[64], const uint32_t (&tapaddr)[9], std::integer_sequence<int, KK...>) {
+  ((v[KK] = load_tap<C, KBASE + KK>(tapaddr)), ...);
+}
+
+constexpr int kFirstStagedWarps = 19;      // warp 0 + warp 18: input stagers, 1: MMA, 2-9: two epilogue sets, 10-17: two builder sets
+template <int C>
+__global__ void __launch_bounds__(kFirstStagedWarps * 32, 1)
+conv_first_staged_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_y,
+                         const FirstParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  using L = FirstStaged<C>;
+  constexpr int kInStages = L::kInStages;
+  constexpr int KB = (9 * C + 63) / 64;
+  constexpr int kWTile = 64 * 128;
+  constexpr int kWBytes = KB * kWTile;
+  constexpr int kStageBytes = KB * kABytes;
+  uint8_t* a_base_ptr = base + kWBytes;
+  uint8_t* ring = a_base_ptr + p.stages * kStageBytes;
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(ring + kInStages * L::kStage);
+  uint64_t* in_empty = in_full + kInStages;
+  uint8_t* zero_page = ring + kInStages * L::kStage + L::kBarBytes;
+  SmemTail t{ring + L::kRing, 2};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.e.m_tiles;
+  if (warp == 2) reinterpret_cast<uint32_t*>(zero_page)[lane] = 0u;        // visible after cta_setup's __syncthreads
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+    for (int s = 0; s < kInStages; ++s) {
+      mbar_init(&in_full[s], 3);        // one arrive.expect_tx per filter row (lanes 0-2 of the stager)
+      mbar_init(&in_empty[s], 4);       // one arrive per builder warp of the set that consumed the stage
+    }
+  }
+  const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane, 4);
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
+
+  if (warp == 0 || warp == kFirstStagedWarps - 1) {
+    if (warp == 0 && lane == 0) {
+      mbar_arrive_expect_tx(t.bres(), kWBytes);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(base + kb * kWTile, &tm_b, t.bres(), kb * kBlockK, 0);
+    }
+    // ================================ input stagers ===============================
+    // two warps, alternate tiles (one warp's per-tile latency - decode four positions per lane, six warp
+    // reductions, plan, issue - was the kernel's critical path)
+    const int pset = warp == 0 ? 0 : 1;
+    int it = pset;
+    for (int tile = blockIdx.x + pset * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int s = it % kInStages;
+      const uint32_t phase = static_cast<uint32_t>(it / kInStages) & 1u;
+      int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = tile * kBlockM + lane + 32 * j;
+        if (r < p.e.R) {
+          const int img = fastdiv(r, p.e.plane_m, p.e.plane_s);
+          const int pr = r - img * p.e.plane;
+          const int yp = fastdiv(pr, p.e.wp_m, p.e.wp_s);
+          const int y = yp - 1, x = pr - yp * p.e.wp;
+          const int cx = x < p.ws ? x : p.ws - 1;
+          const bool interior = (y >= 0) && (y < p.e.hv) && (x < p.e.wv);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            // only positions that read filter row dy count: along those the source index moves by at most one per
+            // raster position, so a tile's run is <= 128 pixels (+ one on either side for the horizontal taps)
+            const int sy = y + dy - 1;
+            if (interior && sy >= 0 && sy < p.hs) {
+              const int v = (img * p.hs + sy) * p.ws + cx;
+              lo[dy] = v < lo[dy] ? v : lo[dy];
+              hi[dy] = v > hi[dy] ? v : hi[dy];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        lo[dy] = __reduce_min_sync(0xffffffffu, lo[dy]);
+        hi[dy] = __reduce_max_sync(0xffffffffu, hi[dy]);
+      }
+      mbar_wait(&in_empty[s], phase ^ 1u);
+      if (lane < 3) {
+        // lane dy plans and issues the copy of filter row dy (three short dependent chains side by side instead of
+        // one long one: this warp's per-tile latency bounds the kernel)
+        uint8_t* stage = ring + s * L::kStage;
+        int* meta = reinterpret_cast<int*>(stage + 3 * L::kSlot);
+        const int mylo = lane == 0 ? lo[0] : lane == 1 ? lo[1] : lo[2];
+        const int myhi = lane == 0 ? hi[0] : lane == 1 ? hi[1] : hi[2];
+        long long f0 = (static_cast<long long>(mylo) - 1) * C;
+        long long f1 = (static_cast<long long>(myhi) + 2) * C;            // exclusive
+        f0 = f0 < 0 ? 0 : f0;
+        f1 = f1 > p.total_floats ? p.total_floats : f1;
+        const long long b0 = (f0 * 4) & ~15ll;
+        const uint32_t bytes = myhi < mylo ? 0u : static_cast<uint32_t>(((f1 * 4 + 15) & ~15ll) - b0);   // no reader: no copy
+        meta[lane] = static_cast<int>(b0 >> 2);
+        mbar_arrive_expect_tx(&in_full[s], bytes);
+        if (bytes)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(stage + lane * L::kSlot)),
+                       "l"(reinterpret_cast<const uint8_t*>(p.x) + b0), "r"(bytes), "r"(smem_u32(&in_full[s]))
+                       : "memory");
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, 64);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base_ptr));
+    const uint32_t b_lo = umma_desc_lo(smem_u32(base));
+    mbar_wait(t.bres(), 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t a = a_lo0 + stage * (kStageBytes >> 4) + kb * (kABytes >> 4);
+          const uint32_t b = b_lo + kb * (kWTile >> 4);
+          umma_bf16_ss_lo(d_tmem, a, b, idesc, kb == 0 ? 0u : 1u);
+          umma_bf16_ss_lo(d_tmem, a + 2, b + 2, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, a + 4, b + 4, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, a + 6, b + 6, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&t.tfull()[buf]);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp < 10) {
+    // two epilogue sets: with the gathers out of the way the tile rate is set by the epilogue's dependent
+    // TMEM load -> pack -> stage -> TMA store stream (~2 300 cycles per tile and set)
+    epilogue_loop(p.e, &tm_y, t, tmem_base, warp, lane);
+  } else {
+    // ================================ A-tile builders ==============================
+    // two sets of four warps, alternate tiles
+    const int bset = (warp - 10) >> 2;
+    const int row_local = ((warp - 10) & 3) * 32 + lane;
+    int it = bset;
+    for (int tile = blockIdx.x + bset * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int stage = it % p.stages;
+      const uint32_t phase = static_cast<uint32_t>(it / p.stages) & 1u;
+      const int sin = it % kInStages;
+      const uint32_t phase_in = static_cast<uint32_t>(it / kInStages) & 1u;
+      const int r = tile * kBlockM + row_local;
+      const int img = fastdiv(r, p.e.plane_m, p.e.plane_s);
+      const int pr = r - img * p.e.plane;
+      const int yp = fastdiv(pr, p.e.wp_m, p.e.wp_s);
+      const int y = yp - 1, x = pr - yp * p.e.wp;
+      const bool interior = (r < p.e.R) && (y >= 0) && (y < p.e.hv) && (x >= 0) && (x < p.e.wv);
+      bool rowok[3], colok[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        rowok[d] = interior && (y + d - 1 >= 0) && (y + d - 1 < p.hs);
+        colok[d] = (x + d - 1 >= 0) && (x + d - 1 < p.ws);
+      }
+      const uint8_t* stage_in = ring + sin * L::kStage;
+      const int* meta = reinterpret_cast<const int*>(stage_in + 3 * L::kSlot);
+      mbar_wait(&in_full[sin], phase_in);
+      // one base address per (filter row, horizontal tap): the pixel's C floats in the staged row, or the zero page
+      // when the tap is outside the source - 9 selects per pixel instead of a compare + select per element, and the
+      // channel offset is an immediate of the load
+      uint32_t tapaddr[9];
+      const uint32_t zaddr = smem_u32(zero_page);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        // float index of (img, y + dy - 1, x - 1, 0) relative to the slot's first float
+        const int off = ((img * p.hs + (y + dy - 1)) * p.ws + (x - 1)) * C - meta[dy];
+        const uint32_t rowaddr = smem_u32(stage_in + dy * L::kSlot) + static_cast<uint32_t>(off) * 4u;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) tapaddr[dy * 3 + g] = (rowok[dy] && colok[g]) ? rowaddr + g * C * 4 : zaddr;
+      }
+      uint32_t pk[KB][32];
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        float v[64];
+#pragma unroll
+        for (int kk = 0; kk < 64; ++kk) v[kk] = 0.f;
+        if (kb == 0) load_taps<C, 0>(v, tapaddr, std::make_integer_sequence<int, 64>{});
+        else load_taps<C, 64>(v, tapaddr, std::make_integer_sequence<int, 64>{});
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[kb][j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&in_empty[sin]);          // the values are in registers: the slot may be refilled
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint32_t rowa = smem_u32(a_base_ptr + stage * kStageBytes + kb * kABytes) + row_local * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128u(rowa + ((j ^ (row_local & 7)) << 4), pk[kb][4 * j], pk[kb][4 * j + 1], pk[kb][4 * j + 2], pk[kb][4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // Second half of a split-K convolution: for every split tile, sums the `ksplit` fp32 slabs in a fixed order, adds the
 // bias, applies ReLU and the border / valid-extent mask, and writes the bf16 rows (8 channels per thread).
 __global__ void __launch_bounds__(256)
@@ -1365,9 +1643,9 @@ splitk_finish_kernel(EpiParams p, uint4* __restrict__ y, int y_pitch_v) {
   if (r >= p.R || col >= p.cout) return;
   bool valid = true;
   if (!p.dense) {
-    const int img = r / p.plane;
+    const int img = fastdiv(r, p.plane_m, p.plane_s);
     const int pr = r - img * p.plane;
-    const int yy = pr / p.wp;
+    const int yy = fastdiv(pr, p.wp_m, p.wp_s);
     const int xx = pr - yy * p.wp;
     valid = (yy >= 1) && (yy <= p.hv) && (xx < p.wv);
   }
@@ -1443,6 +1721,7 @@ static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
 static int g_splitk_tail = 1;        // 0: split-K only for tiny M, not for the last partial wave of larger grids
+static int g_first_gather = 0;       // 1: first layer with per-thread global gathers instead of staged source rows
 static int g_splitk_wide = 1;        // 0: small grids always trade N-tile width for CTAs (the round-1 rule)
 static bool splitk_env() {           // IE_SPLITK=0: A-B timing without a rebuild
   static const bool on = !(getenv("IE_SPLITK") && getenv("IE_SPLITK")[0] == '0');
@@ -1473,6 +1752,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_wide_prefetch = ((flags >> 12) & 1) ? 0 : 1;
   ie::g_splitk_tail = ((flags >> 13) & 1) ? 0 : 1;
   ie::g_splitk_wide = ((flags >> 14) & 1) ? 0 : 1;
+  ie::g_first_gather = (flags >> 15) & 1;
   return IE_OK;
 }
 
@@ -1489,8 +1769,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   e.ksplit = 1;
   e.split_first = 0;                   // irrelevant while ksplit == 1 (every item is a whole tile)
   e.R = (int)R;
-  e.plane = (d->h + 1) * wp;
-  e.wp = wp;
+  set_raster_dims(e, (d->h + 1) * wp, wp);
   e.hv = d->hv;
   e.wv = d->wv;
   e.cout = d->cout;
@@ -1743,8 +2022,7 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   IE_REQUIRE(R < (1ll << 31) - 4096, "conv_first: raster too large for 32-bit rows");
   FirstParams p{};
   p.e.R = (int)R;
-  p.e.plane = (h + 1) * (w + 1);
-  p.e.wp = w + 1;
+  set_raster_dims(p.e, (h + 1) * (w + 1), w + 1);
   p.e.hv = h;
   p.e.wv = w;
   p.e.cout = cout;
@@ -1761,19 +2039,30 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   p.hs = hs;
   p.ws = ws;
   const int kb = (9 * c + 63) / 64;                       // K blocks of 64: w_packed is [64][64 * kb]
-  p.stages = kb == 1 ? 6 : 4;
+  p.total_floats = (long long)n * hs * ws * c;
   CUtensorMap tm_b, tm_y;
   int rc = make_tmap_2d_bf16(&tm_b, w_packed, 64 * kb, 64, 64 * kb, 64, 64);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tm_y, y_bf16, (uint64_t)y_pitch, (uint64_t)R, (uint64_t)y_pitch, 64, 32);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)kb * 64 * 128 + (size_t)p.stages * kb * kABytes + kTailBytes;
+  // staged flavour (bulk copies of the source rows into shared memory) when the copies can be 16-byte aligned
+  const bool staged = !g_first_gather && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && p.total_floats % 4 == 0 &&
+                      p.total_floats < (1ll << 31);
+  p.stages = !staged ? (kb == 1 ? 6 : 4) : c == 5 ? FirstStaged<5>::kAStages : c == 3 ? FirstStaged<3>::kAStages : FirstStaged<10>::kAStages;
+  const int ring = !staged ? 0 : c == 5 ? FirstStaged<5>::kRing : c == 3 ? FirstStaged<3>::kRing : FirstStaged<10>::kRing;
+  const size_t smem = 1024 + (size_t)kb * 64 * 128 + (size_t)p.stages * kb * kABytes + ring + (staged ? kTailBytes2 : kTailBytes);
   const int grid = p.e.m_tiles < sm_count() ? p.e.m_tiles : sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define IE_LAUNCH_FIRST(C_)                                                                                        \
   do {                                                                                                             \
-    IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
-    IE_CUDA(launch_pdl(conv_first_kernel<C_>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));          \
+    if (staged) {                                                                                                  \
+      IE_CUDA(cudaFuncSetAttribute(conv_first_staged_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                   (int)kMaxSmem));                                                                \
+      IE_CUDA(launch_pdl(conv_first_staged_kernel<C_>, dim3(grid), dim3(kFirstStagedWarps * 32), smem, st, tm_b, tm_y, p)); \
+    } else {                                                                                                       \
+      IE_CUDA(cudaFuncSetAttribute(conv_first_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem)); \
+      IE_CUDA(launch_pdl(conv_first_kernel<C_>, dim3(grid), dim3(kFirstThreads), smem, st, tm_b, tm_y, p));        \
+    }                                                                                                              \
   } while (0)
   if (c == 5) IE_LAUNCH_FIRST(5);
   else if (c == 3) IE_LAUNCH_FIRST(3);

@@ -49,10 +49,27 @@ def test_im2col_first_layer(cuda):
 
 @pytest.mark.parametrize("c,n,hs,ws,h,w", [(5, 2, 16, 24, 16, 24), (3, 3, 13, 21, 16, 24), (5, 7, 100, 100, 104, 104),
                                            # Basis_kpn with T = 8 + dualparams: 10 channels, K = 90 -> two K blocks
-                                           (10, 2, 16, 24, 16, 24), (10, 5, 61, 64, 64, 64)])
-def test_first_layer_fused_im2col(cuda, c, n, hs, ws, h, w):
-    """conv_first_kernel (im2col built in-kernel by the builder warps) == im2col raster + 1x1 GEMM, bit for bit,
-    and == Conv2D(64, 3, 'same', relu) of the (zero-padded) input (model_library.py:323, 376)."""
+                                           (10, 2, 16, 24, 16, 24), (10, 5, 61, 64, 64, 64),
+                                           # staged source rows: tiny images (tiles span many rows and images), rows wider
+                                           # than a tile, a source smaller than the raster, one row short of it
+                                           (5, 9, 8, 8, 8, 8), (5, 1, 40, 300, 40, 300), (3, 4, 12, 20, 16, 24),
+                                           (5, 4, 31, 32, 32, 32), (5, 3, 1, 1, 8, 8)])
+@pytest.mark.parametrize("gather", [False, True])
+def test_first_layer_fused_im2col(cuda, c, n, hs, ws, h, w, gather):
+    """conv_first_staged_kernel (source rows staged with bulk copies, im2col rows built in shared memory; the default
+    when the float count is a multiple of 4) and conv_first_kernel (per-thread gathers: `gather`, or the fallback)
+    == im2col raster + 1x1 GEMM, bit for bit, and == Conv2D(64, 3, 'same', relu) of the (zero-padded) input
+    (model_library.py:323, 376)."""
+    from imageenhancement_mp_b200 import _lib, ops
+    lib = _lib.load()
+    lib.ie_conv_set_mode(-1, (1 << 15) if gather else 0)
+    try:
+        _first_layer_case(cuda, c, n, hs, ws, h, w)
+    finally:
+        lib.ie_conv_set_mode(-1, 0)
+
+
+def _first_layer_case(cuda, c, n, hs, ws, h, w):
     from imageenhancement_mp_b200 import ops
     g = torch.Generator().manual_seed(3)
     x = bf16_round(torch.rand(n, hs, ws, c, generator=g))
