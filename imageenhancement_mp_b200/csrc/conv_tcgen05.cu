@@ -180,6 +180,23 @@ __device__ __forceinline__ uint32_t cta_setup(const SmemTail& t, const EpiParams
   return *t.tmem_slot();
 }
 
+// 64 accumulator columns of one row + bias -> 32 packed bf16 pairs
+template <bool RELU>
+__device__ __forceinline__ void bias_pack_64(uint32_t (&pk)[32], const uint32_t (&v0)[32], const uint32_t (&v1)[32], uint32_t bs) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float4 bb = lds128(bs + j * 8);
+    pk[j] = bias_act_pack<RELU>(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]), bb.x, bb.y);
+    pk[j + 1] = bias_act_pack<RELU>(__uint_as_float(v0[2 * j + 2]), __uint_as_float(v0[2 * j + 3]), bb.z, bb.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float4 bb = lds128(bs + 128 + j * 8);
+    pk[16 + j] = bias_act_pack<RELU>(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]), bb.x, bb.y);
+    pk[16 + j + 1] = bias_act_pack<RELU>(__uint_as_float(v1[2 * j + 2]), __uint_as_float(v1[2 * j + 3]), bb.z, bb.w);
+  }
+}
+
 // Epilogue warps (4 warps, one TMEM lane quadrant each): walk the CTA's tiles and drain the accumulator
 // buffers as the MMA warp completes them.
 // With two sets (warps 2-5 and 6-9) set s takes the CTA's tiles it = s, s+2, ... and therefore always drains TMEM
@@ -248,32 +265,22 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
         }
         uint32_t pk[32];
         const uint32_t bs = smem_u32(sbias + n0 + c * 64);
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float4 bb = lds128(bs + j * 8);
-          float a0 = __uint_as_float(v0[2 * j]) + bb.x, a1 = __uint_as_float(v0[2 * j + 1]) + bb.y;
-          float a2 = __uint_as_float(v0[2 * j + 2]) + bb.z, a3 = __uint_as_float(v0[2 * j + 3]) + bb.w;
-          if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-          pk[j] = valid ? pack_bf16x2(a0, a1) : 0u;
-          pk[j + 1] = valid ? pack_bf16x2(a2, a3) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float4 bb = lds128(bs + 128 + j * 8);
-          float a0 = __uint_as_float(v1[2 * j]) + bb.x, a1 = __uint_as_float(v1[2 * j + 1]) + bb.y;
-          float a2 = __uint_as_float(v1[2 * j + 2]) + bb.z, a3 = __uint_as_float(v1[2 * j + 3]) + bb.w;
-          if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-          pk[16 + j] = valid ? pack_bf16x2(a0, a1) : 0u;
-          pk[16 + j + 1] = valid ? pack_bf16x2(a2, a3) : 0u;
-        }
+        if (p.relu) bias_pack_64<true>(pk, v0, v1, bs);
+        else bias_pack_64<false>(pk, v0, v1, bs);
         // staging buffer must have been read by the previous TMA store
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B)
+        // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B); border / masked rows
+        // are written as zeros (a branch per row instead of a select per word)
         const uint32_t rowa = smem_u32(stg) + lane * 128;
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128u(rowa + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            sts128u(rowa + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128u(rowa + (j << 4), 0u, 0u, 0u, 0u);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -711,6 +718,28 @@ struct WideParams {
   int prefetch;          // L2-prefetch the next tile's A boxes (G == 1 variants)
 };
 
+// Horizontal tap combine of 32 accumulator columns (slab tiling: the neighbours are always in the warp): (up + centre)
+// + down on fp32 pairs (FADD2), then bias + ReLU + bf16 rounding in two more instructions per pair.
+template <bool RELU>
+__device__ __forceinline__ void wide_combine_32(uint32_t (&pk)[32], int c, const uint32_t (&z0)[32], const uint32_t (&z1)[32],
+                                                const uint32_t (&z2)[32], uint32_t bs) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bb = lds128(bs + j * 4);
+    const float bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      const float2 up = make_float2(__shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1),           // Z[r-1][co]
+                                    __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e + 1]), 1));
+      const float2 dn = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1),         // Z[r+1][128 + co]
+                                    __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e + 1]), 1));
+      float2 a = __fadd2_rn(up, make_float2(__uint_as_float(z1[j + e]), __uint_as_float(z1[j + e + 1])));
+      a = __fadd2_rn(a, dn);
+      pk[c * 16 + ((j + e) >> 1)] = bias_act_pack<RELU>(a.x, a.y, bbv[e], bbv[e + 1]);
+    }
+  }
+}
+
 // Epilogue of the wide-N kernel, bf16 raster output, gw = 64.
 __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const CUtensorMap* tm_y30, const SmemTail& t,
                                                    uint32_t tmem_base, int warp, int lane) {
@@ -749,22 +778,8 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
         if (lane == 0) mbar_arrive(&t.tempty()[buf]);
       }
       const uint32_t bs = smem_u32(sbias + c * 32);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 bb = lds128(bs + j * 4);
-        const float bbv[4] = {bb.x, bb.y, bb.z, bb.w};
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);      // Z[r-1][co]
-          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);    // Z[r+1][128 + co]
-          float a = up + __uint_as_float(z1[j + e]) + dn + bbv[e];
-          if (p.relu) a = fmaxf(a, 0.f);
-          v[e] = a;
-        }
-        pk[c * 16 + (j >> 1)] = valid ? pack_bf16x2(v[0], v[1]) : 0u;
-        pk[c * 16 + (j >> 1) + 1] = valid ? pack_bf16x2(v[2], v[3]) : 0u;
-      }
+      if (p.relu) wide_combine_32<true>(pk, c, z0, z1, z2, bs);
+      else wide_combine_32<false>(pk, c, z0, z1, z2, bs);
     }
     if (lane == 0) tma_store_wait_read<0>();
     __syncwarp();
@@ -773,9 +788,14 @@ __device__ __forceinline__ void epilogue_wide_bf16(const WideParams& wp_, const 
     if (inner) {
       const int srow = lane - 1;
       const uint32_t rowa = smem_u32(stg) + srow * 128;
+      if (valid) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        sts128u(rowa + ((j ^ (srow & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)
+          sts128u(rowa + ((j ^ (srow & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      } else {                                        // border / masked rows: zeros (a branch per row, not a select per word)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128u(rowa + (j << 4), 0u, 0u, 0u, 0u);
+      }
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -943,19 +963,22 @@ __device__ __forceinline__ void epilogue_wide_bf16_xch(const WideParams& wp_, co
       for (int j = 0; j < 32; j += 4) {
         const float4 pv = lds128(prev + j * 4), nx = lds128(next + j * 4), bb = lds128(bs + j * 4);
         const float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, nxv[4] = {nx.x, nx.y, nx.z, nx.w}, bbv[4] = {bb.x, bb.y, bb.z, bb.w};
-        float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1);
-          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1);
-          up = first ? pvv[e] : up;               // q == 0: row m = 0 is never stored
-          dn = last ? nxv[e] : dn;                // q == 3: row m = 127 is never stored
-          float a = up + __uint_as_float(z1[j + e]) + dn + bbv[e];
-          if (p.relu) a = fmaxf(a, 0.f);
-          v[e] = a;
+        for (int e = 0; e < 4; e += 2) {
+          float2 up = make_float2(__shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e]), 1),
+                                  __shfl_up_sync(0xffffffffu, __uint_as_float(z0[j + e + 1]), 1));
+          float2 dn = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e]), 1),
+                                  __shfl_down_sync(0xffffffffu, __uint_as_float(z2[j + e + 1]), 1));
+          up = first ? make_float2(pvv[e], pvv[e + 1]) : up;               // q == 0: row m = 0 is never stored
+          dn = last ? make_float2(nxv[e], nxv[e + 1]) : dn;                // q == 3: row m = 127 is never stored
+          float2 a = __fadd2_rn(up, make_float2(__uint_as_float(z1[j + e]), __uint_as_float(z1[j + e + 1])));
+          a = __fadd2_rn(a, dn);
+          // (one packed add + the plain conversion; ReLU as a packed max on the two bf16 halves would need HMNMX2 -
+          //  the multi-block layers hide their epilogue anyway)
+          const float2 sb = __fadd2_rn(a, make_float2(bbv[e], bbv[e + 1]));
+          const float r0 = p.relu ? fmaxf(sb.x, 0.f) : sb.x, r1 = p.relu ? fmaxf(sb.y, 0.f) : sb.y;
+          pk[c * 16 + ((j + e) >> 1)] = valid ? pack_bf16x2(r0, r1) : 0u;
         }
-        pk[c * 16 + (j >> 1)] = valid ? pack_bf16x2(v[0], v[1]) : 0u;
-        pk[c * 16 + (j >> 1) + 1] = valid ? pack_bf16x2(v[2], v[3]) : 0u;
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
