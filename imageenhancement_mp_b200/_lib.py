@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
 _P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argument ctypes (every function returns int unless noted)
+SIZE_QUERIES = ("ie_maxpool2_stat_scratch_bytes", "ie_channel_mean_scratch_bytes")      # return a byte count, not a status
 SIGNATURES = {
     "ie_version": [],
     "ie_sm_count": [],
@@ -42,9 +43,11 @@ SIGNATURES = {
     "ie_conv2d_nhwc_bf16": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P],
     "ie_conv_set_mode": [_I, _I],
     "ie_debug_conv2d_naive": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P],
-    "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _LL, _I, _P],
+    "ie_maxpool2_stat_scratch_bytes": [_I, _I, _I, _I, _I],
+    "ie_maxpool2_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P, _LL, _I, _I, _LL, _I, _P],
     "ie_upsample_bilinear_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],
-    "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _LL, _I, _P],
+    "ie_channel_mean_scratch_bytes": [_I, _I, _I, _I, _I, _I],
+    "ie_channel_mean_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _LL, _I, _I, _LL, _I, _P],
     "ie_broadcast_hw_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "ie_raster_to_nhwc_f32": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "ie_softmax_taps_f32": [_P, _I, _I, _I, _P, _P],
@@ -87,7 +90,7 @@ def load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_longlong if name in SIZE_QUERIES else C.c_int
     lib.ie_last_error.argtypes = []
     lib.ie_last_error.restype = C.c_char_p
     _lib = lib

@@ -85,6 +85,22 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
   out[(((long long)img * (h + 1) + yp) * wp + xp) * kvec + chunk] = pack8(f);
 }
 
+// Ordered cross-block reduction: after a block has written its partial result it takes a ticket; the block that draws
+// the last one sees every partial (fence + L2 loads), reduces them in a fixed order and re-arms the counter.
+__device__ __forceinline__ bool stat_finish(int* counter, unsigned nblocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(counter, 1);
+    s_last = (ticket == (int)nblocks - 1);
+    if (s_last) *counter = 0;                    // every block of this group has arrived: ready for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 // ------------------------------------------------------------------------------- max-pool 2x2
 // block = 256 threads = cvb channel chunks (16 B each) x 256/cvb pixel lanes; grid = (cvec/cvb, row groups, n).
 // A block walks the padded output pixels of its rows; consecutive threads touch consecutive channel chunks
@@ -95,7 +111,7 @@ constexpr int kPoolRows = 2;           // padded output rows per block
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, int x_pitch_v, int x_coff_v,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale,
-                int stat_y0, int stat_y1, int bi, int bo) {
+                int stat_y0, int stat_y1, int bi, int bo, float* __restrict__ part, int* __restrict__ counter) {
   pdl_trigger();
   pdl_wait();
   // bi / bo: border of the input / output tensor (1 = shared-border raster, 0 = dense NHWC)
@@ -139,14 +155,25 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = acc[e];
   __syncthreads();
-  // thread t < cvb*8 owns channel (t / 8 -> chunk, t % 8 -> element) and sums over the pixel lanes
+  // thread t < cvb*8 owns channel (t / 8 -> chunk, t % 8 -> element) and sums over the pixel lanes; the row groups
+  // of an image meet in a FIXED order: every block stores its partial sums, the last one to arrive (ticket counter)
+  // adds them up by row group - no floating-point atomics, the means are bit-reproducible
   const int t = threadIdx.x;
-  if (t < cvb * 8) {
+  const int C = cvec * 8;
+  const bool owner = (t < cvb * 8) && (blockIdx.x * cvb + (t >> 3) < cvec);
+  const int ch = (blockIdx.x * cvb + (t >> 3)) * 8 + (t & 7);
+  if (owner) {
     const int chunk = t >> 3, e = t & 7;
     float s = 0.f;
     for (int l = 0; l < npl; ++l) s += red[l * cvb + chunk][e];
-    const int ch = (blockIdx.x * cvb + chunk) * 8 + e;
-    if (blockIdx.x * cvb + chunk < cvec) atomicAdd(&chan_sum[(long long)img * cvec * 8 + ch], s * scale);
+    part[((long long)img * gridDim.y + blockIdx.y) * C + ch] = s;
+  }
+  if (stat_finish(&counter[img * gridDim.x + blockIdx.x], gridDim.y)) {
+    if (owner) {
+      float tot = 0.f;
+      for (int by = 0; by < (int)gridDim.y; ++by) tot += __ldcg(&part[((long long)img * gridDim.y + by) * C + ch]);
+      chan_sum[(long long)img * C + ch] = tot * scale;
+    }
   }
 }
 
@@ -271,7 +298,8 @@ upsample2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int x_pitc
 // ------------------------------------------------------------------------------- channel means
 // block = 256 threads = 32 pixel lanes x 8 vector lanes (64 channels); grid = (c/64, n, splits).
 __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, int x_pitch_v, int x_coff_v,
-                                    float* __restrict__ mean, int c, float scale, int y0, int y1, int bi) {
+                                    float* __restrict__ mean, int c, float scale, int y0, int y1, int bi,
+                                    float* __restrict__ part, int* __restrict__ counter) {
   pdl_trigger();
   pdl_wait();
   const int vl = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -293,11 +321,20 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[pl][vl * 8 + e] = acc[e];
   __syncthreads();
+  const int ch = cb * 64 + threadIdx.x;
   if (threadIdx.x < 64) {
     float s = 0.f;
 #pragma unroll 8
     for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
-    atomicAdd(&mean[(long long)img * c + cb * 64 + threadIdx.x], s * scale);
+    part[((long long)img * gridDim.z + blockIdx.z) * c + ch] = s;
+  }
+  // the splits of an image meet in a fixed order in the last block to arrive (see stat_finish): reproducible means
+  if (stat_finish(&counter[img * gridDim.x + cb], gridDim.z)) {
+    if (threadIdx.x < 64) {
+      float tot = 0.f;
+      for (int z = 0; z < (int)gridDim.z; ++z) tot += __ldcg(&part[((long long)img * gridDim.z + z) * c + ch]);
+      mean[(long long)img * c + ch] = tot * scale;
+    }
   }
 }
 
@@ -504,9 +541,38 @@ static int check_slice(const char* who, int c, int pitch, int coff) {
   return IE_OK;
 }
 
+// scratch of the ordered channel statistics: [n][groups][c] partial sums, then [n][ceil(c/64)... ] ticket counters
+static long long stat_scratch_bytes(int n, int groups, int c, int counters_per_img) {
+  return ((long long)n * groups * c + (long long)n * counters_per_img) * 4;
+}
+static int maxpool_row_groups(int h, int layout) {
+  const int bo = (layout & IE_LAYOUT_Y_DENSE) ? 0 : 1;
+  return (h / 2 + bo + kPoolRows - 1) / kPoolRows;
+}
+static int channel_mean_splits(int n, int h, int w, int c, int y0, int y1) {
+  if (y1 <= 0) { y0 = 0; y1 = h; }
+  const int npix = (y1 - y0) * w;
+  int splits = (8 * sm_count() + (c / 64) * n - 1) / ((c / 64) * n);       // >= 8 blocks per SM in flight
+  const int max_splits = (npix + 31) / 32;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  return splits;
+}
+
+extern "C" long long ie_maxpool2_stat_scratch_bytes(int n, int h, int w, int c, int layout) {
+  (void)w;
+  const int cvec = c / 8, cvb = cvec < 32 ? cvec : 32;
+  return stat_scratch_bytes(n, maxpool_row_groups(h, layout), c, (cvec + cvb - 1) / (cvb > 0 ? cvb : 1));
+}
+extern "C" long long ie_channel_mean_scratch_bytes(int n, int h, int w, int c, int y0, int y1) {
+  return stat_scratch_bytes(n, channel_mean_splits(n, h, w, c, y0, y1), c, c / 64);
+}
+
 extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y,
-                                     int y_pitch, int y_coff, float* chan_mean, int stat_y0, int stat_y1,
-                                     long long stat_count, int layout, void* stream) {
+                                     int y_pitch, int y_coff, float* chan_mean, void* stat_scratch,
+                                     long long stat_scratch_bytes_, int stat_y0, int stat_y1, long long stat_count,
+                                     int layout, void* stream) {
   IE_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "maxpool2: bad arguments (h %d, w %d)", h, w);
   IE_REQUIRE(layout >= 0 && layout <= 3, "maxpool2: bad layout flags %d", layout);
   const int bi = (layout & IE_LAYOUT_X_DENSE) ? 0 : 1, bo = (layout & IE_LAYOUT_Y_DENSE) ? 0 : 1;
@@ -516,8 +582,17 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
   const int cvb = cvec < 32 ? cvec : 32;
   const int row_groups = (h / 2 + bo + kPoolRows - 1) / kPoolRows;
   IE_REQUIRE(n <= 65535 && row_groups <= 65535, "maxpool2: grid too large");
-  if (chan_mean) IE_CUDA(cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
   dim3 grid(ie_ceil_div(cvec, cvb), row_groups, n);
+  float* part = nullptr;
+  int* counter = nullptr;
+  if (chan_mean) {
+    const long long need = stat_scratch_bytes(n, row_groups, c, (int)grid.x);
+    IE_REQUIRE(stat_scratch && stat_scratch_bytes_ >= need, "maxpool2: the channel statistics need %lld bytes of scratch "
+               "(ie_maxpool2_stat_scratch_bytes), got %lld", need, stat_scratch_bytes_);
+    part = static_cast<float*>(stat_scratch);
+    counter = reinterpret_cast<int*>(part + (size_t)n * row_groups * c);
+    IE_CUDA(cudaMemsetAsync(counter, 0, sizeof(int) * (size_t)n * grid.x, S(stream)));
+  }
   const int threads = (256 / cvb) * cvb;
   if (stat_y1 <= 0) { stat_y0 = 0; stat_y1 = h; }
   if (stat_count <= 0) stat_count = (long long)h * w;
@@ -525,7 +600,7 @@ extern "C" int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, 
              "maxpool2: bad statistics row range [%d, %d)", stat_y0, stat_y1);
   IE_CUDA(launch_pdl(maxpool2_kernel, grid, dim3(threads), 0, S(stream), static_cast<const uint4*>(x), h, w, cvec, cvb,
                      x_pitch / 8, x_coff / 8, static_cast<uint4*>(y), y_pitch / 8, y_coff / 8, chan_mean,
-                     1.f / (float)stat_count, stat_y0, stat_y1, bi, bo));
+                     1.f / (float)stat_count, stat_y0, stat_y1, bi, bo, part, counter));
   return IE_OK;
 }
 
@@ -559,26 +634,27 @@ extern "C" int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w
 }
 
 extern "C" int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff,
-                                         float* mean, int y0, int y1, long long count, int layout, void* stream) {
+                                         float* mean, void* scratch, long long scratch_bytes, int y0, int y1,
+                                         long long count, int layout, void* stream) {
   IE_REQUIRE(x && mean && n > 0 && h > 0 && w > 0, "channel_mean: bad arguments");
   IE_REQUIRE(layout == 0 || layout == IE_LAYOUT_X_DENSE, "channel_mean: bad layout flags %d", layout);
   const int bi = (layout & IE_LAYOUT_X_DENSE) ? 0 : 1;
   IE_REQUIRE(c % 64 == 0, "channel_mean: c must be a multiple of 64 (got %d)", c);
   if (int rc = check_slice("channel_mean(x)", c, x_pitch, x_coff)) return rc;
-  IE_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * (size_t)n * c, S(stream)));
+  const int splits = channel_mean_splits(n, h, w, c, y0, y1);
   if (y1 <= 0) { y0 = 0; y1 = h; }
   if (count <= 0) count = (long long)h * w;
   IE_REQUIRE(y0 >= 0 && y1 <= h && y0 < y1, "channel_mean: bad row range [%d, %d)", y0, y1);
-  const int npix = (y1 - y0) * w;
-  int splits = (8 * sm_count() + (c / 64) * n - 1) / ((c / 64) * n);       // >= 8 blocks per SM in flight
-  const int max_splits = (npix + 31) / 32;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
+  const long long need = stat_scratch_bytes(n, splits, c, c / 64);
+  IE_REQUIRE(scratch && scratch_bytes >= need, "channel_mean: needs %lld bytes of scratch (ie_channel_mean_scratch_bytes), "
+             "got %lld", need, scratch_bytes);
+  float* part = static_cast<float*>(scratch);
+  int* counter = reinterpret_cast<int*>(part + (size_t)n * splits * c);
+  IE_CUDA(cudaMemsetAsync(counter, 0, sizeof(int) * (size_t)n * (c / 64), S(stream)));
   IE_REQUIRE(n <= 65535, "channel_mean: n too large");
   dim3 grid(c / 64, n, splits);
   IE_CUDA(launch_pdl(channel_mean_kernel, grid, dim3(256), 0, S(stream), static_cast<const uint4*>(x), h, w, x_pitch / 8,
-                     x_coff / 8, mean, c, 1.f / (float)count, y0, y1, bi));
+                     x_coff / 8, mean, c, 1.f / (float)count, y0, y1, bi, part, counter));
   return IE_OK;
 }
 

@@ -15,6 +15,8 @@ forward is capturable in a CUDA graph.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -81,6 +83,9 @@ class Engine:
         self._plans = {}
         self._graphs = {}
         self._ws = None
+        self._side = None
+        # run the per-image basis branch on a second stream beside the coefficient decoder (see _forward)
+        self.overlap_branches = bool(params.get("overlap_branches", os.environ.get("IE_OVERLAP", "1") != "0"))
         with torch.cuda.device(self.device):
             self.load_weights(weights)
         # small batches are launch-bound (44 kernels through ctypes, ~1.5 ms of host time vs ~0.3 ms of GPU time for
@@ -104,12 +109,17 @@ class Engine:
             self.bias[name] = b.to(self.device, torch.float32).contiguous()
 
     # ------------------------------------------------------------------ buffers
-    def _workspace(self):
-        """Split-K scratch of this engine (one per engine: its kernels are stream-ordered; a captured graph keeps using
-        the buffer it was captured with)."""
+    def _workspace(self, side=False):
+        """Split-K scratch of this engine (its kernels are stream-ordered; a captured graph keeps using the buffer it was
+        captured with).  ``side``: the second buffer, for the basis branch when it runs on its own stream."""
         if self._ws is None:
-            self._ws = torch.empty(ops.SPLITK_WORKSPACE_BYTES, dtype=torch.uint8, device=self.device)
-        return self._ws
+            self._ws = [torch.empty(ops.SPLITK_WORKSPACE_BYTES, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        return self._ws[1 if side else 0]
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     def _plan(self, n, h, w):
         key = (n, h, w)
@@ -241,10 +251,10 @@ class Engine:
 
         # split-K scratch: the library only uses it for layers with too few output tiles to fill the SMs (small inputs,
         # and the per-image basis branch of small batches)
-        ws = self._workspace()
+        wksp = [self._workspace()]
 
         def conv(name, src, dst, k=3, valid=None):
-            ops.conv2d(src, W[name], Bv[name], dst, k=k, relu=True, valid=valid, fn=conv_fn, workspace=ws)
+            ops.conv2d(src, W[name], Bv[name], dst, k=k, relu=True, valid=valid, fn=conv_fn, workspace=wksp[0])
             if taps is not None:
                 hv, wv = (dst.r.h, dst.r.w) if valid is None else valid
                 taps[name] = ops.raster_to_nhwc(dst)[:, :hv, :wv]
@@ -281,53 +291,80 @@ class Engine:
             cur = p[bname].slice()
         bott = cur
         # ---- coefficient decoder (model_library.py:391-406 / 246-255)
-        for name, cout, skip in A["coef_ups"]:
-            cat = p["cat." + skip]
-            ops.upsample_bilinear(cur, cat.slice(0, up_in[skip]), 2)
-            conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
-            conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())
-            conv(name + ".conv2d3", p[name + ".c2"].slice(), p[name + ".c3"].slice())
-            cur = p[name + ".c3"].slice()
-        for hname in A["head"]:
-            conv(hname, cur, p[hname].slice())
-            cur = p[hname].slice()
-        coef, logits = ops.conv2d_f32(cur, W["coef"], Bv["coef"], self.B, softmax=True,
-                                      want_logits=taps is not None, fn=conv_fn)
+        def coef_decoder():
+            cur = bott
+            for name, cout, skip in A["coef_ups"]:
+                cat = p["cat." + skip]
+                ops.upsample_bilinear(cur, cat.slice(0, up_in[skip]), 2)
+                conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
+                conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())
+                conv(name + ".conv2d3", p[name + ".c2"].slice(), p[name + ".c3"].slice())
+                cur = p[name + ".c3"].slice()
+            for hname in A["head"]:
+                conv(hname, cur, p[hname].slice())
+                cur = p[hname].slice()
+            return ops.conv2d_f32(cur, W["coef"], Bv["coef"], self.B, softmax=True, want_logits=taps is not None, fn=conv_fn)
+
         # ---- basis branch (model_library.py:409-438 / 258-281)
-        rows, count = stat_rows(len(A["downs"]))
-        gavg = ops.channel_mean(bott, rows=rows, count=count)            # :409-410
-        if shard is not None:
-            # the exchange step of spatial sharding: partial means (already divided by the global pixel count) of the
-            # bottleneck and of every pooled skip, summed over the ranks
-            names = [d for d in dnames if skip_means.get(d) is not None]
-            packed = torch.cat([gavg] + [skip_means[d] for d in names], dim=1)
-            packed = shard["reduce"](packed)
-            gavg = packed[:, :gavg.shape[1]].contiguous()
-            off = gavg.shape[1]
-            for d in names:
-                cd = skip_means[d].shape[1]
-                skip_means[d] = packed[:, off:off + cd].contiguous()
-                off += cd
-        ops.broadcast_hw(gavg, p["seed"].slice())
-        cur = p["seed"].slice()
-        for name, cout, skip, k, s in A["basis_ups"]:
-            cat = p["bcat." + name]
-            cin_up = cur.c
-            ops.upsample_bilinear(cur, cat.slice(0, cin_up), s)          # Upblock.upsampling :94
-            skip_mean = skip_means[skip]                                  # Poolskip :110, from the max-pool kernel
-            ops.broadcast_hw(skip_mean, cat.slice(cin_up, chans[skip]))  # tile :112, concat :96
-            conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
-            conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())
-            conv(name + ".conv2d3", p[name + ".c2"].slice(), p[name + ".c3"].slice())
-            cur = p[name + ".c3"].slice()
-        tail = A["tail"]
-        conv(tail[0], cur, p[tail[0]].slice(), k=2, valid=(15, 15))      # 2x2 'valid' :364/424
-        cur = p[tail[0]].slice()
-        for tname in tail[1:-1]:
-            conv(tname, cur, p[tname].slice(), valid=(15, 15))
-            cur = p[tname].slice()
-        originbasis = ops.conv2d_f32(cur, W[tail[-1]], Bv[tail[-1]], self.T * self.B, valid=(15, 15), fn=conv_fn)
-        bas = ops.softmax_taps(originbasis, self.T, self.B)              # :436-438
+        def basis_branch():
+            rows, count = stat_rows(len(A["downs"]))
+            gavg = ops.channel_mean(bott, rows=rows, count=count)            # :409-410
+            if shard is not None:
+                # the exchange step of spatial sharding: partial means (already divided by the global pixel count) of
+                # the bottleneck and of every pooled skip, summed over the ranks
+                names = [d for d in dnames if skip_means.get(d) is not None]
+                packed = torch.cat([gavg] + [skip_means[d] for d in names], dim=1)
+                packed = shard["reduce"](packed)
+                gavg = packed[:, :gavg.shape[1]].contiguous()
+                off = gavg.shape[1]
+                for d in names:
+                    cd = skip_means[d].shape[1]
+                    skip_means[d] = packed[:, off:off + cd].contiguous()
+                    off += cd
+            ops.broadcast_hw(gavg, p["seed"].slice())
+            cur = p["seed"].slice()
+            for name, cout, skip, k, s in A["basis_ups"]:
+                cat = p["bcat." + name]
+                cin_up = cur.c
+                ops.upsample_bilinear(cur, cat.slice(0, cin_up), s)          # Upblock.upsampling :94
+                skip_mean = skip_means[skip]                                  # Poolskip :110, from the max-pool kernel
+                ops.broadcast_hw(skip_mean, cat.slice(cin_up, chans[skip]))  # tile :112, concat :96
+                conv(name + ".conv2d1", cat.slice(), p[name + ".c1"].slice())
+                conv(name + ".conv2d2", p[name + ".c1"].slice(), p[name + ".c2"].slice())
+                conv(name + ".conv2d3", p[name + ".c2"].slice(), p[name + ".c3"].slice())
+                cur = p[name + ".c3"].slice()
+            tail = A["tail"]
+            conv(tail[0], cur, p[tail[0]].slice(), k=2, valid=(15, 15))      # 2x2 'valid' :364/424
+            cur = p[tail[0]].slice()
+            for tname in tail[1:-1]:
+                conv(tname, cur, p[tname].slice(), valid=(15, 15))
+                cur = p[tname].slice()
+            originbasis = ops.conv2d_f32(cur, W[tail[-1]], Bv[tail[-1]], self.T * self.B, valid=(15, 15), fn=conv_fn)
+            return ops.softmax_taps(originbasis, self.T, self.B), originbasis              # :436-438
+
+        # The basis branch reads the bottleneck and the pooled skip means only; the coefficient decoder never reads
+        # anything the branch writes.  Its ~15 launches work on 2x2 ... 16x16 pixels per image (tens of CTAs each,
+        # latency-bound), so it runs on a second stream beside the decoder and joins before the filter: at small
+        # batches the two really overlap (32 patches: 1.55 -> 1.4 ms per step; one 32x32 patch: 0.30 -> 0.2x ms),
+        # at 256 patches the small kernels fill the gaps between the decoder's waves.  Fork / join are events, so the
+        # same code is captured into the CUDA graph of the small-batch path.  Tensors the branch allocates come from
+        # the side stream's pool; they are only re-used by a later forward's branch, which starts behind that forward's
+        # fork event and therefore behind every main-stream reader enqueued before it.
+        if self.overlap_branches and shard is None and taps is None:
+            main, side = torch.cuda.current_stream(self.device), self._side_stream()
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                wksp[0] = self._workspace(side=True)
+                bas, originbasis = basis_branch()
+                join.record(side)
+            wksp[0] = self._workspace()
+            coef, logits = coef_decoder()
+            main.wait_event(join)
+        else:
+            coef, logits = coef_decoder()
+            bas, originbasis = basis_branch()
         # ---- per-pixel filter (model_library.py:439-451)
         want = self.filter_precision
         if want in ("auto", "tcgen05") and ops.kpn_tcgen05_supported(self.T, self.K, self.B):

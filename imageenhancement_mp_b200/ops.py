@@ -216,10 +216,17 @@ def maxpool2(src: Slice, dst: Slice, want_mean=False, rows=None, count=0):
     (over input rows ``rows`` = (y0, y1) and divided by ``count`` pixels when given: spatial shards)."""
     r = src.r
     assert (dst.r.n, dst.r.h, dst.r.w) == (r.n, r.h // 2, r.w // 2) and dst.c == src.c
-    mean = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device) if want_mean else None
+    mean = scratch = None
+    nbytes = 0
+    if want_mean:
+        # the statistics are reduced across blocks in a fixed order through a scratch buffer (bit-reproducible means)
+        mean = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device)
+        nbytes = _lib.load().ie_maxpool2_stat_scratch_bytes(r.n, r.h, r.w, src.c, _layout(src, dst))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=r.data.device)
     y0, y1 = rows if rows is not None else (0, 0)
     call("ie_maxpool2_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff,
-         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), y0, y1, int(count), _layout(src, dst), stream())
+         ptr(dst.r.data), dst.r.pitch, dst.coff, ptr(mean), ptr(scratch), nbytes, y0, y1, int(count), _layout(src, dst),
+         stream())
     return mean
 
 
@@ -235,8 +242,10 @@ def channel_mean(src: Slice, out=None, rows=None, count=0):
     if out is None:
         out = torch.empty(r.n, src.c, dtype=torch.float32, device=r.data.device)
     y0, y1 = rows if rows is not None else (0, 0)
-    call("ie_channel_mean_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(out), y0, y1, int(count),
-         _layout(src), stream())
+    nbytes = _lib.load().ie_channel_mean_scratch_bytes(r.n, r.h, r.w, src.c, y0, y1)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=r.data.device)
+    call("ie_channel_mean_nhwc_bf16", ptr(r.data), r.n, r.h, r.w, src.c, r.pitch, src.coff, ptr(out), ptr(scratch), nbytes,
+         y0, y1, int(count), _layout(src), stream())
     return out
 
 

@@ -130,10 +130,14 @@ int ie_debug_conv2d_naive(const ie_conv_desc* d, const void* x, const void* w_pa
  * chan_mean (nullable, [n][c] fp32): also receives the per-image channel means of the INPUT slice - the
  * GlobalAveragePooling2D of Poolskip (model_library.py:110) on the tensor the pool reads anyway.  For a spatial
  * shard of a larger image the statistics cover input rows [stat_y0, stat_y1) only (even numbers; stat_y1 <= 0: all
- * rows) and are divided by stat_count pixels (<= 0: h*w), so that a SUM over the shards is the global mean.      */
+ * rows) and are divided by stat_count pixels (<= 0: h*w), so that a SUM over the shards is the global mean.
+ * The statistics are bit-reproducible: every block stores its partial sums in `stat_scratch` and the last block of an
+ * image to finish adds them in a fixed order (no floating-point atomics).  stat_scratch (device memory, only read and
+ * written by this call; required when chan_mean is given) must hold ie_maxpool2_stat_scratch_bytes(...) bytes.  */
+long long ie_maxpool2_stat_scratch_bytes(int n, int h, int w, int c, int layout);
 int ie_maxpool2_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, void* y, int y_pitch,
-                          int y_coff, float* chan_mean, int stat_y0, int stat_y1, long long stat_count, int layout,
-                          void* stream);
+                          int y_coff, float* chan_mean, void* stat_scratch, long long stat_scratch_bytes, int stat_y0,
+                          int stat_y1, long long stat_count, int layout, void* stream);
 
 /* UpSampling2D(scale, 'bilinear') half-pixel centres (model_library.py:92) written straight into a
  * channel slice of the consumer's concat raster (model_library.py:96); border zeroed.               */
@@ -141,9 +145,12 @@ int ie_upsample_bilinear_nhwc_bf16(const void* x, int n, int h, int w, int c, in
                                    void* y, int y_pitch, int y_coff, int layout, void* stream);
 
 /* Per-image channel means over the interior (reduce_mean x2 :409-410, GlobalAveragePooling2D :110):
- * mean[n][c] fp32.  Rows [y0, y1) only when y1 > 0, divided by `count` pixels when count > 0 (spatial shards). */
-int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* mean, int y0,
-                              int y1, long long count, int layout, void* stream);
+ * mean[n][c] fp32.  Rows [y0, y1) only when y1 > 0, divided by `count` pixels when count > 0 (spatial shards).
+ * Bit-reproducible like the pooled statistics above: `scratch` must hold ie_channel_mean_scratch_bytes(...) bytes. */
+long long ie_channel_mean_scratch_bytes(int n, int h, int w, int c, int y0, int y1);
+int ie_channel_mean_nhwc_bf16(const void* x, int n, int h, int w, int c, int x_pitch, int x_coff, float* mean,
+                              void* scratch, long long scratch_bytes, int y0, int y1, long long count, int layout,
+                              void* stream);
 
 /* tf.tile of a [n][c] vector to a k_h x k_w raster slice (Poolskip :111-112), border zeroed.          */
 int ie_broadcast_hw_bf16(const float* vec, int n, int kh, int kw, int c, void* y, int y_pitch, int y_coff, int layout,

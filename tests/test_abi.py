@@ -69,7 +69,7 @@ def header_prototypes():
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
-    for ret, name, args in re.findall(r"\b(int|const char\s*\*)\s+(ie_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+    for ret, name, args in re.findall(r"\b(long long|int|const char\s*\*)\s+(ie_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
         kinds = []
         for a in [a.strip() for a in args.split(",")]:
             if a in ("", "void"):

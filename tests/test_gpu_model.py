@@ -59,6 +59,51 @@ def test_small_batches_replay_a_cuda_graph(cuda):
     assert len(model._engine._graphs) == 1 and len(eager._engine._graphs) == 0
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 32, 32), (3, 64, 64), (40, 100, 100)])
+def test_basis_branch_on_a_side_stream_changes_nothing(cuda, n, h, w):
+    """The basis branch runs on a second stream beside the coefficient decoder (fork / join events, its own split-K
+    workspace), eagerly and inside the captured graph: same bits as the serial schedule, call after call."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    serial = ml.Simplemodel(dict(params, overlap_branches=False), weights=W)
+    overlap = ml.Simplemodel(dict(params, overlap_branches=True), weights=W)
+    assert overlap._engine.overlap_branches and not serial._engine.overlap_branches
+    for seed in (1, 2, 3, 4):
+        x, _ = synth.make_batch(n, h, w, params, seed=seed)
+        a = overlap(x.to(cuda))
+        b = serial(x.to(cuda))
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+    # Basis_kpn (five levels, the longer branch) too
+    bp = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=8, layer_type="dualparams", Basis_num=10)
+    BW = weights.init_weights(weights.basis_kpn_layers(bp), scheme="stress")
+    x, _ = synth.make_batch(2, 64, 64, bp, seed=5)
+    a = ml.Basis_kpn(dict(bp, overlap_branches=True), weights=BW)(x.to(cuda))
+    b = ml.Basis_kpn(dict(bp, overlap_branches=False), weights=BW)(x.to(cuda))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
+def test_forward_is_bit_reproducible(cuda):
+    """No floating-point atomics on the forward path: the pooled channel statistics that feed the basis branch are
+    reduced across blocks in a fixed order (ie_maxpool2_nhwc_bf16 / ie_channel_mean_nhwc_bf16 with their scratch),
+    split-K sums its slices in a fixed order - the same input gives the same bits, run after run, at sizes where every
+    reduction spans many blocks."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    W = weights.init_weights(weights.simplemodel_layers(params), scheme="stress")
+    model = ml.Simplemodel(params, weights=W)
+    other = ml.Simplemodel(params, weights=W)
+    x, _ = synth.make_batch(48, 100, 100, params, seed=11)
+    x = x.to(cuda)
+    first = model(x)
+    for rep in range(4):
+        again = (model if rep % 2 else other)(x)
+        for u, v in zip(first, again):
+            assert torch.equal(u, v)
+
+
 def test_filter_precision_switch(cuda):
     """filter_precision='fp32' routes the per-pixel filter through the CUDA-core kernel; the default (the tcgen05
     filter-synthesis kernel) and the mma.sync TF32 kernel differ from it by far less than the path's tolerance."""
