@@ -32,6 +32,7 @@ def main():
     else:
         params = dict(synth.DEFAULT_PARAMS, BURST_LENGTH=args.burst, Basis_num=args.bases)
         model = ml.Simplemodel(params, device=dev)
+    model._engine.overlap_branches = False          # serial schedule: a bracket then holds one launch only
     x = synth.make_batch(args.batch, args.size, args.size, params, seed=3)[0].to(dev)
     for _ in range(3):
         model(x)
