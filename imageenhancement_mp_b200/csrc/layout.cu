@@ -170,8 +170,19 @@ maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, in
   }
   if (stat_finish(&counter[img * gridDim.x + blockIdx.x], gridDim.y)) {
     if (owner) {
+      // loads eight at a time (independent), additions in block order
       float tot = 0.f;
-      for (int by = 0; by < (int)gridDim.y; ++by) tot += __ldcg(&part[((long long)img * gridDim.y + by) * C + ch]);
+      const int nb = (int)gridDim.y;
+      const float* src = part + (long long)img * nb * C + ch;
+      int by = 0;
+      for (; by + 8 <= nb; by += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (long long)(by + u) * C);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tot += v[u];
+      }
+      for (; by < nb; ++by) tot += __ldcg(src + (long long)by * C);
       chan_sum[(long long)img * C + ch] = tot * scale;
     }
   }
@@ -332,7 +343,17 @@ __global__ void channel_mean_kernel(const uint4* __restrict__ x, int h, int w, i
   if (stat_finish(&counter[img * gridDim.x + cb], gridDim.z)) {
     if (threadIdx.x < 64) {
       float tot = 0.f;
-      for (int z = 0; z < (int)gridDim.z; ++z) tot += __ldcg(&part[((long long)img * gridDim.z + z) * c + ch]);
+      const int nb = (int)gridDim.z;
+      const float* src = part + (long long)img * nb * c + ch;
+      int z = 0;
+      for (; z + 8 <= nb; z += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (long long)(z + u) * c);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tot += v[u];
+      }
+      for (; z < nb; ++z) tot += __ldcg(src + (long long)z * c);
       mean[(long long)img * c + ch] = tot * scale;
     }
   }

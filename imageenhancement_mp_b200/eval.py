@@ -171,6 +171,7 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
     else:
         fn = lambda m, xb, xt, T_: gpu_step_totals(m, xb, xt, T_, vis=vis, ssim=ssim, ps=ps)
     totals = cv_total = None
+    pinned, pinned_used = None, 0
     nb = 0
     if step_totals is None:
         if device is None:
@@ -187,7 +188,13 @@ def evaluate(model, val_batches, params, step=1, out=print, step_totals=None, st
             t, cv = t
             cv_total = cv.clone() if cv_total is None else cv_total.add_(cv)
         if step_results is not None:
-            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
+            # pinned rows are handed out from blocks of 64 steps: one cudaHostAlloc per step (every result stays alive
+            # in step_results, so the caching host allocator cannot recycle) cost more than the step's metric kernels
+            if pinned is None or pinned_used == pinned.shape[0]:
+                pinned = torch.empty((64,) + tuple(t.shape), dtype=t.dtype, pin_memory=t.is_cuda)
+                pinned_used = 0
+            host = pinned[pinned_used]
+            pinned_used += 1
             host.copy_(t, non_blocking=True)
             step_results.append(host)
         totals = t.clone() if totals is None else totals.add_(t)
