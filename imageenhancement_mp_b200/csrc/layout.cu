@@ -89,15 +89,15 @@ im2col3x3_kernel(const float* __restrict__ x, int hs, int ws, int h, int w, int 
 // the last one sees every partial (fence + L2 loads), reduces them in a fixed order and re-arms the counter.
 __device__ __forceinline__ bool stat_finish(int* counter, unsigned nblocks) {
   __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
+  __syncthreads();                               // the block's partial sums are written (CTA scope)
   if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(counter, 1);
-    s_last = (ticket == (int)nblocks - 1);
+    __threadfence();                             // cumulative: publishes them device-wide before the ticket is drawn
+    const int ticket = atomicAdd(counter, 1);    // (one fence per block - a fence in every thread also waits for that
+    s_last = (ticket == (int)nblocks - 1);       //  thread's output stores and cost 30 us per step in the max-pool)
     if (s_last) *counter = 0;                    // every block of this group has arrived: ready for the next launch
+    __threadfence();
   }
   __syncthreads();
-  if (s_last) __threadfence();
   return s_last != 0;
 }
 
@@ -107,7 +107,7 @@ __device__ __forceinline__ bool stat_finish(int* counter, unsigned nblocks) {
 // (512-byte runs).  Optionally the per-image channel SUMS of the INPUT are accumulated on the way (each input
 // pixel belongs to exactly one 2x2 window): this is the GlobalAveragePooling2D of Poolskip
 // (model_library.py:110) on the very tensor the pool reads, so the basis branch needs no second pass over it.
-constexpr int kPoolRows = 2;           // padded output rows per block
+constexpr int kPoolRows = 4;           // padded output rows per block (2: twice the tickets of the ordered statistics)
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const uint4* __restrict__ x, int h, int w, int cvec, int cvb, int x_pitch_v, int x_coff_v,
                 uint4* __restrict__ y, int y_pitch_v, int y_coff_v, float* __restrict__ chan_sum, float scale,
