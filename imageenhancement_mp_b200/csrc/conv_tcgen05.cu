@@ -81,6 +81,9 @@ struct EpiParams {
   int ksplit;
   int split_first;
   float* part;
+  // M sub-tiles per work item (streaming kernel with N tile 128: two 128-row A tiles share every weight tile, their
+  // accumulators sit side by side in one TMEM buffer; everything else: 1)
+  int msub;
   // r / plane and pr / wp by multiply-high (FastDiv below): every epilogue warp decodes its raster row once per tile
   uint32_t plane_m, plane_s, wp_m, wp_s;
 };
@@ -252,40 +255,55 @@ __device__ __forceinline__ void epilogue_loop(const EpiParams& p, const CUtensor
       }
     } else if (p.epilogue == IE_EPI_BF16_RASTER) {
       const int chunks = p.n_tile >> 6;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_x32(t_base + c * 64, v0);
-        tmem_ld_x32(t_base + c * 64 + 32, v1);
-        tmem_ld_wait();
-        if (c == chunks - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
+      for (int sub = 0; sub < p.msub; ++sub) {
+        // sub-tile `sub` of the item: rows (m_tile * msub + sub) * 128 ..., accumulator columns sub * n_tile ...
+        int rs0 = r0;
+        bool valid_s = valid;
+        if (p.msub > 1) {
+          rs0 = (m_tile * p.msub + sub) * kBlockM;
+          const int rs = rs0 + row_in_tile;
+          const int img_s = fastdiv(rs, p.plane_m, p.plane_s);
+          const int pr_s = rs - img_s * p.plane;
+          const int y_s = fastdiv(pr_s, p.wp_m, p.wp_s);
+          const int x_s = pr_s - y_s * p.wp;
+          valid_s = p.dense ? (rs < p.R) : ((rs < p.R) && (y_s >= 1) && (y_s <= p.hv) && (x_s < p.wv));
+        }
+        const uint32_t ts_base = t_base + static_cast<uint32_t>(sub * p.n_tile);
+        for (int c = 0; c < chunks; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_x32(ts_base + c * 64, v0);
+          tmem_ld_x32(ts_base + c * 64 + 32, v1);
+          tmem_ld_wait();
+          if (c == chunks - 1 && sub == p.msub - 1) {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          }
+          uint32_t pk[32];
+          const uint32_t bs = smem_u32(sbias + n0 + c * 64);
+          if (p.relu) bias_pack_64<true>(pk, v0, v1, bs);
+          else bias_pack_64<false>(pk, v0, v1, bs);
+          // staging buffer must have been read by the previous TMA store
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-        }
-        uint32_t pk[32];
-        const uint32_t bs = smem_u32(sbias + n0 + c * 64);
-        if (p.relu) bias_pack_64<true>(pk, v0, v1, bs);
-        else bias_pack_64<false>(pk, v0, v1, bs);
-        // staging buffer must have been read by the previous TMA store
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B); border / masked rows
-        // are written as zeros (a branch per row instead of a select per word)
-        const uint32_t rowa = smem_u32(stg) + lane * 128;
-        if (valid) {
+          // row `lane` of a 32x128B tile, 16-byte chunk j stored at j ^ (lane & 7)  (SWIZZLE_128B); border / masked
+          // rows are written as zeros (a branch per row instead of a select per word)
+          const uint32_t rowa = smem_u32(stg) + lane * 128;
+          if (valid_s) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128u(rowa + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        } else {
+            for (int j = 0; j < 8; ++j)
+              sts128u(rowa + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sts128u(rowa + (j << 4), 0u, 0u, 0u, 0u);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(tm_y, stg, p.y_coff + n0 + c * 64, r0 + q * 32);
-          tma_store_commit();
+            for (int j = 0; j < 8; ++j) sts128u(rowa + (j << 4), 0u, 0u, 0u, 0u);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tm_y, stg, p.y_coff + n0 + c * 64, rs0 + q * 32);
+            tma_store_commit();
+          }
         }
       }
     } else {
@@ -425,13 +443,17 @@ struct StreamParams {
   int img_h, img_w, kw, pad;
 };
 
-template <bool IM2COL>
+// MSUB = 2 (N tile 128 only): a work item is TWO consecutive 128-row M tiles; every pipeline stage holds both A tiles and
+// ONE weight tile, the two accumulators are columns [0, 128) and [128, 256) of the TMEM buffer.  The N = 128 layers
+// were bound by what a stage moves (32 KB per 256 MMA cycles, 481 cycles per K block measured): per MMA cycle the pair
+// moves 25 % less and every barrier round trip covers twice the math.
+template <bool IM2COL, int MSUB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const __grid_constant__ CUtensorMap tm_y, const StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = align1024(smem_raw);
-  const int stage_bytes = kABytes + p.b_stage_bytes;
+  const int stage_bytes = MSUB * kABytes + p.b_stage_bytes;
   SmemTail t{base + p.stages * stage_bytes};
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -454,22 +476,27 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.e.n_tile) * 128u;
+      const uint32_t tx_bytes = MSUB * kABytes + static_cast<uint32_t>(p.e.n_tile) * 128u;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const WorkItem wi = decode_item(p.e, item);
         const int tile = wi.tile;
         const int m_tile = tile / p.e.n_tiles;
         const int n_idx = tile - m_tile * p.e.n_tiles;
-        const int r0 = m_tile * kBlockM;
+        const int r0 = m_tile * (kBlockM * MSUB);
         const int n0 = n_idx * p.e.n_tile;
-        int px0 = 0, py0 = 0, pn0 = 0;                    // IM2COL: first pixel of the tile in the pixel-box frame
-        if constexpr (IM2COL) {
-          const int plane = p.img_h * p.img_w;
-          pn0 = r0 / plane;
-          const int rem = r0 - pn0 * plane;
-          py0 = rem / p.img_w;
-          px0 = rem - py0 * p.img_w - p.pad;
-          py0 -= p.pad;
+        int px0[MSUB], py0[MSUB], pn0[MSUB];              // IM2COL: first pixel of each sub-tile in the pixel-box frame
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          px0[sub] = py0[sub] = pn0[sub] = 0;
+          if constexpr (IM2COL) {
+            const int rs = r0 + sub * kBlockM;
+            const int plane = p.img_h * p.img_w;
+            pn0[sub] = rs / plane;
+            const int rem = rs - pn0[sub] * plane;
+            py0[sub] = rem / p.img_w;
+            px0[sub] = rem - py0[sub] * p.img_w - p.pad;
+            py0[sub] -= p.pad;
+          }
         }
         const int kb_begin = wi.split ? wi.ks * kb_per : 0;
         const int kb_end = (wi.split && kb_begin + kb_per < kblocks) ? kb_begin + kb_per : kblocks;
@@ -479,13 +506,18 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* a_dst = base + stage * stage_bytes;
-          if constexpr (IM2COL) {
-            const int ti = tap / p.kw, tj = tap - ti * p.kw;
-            tma_load_im2col_4d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, px0, py0, pn0, tj, ti);
-          } else {
-            tma_load_2d(a_dst, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, r0 + p.tap_shift[tap]);
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) {
+            if constexpr (IM2COL) {
+              const int ti = tap / p.kw, tj = tap - ti * p.kw;
+              tma_load_im2col_4d(a_dst + sub * kABytes, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK, px0[sub], py0[sub],
+                                 pn0[sub], tj, ti);
+            } else {
+              tma_load_2d(a_dst + sub * kABytes, &tm_a, &full_bar[stage], p.x_coff + kb * kBlockK,
+                          r0 + sub * kBlockM + p.tap_shift[tap]);
+            }
           }
-          tma_load_2d(a_dst + kABytes, &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
+          tma_load_2d(a_dst + MSUB * kABytes, &tm_b, &full_bar[stage], tap * p.cin + kb * kBlockK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
         }
@@ -496,7 +528,7 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     // Warp-uniform loop (descriptors stay in uniform registers); one elected lane issues.
     const uint32_t idesc = umma_idesc_bf16(kBlockM, p.e.n_tile);
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(base));
-    const uint32_t b_lo0 = umma_desc_lo(smem_u32(base + kABytes));
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(base + MSUB * kABytes));
     const uint32_t stage_stride = static_cast<uint32_t>(stage_bytes) >> 4;
     int stage = 0;
     uint32_t phase = 0;
@@ -517,10 +549,15 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const uint32_t a_lo = a_lo0 + stage * stage_stride;
           const uint32_t b_lo = b_lo0 + stage * stage_stride;
           // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field
-          umma_bf16_ss_lo(d_tmem, a_lo, b_lo, idesc, kbi != kb_begin ? 1u : 0u);
-          umma_bf16_ss_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
-          umma_bf16_ss_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
-          umma_bf16_ss_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) {
+            const uint32_t a_s = a_lo + sub * (kABytes >> 4);
+            const uint32_t d_s = d_tmem + static_cast<uint32_t>(sub * p.e.n_tile);
+            umma_bf16_ss_lo(d_s, a_s, b_lo, idesc, kbi != kb_begin ? 1u : 0u);
+            umma_bf16_ss_lo(d_s, a_s + 2, b_lo + 2, idesc, 1u);
+            umma_bf16_ss_lo(d_s, a_s + 4, b_lo + 4, idesc, 1u);
+            umma_bf16_ss_lo(d_s, a_s + 6, b_lo + 6, idesc, 1u);
+          }
           umma_commit(&empty_bar[stage]);                            // frees the smem slot when these retire
           if (kbi == kb_end - 1) umma_commit(&t.tfull()[buf]);       // accumulator complete
         }
@@ -1744,6 +1781,7 @@ static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
 static int g_splitk_tail = 1;        // 0: split-K only for tiny M, not for the last partial wave of larger grids
+static int g_stream_pairs = 1;       // 0: N = 128 streaming layers one M tile per work item (A-B timing)
 static int g_first_gather = 0;       // 1: first layer with per-thread global gathers instead of staged source rows
 static int g_splitk_wide = 1;        // 0: small grids always trade N-tile width for CTAs (the round-1 rule)
 static bool splitk_env() {           // IE_SPLITK=0: A-B timing without a rebuild
@@ -1776,6 +1814,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_splitk_tail = ((flags >> 13) & 1) ? 0 : 1;
   ie::g_splitk_wide = ((flags >> 14) & 1) ? 0 : 1;
   ie::g_first_gather = (flags >> 15) & 1;
+  ie::g_stream_pairs = ((flags >> 16) & 1) ? 0 : 1;
   return IE_OK;
 }
 
@@ -1790,6 +1829,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   EpiParams e{};
   e.dense = d->dense;
   e.ksplit = 1;
+  e.msub = 1;
   e.split_first = 0;                   // irrelevant while ksplit == 1 (every item is a whole tile)
   e.R = (int)R;
   set_raster_dims(e, (d->h + 1) * wp, wp);
@@ -1976,13 +2016,22 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   p.x_coff = d->x_coff;
   p.cin = d->cin;
   p.b_stage_bytes = ((e.n_tile * 128 + 1023) / 1024) * 1024;
-  int stages = (int)((kMaxSmem - 1024 - kTailBytes) / (kABytes + p.b_stage_bytes));
+  // N tile 128 with one N tile (the cout = 128 layers) and enough rows to fill the machine twice: pairs of M tiles per
+  // work item sharing every weight tile (conv_stream_kernel<.., 2>)
+  const int msub = (g_stream_pairs && e.n_tile == 128 && e.n_tiles == 1 && d->epilogue == IE_EPI_BF16_RASTER &&
+                    e.m_tiles >= 2 * sm_count()) ? 2 : 1;
+  if (msub == 2) {
+    p.e.msub = 2;
+    p.e.m_tiles = (e.m_tiles + 1) / 2;
+    e.m_tiles = p.e.m_tiles;
+  }
+  int stages = (int)((kMaxSmem - 1024 - kTailBytes) / (msub * kABytes + p.b_stage_bytes));
   p.stages = stages > kMaxStages ? kMaxStages : stages;
   p.img_h = d->h;
   p.img_w = d->w;
   p.kw = d->kw;
   p.pad = d->kh / 2;
-  const size_t smem = 1024 + (size_t)p.stages * (kABytes + p.b_stage_bytes) + kTailBytes;
+  const size_t smem = 1024 + (size_t)p.stages * (msub * kABytes + p.b_stage_bytes) + kTailBytes;
   const int tiles = e.m_tiles * e.n_tiles;
   // split-K (see EpiParams): (a) tiny M - eval.py's default call is ONE 32 x 32 patch: the 1024-channel layers are
   // then 1 M tile x 16 N tiles with K = 9216 - 18432, i.e. 16 CTAs streaming 19 - 38 MB of weights while 132 SMs idle -
@@ -1991,7 +2040,7 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   const int kblocks = ntaps * p.kblocks_per_tap;
   int ksplit = 1, split_first = tiles;
   const size_t slab_bytes = (size_t)kBlockM * e.n_tile * sizeof(float);
-  if (can_split) {
+  if (can_split && msub == 1) {
     int tail = tiles * 2 <= grid_cap ? tiles : tiles % grid_cap;            // (a) all tiles, (b) the last wave
     if (tiles * 2 > grid_cap && (g_splitk_tail == 0 || tiles < grid_cap)) tail = 0;
     if (tail > 0 && tail * 2 <= grid_cap) {
@@ -2013,14 +2062,24 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   if (d->dense) {
     rc = make_tmap_im2col_bf16(&tm_a, x, d->n_img, d->h, d->w, (uint64_t)d->x_pitch, p.pad, kBlockM);
     if (rc) return rc;
-    IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    IE_CUDA(launch_pdl(conv_stream_kernel<true>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
+    if (msub == 2) {
+      IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      IE_CUDA(launch_pdl(conv_stream_kernel<true, 2>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
+    } else {
+      IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      IE_CUDA(launch_pdl(conv_stream_kernel<true, 1>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
+    }
   } else {
     rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kBlockM);
     if (rc) return rc;
     if (d->epilogue != IE_EPI_BF16_RASTER) tm_y = tm_a;
-    IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    IE_CUDA(launch_pdl(conv_stream_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
+    if (msub == 2) {
+      IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      IE_CUDA(launch_pdl(conv_stream_kernel<false, 2>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
+    } else {
+      IE_CUDA(cudaFuncSetAttribute(conv_stream_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      IE_CUDA(launch_pdl(conv_stream_kernel<false, 1>, dim3(grid), dim3(kThreads), smem, st, tm_a, tm_b, tm_y, p));
+    }
   }
   IE_LAUNCH_CHECK();
   if (ksplit > 1) {
@@ -2056,6 +2115,7 @@ extern "C" int ie_conv_first_layer_f32(const float* x, int n, int hs, int ws, in
   p.e.relu = relu;
   p.e.epilogue = IE_EPI_BF16_RASTER;
   p.e.ksplit = 1;
+  p.e.msub = 1;
   p.e.split_first = 0;
   p.e.bias = bias;
   p.x = x;
