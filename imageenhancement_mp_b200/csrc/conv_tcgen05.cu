@@ -15,15 +15,17 @@
 //               (or fp32 global stores / per-pixel softmax for the two small heads)
 //
 // Main-loop flavours (the first three share epilogue_loop):
-//   conv_stream_kernel<IM2COL>  wide layers (n_tile 128/256): every (tap, 64-channel block) is one pipeline stage =
+//   conv_stream_kernel<IM2COL, MSUB>  wide layers (n_tile 128/256): every (tap, 64-channel block) is one pipeline stage =
 //                         A box [128 rows x 64 ch] + B box [n_tile x 64]; MMA-bound (88-94 % tensor-pipe active in
 //                         ncu).  IM2COL: dense NHWC activations, the A box is a TMA im2col-mode load (no border rows).
+//                         MSUB = 2: two M tiles per work item share every B box (n_tile 128, the cout = 128 layers).
 //                         Split-K over CTAs for layers with very few tiles (+ splitk_finish_kernel).
 //   conv_resident_kernel  1x1 / 2x2 / narrow 3x3 layers whose whole weight matrix fits in smem: loaded once per CTA;
 //                         a stage is one A box of 128+2 rows per (filter row, channel block), and the horizontal
 //                         taps read it at +0/+1/+2 rows through the descriptor start address.
-//   conv_first_kernel     first layer on the raw fp32 input: builder warps gather the 3x3xC neighbourhood and write the
-//                         swizzled A tile themselves (C = 3, 5, 10).
+//   conv_first_staged_kernel  first layer on the raw fp32 input (C = 3, 5, 10): stager warps bulk-copy the source rows a
+//                         tile touches into a shared-memory ring, builder warps assemble the swizzled A tile from it.
+//                         conv_first_kernel: the same with per-thread global gathers (unaligned sources).
 //   conv_wide_kernel      3x3 layers with cout <= 64 and the fp32 coef head: the three horizontal taps are three column
 //                         groups of ONE N = 192 accumulator, combined in the epilogue (own epilogues; see below).
 // Every kernel is launched with programmatic stream serialization: cta_setup() ends with griddepcontrol.wait.
