@@ -367,8 +367,10 @@ def run_ours(args, cfg_name):
     # (with the serial schedule: when the basis branch runs on its second stream, a bracket around one of its launches
     #  also holds whatever the decoder runs beside it - the sum of brackets would count that time twice)
     n_rf = max(1, min(args.steps, 5))
-    overlap = model._engine.overlap_branches
+    # and with eager launches: a replayed CUDA graph (small configurations) has no per-launch brackets at all
+    overlap, graph_px = model._engine.overlap_branches, model._engine.graph_max_pixels
     model._engine.overlap_branches = False
+    model._engine.graph_max_pixels = 0
     ops.CONV_EVENTS = []
     for i in range(n_rf):
         step(i)
@@ -393,7 +395,7 @@ def run_ours(args, cfg_name):
             print(f"breakdown: {name:34s} {cnt // 3:3d} launches/step {t / 3:8.3f} ms/step {100 * t / 3 / tsum:5.1f}%", file=sys.stderr)
         print(f"breakdown: sum of kernel times {tsum:.3f} ms/step (events around every launch; includes launch gaps "
               f"inside each bracket; serial schedule)", file=sys.stderr)
-    model._engine.overlap_branches = overlap
+    model._engine.overlap_branches, model._engine.graph_max_pixels = overlap, graph_px
 
     # ---- end-to-end timing from pinned host buffers through the public API.  fp32 configurations: eval.evaluate()
     # stages every batch host->device on a side stream (overlapping the previous step), runs forward + fused metrics,

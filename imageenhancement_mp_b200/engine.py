@@ -19,7 +19,7 @@ import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import IE_EPI_BF16_RASTER, IE_EPI_F32_NHWC, IE_EPI_F32_SOFTMAX, ImgEnhError
 from .weights import ADD_LENGTHS, basis_kpn_layers, simplemodel_layers
 
@@ -88,9 +88,12 @@ class Engine:
         self.overlap_branches = bool(params.get("overlap_branches", os.environ.get("IE_OVERLAP", "1") != "0"))
         with torch.cuda.device(self.device):
             self.load_weights(weights)
-        # small batches are launch-bound (44 kernels through ctypes, ~1.5 ms of host time vs ~0.3 ms of GPU time for
-        # eval.py's default batch of one 32x32 patch): replay a captured CUDA graph below this many pixels
-        self.graph_max_pixels = int(params.get("graph_max_pixels", 1 << 17))
+        # small batches are launch-bound (44 kernels through ctypes, ~1.0 ms of host time per forward against ~0.25 ms
+        # of GPU time for eval.py's default batch of one 32x32 patch, and still against 1.5 ms at 32 patches of 100x100
+        # once a loop around the forward adds its own host work): replay a captured CUDA graph below this many pixels.
+        # On the GPU eager and replay cost the same from 16 x 100 x 100 up (profiles/r02_latency_small_final.txt); the
+        # threshold is where the host stops mattering (64 x 100 x 100: 2.8 ms of GPU time per forward).
+        self.graph_max_pixels = int(params.get("graph_max_pixels", 1 << 19))
 
     # ------------------------------------------------------------------ weights
     def load_weights(self, weights):
@@ -195,12 +198,15 @@ class Engine:
                 self.forward(static_x)
             torch.cuda.current_stream(x.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
+            before = sum(_lib.LAUNCHES.values())
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 outs = self.forward(static_x)
-            ent = self._graphs[key] = (g, static_x, outs)
-        g, static_x, outs = ent
+            calls = sum(_lib.LAUNCHES.values()) - before          # C-ABI calls recorded into the graph
+            ent = self._graphs[key] = (g, static_x, outs, calls)
+        g, static_x, outs, calls = ent
         static_x.copy_(x)
         g.replay()
+        _lib.LAUNCHES["(graph replay)"] += calls                 # the launch accounting (bench.py gpu_launches) stays honest
         return tuple(o.clone() for o in outs)               # the graph's output buffers are overwritten by the next replay
 
     # ------------------------------------------------------------------ forward
