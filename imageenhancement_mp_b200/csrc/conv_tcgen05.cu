@@ -19,6 +19,7 @@
 //                         A box [128 rows x 64 ch] + B box [n_tile x 64]; MMA-bound (88-94 % tensor-pipe active in
 //                         ncu).  IM2COL: dense NHWC activations, the A box is a TMA im2col-mode load (no border rows).
 //                         MSUB = 2: two M tiles per work item share every B box (n_tile 128, the cout = 128 layers).
+//   conv_streamT_kernel   cout = 128, cin >= 128: D^T = W X^T, 256 pixels as the N dimension, transposing epilogue.
 //                         Split-K over CTAs for layers with very few tiles (+ splitk_finish_kernel).
 //   conv_resident_kernel  1x1 / 2x2 / narrow 3x3 layers whose whole weight matrix fits in smem: loaded once per CTA;
 //                         a stage is one A box of 128+2 rows per (filter row, channel block), and the horizontal
@@ -577,6 +578,183 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 }
 
 // =================================================================================================
+// Transposed flavour for the cout = 128 layers: D^T = W * X^T.  The A operand is the weight tile [128 cout][64 k], the
+// B operand a box of 256 PIXELS [256][64 k] (same K-major 128B-swizzled tiles as everywhere), the accumulator is
+// [128 lanes = output channels][256 columns = pixels].  Why: an M = 128, N = 128 MMA reads 8 KB of operands from shared
+// memory in its 64 cycles - the whole 128 B/clk port, the N = 128 kernels stop at 60 - 67 % tensor-pipe - while the
+// M = 128, N = 256 MMA used here reads 12 KB in 128 cycles like the big layers (96 B/clk, 95 %).  The price is a
+// transposing epilogue: the thread that owns TMEM lane c holds ONE channel of 32 consecutive pixels per tcgen05.ld, so
+// the bf16 values go to the [pixel][channel] staging tile with 2-byte stores (a warp's 32 channels of one pixel are 64
+// contiguous bytes: one wavefront), the four epilogue warps meet at a named barrier and one thread issues the two
+// 64-channel TMA stores of the 32 pixels.  Same accumulation order as the other kernels: bit-identical output.
+// =================================================================================================
+constexpr int kPixT = 256;                 // pixels (GEMM N) per work item
+__device__ __forceinline__ void epi_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory");
+}
+
+template <bool IM2COL>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_streamT_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                    const __grid_constant__ CUtensorMap tm_y, const StreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = align1024(smem_raw);
+  constexpr int kWBytes = 128 * 128;                       // weight tile: 128 cout x 64 k
+  constexpr int kXBytes = kPixT * 128;                     // pixel box: 256 x 64 k
+  constexpr int stage_bytes = kWBytes + kXBytes;
+  SmemTail t{base + p.stages * stage_bytes};
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_items = p.e.m_tiles;                       // items of 256 pixels
+  const int kblocks = p.ntaps * p.kblocks_per_tap;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_y);
+  }
+  const uint32_t tmem_base = cta_setup(t, p.e, p.stages, warp, lane);
+  uint64_t* full_bar = t.full();
+  uint64_t* empty_bar = t.empty();
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int r0 = item * kPixT;
+        int px0 = 0, py0 = 0, pn0 = 0;
+        if constexpr (IM2COL) {
+          const int plane = p.img_h * p.img_w;
+          pn0 = r0 / plane;
+          const int rem = r0 - pn0 * plane;
+          py0 = rem / p.img_w;
+          px0 = rem - py0 * p.img_w - p.pad;
+          py0 -= p.pad;
+        }
+        int tap = 0, kb = 0;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* dst = base + stage * stage_bytes;
+          tma_load_2d(dst, &tm_w, &full_bar[stage], tap * p.cin + kb * kBlockK, 0);
+          if constexpr (IM2COL) {
+            const int ti = tap / p.kw, tj = tap - ti * p.kw;
+            tma_load_im2col_4d(dst + kWBytes, &tm_x, &full_bar[stage], p.x_coff + kb * kBlockK, px0, py0, pn0, tj, ti);
+          } else {
+            tma_load_2d(dst + kWBytes, &tm_x, &full_bar[stage], p.x_coff + kb * kBlockK, r0 + p.tap_shift[tap]);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (++kb == p.kblocks_per_tap) { kb = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = umma_idesc_bf16(128, kPixT);
+    const uint32_t w_lo0 = umma_desc_lo(smem_u32(base));
+    const uint32_t x_lo0 = umma_desc_lo(smem_u32(base + kWBytes));
+    constexpr uint32_t stage_stride = static_cast<uint32_t>(stage_bytes) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      mbar_wait(&t.tempty()[buf], (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * kAccStride);
+      for (int kbi = 0; kbi < kblocks; ++kbi) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t w_lo = w_lo0 + stage * stage_stride;
+          const uint32_t x_lo = x_lo0 + stage * stage_stride;
+          umma_bf16_ss_lo(d_tmem, w_lo, x_lo, idesc, kbi != 0 ? 1u : 0u);
+          umma_bf16_ss_lo(d_tmem, w_lo + 2, x_lo + 2, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, w_lo + 4, x_lo + 4, idesc, 1u);
+          umma_bf16_ss_lo(d_tmem, w_lo + 6, x_lo + 6, idesc, 1u);
+          umma_commit(&empty_bar[stage]);
+          if (kbi == kblocks - 1) umma_commit(&t.tfull()[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ transposing epilogue ========================
+    const EpiParams& e = p.e;
+    const int q = warp & 3;                          // TMEM lane quadrant = output channels 32q .. 32q + 31
+    const int co = q * 32 + lane;
+    const float bias_c = t.bias()[co];
+    uint8_t* stg0 = t.stg(0);                        // 16 KB: two [32 px][128 ch] bf16 buffers, each two 64-channel halves
+    const bool issuer = (warp == 2 && lane == 0);
+    // byte offset of channel `co` in pixel row j of a buffer: half (co / 64) * 4 KB + row * 128 + swizzled 16-byte chunk
+    const uint32_t half_off = static_cast<uint32_t>(co >> 6) * 4096u;
+    const uint32_t chunk16 = static_cast<uint32_t>((co & 63) >> 3);
+    const uint32_t in_chunk = static_cast<uint32_t>(co & 7) * 2u;
+    int it = 0;
+    int nchunk = 0;                                  // staging buffers alternate over the whole kernel
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = static_cast<uint32_t>(it >> 1);
+      const int r0 = item * kPixT;
+      mbar_wait(&t.tfull()[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * kAccStride);
+      for (int c = 0; c < kPixT / 32; ++c, ++nchunk) {
+        uint32_t v[32];
+        tmem_ld_x32(t_base + c * 32, v);
+        tmem_ld_wait();
+        if (c == kPixT / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t.tempty()[buf]);
+        }
+        // which of the chunk's 32 pixels are kept outputs: lane j decodes pixel j, the ballot is every lane's mask
+        const int r = r0 + c * 32 + lane;
+        bool valid;
+        if (e.dense) {
+          valid = r < e.R;
+        } else {
+          const int img = fastdiv(r, e.plane_m, e.plane_s);
+          const int pr = r - img * e.plane;
+          const int y = fastdiv(pr, e.wp_m, e.wp_s);
+          const int x = pr - y * e.wp;
+          valid = (r < e.R) && (y >= 1) && (y <= e.hv) && (x < e.wv);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+        uint8_t* sb = stg0 + (nchunk & 1) * 8192;
+        // the buffer was the source of the TMA stores two chunks ago
+        if (issuer) tma_store_wait_read<1>();
+        epi_bar_sync(0);
+        const uint32_t colbase = smem_u32(sb) + half_off + in_chunk;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]) + bias_c;
+          uint32_t w = e.relu ? pack_relu_bf16x2(s, 0.f) : pack_bf16x2(s, 0.f);
+          w = ((mask >> j) & 1u) ? w : 0u;
+          sts16(colbase + j * 128 + ((chunk16 ^ (j & 7)) << 4), w);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync(0);
+        if (issuer) {
+          tma_store_2d(&tm_y, sb, e.y_coff, r0 + c * 32);
+          tma_store_2d(&tm_y, sb + 4096, e.y_coff + 64, r0 + c * 32);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
 // Resident-weights kernel: all taps' weights stay in smem; stage = one A box of 128+ndx-1 rows per
 // (filter row, channel block); the ndx horizontal taps address it at +dx rows.
 // =================================================================================================
@@ -741,7 +919,6 @@ constexpr int kSlabOut = 30;           // of which are outputs
 constexpr int kWideTileRows = 4 * kSlabOut;
 constexpr int kXchTileRows = kBlockM - 2;          // exchange variant: one 128-row box, 126 outputs
 
-__device__ __forceinline__ void epi_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(set + 1) : "memory"); }
 
 struct WideParams {
   EpiParams e;
@@ -1783,6 +1960,7 @@ static int g_force_mode = -1;        // -1 auto, 0 stream, 1 resident, 2 wide-N
 static int g_fuse_rows = 1;
 static int g_splitk = 1;             // 0: never split the K loop of the streaming kernel (tests / A-B timing)
 static int g_splitk_tail = 1;        // 0: split-K only for tiny M, not for the last partial wave of larger grids
+static int g_stream_transposed = 1;  // 0: cout = 128 layers through M-tile pairs instead of the transposed kernel (A-B timing)
 static int g_stream_pairs = 1;       // 0: N = 128 streaming layers one M tile per work item (A-B timing)
 static int g_first_gather = 0;       // 1: first layer with per-thread global gathers instead of staged source rows
 static int g_splitk_wide = 1;        // 0: small grids always trade N-tile width for CTAs (the round-1 rule)
@@ -1817,6 +1995,7 @@ extern "C" int ie_conv_set_mode(int mode, int flags) {
   ie::g_splitk_wide = ((flags >> 14) & 1) ? 0 : 1;
   ie::g_first_gather = (flags >> 15) & 1;
   ie::g_stream_pairs = ((flags >> 16) & 1) ? 0 : 1;
+  ie::g_stream_transposed = ((flags >> 17) & 1) ? 0 : 1;
   return IE_OK;
 }
 
@@ -2022,18 +2201,23 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   // work item sharing every weight tile (conv_stream_kernel<.., 2>)
   const int msub = (g_stream_pairs && e.n_tile == 128 && e.n_tiles == 1 && d->epilogue == IE_EPI_BF16_RASTER &&
                     e.m_tiles >= 2 * sm_count()) ? 2 : 1;
-  if (msub == 2) {
+  // ... or, better, the transposed flavour (pixels as the N = 256 dimension) when cout is exactly one 128-row A tile
+  // (from cin = 128 up: with 9 K blocks per item the transposing epilogue - 16 named barriers per 256 pixels - is not
+  //  hidden behind 4 600 MMA cycles; measured 64->128 @52^2: 99 us with pairs, 115 transposed; 128->128: 172 vs 153)
+  const bool transposed = msub == 2 && g_stream_transposed && d->cout == 128 && kblocks_all >= 16;
+  if (msub == 2 && !transposed) {
     p.e.msub = 2;
     p.e.m_tiles = (e.m_tiles + 1) / 2;
     e.m_tiles = p.e.m_tiles;
   }
-  int stages = (int)((kMaxSmem - 1024 - kTailBytes) / (msub * kABytes + p.b_stage_bytes));
+  const int msub_k = transposed ? 1 : msub;            // (the transposed launch sizes its own pipeline)
+  int stages = (int)((kMaxSmem - 1024 - kTailBytes) / (msub_k * kABytes + p.b_stage_bytes));
   p.stages = stages > kMaxStages ? kMaxStages : stages;
   p.img_h = d->h;
   p.img_w = d->w;
   p.kw = d->kw;
   p.pad = d->kh / 2;
-  const size_t smem = 1024 + (size_t)p.stages * (msub * kABytes + p.b_stage_bytes) + kTailBytes;
+  const size_t smem = 1024 + (size_t)p.stages * (msub_k * kABytes + p.b_stage_bytes) + kTailBytes;
   const int tiles = e.m_tiles * e.n_tiles;
   // split-K (see EpiParams): (a) tiny M - eval.py's default call is ONE 32 x 32 patch: the 1024-channel layers are
   // then 1 M tile x 16 N tiles with K = 9216 - 18432, i.e. 16 CTAs streaming 19 - 38 MB of weights while 132 SMs idle -
@@ -2061,6 +2245,29 @@ extern "C" int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const v
   p.e.part = static_cast<float*>(workspace);
   const int items = split_first + (tiles - split_first) * ksplit;
   const int grid = items < grid_cap ? items : grid_cap;
+  if (transposed) {
+    // D^T = W * X^T (conv_streamT_kernel): items of 256 pixels, weights as the A operand
+    StreamParams pt = p;
+    pt.e.msub = 1;
+    pt.e.m_tiles = (int)((R + kPixT - 1) / kPixT);
+    pt.stages = (int)((kMaxSmem - 1024 - kTailBytes) / (128 * 128 + kPixT * 128));
+    if (pt.stages > kMaxStages) pt.stages = kMaxStages;
+    const size_t smem_t = 1024 + (size_t)pt.stages * (128 * 128 + kPixT * 128) + kTailBytes;
+    const int grid_t = pt.e.m_tiles < grid_cap ? pt.e.m_tiles : grid_cap;
+    if (d->dense) {
+      rc = make_tmap_im2col_bf16(&tm_a, x, d->n_img, d->h, d->w, (uint64_t)d->x_pitch, pt.pad, kPixT);
+      if (rc) return rc;
+      IE_CUDA(cudaFuncSetAttribute(conv_streamT_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      IE_CUDA(launch_pdl(conv_streamT_kernel<true>, dim3(grid_t), dim3(kThreads), smem_t, st, tm_a, tm_b, tm_y, pt));
+    } else {
+      rc = make_tmap_2d_bf16(&tm_a, x, (uint64_t)d->x_pitch, (uint64_t)R, (uint64_t)d->x_pitch, 64, kPixT);
+      if (rc) return rc;
+      IE_CUDA(cudaFuncSetAttribute(conv_streamT_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      IE_CUDA(launch_pdl(conv_streamT_kernel<false>, dim3(grid_t), dim3(kThreads), smem_t, st, tm_a, tm_b, tm_y, pt));
+    }
+    IE_LAUNCH_CHECK();
+    return IE_OK;
+  }
   if (d->dense) {
     rc = make_tmap_im2col_bf16(&tm_a, x, d->n_img, d->h, d->w, (uint64_t)d->x_pitch, p.pad, kBlockM);
     if (rc) return rc;

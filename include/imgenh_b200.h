@@ -115,7 +115,8 @@ int ie_conv2d_nhwc_bf16(const ie_conv_desc* d, const void* x, const void* w_pack
  * stream-ordered launches instead of programmatic dependent launch, bit 11 exchange epilogue for the one-block wide-N
  * layers, bit 12 no L2 prefetch in wide-N, bit 13 split-K only for tiny M, bit 14 narrow N tiles
  * instead of split-K on small grids, bit 15 first layer with per-thread gathers instead of staged source rows,
- * bit 16 N = 128 streaming layers without M-tile pairs.  Process-wide.                        */
+ * bit 16 N = 128 streaming layers without M-tile pairs, bit 17 cout = 128 layers through M-tile pairs instead of the
+ * transposed kernel.  Process-wide.                        */
 int ie_conv_set_mode(int mode, int flags);
 
 /* Slow CUDA-core convolution with the same contract; TESTS ONLY (cross-checks the tcgen05 kernel at

@@ -65,7 +65,7 @@ CASES = [
     (1, 16, 16, 128, 128, 2),      # the 2x2 'valid' conv (model_library.py:364)
     (2, 24, 40, 64, 64, 1),        # 1x1 (first layer over im2col rows), non-square
     (3, 26, 26, 1024, 1024, 3),    # the dominant quarter-resolution layer shape
-    (5, 100, 100, 64, 128, 3),     # N tile 128 with >= 2 x SMs M tiles: pairs of M tiles per work item (399 tiles: odd)
+    (5, 100, 100, 64, 128, 3),     # cout = 128 with >= 2 x SMs M tiles: the transposed kernel (51005 rows: ragged last item)
     (4, 104, 104, 128, 128, 3),    # same with two K blocks per tap (345 tiles)
 ]
 
@@ -103,7 +103,7 @@ DENSE_CASES = [
     (2, 4, 8, 64, 64, 3),          # narrow layer through the streaming kernel
     (1, 24, 40, 192, 128, 1),      # 1x1 convolution (pad 0)
     (2, 9, 31, 64, 128, 3),        # odd sizes, 558 pixels
-    (60, 26, 26, 128, 128, 3),     # 317 tiles of N = 128: M-tile pairs through the im2col loads (last pair half empty)
+    (60, 26, 26, 128, 128, 3),     # cout = 128, 40560 pixels: the transposed kernel through 256-pixel im2col boxes (ragged last item)
 ]
 
 
@@ -339,9 +339,11 @@ def test_conv_random_shape_sweep_vs_naive(cuda):
 
 
 @pytest.mark.parametrize("dense", [False, True])
-def test_m_tile_pairs_are_bit_identical_to_single_tiles(cuda, dense):
-    """conv_stream_kernel<.., 2> (two 128-row M tiles per work item sharing each weight tile; N tile 128, large grids)
-    accumulates every output in the same order as the one-tile kernel: same bits (flag 1 << 16 = pairs off)."""
+def test_cout128_flavours_are_bit_identical(cuda, dense):
+    """The three ways a cout = 128 layer with a large grid can run - conv_streamT_kernel (D^T = W X^T: pixels as the
+    N = 256 dimension, transposing epilogue; the default), conv_stream_kernel<.., 2> (two 128-row M tiles per work item
+    sharing each weight tile; flag 1 << 17) and one tile per item (flag 1 << 16) - accumulate every output in the same
+    order: same bits, borders and masked rows included."""
     from imageenhancement_mp_b200 import _lib, ops
     lib = _lib.load()
     n, h, w, cin, cout = (60, 26, 26, 192, 128) if dense else (5, 100, 100, 128, 128)
@@ -350,14 +352,16 @@ def test_m_tile_pairs_are_bit_identical_to_single_tiles(cuda, dense):
     wp = ops.pack_conv_weights(wt.to(cuda))
     outs = []
     try:
-        for flags in (0, 1 << 16):
+        for flags in (0, 1 << 17, 1 << 16):
             lib.ie_conv_set_mode(-1, flags)
-            dst = ops.new_raster(n, h, w, cout, cuda, dense=dense)
+            dst = ops.new_raster(n, h, w, 2 * cout, cuda, dense=dense)          # written as the upper channel slice
             dst.data.fill_(float("nan"))
-            ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice(), k=3)
+            ops.conv2d(src.slice(), wp, b.to(cuda), dst.slice(cout, cout), k=3)
             torch.cuda.synchronize()
-            outs.append(dst.data.clone())
+            assert bool(torch.isnan(dst.data[:, :cout].float()).all())             # wrote only its slice
+            outs.append(dst.data[:, cout:].clone())
     finally:
         lib.ie_conv_set_mode(-1, 0)
     assert not torch.isnan(outs[0].float()).any()
     assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])
