@@ -295,3 +295,78 @@ def test_draw_burst_params_follows_the_reference_crops():
     # source smaller than the crop: the reference pads (h_up - Hs + 1)//2 on both sides (:435-438) -> fixed negative origin
     small = du.draw_burst_params(4, (100, 120), params, generator=g)
     assert torch.equal(small["crop0"], torch.tensor([[-((h_up - 100 + 1) // 2), -((w_up - 120 + 1) // 2)]] * 4))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Invariants the CUDA kernels rely on, restated in Python (the device code cannot run here; these pin the arithmetic
+# the host side and the kernels share).
+
+def _fastdiv_magic(d):
+    """make_fastdiv of csrc/conv_tcgen05.cu: q = umulhi(n, m) >> s for 0 <= n < 2^31, d >= 2."""
+    l = 0
+    while (1 << l) < d:
+        l += 1
+    m = ((1 << (31 + l)) // d) + 1
+    assert m < (1 << 32), d
+    return m, l - 1
+
+
+def test_multiply_high_division_is_exact():
+    """The epilogues / builders / stagers decode raster rows with a multiply-high instead of a division
+    (EpiParams::plane_m ...): exact for every dividend below 2^31 and every divisor the rasters produce."""
+    import random
+    rnd = random.Random(7)
+    divisors = list(range(2, 700)) + [(h + 1) * (w + 1) for h, w in ((8, 8), (104, 104), (720, 1280), (2448, 3264))] \
+        + [rnd.randrange(2, 1 << 30) for _ in range(500)] + [1 << k for k in range(1, 31)] + [(1 << k) + 1 for k in range(1, 30)]
+    for d in divisors:
+        m, s = _fastdiv_magic(d)
+        for n in (0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - d, rnd.randrange(1 << 31), rnd.randrange(1 << 31)):
+            if 0 <= n < (1 << 31):
+                assert ((n * m) >> 32) >> s == n // d, (n, d)
+
+
+@pytest.mark.parametrize("n,h,w,hs,ws,c", [(3, 104, 104, 100, 100, 5), (2, 32, 32, 32, 32, 5), (5, 8, 8, 8, 8, 5), (4, 8, 8, 5, 6, 3),
+                                           (2, 16, 24, 13, 20, 10), (1, 40, 300, 40, 300, 5), (2, 40, 200, 33, 190, 3),
+                                           (4, 4, 4, 2, 2, 5), (8, 2, 2, 1, 1, 3)])
+def test_first_layer_staging_plan_covers_every_read(n, h, w, hs, ws, c):
+    """conv_first_staged_kernel (csrc/conv_tcgen05.cu): per 128-row tile and filter row the stager copies ONE contiguous
+    run of source pixels [lo - 1, hi + 1] (16-byte aligned) into a slot of 130 pixels; the builders then read pixel
+    (y + dy - 1, x + dx - 1) at a slot-relative offset.  Restated with numpy: the run never exceeds the slot and every
+    read a builder makes lands inside its run at the right element."""
+    import numpy as np
+    wp, plane = w + 1, (h + 1) * (w + 1)
+    R = n * plane
+    x = np.arange(n * hs * ws * c, dtype=np.int64)                      # element index = its own value
+    total = x.size
+    if total % 4:
+        pytest.skip("the staged kernel needs a float count that is a multiple of 4 (the gather kernel runs instead)")
+    slot_bytes = ((130 * c * 4 + 32 + 127) // 128) * 128
+    r = np.arange(((R + 127) // 128) * 128)
+    img, pr = r // plane, r % plane
+    yp, xx = pr // wp, pr % wp
+    y = yp - 1
+    interior = (r < R) & (y >= 0) & (y < h) & (xx < w)
+    for dy in range(3):
+        sy = y + dy - 1
+        rowok = interior & (sy >= 0) & (sy < hs)
+        v = (img * hs + sy) * ws + np.minimum(xx, ws - 1)
+        vt = np.where(rowok, v, -1).reshape(-1, 128)
+        hi = vt.max(axis=1)
+        lo = np.where(vt < 0, 1 << 60, vt).min(axis=1)
+        for t in range(vt.shape[0]):
+            if hi[t] < 0:
+                continue                                                  # no reader in this tile: no copy
+            f0, f1 = max((lo[t] - 1) * c, 0), min((hi[t] + 2) * c, total)
+            b0 = (f0 * 4) & ~15
+            nbytes = ((f1 * 4 + 15) & ~15) - b0
+            assert nbytes <= slot_bytes, (t, dy, nbytes, slot_bytes)
+            assert b0 + nbytes <= total * 4
+            run = x[b0 // 4:(b0 + nbytes) // 4]
+            rows = np.nonzero(rowok.reshape(-1, 128)[t])[0] + t * 128
+            for g in range(3):
+                sx = xx[rows] + g - 1
+                ok = (sx >= 0) & (sx < ws)
+                off = ((img[rows] * hs + sy[rows]) * ws + (xx[rows] - 1)) * c - b0 // 4 + g * c
+                off, want = off[ok], ((img[rows] * hs + sy[rows]) * ws + sx)[ok] * c
+                assert (off >= 0).all() and (off + c <= run.size).all()
+                assert (run[off] == want).all()
