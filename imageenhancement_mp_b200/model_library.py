@@ -54,6 +54,15 @@ class _KpnModel:
     def _forward(self, inputs, taps=None, conv_fn="ie_conv2d_nhwc_bf16"):
         if not isinstance(inputs, torch.Tensor) or not inputs.is_cuda:
             raise ImgEnhError("inputs must be a CUDA torch.Tensor [N,H,W,T+add] (no CPU fallback)")
+        if inputs.dim() != 4:
+            raise ImgEnhError(f"inputs must be [N,H,W,T+add], got shape {tuple(inputs.shape)}")
+        if inputs.shape[0] == 0:
+            # an empty batch (a rank whose shard of the last batch is empty): empty outputs, no launch - the reference's
+            # Keras model returns empty tensors of the same trailing shapes
+            e = self._engine
+            n, hs, ws, _ = inputs.shape
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=inputs.device)
+            return f(0, hs, ws, e.T + 1), f(0, e.K, e.K, e.T, e.B), f(0, e.K, e.K, e.T * e.B)
         # sizes that are not multiples of the network stride are zero-padded implicitly by the engine
         if taps is None and conv_fn == "ie_conv2d_nhwc_bf16":
             return self._engine.forward_auto(inputs)          # CUDA-graph replay when the batch is launch-bound

@@ -85,6 +85,19 @@ def test_basis_branch_on_a_side_stream_changes_nothing(cuda, n, h, w):
         assert torch.equal(u, v)
 
 
+def test_empty_batch_gives_empty_outputs(cuda):
+    """N = 0 (a rank whose shard of a batch is empty) launches nothing and returns empty tensors with the trailing
+    shapes of model_library.py:452 / :295."""
+    from imageenhancement_mp_b200 import model_library as ml
+    params = dict(synth.DEFAULT_PARAMS)
+    model = ml.Simplemodel(params, weights=weights.init_weights(weights.simplemodel_layers(params)))
+    T, K, B = params["BURST_LENGTH"], params["Kernel_size"], params["Basis_num"]
+    x = torch.zeros(0, 40, 48, T + 1, device=cuda)
+    out, bas, ob = model(x)
+    assert out.shape == (0, 40, 48, T + 1) and bas.shape == (0, K, K, T, B) and ob.shape == (0, K, K, T * B)
+    assert out.is_cuda and out.dtype == torch.float32
+
+
 def test_forward_is_bit_reproducible(cuda):
     """No floating-point atomics on the forward path: the pooled channel statistics that feed the basis branch are
     reduced across blocks in a fixed order (ie_maxpool2_nhwc_bf16 / ie_channel_mean_nhwc_bf16 with their scratch),
